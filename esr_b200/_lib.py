@@ -1,0 +1,70 @@
+"""ctypes binding of libesr_b200.so (the C ABI declared in include/esr_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libesr_b200.so")
+
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_size_t = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/esr_b200.h (tests/test_capi_symbols.py checks)
+SIGNATURES = {
+    "esr_version": (c_int, []),
+    "esr_last_error": (ctypes.c_char_p, []),
+    "esr_launch_count": (c_i64, []),
+    "esr_scatter_cnt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int,
+                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "esr_scatter_image": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "esr_expand_count": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "esr_expand_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_i64]),
+    "esr_expand_emit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+
+class ESRError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library.  Raises if it has not been built (python -m esr_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ESRError(f"{LIB_PATH} not found: build it with `python -m esr_b200.build` "
+                           "(there is no CPU fallback)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().esr_last_error().decode("utf-8", "replace")
+        if rc == -2:
+            raise ValueError(f"{what}: negative dimensions are not allowed ({msg})")
+        raise ESRError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())

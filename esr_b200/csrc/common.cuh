@@ -1,0 +1,69 @@
+// common.cuh -- shared host/device helpers of libesr_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/esr_b200.h"
+
+namespace esr {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define ESR_CUDA_CHECK(expr)                                                                       \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            esr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return ESR_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+#define ESR_LAUNCH_CHECK()                                                                         \
+    do {                                                                                           \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess) {                                                                   \
+            esr::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return ESR_ECUDA;                                                                      \
+        }                                                                                          \
+        esr::count_launch();                                                                       \
+    } while (0)
+
+#define ESR_REQUIRE(cond, ...)                                                                     \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            esr::set_error(__VA_ARGS__);                                                           \
+            return ESR_EINVAL;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// device properties cache (immutable after first use)
+struct DevInfo { int sm_count; int max_smem_optin; };
+const DevInfo &dev_info();
+
+// ---------------------------------------------------------------------------------------------
+// split-bf16 activation storage: value = float(hi) + float(lo).  hi = RN_bf16(v), lo = RN_bf16(v - hi).
+// The two planes are what the tcgen05 kernels consume directly as MMA operands (3-pass product
+// hi*hi + lo*hi + hi*lo, fp32 accumulate), giving ~2^-17 relative operand error.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
+{
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo)
+{
+    return __bfloat162float(hi) + __bfloat162float(lo);
+}
+#endif
+
+} // namespace esr

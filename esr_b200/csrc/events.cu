@@ -1,0 +1,485 @@
+// events.cu -- the integer/byte side of the hot path on sm_100a:
+//   events -> polarity count images (atomic scatter), dense counts / stacks -> time-sorted event lists
+//   (round-half-even -> exclusive scan -> expand -> stable LSD radix sort on (sample, t) -> padded rows).
+// Reference behaviour restated from dataloader/encodings.py:243-304, dataloader/h5dataset.py:508-528,
+// dataloader/cython_cnt2event/cnt2event.pyx:18-116, dataloader/cython_event_redistribute/event_redistribute.pyx:17-153.
+// All of this is HBM/L2-bound integer work: coalesced streaming reads, L2-resident atomics, no tensor cores.
+#include "common.cuh"
+
+namespace esr {
+
+// =============================================================================================
+// 1. events -> count images
+// =============================================================================================
+// One thread per event (grid-stride inside a frame).  Each event contributes ps*ps to its polarity
+// channel (encodings.py:296-302: ps * mask where mask is ps with the other sign zeroed).
+// Quirk bookkeeping (encodings.py:251-256 mutates xs/ys in place during the FIRST, positive, call):
+//   out-of-range event:  positive -> dropped (its weight was zeroed);  negative -> lands on neg[0,0]
+//   because by the second call its coordinates are already (0,0) and nothing masks it any more.
+__global__ void __launch_bounds__(256)
+k_scatter_cnt(float *__restrict__ xs, float *__restrict__ ys, const float *__restrict__ ps,
+              const int64_t *__restrict__ frame_off, int64_t n_single, int H, int W, float w_lr, float w_hr, float h_lr,
+              float h_hr, int do_lift, int writeback, float *__restrict__ out)
+{
+    const int f = blockIdx.y;
+    const int64_t beg = frame_off ? frame_off[f] : 0, end = frame_off ? frame_off[f + 1] : n_single;
+    float *img = out + (size_t)f * 2 * H * W;
+    const float fW = (float)W, fH = (float)H;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = beg + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+        float x = xs[i], y = ys[i];
+        const float p = ps[i];
+        if (do_lift) {
+            // h5dataset.py:515 then :526 -- two separately rounded fp32 ops; intrinsics forbid FMA contraction
+            x = __fmul_rn(__fdiv_rn(x, w_lr), w_hr);
+            y = __fmul_rn(__fdiv_rn(y, h_lr), h_hr);
+        }
+        const bool oor = (x >= fW) | (x < 0.0f) | (y >= fH) | (y < 0.0f);
+        float vpos = __fmul_rn(p, p < 0.0f ? 0.0f : p);
+        const float vneg = __fmul_rn(p, p > 0.0f ? 0.0f : p);
+        if (oor) { x = 0.0f; y = 0.0f; vpos = 0.0f; }
+        const long long xi = (long long)x, yi = (long long)y;   // .long(): truncation toward zero
+        const size_t pix = (size_t)yi * W + (size_t)xi;
+        if (vpos != 0.0f) atomicAdd(img + pix, vpos);
+        if (vneg != 0.0f) atomicAdd(img + (size_t)H * W + pix, vneg);
+        if (writeback && oor) { xs[i] = 0.0f; ys[i] = 0.0f; }
+    }
+}
+
+// events_to_image (encodings.py:243-268): one image, raw weights ps, out-of-range events dropped and
+// xs/ys/ps zeroed in place when writeback is set.
+__global__ void __launch_bounds__(256)
+k_scatter_image(float *__restrict__ xs, float *__restrict__ ys, float *__restrict__ ps, int64_t n, int H, int W,
+                int writeback, float *__restrict__ img)
+{
+    const float fW = (float)W, fH = (float)H;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float x = xs[i], y = ys[i], p = ps[i];
+        const bool oor = (x >= fW) | (x < 0.0f) | (y >= fH) | (y < 0.0f);
+        if (oor) {
+            if (writeback) { xs[i] = 0.0f; ys[i] = 0.0f; ps[i] = 0.0f; }
+            continue;
+        }
+        if (p != 0.0f) atomicAdd(img + (size_t)(long long)y * W + (size_t)(long long)x, p);
+    }
+}
+
+// =============================================================================================
+// 2. exclusive scan of uint32 (multi-level, tile = 1024 threads x 4)
+// =============================================================================================
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_TILE = SCAN_THREADS * 4;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tiles(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t *__restrict__ tile_sums, int64_t n)
+{
+    __shared__ uint32_t warp_sums[32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (base + k < n) ? in[base + k] : 0u;
+    const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = tsum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - w;                 // exclusive prefix of warp totals
+        if (lane == 31 && tile_sums) tile_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[warp] + incl - tsum;  // exclusive prefix of this thread within the tile
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_add(uint32_t *__restrict__ out, const uint32_t *__restrict__ tile_prefix, int64_t n)
+{
+    const uint32_t add = tile_prefix[blockIdx.x];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+static size_t scan_ws_elems(int64_t n)
+{
+    size_t tot = 0;
+    while (n > SCAN_TILE) { n = ceil_div64(n, SCAN_TILE); tot += align_up((size_t)n, 64); }
+    return tot + 64;
+}
+
+// in-place allowed (in == out).  ws needs scan_ws_elems(n) uint32.
+static int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *ws, cudaStream_t st)
+{
+    if (n <= 0) return ESR_OK;
+    const int64_t nt = ceil_div64(n, SCAN_TILE);
+    if (nt == 1) {
+        k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(in, out, nullptr, n);
+        ESR_LAUNCH_CHECK();
+        return ESR_OK;
+    }
+    k_scan_tiles<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(in, out, ws, n);
+    ESR_LAUNCH_CHECK();
+    int rc = exclusive_scan_u32(ws, ws, nt, ws + align_up((size_t)nt, 64), st);
+    if (rc) return rc;
+    k_scan_add<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(out, ws, n);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+// =============================================================================================
+// 3. round + count (phase 1 of cnt2event / event_redistribute)
+// =============================================================================================
+// grid = (tiles per sample, B).  counts[slot] = number of events the slot emits; per-sample stats are
+// reduced in the block and added with one atomic per block.
+__global__ void __launch_bounds__(256)
+k_expand_count(const float *__restrict__ vals, int64_t S, int kind, uint32_t *__restrict__ counts,
+               unsigned long long *__restrict__ stats /*[B,4]: sum(as i64), nev, neg, maxn*/)
+{
+    const int b = blockIdx.y;
+    const float *v = vals + (size_t)b * S;
+    uint32_t *c = counts + (size_t)b * S;
+    long long sum = 0, nev = 0;
+    int neg = 0;
+    unsigned int mx = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        const float r = rintf(v[s]);               // numpy round(): half to even (cnt2event.pyx:31)
+        const long long ri = (long long)r;
+        sum += ri;
+        unsigned int n;
+        if (kind == 0) { if (ri < 0) { neg = 1; n = 0; } else n = (unsigned int)ri; }
+        else n = (unsigned int)(ri < 0 ? -ri : ri);
+        nev += n;
+        mx = max(mx, n);
+        c[s] = n;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        nev += __shfl_xor_sync(0xffffffffu, nev, d);
+        neg |= __shfl_xor_sync(0xffffffffu, neg, d);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    __shared__ long long s_sum[8], s_nev[8];
+    __shared__ int s_neg[8];
+    __shared__ unsigned int s_mx[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_sum[warp] = sum; s_nev[warp] = nev; s_neg[warp] = neg; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { sum += s_sum[w]; nev += s_nev[w]; neg |= s_neg[w]; mx = max(mx, s_mx[w]); }
+        unsigned long long *st = stats + (size_t)b * 4;
+        if (sum != 0) atomicAdd(st + 0, (unsigned long long)sum);   // two's complement add == signed add
+        if (nev != 0) atomicAdd(st + 1, (unsigned long long)nev);
+        if (neg) atomicOr(st + 2, 1ull);
+        if (mx) atomicMax(st + 3, (unsigned long long)mx);
+    }
+}
+
+// =============================================================================================
+// 4. expand: one sort item per event, in emission order
+// =============================================================================================
+// item = { t_bits | (negative polarity << 31), global slot }.  t >= 0 always, so bit 31 is free.
+struct __align__(8) Item { uint32_t tkey; uint32_t slot; };
+
+// numpy.linspace(t0, t1, n)[j] in float64, rounded once to fp32 (cnt2event.pyx:74; event_redistribute.pyx:63).
+// __d*_rn intrinsics keep the three float64 roundings separate (no FMA), like numpy's array ops.
+__device__ __forceinline__ float linspace_f32(double t0, double t1, unsigned int n, unsigned int j)
+{
+    if (n == 1) return (float)t0;
+    if (j == n - 1) return (float)t1;
+    const double step = __ddiv_rn(__dsub_rn(t1, t0), (double)(n - 1));
+    return (float)__dadd_rn(__dmul_rn((double)j, step), t0);
+}
+
+__global__ void __launch_bounds__(256)
+k_expand_emit(const float *__restrict__ vals, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offs,
+              int64_t total_slots, int C, int HW, int kind, int mode, const double *__restrict__ rnd,
+              Item *__restrict__ items)
+{
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total_slots;
+         s += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t n = counts[s];
+        if (n == 0) continue;
+        const uint32_t off = offs[s];
+        uint32_t negbit;
+        double t0 = 0.0, t1 = 1.0;
+        float t0f = 0.0f, t1f = 1.0f;
+        if (kind == 0) {
+            negbit = (uint32_t)((s / HW) & 1);                    // channel 1 = negative (cnt2event.pyx:80-90)
+        } else {
+            negbit = vals[s] < 0.0f ? 1u : 0u;                    // p = sign(value); P index ignored
+            const int c = (int)((s / HW) % C);
+            // cdef float t0, t1 <- float64 expressions (event_redistribute.pyx:61-62)
+            t0f = (float)__dadd_rn(__ddiv_rn((double)c, (double)C), __ddiv_rn(1.0, (double)(100 * C)));
+            t1f = (float)__ddiv_rn((double)(c + 1), (double)C);
+            t0 = (double)t0f; t1 = (double)t1f;
+        }
+        for (uint32_t j = 0; j < n; ++j) {
+            float t;
+            if (mode == 0) t = linspace_f32(t0, t1, n, j);
+            else if (kind == 0) t = (float)rnd[(size_t)off + j];
+            else t = (float)__dadd_rn(__dmul_rn(rnd[(size_t)off + j], (double)__fsub_rn(t1f, t0f)), t0);
+            Item it;
+            it.tkey = __float_as_uint(t) | (negbit << 31);
+            it.slot = (uint32_t)s;
+            items[(size_t)off + j] = it;
+        }
+    }
+}
+
+// =============================================================================================
+// 5. stable LSD radix sort, 8 bits per pass, key = (sample, t)
+// =============================================================================================
+// pass p < 4 : digit = byte p of the fp32 timestamp bits (non-negative floats order like integers);
+// pass 4     : digit = sample index (emission order is sample-major, so this pass only matters when
+//              B > 1; B <= 256 per call, larger batches are split by the host wrapper).
+// Each warp owns a contiguous sub-tile so that (warp, round, lane) order == input order => stable.
+constexpr int RS_WARPS = 8;
+constexpr int RS_IPT = 8;                                  // rounds of 32 consecutive items per warp
+constexpr int RS_TILE = RS_WARPS * 32 * RS_IPT;            // 2048 items per block
+
+__device__ __forceinline__ uint32_t rs_digit(const Item &it, int pass, uint32_t slots_per_sample)
+{
+    if (pass < 4) return ((it.tkey & 0x7fffffffu) >> (8 * pass)) & 255u;
+    return (it.slot / slots_per_sample) & 255u;
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_radix_hist(const Item *__restrict__ items, int64_t n, int pass, uint32_t slots_per_sample,
+             uint32_t *__restrict__ hist /*[256][nblocks]*/)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+    for (int k = threadIdx.x; k < RS_TILE; k += RS_WARPS * 32) {
+        const int64_t i = base + k;
+        if (i < n) atomicAdd(&h[rs_digit(items[i], pass, slots_per_sample)], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+// Final pass writes the padded [B, maxlen, 4] rows directly instead of items.
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, int64_t n, int pass, uint32_t slots_per_sample,
+                const uint32_t *__restrict__ hist_scanned /*[256][nblocks] exclusive*/,
+                int final_pass, float *__restrict__ rows, const int64_t *__restrict__ sample_start, int64_t maxlen,
+                int W, int H)
+{
+    __shared__ uint32_t cnt[RS_WARPS][256];     // per-warp digit counters -> then per-warp bases
+    __shared__ uint32_t gbase[256];
+    for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_WARPS * 32) (&cnt[0][0])[k] = 0;
+    gbase[threadIdx.x] = hist_scanned[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_IPT);
+    Item it[RS_IPT];
+    uint32_t dig[RS_IPT], rank[RS_IPT];
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {
+        const int64_t i = wbase + r * 32 + lane;
+        const bool valid = i < n;
+        if (valid) it[r] = in[i];
+        dig[r] = valid ? rs_digit(it[r], pass, slots_per_sample) : 0xffffffffu;
+        // rank among the lanes of this round holding the same digit
+        const uint32_t peers = __match_any_sync(0xffffffffu, dig[r]);
+        const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+        uint32_t old = 0;
+        if (valid) {
+            const int leader = __ffs(peers) - 1;
+            if (lane == leader) { old = cnt[warp][dig[r]]; cnt[warp][dig[r]] = old + __popc(peers); }
+            old = __shfl_sync(peers, old, leader);
+        }
+        rank[r] = old + before;
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix over warps for every digit (thread d handles digit d)
+    {
+        uint32_t run = 0;
+        const int d = threadIdx.x;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { const uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {
+        const int64_t i = wbase + r * 32 + lane;
+        if (i >= n) continue;
+        const size_t pos = (size_t)gbase[dig[r]] + cnt[warp][dig[r]] + rank[r];
+        if (!final_pass) { out[pos] = it[r]; continue; }
+        const uint32_t slot = it[r].slot;
+        const uint32_t b = slot / slots_per_sample;
+        const uint32_t in_s = slot - b * slots_per_sample;
+        const uint32_t x = in_s % (uint32_t)W, y = (in_s / (uint32_t)W) % (uint32_t)H;
+        float4 row;
+        row.x = (float)x; row.y = (float)y;
+        row.z = __uint_as_float(it[r].tkey & 0x7fffffffu);
+        row.w = (it[r].tkey >> 31) ? -1.0f : 1.0f;
+        const int64_t local = (int64_t)pos - sample_start[b];
+        reinterpret_cast<float4 *>(rows)[(size_t)b * maxlen + local] = row;
+    }
+}
+
+} // namespace esr
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace esr;
+
+extern "C" int esr_scatter_cnt(float *xs, float *ys, const float *ps, const int64_t *frame_off, int F,
+                               int64_t n_max_frame, int H, int W, int lift_w_lr, int lift_w_hr, int lift_h_lr,
+                               int lift_h_hr, int writeback, float *out, esr_stream_t stream)
+{
+    ESR_REQUIRE(F >= 0 && H > 0 && W > 0 && out, "esr_scatter_cnt: bad dims F=%d H=%d W=%d", F, H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (F == 0) return ESR_OK;
+    ESR_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)F * 2 * H * W, st));
+    if (n_max_frame <= 0) return ESR_OK;
+    ESR_REQUIRE(xs && ys && ps, "esr_scatter_cnt: null event arrays");
+    ESR_REQUIRE(frame_off || F == 1, "esr_scatter_cnt: frame_off may be null only for a single frame");
+    const int do_lift = (lift_w_lr > 0 && lift_w_hr > 0 && lift_h_lr > 0 && lift_h_hr > 0) ? 1 : 0;
+    // enough blocks per frame to cover the longest frame at ~8 events per thread, capped for huge frames
+    int64_t bx = ceil_div64(n_max_frame, 256 * 8);
+    const int64_t cap = (int64_t)dev_info().sm_count * 16;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    ESR_REQUIRE(F <= 65535, "esr_scatter_cnt: at most 65535 frames per call");
+    dim3 grid((unsigned)bx, (unsigned)F);
+    k_scatter_cnt<<<grid, 256, 0, st>>>(xs, ys, ps, frame_off, n_max_frame, H, W, (float)lift_w_lr, (float)lift_w_hr,
+                                         (float)lift_h_lr, (float)lift_h_hr, do_lift, writeback && !do_lift, out);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+extern "C" int esr_scatter_image(float *xs, float *ys, float *ps, int64_t n, int H, int W, int writeback, float *out,
+                                 esr_stream_t stream)
+{
+    ESR_REQUIRE(H > 0 && W > 0 && out && n >= 0, "esr_scatter_image: bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)H * W, st));
+    if (n == 0) return ESR_OK;
+    ESR_REQUIRE(xs && ys && ps, "esr_scatter_image: null event arrays");
+    int64_t bx = ceil_div64(n, 256 * 8);
+    const int64_t cap = (int64_t)dev_info().sm_count * 16;
+    if (bx > cap) bx = cap;
+    k_scatter_image<<<(unsigned)bx, 256, 0, st>>>(xs, ys, ps, n, H, W, writeback, out);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+extern "C" int esr_expand_count(const float *vals, int B, int P, int C, int H, int W, int kind, int64_t *stats,
+                                uint32_t *counts, esr_stream_t stream)
+{
+    ESR_REQUIRE(vals && stats && counts, "esr_expand_count: null pointer");
+    ESR_REQUIRE(B > 0 && P > 0 && C > 0 && H > 0 && W > 0 && (kind == 0 || kind == 1), "esr_expand_count: bad dims");
+    ESR_REQUIRE(kind != 0 || (P == 2 && C == 1), "esr_expand_count: cnt2event needs [B,2,H,W]");
+    ESR_REQUIRE(B <= 256, "esr_expand_count: at most 256 samples per call");
+    const int64_t S = (int64_t)P * C * H * W;
+    ESR_REQUIRE((int64_t)B * S < (1ll << 32), "esr_expand_count: more than 2^32 slots");
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(int64_t) * 4 * (size_t)B, st));
+    int64_t bx = ceil_div64(S, 256 * 4);
+    const int64_t cap = (int64_t)dev_info().sm_count * 8;
+    if (bx > cap) bx = cap;
+    dim3 grid((unsigned)bx, (unsigned)B);
+    k_expand_count<<<grid, 256, 0, st>>>(vals, S, kind, counts, reinterpret_cast<unsigned long long *>(stats));
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+static size_t expand_ws_layout(int64_t slots, int64_t E, size_t *o_offs, size_t *o_scanws, size_t *o_items0,
+                               size_t *o_items1, size_t *o_hist, size_t *o_histws, size_t *o_start)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off = align_up(off + bytes, 256); return r; };
+    const int64_t nblk = ceil_div64(E > 0 ? E : 1, RS_TILE);
+    *o_offs = take(sizeof(uint32_t) * (size_t)slots);
+    *o_scanws = take(sizeof(uint32_t) * scan_ws_elems(slots));
+    *o_items0 = take(sizeof(Item) * (size_t)(E > 0 ? E : 1));
+    *o_items1 = take(sizeof(Item) * (size_t)(E > 0 ? E : 1));
+    *o_hist = take(sizeof(uint32_t) * 256 * (size_t)nblk);
+    *o_histws = take(sizeof(uint32_t) * scan_ws_elems(256 * nblk));
+    *o_start = take(sizeof(int64_t) * 256);
+    return off;
+}
+
+extern "C" size_t esr_expand_workspace_bytes(int B, int P, int C, int H, int W, int64_t total_events)
+{
+    size_t a, b, c, d, e, f, g;
+    return expand_ws_layout((int64_t)B * P * C * H * W, total_events, &a, &b, &c, &d, &e, &f, &g);
+}
+
+extern "C" int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P, int C, int H, int W, int kind,
+                               int mode, const double *rnd, const int32_t *active_host, const int64_t *start_host,
+                               int64_t total_events, int64_t maxlen, float *out, void *workspace,
+                               size_t workspace_bytes, esr_stream_t stream)
+{
+    ESR_REQUIRE(vals && counts && active_host && start_host && out && workspace, "esr_expand_emit: null pointer");
+    ESR_REQUIRE(B > 0 && B <= 256 && (mode == 0 || mode == 1), "esr_expand_emit: bad B/mode");
+    ESR_REQUIRE(mode == 0 || rnd, "esr_expand_emit: mode 1 needs the random stream");
+    ESR_REQUIRE(total_events >= 0 && total_events < (1ll << 31), "esr_expand_emit: more than 2^31 events");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t S = (int64_t)P * C * H * W, slots = (int64_t)B * S;
+    if (total_events == 0) return ESR_OK;
+    size_t o_offs, o_scanws, o_i0, o_i1, o_hist, o_histws, o_start;
+    const size_t need = expand_ws_layout(slots, total_events, &o_offs, &o_scanws, &o_i0, &o_i1, &o_hist, &o_histws, &o_start);
+    if (workspace_bytes < need) { set_error("esr_expand_emit: workspace %zu < %zu", workspace_bytes, need); return ESR_EWORKSPACE; }
+    char *ws = (char *)workspace;
+    uint32_t *offs = (uint32_t *)(ws + o_offs), *scanws = (uint32_t *)(ws + o_scanws);
+    Item *items[2] = {(Item *)(ws + o_i0), (Item *)(ws + o_i1)};
+    uint32_t *hist = (uint32_t *)(ws + o_hist), *histws = (uint32_t *)(ws + o_histws);
+    int64_t *d_start = (int64_t *)(ws + o_start);
+
+    // samples the reference treats as empty (rounded values sum to zero) emit nothing
+    for (int b = 0; b < B; ++b)
+        if (!active_host[b]) ESR_CUDA_CHECK(cudaMemsetAsync(counts + (size_t)b * S, 0, sizeof(uint32_t) * (size_t)S, st));
+    ESR_CUDA_CHECK(cudaMemcpyAsync(d_start, start_host, sizeof(int64_t) * (size_t)B, cudaMemcpyHostToDevice, st));
+
+    int rc = exclusive_scan_u32(counts, offs, slots, scanws, st);
+    if (rc) return rc;
+    {
+        int64_t bx = ceil_div64(slots, 256 * 2);
+        const int64_t cap = (int64_t)dev_info().sm_count * 32;
+        if (bx > cap) bx = cap;
+        k_expand_emit<<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, slots, C, H * W, kind, mode, rnd, items[0]);
+        ESR_LAUNCH_CHECK();
+    }
+    const int64_t nblk = ceil_div64(total_events, RS_TILE);
+    const int npass = B > 1 ? 5 : 4;
+    int cur = 0;
+    for (int p = 0; p < npass; ++p) {
+        k_radix_hist<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], total_events, p, (uint32_t)S, hist);
+        ESR_LAUNCH_CHECK();
+        rc = exclusive_scan_u32(hist, hist, 256 * nblk, histws, st);
+        if (rc) return rc;
+        const int fin = p == npass - 1;
+        k_radix_scatter<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], items[cur ^ 1], total_events, p, (uint32_t)S,
+                                                                  hist, fin, out, d_start, maxlen, W, H);
+        ESR_LAUNCH_CHECK();
+        cur ^= 1;
+    }
+    return ESR_OK;
+}

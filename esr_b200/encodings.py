@@ -1,0 +1,129 @@
+"""GPU mirror of the reference's dataloader/encodings.py for the functions on the hot path.
+
+Same names, positional arguments and side effects as the reference:
+  events_to_image(xs, ys, ps, sensor_size)        encodings.py:243-268
+  events_to_channels(xs, ys, ps, sensor_size)     encodings.py:289-304
+  cython_event_redistribute(event_stack, mode)    encodings.py:466-484
+  multiprocess_cython(event_stack, mode)          encodings.py:495-533 (per-sample calls, no process pool)
+  stack2cnt(stack)                                encodings.py:652-670
+plus the batched entry point the B200 pipeline uses:
+  encode_frames(xs, ys, ps, frame_off, lr_size, hr_size)  -> [F,2,kH,kW] on the GPU, fusing the LR->HR lift of
+                                                            dataloader/h5dataset.py:508-528.
+CPU tensors are accepted (copied to the current CUDA device, result and in-place side effects copied back);
+CUDA tensors are processed in place.  There is no CPU implementation here.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import event_redistribute as c_event_redistribute
+from .expand import expand
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_dev_f32(t, dev):
+    """(device fp32 contiguous tensor, needs_copy_back)"""
+    if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+        return t, False
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous(), True
+
+
+def events_to_image(xs, ys, ps, sensor_size=(180, 240)):
+    """Accumulate events into an image (raw weights).  xs, ys, ps are modified in place like the reference."""
+    dev = xs.device if xs.is_cuda else _dev()
+    dx, cbx = _to_dev_f32(xs, dev)
+    dy, cby = _to_dev_f32(ys, dev)
+    dp, cbp = _to_dev_f32(ps, dev)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    out = torch.empty((H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().esr_scatter_image(_lib.ptr(dx), _lib.ptr(dy), _lib.ptr(dp), dx.numel(), H, W, 1,
+                                                _lib.ptr(out), _lib.stream_ptr()), "esr_scatter_image")
+    for src, d, cb in ((xs, dx, cbx), (ys, dy, cby), (ps, dp, cbp)):
+        if cb and src.dtype == torch.float32:
+            src.copy_(d)
+    return out if xs.is_cuda else out.cpu()
+
+
+def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
+    """Two-channel event count image [2,H,W] (0: positive, 1: negative).  xs, ys are modified in place
+    (out-of-range coordinates -> 0) exactly as the reference does."""
+    assert len(xs) == len(ys) and len(ys) == len(ps)
+    dev = xs.device if xs.is_cuda else _dev()
+    dx, cbx = _to_dev_f32(xs, dev)
+    dy, cby = _to_dev_f32(ys, dev)
+    dp, _ = _to_dev_f32(ps, dev)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    out = torch.empty((2, H, W), dtype=torch.float32, device=dev)
+    n = dx.numel()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().esr_scatter_cnt(_lib.ptr(dx), _lib.ptr(dy), _lib.ptr(dp), None, 1, n, H, W,
+                                              0, 0, 0, 0, 1, _lib.ptr(out), _lib.stream_ptr()), "esr_scatter_cnt")
+    if cbx and xs.dtype == torch.float32:
+        xs.copy_(dx)
+    if cby and ys.dtype == torch.float32:
+        ys.copy_(dy)
+    return out if xs.is_cuda else out.cpu()
+
+
+def encode_frames(xs, ys, ps, frame_off, lr_size=None, hr_size=(180, 240), n_max_frame=None):
+    """F frames of events -> [F,2,H,W] count images in one launch.
+
+    xs, ys, ps: CUDA fp32 [n_total]; frame_off: CUDA int64 [F+1].  With lr_size=(H_lr,W_lr) the coordinates
+    are lifted x/W_lr*W_hr (two fp32 roundings, h5dataset.py:515,526) before the scatter = `inp_scaled_cnt`."""
+    assert xs.is_cuda and ys.is_cuda and ps.is_cuda and frame_off.is_cuda
+    F = frame_off.numel() - 1
+    H, W = int(hr_size[0]), int(hr_size[1])
+    out = torch.empty((F, 2, H, W), dtype=torch.float32, device=xs.device)
+    if n_max_frame is None:
+        n_max_frame = xs.numel()
+    lift = (int(lr_size[1]), W, int(lr_size[0]), H) if lr_size is not None else (0, 0, 0, 0)
+    with torch.cuda.device(xs.device):
+        _lib.check(_lib.lib().esr_scatter_cnt(_lib.ptr(xs), _lib.ptr(ys), _lib.ptr(ps), _lib.ptr(frame_off), F,
+                                              int(n_max_frame), H, W, *lift, 0, _lib.ptr(out), _lib.stream_ptr()),
+                   "esr_scatter_cnt")
+    return out
+
+
+def cython_event_redistribute(event_stack, mode='linear'):
+    if mode == 'linear':
+        cmode = 0
+    elif mode == 'random':
+        cmode = 1
+    else:
+        raise Exception(f'Not support {mode}')
+    if len(event_stack.shape) not in (4, 5):
+        raise Exception('wrong event stack')
+    dev = event_stack.device if event_stack.is_cuda else _dev()
+    return expand(event_stack.detach().to(dev, torch.float32), 1, cmode).cpu()
+
+
+def multiprocess_cython(event_stack, mode='linear'):
+    """Reference: one Pool() task per batch element (each reseeding numpy to 123); here one GPU call per element."""
+    if mode == 'linear':
+        cmode = 0
+    elif mode == 'random':
+        cmode = 1
+    else:
+        raise Exception(f'Not support {mode}')
+    if len(event_stack.shape) not in (4, 5):
+        raise Exception('wrong event stack')
+    dev = event_stack.device if event_stack.is_cuda else _dev()
+    st = event_stack.detach().to(dev, torch.float32)
+    clouds = [expand(st[i:i + 1], 1, cmode) for i in range(st.shape[0])]
+    maxlen = max(c.shape[1] for c in clouds)
+    out = torch.zeros((st.shape[0], maxlen, 4), dtype=torch.float32, device=dev)
+    for i, c in enumerate(clouds):
+        out[i, :c.shape[1]] = c[0]
+    return out.cpu()
+
+
+def stack2cnt(stack):
+    """stack BxTBxHxW -> Bx2xHxW (0 positive, 1 negative).  encodings.py:652-670 (pure tensor algebra)."""
+    stack = stack.clone().detach().round()
+    pos = stack.clamp(min=0).sum(1)
+    neg = (-stack.clamp(max=0)).sum(1)
+    return torch.stack([pos, neg], dim=1).cpu()

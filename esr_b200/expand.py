@@ -1,0 +1,81 @@
+"""Host side of the dense-counts -> event-list kernels (esr_expand_count / esr_expand_emit).
+
+Shared by esr_b200.cnt2event (cnt2event.pyx:18-116) and esr_b200.event_redistribute
+(event_redistribute.pyx:17-153).  The one host synchronisation (reading the per-sample statistics) is
+inherent: the output length is data dependent, exactly like the reference's np.zeros([batch, maxlen, 4]).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _numpy_stream(n):
+    """The reference reseeds numpy's GLOBAL legacy RNG on every call (cnt2event.pyx:25) and then draws one
+    float64 per event in emission order; reproduce both the values and the side effect."""
+    np.random.seed(123)
+    return np.random.random([int(n)])
+
+
+def expand(vals, kind, mode):
+    """vals: CUDA fp32 tensor [B,2,H,W] (kind 0) or [B,P,C,H,W] / [B,C,H,W] (kind 1) -> CUDA fp32 [B,maxlen,4]."""
+    if not vals.is_cuda:
+        raise _lib.ESRError("esr_b200.expand needs a CUDA tensor (no CPU fallback)")
+    vals = vals.contiguous().float()
+    if kind == 0:
+        assert vals.dim() == 4 and vals.shape[1] == 2, "Wrong event count data!"
+        B, P, H, W = vals.shape
+        C = 1
+    elif vals.dim() == 5:
+        B, P, C, H, W = vals.shape
+    elif vals.dim() == 4:
+        B, C, H, W = vals.shape
+        P = 1
+    else:
+        raise Exception("wrong event stack")
+    if B > 256:   # the radix sort carries the sample index in one 8-bit digit
+        parts = [expand(vals[i:i + 256], kind, mode) for i in range(0, B, 256)]
+        maxlen = max(p.shape[1] for p in parts)
+        out = vals.new_zeros((B, maxlen, 4))
+        for i, p in enumerate(parts):
+            out[i * 256:i * 256 + p.shape[0], :p.shape[1]] = p
+        return out
+    L = _lib.lib()
+    dev = vals.device
+    S = P * C * H * W
+    stats = torch.empty((B, 4), dtype=torch.int64, device=dev)
+    counts = torch.empty((B * S,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr()
+        _lib.check(L.esr_expand_count(_lib.ptr(vals), B, P, C, H, W, kind, _lib.ptr(stats), _lib.ptr(counts), st),
+                   "esr_expand_count")
+        h = stats.cpu().numpy()                     # the one host sync
+        sums, nev, neg = h[:, 0], h[:, 1], h[:, 2]
+        if int(sums.sum()) == 0:                    # `if event_cnt_round.sum() != 0` (cnt2event.pyx:56)
+            if mode == 1:
+                np.random.seed(123)
+            return torch.zeros((B, 1, 4), dtype=torch.float32, device=dev)
+        active = (sums != 0)
+        if kind == 0 and bool((active & (neg != 0)).any()):
+            np.random.seed(123)
+            raise ValueError("negative dimensions are not allowed")     # np.zeros([-n, 4]) in the reference
+        lens = np.where(active, nev, 1).astype(np.int64)
+        maxlen = int(lens.max())
+        ev = np.where(active, nev, 0).astype(np.int64)
+        total = int(ev.sum())
+        start = np.concatenate([[0], np.cumsum(ev)[:-1]]).astype(np.int64)
+        out = torch.zeros((B, maxlen, 4), dtype=torch.float32, device=dev)
+        rnd = None
+        if mode == 1:
+            rnd = torch.from_numpy(_numpy_stream(total)).to(dev)
+        else:
+            np.random.seed(123)                     # visible side effect of every reference call
+        nbytes = L.esr_expand_workspace_bytes(B, P, C, H, W, total)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        act32 = np.ascontiguousarray(active.astype(np.int32))
+        _lib.check(L.esr_expand_emit(_lib.ptr(vals), _lib.ptr(counts), B, P, C, H, W, kind, int(mode), _lib.ptr(rnd),
+                                     act32.ctypes.data_as(ctypes.c_void_p), start.ctypes.data_as(ctypes.c_void_p),
+                                     total, maxlen, _lib.ptr(out), _lib.ptr(ws), nbytes, st), "esr_expand_emit")
+    return out

@@ -1,0 +1,82 @@
+/*
+ * esr_b200.h -- C ABI of libesr_b200.so, the B200 (sm_100a) implementation of WarranWeng/ESR's
+ * per-timestep hot path.  Plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ * its name ends in _host.  The caller owns every buffer and the stream; the library allocates no
+ * user-visible memory (workspaces are sized by *_workspace_bytes and passed in).  All functions return
+ * ESR_OK (0) or a negative error code; esr_last_error() gives the message for the calling thread.
+ * Calls are asynchronous on `stream` unless stated otherwise.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef ESR_B200_H
+#define ESR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESR_OK 0
+#define ESR_EINVAL (-1)       /* bad argument */
+#define ESR_ENEGCOUNT (-2)    /* negative rounded count: the reference raises ValueError (cnt2event.pyx:71) */
+#define ESR_ECUDA (-3)        /* CUDA runtime / driver error */
+#define ESR_EUNSUPPORTED (-4) /* configuration outside what the sm_100a kernels implement */
+#define ESR_EWORKSPACE (-5)   /* workspace too small */
+
+typedef void *esr_stream_t; /* cudaStream_t */
+
+int esr_version(void);
+const char *esr_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+int64_t esr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * events -> 2-channel polarity count images
+ * Replaces: dataloader/encodings.py:289-304 events_to_channels (+ :243-268 events_to_image), and, with
+ * lift_* set, the LR->HR coordinate lift of dataloader/h5dataset.py:508-528 (x / W_lr * W_hr in fp32,
+ * two roundings).  F frames in one launch: frame f owns events [frame_off[f], frame_off[f+1]).
+ *   xs, ys, ps : fp32 [n_total]        frame_off : int64 [F+1] (device)
+ *   out        : fp32 [F, 2, H, W], overwritten (zeroed by the call)
+ *   lift_w_lr/lift_w_hr/lift_h_lr/lift_h_hr : 0 = coordinates used as given
+ *   writeback  : 1 = reproduce the reference's in-place side effect (out-of-range xs, ys set to 0)
+ * Reference quirks kept: out-of-range positive events are dropped, out-of-range NEGATIVE events are
+ * counted at neg[0,0]; fractional coordinates truncate toward zero; each event adds ps*ps.
+ * --------------------------------------------------------------------------------------------- */
+int esr_scatter_cnt(float *xs, float *ys, const float *ps, const int64_t *frame_off, int F, int64_t n_max_frame,
+                    int H, int W, int lift_w_lr, int lift_w_hr, int lift_h_lr, int lift_h_hr, int writeback,
+                    float *out, esr_stream_t stream);
+
+/* Replaces: dataloader/encodings.py:243-268 events_to_image.  One image, raw weights: out[(long)y,(long)x] += ps;
+ * out-of-range events are dropped and, with writeback = 1, xs/ys/ps are zeroed in place like the reference. */
+int esr_scatter_image(float *xs, float *ys, float *ps, int64_t n, int H, int W, int writeback, float *out,
+                      esr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * dense counts / time-bin stacks -> time-sorted event lists
+ * Replaces: dataloader/cython_cnt2event/cnt2event.pyx:18-116 (kind 0: vals = [B,2,H,W], P=2, C=1) and
+ * dataloader/cython_event_redistribute/event_redistribute.pyx:17-83 / :88-153 (kind 1: vals =
+ * [B,P,C,H,W], P=1 for the NoPolarity form).
+ *
+ * Two phases, because the output length depends on the data:
+ *  1. esr_expand_count: rounds (half-to-even) and counts.  stats : int64 [B,4] (device) =
+ *     {sum of rounded values, number of events, any-negative flag, max per-slot count}; counts : uint32
+ *     [B*P*C*H*W] (device, kept for phase 2).
+ *  2. the host reads stats, applies the reference's emptiness rules (a sample whose rounded values sum to
+ *     zero yields one zero row; an all-zero call yields [B,1,4]), sizes out = [B, maxlen, 4] (zero-filled)
+ *     and calls esr_expand_emit with active_host[b] / start_host[b] (first sorted row of sample b in the
+ *     global event order).  mode 0 = linear timestamps (float64 linspace -> fp32), mode 1 = the caller's
+ *     random stream rnd[total_events] (float64, numpy MT19937 seed 123, one value per event in emission order).
+ * --------------------------------------------------------------------------------------------- */
+int esr_expand_count(const float *vals, int B, int P, int C, int H, int W, int kind, int64_t *stats, uint32_t *counts,
+                     esr_stream_t stream);
+size_t esr_expand_workspace_bytes(int B, int P, int C, int H, int W, int64_t total_events);
+int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P, int C, int H, int W, int kind, int mode,
+                    const double *rnd, const int32_t *active_host, const int64_t *start_host, int64_t total_events,
+                    int64_t maxlen, float *out, void *workspace, size_t workspace_bytes, esr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESR_B200_H */

@@ -1,0 +1,148 @@
+"""GPU parity of the event path: CUDA kernels (through the C ABI) vs the C oracle and the reference-generated
+golden vectors.  Bit-exact (integer / index work; fp32 timestamps are produced by identical float64 arithmetic)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def test_events_to_channels_golden(golden_events, dev):
+    from esr_b200 import encodings as enc
+    g = golden_events
+    for i in range(int(g["n_e2c"])):
+        xs, ys, ps = (torch.from_numpy(g[f"e2c{i}_{k}"].copy()) for k in ("xs", "ys", "ps"))
+        H, W = g[f"e2c{i}_hw"]
+        out = enc.events_to_channels(xs, ys, ps, sensor_size=(int(H), int(W)))      # CPU tensors in, like the reference
+        assert not out.is_cuda
+        assert np.array_equal(out.numpy(), g[f"e2c{i}_out"]), i
+        assert np.array_equal(xs.numpy(), g[f"e2c{i}_xs_after"]) and np.array_equal(ys.numpy(), g[f"e2c{i}_ys_after"])
+        # CUDA tensors in place
+        cx, cy, cp = (torch.from_numpy(g[f"e2c{i}_{k}"].copy()).to(dev) for k in ("xs", "ys", "ps"))
+        out = enc.events_to_channels(cx, cy, cp, sensor_size=(int(H), int(W)))
+        assert out.is_cuda and np.array_equal(out.cpu().numpy(), g[f"e2c{i}_out"])
+        assert np.array_equal(cx.cpu().numpy(), g[f"e2c{i}_xs_after"])
+
+
+def test_lift_golden(golden_events, dev):
+    from esr_b200 import encodings as enc
+    g = golden_events
+    for i in range(int(g["n_lift"])):
+        H, W, k = (int(v) for v in g[f"lift{i}_dims"])
+        xs, ys, ps = (torch.from_numpy(g[f"lift{i}_{n}"]).to(dev) for n in ("xs", "ys", "ps"))
+        off = torch.tensor([0, xs.numel()], dtype=torch.int64, device=dev)
+        out = enc.encode_frames(xs, ys, ps, off, lr_size=(H, W), hr_size=(H * k, W * k))
+        assert np.array_equal(out[0].cpu().numpy(), g[f"lift{i}_out"]), i
+
+
+def test_events_to_image_vs_oracle(dev):
+    from esr_b200 import encodings as enc
+    rng = np.random.default_rng(5)
+    n, H, W = 30000, 37, 61
+    xs = (rng.random(n) * (W + 8) - 4).astype(np.float32)
+    ys = (rng.random(n) * (H + 8) - 4).astype(np.float32)
+    ps = rng.integers(-3, 4, n).astype(np.float32)
+    tx, ty, tp = torch.from_numpy(xs.copy()), torch.from_numpy(ys.copy()), torch.from_numpy(ps.copy())
+    img = enc.events_to_image(tx, ty, tp, sensor_size=(H, W))
+    oor = (xs >= W) | (xs < 0) | (ys >= H) | (ys < 0)
+    want = np.zeros((H, W), np.float32)
+    np.add.at(want, (ys[~oor].astype(np.int64), xs[~oor].astype(np.int64)), ps[~oor])
+    assert np.array_equal(img.numpy(), want)
+    assert (tx.numpy()[oor] == 0).all() and (tp.numpy()[oor] == 0).all() and np.array_equal(tx.numpy()[~oor], xs[~oor])
+
+
+def test_encode_frames_batched_vs_oracle(dev):
+    from esr_b200 import encodings as enc
+    from oracle import events as oe
+    rng = np.random.default_rng(11)
+    F, Hl, Wl, k = 9, 45, 80, 2
+    lens = rng.integers(0, 5000, F)
+    lens[3] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n = int(off[-1])
+    xs = rng.integers(-2, Wl + 2, n).astype(np.float32)
+    ys = rng.integers(-2, Hl + 2, n).astype(np.float32)
+    ps = rng.choice(np.array([-1, 1], np.float32), n)
+    out = enc.encode_frames(torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev), torch.from_numpy(ps).to(dev),
+                            torch.from_numpy(off).to(dev), lr_size=(Hl, Wl), hr_size=(Hl * k, Wl * k),
+                            n_max_frame=int(lens.max())).cpu().numpy()
+    for f in range(F):
+        a, b = off[f], off[f + 1]
+        want = oe.events_to_channels(oe.lift_coords(xs[a:b], Wl, Wl * k), oe.lift_coords(ys[a:b], Hl, Hl * k),
+                                     ps[a:b], (Hl * k, Wl * k))
+        assert np.array_equal(out[f], want), f
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_cnt2event_golden(golden_events, mode, dev):
+    from esr_b200 import cnt2event as c2e
+    g = golden_events
+    for i in range(int(g["n_c2e"])):
+        got = c2e.cnt2event(g[f"c2e{i}_in"], mode)
+        assert got.dtype == np.float32 and np.array_equal(got, g[f"c2e{i}_out{mode}"]), i
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_event_redistribute_golden(golden_events, mode, dev):
+    from esr_b200 import event_redistribute as er
+    g = golden_events
+    for i in range(int(g["n_er"])):
+        v = g[f"er{i}_in"]
+        fn = er.event_redistribute_PolarityStack if v.ndim == 5 else er.event_redistribute_NoPolarityStack
+        assert np.array_equal(fn(v, mode), g[f"er{i}_out{mode}"]), i
+
+
+@pytest.mark.parametrize("shape,lam", [((1, 2, 64, 64), 0.3), ((8, 2, 256, 256), 0.3), ((3, 2, 100, 37), 2.5),
+                                       ((2, 2, 8, 8), 40.0)])
+def test_cnt2event_vs_oracle(shape, lam, dev):
+    from esr_b200 import cnt2event as c2e
+    from oracle import events as oe
+    rng = np.random.default_rng(hash(shape) % 1000)
+    cnt = rng.poisson(lam, shape).astype(np.float32) + ((rng.random(shape) - 0.5) * 0.9).astype(np.float32)
+    cnt = np.maximum(cnt, 0).astype(np.float32)
+    for mode in (0, 1):
+        got = c2e.cnt2event_cuda(torch.from_numpy(cnt).to(dev), mode).cpu().numpy()
+        assert np.array_equal(got, oe.cnt2event(cnt, mode)), (shape, mode)
+
+
+def test_redistribute_vs_oracle_and_roundtrip(dev):
+    from esr_b200 import encodings as enc
+    from oracle import events as oe
+    rng = np.random.default_rng(3)
+    st = (rng.poisson(0.5, (4, 2, 5, 40, 56)) * rng.choice([-1, 1], (4, 2, 5, 40, 56))).astype(np.float32)
+    for mode, name in ((0, "linear"), (1, "random")):
+        got = enc.cython_event_redistribute(torch.from_numpy(st), name).numpy()
+        assert np.array_equal(got, oe.event_redistribute(st, mode))
+        got1 = enc.multiprocess_cython(torch.from_numpy(st), name).numpy()
+        per = [oe.event_redistribute(st[i:i + 1], mode)[0] for i in range(4)]
+        for i in range(4):
+            assert np.array_equal(got1[i, :len(per[i])], per[i])
+    # cnt -> events -> cnt round trip at a BASELINE-sized grid (size-independent property)
+    cnt = rng.poisson(0.3, (2, 2, 512, 512)).astype(np.float32)
+    ev = __import__("esr_b200.cnt2event", fromlist=["x"]).cnt2event_cuda(torch.from_numpy(cnt).to(dev), 0)
+    for b in range(2):
+        e = ev[b]
+        e = e[e[:, 3] != 0]
+        back = enc.events_to_channels(e[:, 0].contiguous(), e[:, 1].contiguous(), e[:, 3].contiguous(), (512, 512))
+        assert torch.equal(back.cpu(), torch.from_numpy(cnt[b]))
+        t = ev[b, :, 2]
+        n = int((ev[b, :, 3] != 0).sum())
+        assert bool((t[1:n] >= t[:n - 1]).all())      # sortedness
+
+
+def test_empty_and_error_cases(dev):
+    from esr_b200 import cnt2event as c2e
+    z = np.zeros((3, 2, 5, 5), np.float32)
+    assert c2e.cnt2event(z, 0).shape == (3, 1, 4)
+    c = np.zeros((1, 2, 2, 2), np.float32)
+    c[0, 0, 0, 0], c[0, 1, 1, 1] = 3, -1
+    with pytest.raises(ValueError):
+        c2e.cnt2event(c, 0)
+    with pytest.raises(ValueError):
+        c2e.cnt2event(z.astype(np.float64), 0)
