@@ -30,6 +30,27 @@ SIGNATURES = {
 }
 
 
+class ConvDesc(ctypes.Structure):
+    """struct esr_conv_desc of include/esr_b200.h"""
+    _fields_ = [
+        ("src", c_void_p * 3), ("src_C", c_int * 3), ("src_n_img", c_int * 3), ("src_img", c_void_p * 3),
+        ("n_src", c_int), ("H", c_int), ("W", c_int), ("n_img", c_int), ("ntaps", c_int), ("cout", c_int),
+        ("wpacked", c_void_p), ("bias", c_void_p), ("act", c_int), ("act_from", c_int), ("res_mode", c_int),
+        ("epi_mode", c_int), ("res", c_void_p), ("res_C", c_int), ("res_n_img", c_int), ("res_img", c_void_p),
+        ("out", c_void_p), ("out_C", c_int), ("out_n_img", c_int), ("out_coff", c_int),
+        ("out_f32", c_void_p), ("out_f32_C", c_int), ("h_prev", c_void_p), ("h_n_img", c_int), ("z_buf", c_void_p),
+    ]
+
+
+SIGNATURES.update({
+    "esr_conv_tc": (c_int, [ctypes.POINTER(ConvDesc), c_void_p]),
+    "esr_conv_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "esr_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "esr_split_from_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "esr_split_to_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+})
+
+
 class ESRError(RuntimeError):
     pass
 

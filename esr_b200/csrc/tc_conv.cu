@@ -1,0 +1,603 @@
+// tc_conv.cu -- 3x3 / 1x1 convolution as an implicit GEMM on the 5th-gen tensor cores (sm_100a).
+//
+//   D[128 pixels, Cout] += A[128 pixels, 64 ch of one tap] * B[Cout, 64]^T      per K-block (tap x 64-channel chunk)
+//
+// * Activations live in HBM as "split bf16" NHWC tensors (value = hi + lo).  A K-block's A tile is ONE TMA box
+//   (64 ch, TW, TH, 1 image, 1 plane) taken at the tap's (dy, dx) shift; out-of-image coordinates are zero-filled
+//   by TMA, which is exactly the conv's zero padding.  The box lands in shared memory in the 128B-swizzled K-major
+//   layout that tcgen05.mma consumes, so no thread touches the operands.
+// * Channel concatenation (torch.cat in the reference) is a K-split over up to 3 source tensors.
+// * fp32 parity: three bf16 MMAs per K-step (lo*hi + hi*lo + hi*hi) accumulate in fp32 in TMEM => ~2^-17 relative
+//   operand error instead of bf16's 2^-9 (the reference network is fp32-only).
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> bias / residual / activation / GRU gating -> split-bf16 or fp32 NHWC stores).
+// * mbarrier ring: full[s] (TMA -> MMA), empty[s] (tcgen05.commit -> TMA), accum_full (tcgen05.commit -> epilogue).
+//
+// Reference layers served: every Conv2d of models/model.py at feature resolution (Cin multiple of 64), the ConvGRU
+// gates (models/submodules.py:496-514) and the DCNv2 contraction (models/DCNv2/src/cuda/dcn_v2_cuda.cu:90-92).
+#include "tc_conv.cuh"
+
+namespace esr {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_A_BYTES = TC_BLOCK_M * 128;          // one plane of one A tile: 128 rows x 64 bf16
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+                 " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart).
+// Bits: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO = 1024 B
+    d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// c=F32 [4,6)=1 | a=BF16 [7,10)=1 | b=BF16 [10,13)=1 | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act)
+{
+    if (act == ACT_RELU) return fmaxf(x, 0.0f);
+    if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
+    if (act == ACT_TANH) return tanhf(x);
+    return x;
+}
+
+// 32 consecutive channels of one pixel of a split tensor -> fp32
+__device__ __forceinline__ void load_split32(const __nv_bfloat16 *hi_ptr, size_t plane, float (&o)[32])
+{
+    const uint4 *ph = reinterpret_cast<const uint4 *>(hi_ptr);
+    const uint4 *pl = reinterpret_cast<const uint4 *>(hi_ptr + plane);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 h = ph[q], l = pl[q];
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            o[q * 8 + e * 2 + 0] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            o[q * 8 + e * 2 + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+        }
+    }
+}
+__device__ __forceinline__ void store_split32(__nv_bfloat16 *hi_ptr, size_t plane, const float (&x)[32])
+{
+    uint32_t hw[16], lw[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(x[2 * e], h0, l0);
+        split_bf16(x[2 * e + 1], h1, l1);
+        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    uint4 *ph = reinterpret_cast<uint4 *>(hi_ptr);
+    uint4 *pl = reinterpret_cast<uint4 *>(hi_ptr + plane);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        ph[q] = make_uint4(hw[q * 4], hw[q * 4 + 1], hw[q * 4 + 2], hw[q * 4 + 3]);
+        pl[q] = make_uint4(lw[q * 4], lw[q * 4 + 1], lw[q * 4 + 2], lw[q * 4 + 3]);
+    }
+}
+
+// One thread's 32 accumulator columns [n0, n0+32) of one valid output pixel -> global memory.
+__device__ __forceinline__ void epilogue_chunk(const ConvTCArgs &a, const uint32_t (&raw)[32], int n0, size_t pix, int img,
+                                               int y, int x)
+{
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + (n0 + j < a.npad ? a.bias[n0 + j] : 0.0f);
+
+    if (a.epi_mode == EPI_GRU_ZR) {
+        // channels [0,64): update gate z -> fp32; [64,128): reset gate r -> rh = h * r (split)
+        if (n0 < 64) {
+            float4 *zp = reinterpret_cast<float4 *>(a.z_buf + pix * 64 + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                zp[q] = make_float4(apply_act(v[4 * q], ACT_SIGMOID), apply_act(v[4 * q + 1], ACT_SIGMOID),
+                                    apply_act(v[4 * q + 2], ACT_SIGMOID), apply_act(v[4 * q + 3], ACT_SIGMOID));
+        } else {
+            float h[32];
+            load_split32(a.h_prev + pix * 64 + (n0 - 64), a.h_plane, h);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = h[j] * apply_act(v[j], ACT_SIGMOID);
+            store_split32(a.out + pix * a.out_C + a.out_coff + (n0 - 64), a.out_plane, v);
+        }
+        return;
+    }
+    if (a.epi_mode == EPI_GRU_OUT) {
+        // h' = h (1 - z) + tanh(.) z        (models/submodules.py:511-512)
+        float h[32];
+        load_split32(a.h_prev + pix * 64 + n0, a.h_plane, h);
+        const float4 *zp = reinterpret_cast<const float4 *>(a.z_buf + pix * 64 + n0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 z = zp[q];
+            const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * q + e;
+                v[j] = h[j] * (1.0f - zz[e]) + apply_act(v[j], ACT_TANH) * zz[e];
+            }
+        }
+        store_split32(a.out + pix * a.out_C + a.out_coff + n0, a.out_plane, v);
+        return;
+    }
+    // ---- standard epilogue: bias (+ residual before or after the activation)
+    if (a.res_mode != RES_NONE && n0 < a.cout) {
+        float r[32];
+        const size_t rpix = ((size_t)(a.res_img ? a.res_img[img] : img) * a.H + y) * a.W + x;
+        load_split32(a.res + rpix * a.res_C + n0, a.res_plane, r);
+        if (a.res_mode == RES_PRE_ACT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + r[j], (n0 + j >= a.act_from) ? a.act : ACT_NONE);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], (n0 + j >= a.act_from) ? a.act : ACT_NONE) + r[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], (n0 + j >= a.act_from) ? a.act : ACT_NONE);
+    }
+    if (a.out && n0 + 32 <= a.cout) store_split32(a.out + pix * a.out_C + a.out_coff + n0, a.out_plane, v);
+    if (a.out_f32) {
+        float *op = a.out_f32 + pix * a.out_f32_C + n0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (n0 + j < a.cout) op[j] = v[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel: one CTA = one tile of 128 output pixels (TH x TW) of one image, all output channels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTCArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-B alignment
+    const uint32_t b_bytes = (uint32_t)a.npad * 128u;
+    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
+    // barriers: full[stages], empty[stages], accum_full, then the TMEM base address slot
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages, bar_accum = bar_base + 16u * a.stages;
+    const uint32_t tmem_slot = bar_accum + 8u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < a.npad) tmem_cols <<= 1;
+
+    // tile -> (image, y0, x0)
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            int src = 0, chunk_base = 0;
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                const int gchunk = kb / a.ntaps, tap = kb - gchunk * a.ntaps;
+                while (gchunk >= a.chunk_end[src]) { chunk_base = a.chunk_end[src]; ++src; }
+                const int dy = a.ntaps == 9 ? tap / 3 - 1 : 0, dx = a.ntaps == 9 ? tap % 3 - 1 : 0;
+                const int simg = a.src_img[src] ? a.src_img[src][img] : img;
+                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                mbar_expect_tx(bar_full + 8u * s, stage_bytes);
+                const uint32_t st = smem_base + s * stage_bytes;
+                const int c0 = (gchunk - chunk_base) * 64;
+                tma_load_5d(&a.amap[src], bar_full + 8u * s, st, c0, x0 + dx, y0 + dy, simg, 0);
+                tma_load_5d(&a.amap[src], bar_full + 8u * s, st + TC_A_BYTES, c0, x0 + dx, y0 + dy, simg, 1);
+                tma_load_3d(&a.bmap, bar_full + 8u * s, st + 2u * TC_A_BYTES, 0, 0, kb);
+                tma_load_3d(&a.bmap, bar_full + 8u * s, st + 2u * TC_A_BYTES + b_bytes, 0, 0, a.nkb + kb);
+                if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(TC_BLOCK_M, a.npad);
+            uint32_t s = 0, ph = 0;
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                mbar_wait(bar_full + 8u * s, ph);
+                tc_fence_after();
+                const uint32_t st = smem_base + s * stage_bytes;
+                const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                       // 4 x (K = 16 bf16 = 32 bytes) per 128-byte row
+                    const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                    umma_bf16(tmem_base, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+                    umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+                }
+                umma_commit(bar_empty + 8u * s);                    // frees the stage once these MMAs retire
+                if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(bar_accum);                                 // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+        const int quad = warp & 3;                                  // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
+        const int m = quad * 32 + lane;                             // accumulator row = pixel within the tile
+        const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+        const bool valid = (y < a.H) && (x < a.W);
+        const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);
+        mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int n0 = 0; n0 < a.npad; n0 += 32) {
+            uint32_t raw[32];
+            if (a.npad - n0 >= 32) {
+                tmem_ld32(taddr + (uint32_t)n0, raw);
+            } else {                                                // npad is a multiple of 16: a 16-column tail
+                uint32_t r16[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]),
+                               "=r"(r16[6]), "=r"(r16[7]), "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]),
+                               "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
+                             : "r"(taddr + (uint32_t)n0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { raw[j] = r16[j]; raw[16 + j] = 0u; }
+            }
+            if (valid) epilogue_chunk(a, raw, n0, pix, img, y, x);
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps and launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode()
+{
+    static PFN_tmapEncodeTiled fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (PFN_tmapEncodeTiled)p;
+    }();
+    return fn;
+}
+
+static int make_amap(const SplitTensor &t, int TW, int TH, CUtensorMap *out)
+{
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ESR_ECUDA; }
+    const cuuint64_t C = t.C, W = t.W, H = t.H, N = t.n_img;
+    cuuint64_t gdim[5] = {C, W, H, N, 2};
+    cuuint64_t gstr[4] = {C * 2, W * C * 2, H * W * C * 2, N * H * W * C * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d N=%d)", (int)r, t.C, t.W, t.H, t.n_img); return ESR_ECUDA; }
+    return ESR_OK;
+}
+
+static int make_bmap(const void *w, int npad, int nkb, CUtensorMap *out)
+{
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ESR_ECUDA; }
+    cuuint64_t gdim[3] = {64, (cuuint64_t)npad, (cuuint64_t)2 * nkb};
+    cuuint64_t gstr[2] = {128, (cuuint64_t)npad * 128};
+    cuuint32_t box[3] = {64, (cuuint32_t)npad, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(w), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d (npad=%d nkb=%d)", (int)r, npad, nkb); return ESR_ECUDA; }
+    return ESR_OK;
+}
+
+static size_t tc_smem_bytes(int npad, int stages)
+{
+    return 1024 + (size_t)stages * (2 * TC_A_BYTES + 2 * (size_t)npad * 128) + 16 * (size_t)stages + 64;
+}
+
+int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
+{
+    ConvTCArgs &a = *args;
+    memset(&a, 0, sizeof(a));
+    ESR_REQUIRE(d.n_src >= 1 && d.n_src <= TC_MAX_SRC, "conv_tc: n_src=%d", d.n_src);
+    ESR_REQUIRE(d.ntaps == 9 || d.ntaps == 1, "conv_tc: ntaps=%d", d.ntaps);
+    const int H = d.src[0].H, W = d.src[0].W;
+    int chunks = 0;
+    // tile shape: 128 pixels; prefer wide tiles, but do not waste more than half a tile on narrow images
+    int TW = W >= 24 ? 32 : (W >= 12 ? 16 : 8);
+    if (H <= 128 / TW / 2 && TW > 8) { /* very flat image: keep TW */ }
+    int TH = TC_BLOCK_M / TW;
+    for (int s = 0; s < d.n_src; ++s) {
+        const SplitTensor &t = d.src[s];
+        ESR_REQUIRE(t.base && t.C % 64 == 0 && t.H == H && t.W == W, "conv_tc: source %d has C=%d H=%d W=%d", s, t.C, t.H, t.W);
+        chunks += t.C / 64;
+        a.chunk_end[s] = chunks;
+        a.src_img[s] = d.src_img[s];
+        int rc = make_amap(t, TW, TH, &a.amap[s]);
+        if (rc) return rc;
+    }
+    for (int s = d.n_src; s < TC_MAX_SRC; ++s) a.chunk_end[s] = 1 << 30;
+    a.n_src = d.n_src; a.ntaps = d.ntaps; a.nkb = chunks * d.ntaps;
+    a.npad = tc_npad(d.cout); a.cout = d.cout;
+    ESR_REQUIRE(a.npad <= 256, "conv_tc: cout=%d too large", d.cout);
+    int rc = make_bmap(d.wpacked, a.npad, a.nkb, &a.bmap);
+    if (rc) return rc;
+    a.H = H; a.W = W; a.TW = TW; a.TH = TH;
+    a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH; a.n_img = d.n_img;
+    int stages = 6;
+    while (stages > 2 && tc_smem_bytes(a.npad, stages) > (size_t)dev_info().max_smem_optin) --stages;
+    if (stages > a.nkb) stages = a.nkb < 2 ? 2 : a.nkb;
+    a.stages = stages;
+    a.bias = d.bias;
+    a.act = d.act; a.act_from = d.act_from; a.res_mode = d.res_mode; a.epi_mode = d.epi_mode;
+    if (d.res_mode != RES_NONE) {
+        ESR_REQUIRE(d.res.base && d.res.H == H && d.res.W == W && d.cout % 32 == 0 && d.res.C >= d.cout, "conv_tc: bad residual");
+        a.res = d.res.base; a.res_plane = d.res.plane(); a.res_C = d.res.C; a.res_img = d.res_img;
+    }
+    if (d.out.base) {
+        ESR_REQUIRE(d.out.H == H && d.out.W == W && d.out.n_img >= d.n_img && d.out.C % 8 == 0 && d.out_coff % 8 == 0,
+                    "conv_tc: bad split output");
+        a.out = d.out.base; a.out_plane = d.out.plane(); a.out_C = d.out.C; a.out_coff = d.out_coff;
+    }
+    a.out_f32 = d.out_f32; a.out_f32_C = d.out_f32_C;
+    if (d.epi_mode != EPI_STD) {
+        ESR_REQUIRE(d.h_prev.base && d.h_prev.C == 64 && d.z_buf && d.out.base, "conv_tc: GRU epilogue needs h_prev, z_buf, out");
+        ESR_REQUIRE((d.epi_mode == EPI_GRU_ZR && a.npad == 128) || (d.epi_mode == EPI_GRU_OUT && a.npad == 64), "conv_tc: GRU epilogue width");
+        a.h_prev = d.h_prev.base; a.h_plane = d.h_prev.plane(); a.z_buf = d.z_buf;
+    } else {
+        ESR_REQUIRE(!d.out.base || d.cout % 32 == 0, "conv_tc: split output needs cout %% 32 == 0");
+    }
+    return ESR_OK;
+}
+
+int conv_tc_launch(const ConvTCArgs &a, cudaStream_t st)
+{
+    static int max_set = 0;
+    const size_t smem = tc_smem_bytes(a.npad, a.stages);
+    if ((int)smem > max_set) {
+        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set = (int)smem;
+    }
+    const unsigned grid = (unsigned)(a.n_img * a.tiles_x * a.tiles_y);
+    k_conv_tc<<<grid, TC_THREADS, smem, st>>>(a);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing and layout conversion kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_weight(const float *__restrict__ w0, const float *__restrict__ w1, int cout_each, int cin, int ksz,
+                              int npad, int nkb, __nv_bfloat16 *__restrict__ dst)
+{
+    const int ntaps = ksz * ksz;
+    const size_t total = (size_t)nkb * npad * 64;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % 64);
+        const int n = (int)((i / 64) % npad);
+        const int kb = (int)(i / ((size_t)64 * npad));
+        const int chunk = kb / ntaps, tap = kb % ntaps;
+        const int ci = chunk * 64 + c;
+        float v = 0.0f;
+        const int cout_tot = w1 ? 2 * cout_each : cout_each;
+        if (n < cout_tot) {
+            const float *w = (n < cout_each) ? w0 : w1;
+            const int nn = n < cout_each ? n : n - cout_each;
+            v = w[((size_t)nn * cin + ci) * ntaps + tap];
+        }
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        dst[i] = hi;
+        dst[total + i] = lo;
+    }
+}
+
+int pack_conv_weight2(const float *w0, const float *w1, int cout_each, int cin, int ksz, void *dst, cudaStream_t st)
+{
+    ESR_REQUIRE(cin % 64 == 0 && (ksz == 1 || ksz == 3), "pack_conv_weight: cin=%d ksz=%d", cin, ksz);
+    const int cout = w1 ? 2 * cout_each : cout_each;
+    const int npad = tc_npad(cout), nkb = tc_nkb(cin, ksz * ksz);
+    const size_t total = (size_t)nkb * npad * 64;
+    k_pack_weight<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(w0, w1, cout_each, cin, ksz, npad, nkb,
+                                                                             (__nv_bfloat16 *)dst);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+int pack_conv_weight(const float *w, int cout, int cin, int ksz, void *dst, cudaStream_t st)
+{
+    return pack_conv_weight2(w, nullptr, cout, cin, ksz, dst, st);
+}
+
+__global__ void k_split_from_nchw(const float *__restrict__ src, int n_img, int C, int H, int W, __nv_bfloat16 *__restrict__ dst)
+{
+    const size_t plane = (size_t)n_img * H * W * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t p = i / C;
+        const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((size_t)W * H));
+        __nv_bfloat16 hi, lo;
+        split_bf16(src[(((size_t)n * C + c) * H + y) * W + x], hi, lo);
+        dst[i] = hi;
+        dst[plane + i] = lo;
+    }
+}
+__global__ void k_split_to_nchw(const __nv_bfloat16 *__restrict__ src, int n_img, int C, int H, int W, float *__restrict__ dst)
+{
+    const size_t plane = (size_t)n_img * H * W * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H);
+        const int c = (int)((i / ((size_t)W * H)) % C), n = (int)(i / ((size_t)W * H * C));
+        const size_t s = (((size_t)n * H + y) * W + x) * C + c;
+        dst[i] = join_bf16(src[s], src[plane + s]);
+    }
+}
+int split_from_nchw(const float *src, int n_img, int C, int H, int W, __nv_bfloat16 *dst, cudaStream_t st)
+{
+    const size_t plane = (size_t)n_img * H * W * C;
+    k_split_from_nchw<<<(unsigned)ceil_div64((int64_t)plane, 256), 256, 0, st>>>(src, n_img, C, H, W, dst);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+int split_to_nchw(const __nv_bfloat16 *src, int n_img, int C, int H, int W, float *dst, cudaStream_t st)
+{
+    const size_t plane = (size_t)n_img * H * W * C;
+    k_split_to_nchw<<<(unsigned)ceil_div64((int64_t)plane, 256), 256, 0, st>>>(src, n_img, C, H, W, dst);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+} // namespace esr
+
+// ------------------------------------------------------------------------------------------------
+// C ABI (layer level)
+// ------------------------------------------------------------------------------------------------
+using namespace esr;
+
+static SplitTensor mk_split(const void *p, int n_img, int H, int W, int C)
+{
+    SplitTensor t;
+    t.base = (__nv_bfloat16 *)const_cast<void *>(p);
+    t.n_img = n_img; t.H = H; t.W = W; t.C = C;
+    return t;
+}
+
+extern "C" int esr_conv_tc(const esr_conv_desc *c, esr_stream_t stream)
+{
+    ESR_REQUIRE(c, "esr_conv_tc: null descriptor");
+    ConvTCDesc d;
+    d.n_src = c->n_src;
+    for (int s = 0; s < c->n_src && s < TC_MAX_SRC; ++s) {
+        d.src[s] = mk_split(c->src[s], c->src_n_img[s], c->H, c->W, c->src_C[s]);
+        d.src_img[s] = c->src_img[s];
+    }
+    d.ntaps = c->ntaps; d.cout = c->cout; d.wpacked = c->wpacked; d.bias = c->bias; d.n_img = c->n_img;
+    d.act = c->act; d.act_from = c->act_from; d.res_mode = c->res_mode; d.epi_mode = c->epi_mode;
+    if (c->res) { d.res = mk_split(c->res, c->res_n_img, c->H, c->W, c->res_C); d.res_img = c->res_img; }
+    if (c->out) { d.out = mk_split(c->out, c->out_n_img, c->H, c->W, c->out_C); d.out_coff = c->out_coff; }
+    d.out_f32 = c->out_f32; d.out_f32_C = c->out_f32_C;
+    if (c->h_prev) d.h_prev = mk_split(c->h_prev, c->h_n_img, c->H, c->W, 64);
+    d.z_buf = c->z_buf;
+    ConvTCArgs args;
+    int rc = conv_tc_prepare(d, &args);
+    if (rc) return rc;
+    return conv_tc_launch(args, (cudaStream_t)stream);
+}
+extern "C" size_t esr_conv_weight_bytes(int cout, int cin, int ksz) { return tc_packed_weight_bytes(cout, cin, ksz * ksz); }
+extern "C" int esr_pack_conv_weight(const float *w0, const float *w1, int cout_each, int cin, int ksz, void *dst, esr_stream_t st)
+{
+    return pack_conv_weight2(w0, w1, cout_each, cin, ksz, dst, (cudaStream_t)st);
+}
+extern "C" int esr_split_from_nchw(const float *src, int n_img, int C, int H, int W, void *dst, esr_stream_t st)
+{
+    return split_from_nchw(src, n_img, C, H, W, (__nv_bfloat16 *)dst, (cudaStream_t)st);
+}
+extern "C" int esr_split_to_nchw(const void *src, int n_img, int C, int H, int W, float *dst, esr_stream_t st)
+{
+    return split_to_nchw((const __nv_bfloat16 *)src, n_img, C, H, W, dst, (cudaStream_t)st);
+}

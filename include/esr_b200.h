@@ -76,6 +76,47 @@ int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P, int C, in
                     const double *rnd, const int32_t *active_host, const int64_t *start_host, int64_t total_events,
                     int64_t maxlen, float *out, void *workspace, size_t workspace_bytes, esr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core convolution (tcgen05, TMA-tiled implicit GEMM), layer-level entry point.
+ * Replaces: every stride-1 nn.Conv2d at feature resolution in models/model.py / models/submodules.py
+ * (3x3 pad 1 or 1x1; Cin a multiple of 64, Cout <= 256), including torch.cat inputs (K-split over up to 3
+ * sources), the fused bias / residual / activation tail of ConvLayer / ResidualBlock
+ * (models/submodules.py:159-200, 347-409) and the ConvGRU gating (models/submodules.py:496-514).
+ *
+ * Activation tensors are "split bf16" NHWC: [2 planes][n_img][H][W][C] bf16, value = hi + lo
+ * (esr_split_from_nchw / esr_split_to_nchw convert from / to the reference's fp32 NCHW layout).
+ * Weights are packed once by esr_pack_conv_weight (fp32 [Cout,Cin,k,k] -> split bf16 K-blocks).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct esr_conv_desc {
+    const void *src[3];        /* split tensors */
+    int src_C[3];              /* channels of each source (multiple of 64) */
+    int src_n_img[3];          /* images in each source tensor */
+    const int32_t *src_img[3]; /* optional: output image -> source image index (device), NULL = identity */
+    int n_src;
+    int H, W;                  /* spatial size (input == output) */
+    int n_img;                 /* output images */
+    int ntaps;                 /* 9 = 3x3 pad 1, 1 = 1x1 */
+    int cout;
+    const void *wpacked;       /* from esr_pack_conv_weight */
+    const float *bias;         /* fp32 [ceil16(cout)], zero padded */
+    int act;                   /* 0 none, 1 relu, 2 sigmoid, 3 tanh; applied to channels >= act_from */
+    int act_from;
+    int res_mode;              /* 0 none, 1 add before activation, 2 add after activation */
+    int epi_mode;              /* 0 standard, 1 ConvGRU update|reset gates, 2 ConvGRU candidate + blend */
+    const void *res; int res_C; int res_n_img; const int32_t *res_img;
+    void *out; int out_C; int out_n_img; int out_coff;   /* split output (NULL = none), channel offset */
+    float *out_f32; int out_f32_C;                        /* fp32 NHWC output (NULL = none) */
+    const void *h_prev; int h_n_img; float *z_buf;        /* ConvGRU: previous state (split, 64 ch), z gate fp32 */
+} esr_conv_desc;
+
+int esr_conv_tc(const esr_conv_desc *desc, esr_stream_t stream);
+size_t esr_conv_weight_bytes(int cout, int cin, int ksz);
+/* w1 != NULL: two [cout_each,cin,k,k] tensors concatenated along Cout (GRU update|reset) */
+int esr_pack_conv_weight(const float *w0, const float *w1, int cout_each, int cin, int ksz, void *dst,
+                         esr_stream_t stream);
+int esr_split_from_nchw(const float *src, int n_img, int C, int H, int W, void *dst, esr_stream_t stream);
+int esr_split_to_nchw(const void *src, int n_img, int C, int H, int W, float *dst, esr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
