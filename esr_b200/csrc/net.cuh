@@ -1,0 +1,56 @@
+// net.cuh -- shared declarations of the DeepRecurrNet forward pipeline (direct convs, element-wise kernels, DCN).
+#pragma once
+#include "tc_conv.cuh"
+
+namespace esr {
+
+enum Fmt : int { FMT_NCHW_F32 = 0, FMT_SPLIT = 1, FMT_NHWC_F32 = 2 };
+
+enum DirectKind : int { DK_HEAD, DK_ENC0, DK_ENC1, DK_ENC2, DK_ATT32, DK_ATT16, DK_RECON0, DK_RECON1, DK_RECON2, DK_TAIL };
+
+struct DirectArgs {
+    // input
+    const float *in_f32 = nullptr;              // NCHW fp32 [*, CIN, Hin, Win]   (head)
+    const __nv_bfloat16 *in_split = nullptr;    // split NHWC [*, Hin, Win, CIN]
+    size_t in_plane = 0;
+    const int *in_img = nullptr;                // output image -> input image (nullptr = identity)
+    int Hin = 0, Win = 0;
+    int pad_top = 0, pad_bottom = 0, pad_left = 0, pad_right = 0;   // CropSize zero padding of the network input
+    // weights
+    const float *w = nullptr;                   // [9][CIN][COUT]
+    const float *bias = nullptr;                // [COUT]
+    int act = ACT_NONE;
+    // output
+    int n_img = 0, Hout = 0, Wout = 0;
+    __nv_bfloat16 *out_split = nullptr;
+    size_t out_plane = 0;
+    float *out_f32 = nullptr;
+    int crop_top = 0, crop_left = 0, out_H = 0, out_W = 0;          // NCHW output window (tail)
+};
+
+int conv_direct(DirectKind kind, const DirectArgs &a, cudaStream_t st);
+int pack_direct_weight(const float *w, int cout, int cin, float *dst, cudaStream_t st);
+
+// ---- element-wise / reduction kernels (elementwise.cu)
+// local_fusion input: out[img=(b,i)] = cat(f[i0]*map[p0], f[i1], f[i2]*map[p1])  (models/model.py:82-86)
+int ltc_cat(const SplitTensor &f, const float *maps, const int *idx /*[n_img][5]: f0,f1,f2,map0,map1*/, int n_img,
+            const SplitTensor &out /*C=192*/, cudaStream_t st);
+// per-image channel max of a 64-channel split tensor -> [n_img, 64] fp32   (models/model.py:221)
+int chan_max(const SplitTensor &t, int n_img, float *out, cudaStream_t st);
+// channel attention MLP 64 -> 32 relu -> 128 sigmoid (models/submodules.py:67-77, model.py:186-189)
+int attn_mlp(const float *mx, int n_img, const float *w0, const float *b0, const float *w1, const float *b1, float *ck,
+             cudaStream_t st);
+// y = cat(aligned * sk[...,0] * ck[:64], mid * sk[...,1] * ck[64:])   (models/model.py:224-227)
+int attn_apply(const SplitTensor &aligned, const SplitTensor &mid_src, const int *mid_img, const float *sk, const float *ck,
+               int n_img, const SplitTensor &out /*C=128*/, cudaStream_t st);
+// out[b] = x[b] + mean_n(feats[b*N+n] * att[b*N+n])     (models/model.py:259-267)
+int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float *att, int B, int N, const SplitTensor &out,
+                    cudaStream_t st);
+int copy_split(const SplitTensor &src, const int *src_img, int n_img, const SplitTensor &dst, cudaStream_t st);
+
+// ---- deformable sampling (dcn.cu): columns[img][y][x][tap*64 + c] = bilinear(feat[c], y-1+i+off_h, x-1+j+off_w) * mask
+// om: fp32 NHWC [n_img, H, W, 216] = {144 offsets (group-major, (h,w) pairs per tap), 72 masks (already sigmoid)}
+int dcn_columns(const SplitTensor &feat, const int *feat_img, const float *om, int n_img, const SplitTensor &cols /*C=576*/,
+                cudaStream_t st);
+
+} // namespace esr

@@ -514,10 +514,11 @@ int pack_conv_weight(const float *w, int cout, int cin, int ksz, void *dst, cuda
     return pack_conv_weight2(w, nullptr, cout, cin, ksz, dst, st);
 }
 
-__global__ void k_split_from_nchw(const float *__restrict__ src, int n_img, int C, int H, int W, __nv_bfloat16 *__restrict__ dst)
+__global__ void k_split_from_nchw(const float *__restrict__ src, int n_img, int C, int H, int W, __nv_bfloat16 *__restrict__ dst,
+                                  size_t plane)
 {
-    const size_t plane = (size_t)n_img * H * W * C;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t count = (size_t)n_img * H * W * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         const size_t p = i / C;
         const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((size_t)W * H));
@@ -527,29 +528,38 @@ __global__ void k_split_from_nchw(const float *__restrict__ src, int n_img, int 
         dst[plane + i] = lo;
     }
 }
-__global__ void k_split_to_nchw(const __nv_bfloat16 *__restrict__ src, int n_img, int C, int H, int W, float *__restrict__ dst)
+__global__ void k_split_to_nchw(const __nv_bfloat16 *__restrict__ src, size_t plane, int n_img, int C, int H, int W,
+                                float *__restrict__ dst)
 {
-    const size_t plane = (size_t)n_img * H * W * C;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t count = (size_t)n_img * H * W * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(i % W), y = (int)((i / W) % H);
         const int c = (int)((i / ((size_t)W * H)) % C), n = (int)(i / ((size_t)W * H * C));
         const size_t s = (((size_t)n * H + y) * W + x) * C + c;
         dst[i] = join_bf16(src[s], src[plane + s]);
     }
 }
-int split_from_nchw(const float *src, int n_img, int C, int H, int W, __nv_bfloat16 *dst, cudaStream_t st)
+int split_from_nchw_planes(const float *src, int n_img, int C, int H, int W, __nv_bfloat16 *dst, size_t plane, cudaStream_t st)
 {
-    const size_t plane = (size_t)n_img * H * W * C;
-    k_split_from_nchw<<<(unsigned)ceil_div64((int64_t)plane, 256), 256, 0, st>>>(src, n_img, C, H, W, dst);
+    const size_t count = (size_t)n_img * H * W * C;
+    k_split_from_nchw<<<(unsigned)ceil_div64((int64_t)count, 256), 256, 0, st>>>(src, n_img, C, H, W, dst, plane);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
-int split_to_nchw(const __nv_bfloat16 *src, int n_img, int C, int H, int W, float *dst, cudaStream_t st)
+int split_to_nchw_planes(const __nv_bfloat16 *src, size_t plane, int n_img, int C, int H, int W, float *dst, cudaStream_t st)
 {
-    const size_t plane = (size_t)n_img * H * W * C;
-    k_split_to_nchw<<<(unsigned)ceil_div64((int64_t)plane, 256), 256, 0, st>>>(src, n_img, C, H, W, dst);
+    const size_t count = (size_t)n_img * H * W * C;
+    k_split_to_nchw<<<(unsigned)ceil_div64((int64_t)count, 256), 256, 0, st>>>(src, plane, n_img, C, H, W, dst);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
+}
+int split_from_nchw(const float *src, int n_img, int C, int H, int W, __nv_bfloat16 *dst, cudaStream_t st)
+{
+    return split_from_nchw_planes(src, n_img, C, H, W, dst, (size_t)n_img * H * W * C, st);
+}
+int split_to_nchw(const __nv_bfloat16 *src, int n_img, int C, int H, int W, float *dst, cudaStream_t st)
+{
+    return split_to_nchw_planes(src, (size_t)n_img * H * W * C, n_img, C, H, W, dst, st);
 }
 
 } // namespace esr

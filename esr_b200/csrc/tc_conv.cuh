@@ -13,7 +13,8 @@ enum ResMode : int { RES_NONE = 0, RES_PRE_ACT = 1, RES_POST_ACT = 2 };
 struct SplitTensor {
     __nv_bfloat16 *base = nullptr;
     int n_img = 0, H = 0, W = 0, C = 0;
-    size_t plane() const { return (size_t)n_img * H * W * C; }
+    size_t plane_override = 0;      // set on views into a larger tensor (distance between the hi and lo planes)
+    size_t plane() const { return plane_override ? plane_override : (size_t)n_img * H * W * C; }
     size_t bytes() const { return plane() * 2 * sizeof(__nv_bfloat16); }
 };
 
@@ -75,5 +76,8 @@ int pack_conv_weight2(const float *w0, const float *w1, int cout_each, int cin, 
 // NCHW fp32 <-> split NHWC
 int split_from_nchw(const float *src, int n_img, int C, int H, int W, __nv_bfloat16 *dst, cudaStream_t st);
 int split_to_nchw(const __nv_bfloat16 *src, int n_img, int C, int H, int W, float *dst, cudaStream_t st);
+// same, with an explicit hi->lo plane distance (views into a larger split tensor)
+int split_from_nchw_planes(const float *src, int n_img, int C, int H, int W, __nv_bfloat16 *dst, size_t plane, cudaStream_t st);
+int split_to_nchw_planes(const __nv_bfloat16 *src, size_t plane, int n_img, int C, int H, int W, float *dst, cudaStream_t st);
 
 } // namespace esr

@@ -117,6 +117,37 @@ int esr_pack_conv_weight(const float *w0, const float *w1, int cout_each, int ci
 int esr_split_from_nchw(const float *src, int n_img, int C, int H, int W, void *dst, esr_stream_t stream);
 int esr_split_to_nchw(const void *src, int n_img, int C, int H, int W, float *dst, esr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The network: DeepRecurrNet.forward with carried ConvGRU states.
+ * Replaces: models/model.py:294-344 (DeepRecurrNet.forward / reset_states), and underneath it
+ * models/model.py:20-291, models/submodules.py (ConvLayer, UpsampleConvLayer, ResidualBlock, RecurrentConvLayer,
+ * ConvGRU, MLP), models/model_util.py:133-164 (CropSize) and the `_ext.dcn_v2_forward` operator
+ * (models/DCNv2/src/dcn_v2.h:9-27, src/cuda/dcn_v2_cuda.cu:20-95) for the shipped configuration
+ * (inch=2, basech=8, num_frame=3, norm=None, relu, all sub-blocks enabled; config/train_ours_enfssyn.yml:21-26).
+ *
+ *  params    : 68 device pointers to fp32 tensors in the reference's state_dict order
+ *              (head.conv2d.weight, head.conv2d.bias, feat_extract.convblock.0.conv2d.weight, ... tail.conv2d.bias)
+ *  blob      : esr_net_param_bytes() bytes; repack whenever the parameters change
+ *  workspace : esr_net_workspace_bytes(B,N,H,W) bytes, owned by the caller, must outlive the net; holds all
+ *              intermediates AND the recurrent states (which persist across esr_net_forward calls)
+ *  input     : fp32 [B,N,2,H,W] (the reference layout), or -- with in_img != NULL -- a bank of frames
+ *              [n_frames,2,H,W] where in_img[b*N+n] (device int32) selects the frame of window slot (b,n)
+ *  output    : fp32 [B,2,H,W]
+ * H, W need not be multiples of 8: the CropSize pad / crop is folded into the first and last kernels.
+ * --------------------------------------------------------------------------------------------- */
+typedef void *esr_net_t;
+size_t esr_net_param_bytes(void);
+int esr_net_pack_params(const float *const *params_host_array_of_device_ptrs, void *blob, esr_stream_t stream);
+size_t esr_net_workspace_bytes(int B, int N, int H, int W);
+int esr_net_create(esr_net_t *net, int B, int N, int H, int W, void *blob, void *workspace, size_t workspace_bytes,
+                   esr_stream_t stream);
+int esr_net_destroy(esr_net_t net);
+int esr_net_reset_states(esr_net_t net, esr_stream_t stream);
+int esr_net_forward(esr_net_t net, const float *input, const int32_t *in_img, float *output, esr_stream_t stream);
+/* states: fp32 [2,B,64,H/8,W/8] (forward-direction state, reverse-direction state), the reference's self.states */
+int esr_net_get_states(esr_net_t net, float *states, esr_stream_t stream);
+int esr_net_set_states(esr_net_t net, const float *states, esr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
