@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- LR event-frames/sec of the ESR hot path on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one batch of B sequences x L LR event frames taken from raw events to redistributed SR events:
+  encode L frames (LR->HR lift + count scatter) -> L-2 DeepRecurrNet forwards with carried ConvGRU state
+  -> cnt2event of the L-2 SR count tensors.          (infer_ours_cnt.py:54-75)
+value   : events already resident in HBM when a timed step starts.
+e2e     : the same step through the public API with pinned HOST buffers: H2D of the events and D2H of the
+          resulting event lists inside the timed region.
+Multi-GPU: the path shards by batch with no data-path collective (inference); every rank runs the per-GPU batch of
+the workload on its own shard (weak scaling) and the time is the max over ranks.
+`--impl reference` times the CPU oracle port of the same path on the host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: 2x SR, seq_len=8, LR 128x128, batch=8 per GPU
+    "cfg2": dict(scale=2, L=8, lr=(128, 128), B=8, desc="2x SR, seq_len=8, LR 128x128 synthetic events, batch=8/GPU"),
+    # BASELINE.json configs[2]: 4x SR, seq_len=8, LR 128x128, batch=32 over 8 GPUs = 4 per GPU
+    "cfg3": dict(scale=4, L=8, lr=(128, 128), B=4, desc="4x SR, seq_len=8, LR 128x128 synthetic events, batch=4/GPU"),
+}
+EVENTS_PER_FRAME = 2048          # shipped WINDOW (config/train_ours_enfssyn.yml:9)
+FLOP_PER_HR_PIXEL = 184.7e3
+
+
+def synth_events(B, L, lr, seed):
+    """SURVEY 8d synthetic input: n=2048 events per frame, x~U{0..W-1}, y~U{0..H-1}, p~U{-1,+1}."""
+    g = torch.Generator().manual_seed(seed)
+    n = B * L * EVENTS_PER_FRAME
+    xs = torch.randint(0, lr[1], (n,), generator=g).float()
+    ys = torch.randint(0, lr[0], (n,), generator=g).float()
+    ps = (torch.randint(0, 2, (n,), generator=g) * 2 - 1).float()
+    off = torch.arange(0, n + 1, EVENTS_PER_FRAME, dtype=torch.int64)
+    return xs, ys, ps, off
+
+
+def synth_sr_bias(B, L, hr, seed):
+    """A random-init network's output rounds to zero events, so the redistribution stage is fed
+    `model output + Poisson(0.3)` synthetic counts to do representative work."""
+    g = torch.Generator().manual_seed(seed + 17)
+    return torch.poisson(torch.full(((L - 2) * B, 2, hr[0], hr[1]), 0.3), generator=g)
+
+
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1443.7), d.get("hbm_gbs", 6574.1), "measured (MEASURED_PEAKS.json)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_step(wl, B_sample, sd, seed):
+    """One step of the CPU oracle port on a sample of B_sample sequences.  Returns seconds."""
+    from oracle import events as oe
+    from oracle import model_ref
+    scale, L, lr = wl["scale"], wl["L"], wl["lr"]
+    hr = (lr[0] * scale, lr[1] * scale)
+    xs, ys, ps, off = synth_events(B_sample, L, lr, seed)
+    xs, ys, ps, off = xs.numpy(), ys.numpy(), ps.numpy(), off.numpy()
+    bias = synth_sr_bias(B_sample, L, hr, seed)
+    net = model_ref.OracleNet(sd)
+    t0 = time.perf_counter()
+    frames = np.empty((B_sample * L, 2, hr[0], hr[1]), np.float32)
+    for f in range(B_sample * L):
+        a, b = off[f], off[f + 1]
+        frames[f] = oe.events_to_channels(oe.lift_coords(xs[a:b], lr[1], hr[1]), oe.lift_coords(ys[a:b], lr[0], hr[0]),
+                                          ps[a:b], hr)
+    bank = torch.from_numpy(frames).view(B_sample, L, 2, hr[0], hr[1])
+    net.reset_states()
+    outs = [net(bank[:, w:w + 3].contiguous()) for w in range(L - 2)]
+    sr = torch.cat(outs, 0) + bias
+    ev = oe.cnt2event(sr.numpy(), 0)
+    dt = time.perf_counter() - t0
+    return dt, int((ev[:, :, 3] != 0).sum())
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    from oracle import model_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = model_ref.seeded_state_dict(0)
+    B_sample = 1
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_oracle_step(wl, B_sample, sd, 1)
+    times = [cpu_oracle_step(wl, B_sample, sd, 1)[0] for _ in range(max(1, min(args.steps, 10)))]
+    t = float(np.mean(times))
+    val = B_sample * wl["L"] / t
+    sample = f"{B_sample} sequence x {wl['L']} LR frames per step (B={wl['B']} in the GPU arm), fp32, torch CPU + C oracle"
+    line = {"impl": "reference", "metric": "LR event-frames/sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": len(times), "warmup": min(args.warmup, 2), "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "impl_note": "CPU restatement of the reference path (oracle/), "
+                       "the reference's own Python cannot travel to the GPU box"},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-launch timing table of one window here")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch.distributed as dist
+    from esr_b200 import _lib
+    from esr_b200.model import DeepRecurrNet
+    from esr_b200.pipeline import EventSRPipeline
+    from oracle import model_ref    # only for the seeded weights + the cpu_baseline leg
+
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    scale, L, lr, B = wl["scale"], wl["L"], wl["lr"], wl["B"]
+    hr = (lr[0] * scale, lr[1] * scale)
+    sd = model_ref.seeded_state_dict(0)
+    net = DeepRecurrNet(inch=2, basech=8, num_frame=3)
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+    pipe = EventSRPipeline(net, B, L, lr, scale, dev)
+    pipe.sr_bias = synth_sr_bias(B, L, hr, 100 + rank).to(dev)
+
+    xs, ys, ps, off = synth_events(B, L, lr, 100 + rank)
+    h_xs, h_ys, h_ps, h_off = (t.pin_memory() for t in (xs, ys, ps, off))
+    d_xs, d_ys, d_ps, d_off = (t.to(dev) for t in (xs, ys, ps, off))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """per-step CUDA-event timing with an (untimed) L2 flush between steps; returns total ms"""
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot
+
+    dev_step = lambda: pipe.run_device(d_xs, d_ys, d_ps, d_off, EVENTS_PER_FRAME)
+    host_step = lambda: pipe.run_host(h_xs, h_ys, h_ps, h_off, EVENTS_PER_FRAME)
+
+    for _ in range(args.warmup):
+        dev_step()
+        host_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = _lib.lib().esr_launch_count()
+    ms_dev = timed(dev_step, args.steps)
+    launches = _lib.lib().esr_launch_count() - l0
+    barrier()
+    ms_e2e = timed(host_step, args.steps)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    frames_per_step = world * B * L
+    value = frames_per_step * args.steps / (ms_dev / 1e3)
+    e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (k_conv_tc): per-launch CUDA events over one window of the same workload
+    roofline, prof_rows = None, []
+    if rank == 0:
+        import ctypes
+        plan = net._plans[(B, 3, hr[0], hr[1])]
+        bank = torch.poisson(torch.full((B * L, 2, hr[0], hr[1]), 0.1)).to(dev)
+        out = torch.empty((B, 2, hr[0], hr[1]), device=dev)
+        cap = 128
+        cls = (ctypes.c_int * cap)()
+        ms = (ctypes.c_float * cap)()
+        fl = (ctypes.c_double * cap)()
+        cnt = ctypes.c_int(0)
+        acc = {0: [0.0, 0.0, 0], 1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0]}
+        reps = 5
+        for r in range(reps + 1):
+            _lib.check(_lib.lib().esr_net_forward_profiled(plan.handle, _lib.ptr(bank), _lib.ptr(pipe.window_index[0]), _lib.ptr(out),
+                                                           cap, ctypes.byref(cnt), cls, ms, fl, _lib.stream_ptr()), "profiled forward")
+            if r == 0:
+                continue                                             # warm-up
+            for i in range(cnt.value):
+                a = acc[cls[i]]
+                a[0] += ms[i]; a[1] += fl[i]; a[2] += 1
+            if r == reps:
+                prof_rows = [(i, int(cls[i]), float(ms[i]), float(fl[i])) for i in range(cnt.value)]
+        tc_ms, tc_fl, tc_n = acc[0]
+        peak_tf, peak_hbm, peak_src = measured_peaks()
+        achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        tot_ms = sum(a[0] for a in acc.values())
+        roofline = {"kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, all launches of one window)", "bound": "tensor",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "peak_source": peak_src + ", bf16 sustained", "traffic": None,
+                    "launches_per_window": tc_n // reps, "avg_launch_us": tc_ms / max(tc_n, 1) * 1e3,
+                    "algorithmic_gflop_per_window": tc_fl / reps / 1e9,
+                    "share_of_window_time": tc_ms / tot_ms if tot_ms else None,
+                    "note": "algorithmic FLOPs (1x); the fp32-parity 3-pass split-bf16 product issues 3x that on the tensor pipe",
+                    "cuda_core_conv_ms_per_window": acc[1][0] / reps, "elementwise_ms_per_window": acc[2][0] / reps,
+                    "tc_ms_per_window": tc_ms / reps}
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                f.write("idx,class(0=tc,1=direct,2=other),ms,algorithmic_flops\n")
+                for row in prof_rows:
+                    f.write("%d,%d,%.5f,%.0f\n" % row)
+
+    # ---- CPU baseline (oracle port) on rank 0, N=1 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_oracle_step(wl, 1, sd, 1)
+        ts = [cpu_oracle_step(wl, 1, sd, 1)[0] for _ in range(3)]
+        tcpu = float(np.mean(ts))
+        cpu_baseline = {"value": 1 * L / tcpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                        "sample": f"1 sequence x {L} LR frames (same per-sequence work as the GPU arm's B={B}), mean of 3, fp32"}
+
+    if rank == 0:
+        n_ev = EVENTS_PER_FRAME * B * L
+        ev_out = pipe.run_device(d_xs, d_ys, d_ps, d_off, EVENTS_PER_FRAME)[1]
+        line = {"metric": "LR event-frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate) / fp32 elsewhere",
+                "data": "synthetic",
+                "config": {"workload": wl["desc"], "scale": scale, "seq_len": L, "lr": list(lr), "batch_per_gpu": B,
+                           "events_per_frame": EVENTS_PER_FRAME, "windows_per_sequence": L - 2,
+                           "redistribute_input": "model output + Poisson(0.3) synthetic counts",
+                           "l2": "256 MiB buffer rewritten between timed steps (outside the timed intervals)",
+                           "parallelism": f"dp{world} (batch shards, no data-path collective)"},
+                "sr_frames_per_s": value * (L - 2) / L,
+                "clocks": sampler.summary(),
+                "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(n_ev * 12 + (B * L + 1) * 8), "d2h_bytes_per_step": int(ev_out.numel() * 4)},
+                "gpu_launches": int(launches),
+                "tensor_roofline_whole_path": {"algorithmic_tflops": FLOP_PER_HR_PIXEL * hr[0] * hr[1] * B * (L - 2) * world /
+                                               (ms_dev / args.steps / 1e3) / 1e12},
+                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

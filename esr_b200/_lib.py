@@ -59,6 +59,8 @@ SIGNATURES.update({
     "esr_net_destroy": (c_int, [c_void_p]),
     "esr_net_reset_states": (c_int, [c_void_p, c_void_p]),
     "esr_net_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "esr_net_forward_profiled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
     "esr_net_get_states": (c_int, [c_void_p, c_void_p, c_void_p]),
     "esr_net_set_states": (c_int, [c_void_p, c_void_p, c_void_p]),
 })

@@ -334,65 +334,97 @@ static int build(Net &n, cudaStream_t st)
     return ESR_OK;
 }
 
-static int forward(Net &n, const float *input, const int *in_img, float *output, cudaStream_t st)
+// Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every kernel.
+struct Prof {
+    struct Entry { cudaEvent_t e0, e1; int cls; double flops; };
+    std::vector<Entry> entries;
+};
+enum ProfClass : int { PC_TC = 0, PC_DIRECT = 1, PC_OTHER = 2 };
+
+static double tc_flops(const ConvTCArgs &a) { return 2.0 * a.n_img * a.H * a.W * (double)a.cout * (double)a.nkb * 64.0; }
+static double direct_flops(int dl, const DirectArgs &a)
+{
+    return 2.0 * a.n_img * a.Hout * a.Wout * (double)DLS[dl].cout * (double)DLS[dl].cin * 9.0;
+}
+
+static int forward(Net &n, const float *input, const int *in_img, float *output, cudaStream_t st, Prof *prof = nullptr)
 {
     int rc;
-#define RUN(x) do { if ((rc = (x))) return rc; } while (0)
+    auto run = [&](int cls, double flops, int r_unused) { (void)cls; (void)flops; return r_unused; };
+    (void)run;
+#define RUNC(cls_, flops_, x)                                                              \
+    do {                                                                                   \
+        Prof::Entry pe{};                                                                  \
+        if (prof) {                                                                        \
+            cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1);                              \
+            pe.cls = (cls_); pe.flops = (flops_);                                          \
+            cudaEventRecord(pe.e0, st);                                                    \
+        }                                                                                  \
+        rc = (x);                                                                          \
+        if (prof) { cudaEventRecord(pe.e1, st); prof->entries.push_back(pe); }             \
+        if (rc) return rc;                                                                 \
+    } while (0)
+#define RUN(x) RUNC(PC_OTHER, 0.0, x)
+#define RUNT(args) RUNC(PC_TC, tc_flops(args), conv_tc_launch(args, st))
+#define RUND(kind, dl, args) RUNC(PC_DIRECT, direct_flops(dl, args), conv_direct(kind, args, st))
     const int B = n.B, N = n.N, BN = B * N, nf = (N - 1) * B;
     const ParamLayout &L = param_layout();
     // ---- head + encoder (models/model.py:329-331)
     DirectArgs a = n.d[D_HEAD]; a.in_f32 = input; a.in_img = in_img;
-    RUN(conv_direct(DK_HEAD, a, st));
-    RUN(conv_direct(DK_ENC0, n.d[D_ENC0], st));
-    RUN(conv_direct(DK_ENC1, n.d[D_ENC1], st));
-    RUN(conv_direct(DK_ENC2, n.d[D_ENC2], st));
+    RUND(DK_HEAD, D_HEAD, a);
+    RUND(DK_ENC0, D_ENC0, n.d[D_ENC0]);
+    RUND(DK_ENC1, D_ENC1, n.d[D_ENC1]);
+    RUND(DK_ENC2, D_ENC2, n.d[D_ENC2]);
     // ---- TimePropagation.local_time_corre (model.py:77-89,133-146)
-    RUN(conv_tc_launch(n.c_pm0, st));
-    RUN(conv_tc_launch(n.c_pm1, st));
+    RUNT(n.c_pm0);
+    RUNT(n.c_pm1);
     RUN(ltc_cat(n.F, n.maps, n.m_ltc5, BN, n.t_cat, st));
-    RUN(conv_tc_launch(n.c_lf1, st));
-    RUN(conv_tc_launch(n.c_lf2, st));
-    RUN(conv_tc_launch(n.c_lf3, st));
+    RUNT(n.c_lf1);
+    RUNT(n.c_lf2);
+    RUNT(n.c_lf3);
     // ---- TimePropagation.global_time_corre: bidirectional ConvGRU (model.py:91-124)
-    RUN(conv_tc_launch(n.c_gx, st));
+    RUNT(n.c_gx);
     for (int s = 0; s < N; ++s) {
-        RUN(conv_tc_launch(n.c_gzr[s], st));
-        RUN(conv_tc_launch(n.c_go[s], st));
+        RUNT(n.c_gzr[s]);
+        RUNT(n.c_go[s]);
     }
-    RUN(conv_tc_launch(n.c_gf, st));
+    RUNT(n.c_gf);
     // carried states: slot N (after the last step) becomes slot 0 of the next forward()
     RUN(copy_split(view_imgs(n.hs, N * 2 * B), nullptr, 2 * B, view_imgs(n.hs, 0), st));
     // ---- STFusion.fuse for the non-middle frames (model.py:208-231)
-    RUN(conv_tc_launch(n.c_of0, st));
-    RUN(conv_tc_launch(n.c_of1, st));
-    RUN(conv_tc_launch(n.c_com, st));
+    RUNT(n.c_of0);
+    RUNT(n.c_of1);
+    RUNT(n.c_com);
     RUN(dcn_columns(n.tp, n.m_f0, n.om, nf, n.cols, st));
-    RUN(conv_tc_launch(n.c_dcn, st));
-    RUN(conv_tc_launch(n.c_cb0, st));
-    RUN(conv_tc_launch(n.c_cb1, st));
-    RUN(conv_tc_launch(n.c_ker, st));
+    RUNT(n.c_dcn);
+    RUNT(n.c_cb0);
+    RUNT(n.c_cb1);
+    RUNT(n.c_ker);
     RUN(chan_max(n.feat, nf, n.mx, st));
     RUN(attn_mlp(n.mx, nf, (const float *)(n.params + L.fc0w), (const float *)(n.params + L.fc0b),
                  (const float *)(n.params + L.fc1w), (const float *)(n.params + L.fc1b), n.ck, st));
     RUN(attn_apply(n.aligned, n.tp, n.m_fm, n.sk, n.ck, nf, n.ycat, st));
-    RUN(conv_tc_launch(n.c_df0, st));
-    RUN(conv_tc_launch(n.c_df1, st));
+    RUNT(n.c_df0);
+    RUNT(n.c_df1);
     // ---- dense fusion (model.py:233-251)
-    RUN(conv_tc_launch(n.c_dn0, st));
-    RUN(conv_tc_launch(n.c_dn1, st));
+    RUNT(n.c_dn0);
+    RUNT(n.c_dn1);
     // ---- scale aggregation + reconstruction x3 (model.py:253-291), tail (model.py:337)
-    RUN(conv_tc_launch(n.c_at0, st));
+    RUNT(n.c_at0);
     RUN(scale_aggregate(n.x0, n.F, n.att0, B, N, n.pre0, st));
-    RUN(conv_direct(DK_RECON0, n.d[D_RC0], st));
-    RUN(conv_direct(DK_ATT32, n.d[D_AT1], st));
+    RUND(DK_RECON0, D_RC0, n.d[D_RC0]);
+    RUND(DK_ATT32, D_AT1, n.d[D_AT1]);
     RUN(scale_aggregate(n.x1, n.t_e1, n.att1, B, N, n.pre1, st));
-    RUN(conv_direct(DK_RECON1, n.d[D_RC1], st));
-    RUN(conv_direct(DK_ATT16, n.d[D_AT2], st));
+    RUND(DK_RECON1, D_RC1, n.d[D_RC1]);
+    RUND(DK_ATT16, D_AT2, n.d[D_AT2]);
     RUN(scale_aggregate(n.x2, n.t_e0, n.att2, B, N, n.pre2, st));
-    RUN(conv_direct(DK_RECON2, n.d[D_RC2], st));
+    RUND(DK_RECON2, D_RC2, n.d[D_RC2]);
     a = n.d[D_TAIL]; a.out_f32 = output;
-    RUN(conv_direct(DK_TAIL, a, st));
+    RUND(DK_TAIL, D_TAIL, a);
 #undef RUN
+#undef RUNT
+#undef RUND
+#undef RUNC
     return ESR_OK;
 }
 
@@ -493,6 +525,28 @@ extern "C" int esr_net_forward(esr_net_t net, const float *input, const int32_t 
 {
     ESR_REQUIRE(net && input && output, "esr_net_forward: null pointer");
     return forward(*(Net *)net, input, in_img, output, (cudaStream_t)stream);
+}
+
+extern "C" int esr_net_forward_profiled(esr_net_t net, const float *input, const int32_t *in_img, float *output,
+                                        int max_entries, int *n_entries_host, int *cls_host, float *ms_host,
+                                        double *flops_host, esr_stream_t stream)
+{
+    ESR_REQUIRE(net && input && output && n_entries_host && cls_host && ms_host && flops_host, "esr_net_forward_profiled: null pointer");
+    Prof prof;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = forward(*(Net *)net, input, in_img, output, st, &prof);
+    cudaError_t e = cudaStreamSynchronize(st);
+    int k = 0;
+    for (auto &pe : prof.entries) {
+        float ms = 0.0f;
+        if (e == cudaSuccess) cudaEventElapsedTime(&ms, pe.e0, pe.e1);
+        if (k < max_entries) { cls_host[k] = pe.cls; ms_host[k] = ms; flops_host[k] = pe.flops; ++k; }
+        cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1);
+    }
+    *n_entries_host = k;
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_error("esr_net_forward_profiled: %s", cudaGetErrorString(e)); return ESR_ECUDA; }
+    return ESR_OK;
 }
 
 extern "C" int esr_net_get_states(esr_net_t net, float *states, esr_stream_t stream)

@@ -1,0 +1,52 @@
+"""End-to-end hot path on one GPU: raw events -> count tensors -> DeepRecurrNet over sliding windows (state carried)
+-> SR count tensors -> time-sorted SR event lists.
+
+This is the per-batch body of the reference's inference loop (infer_ours_cnt.py:54-75) together with the dataloader
+encodings it depends on (dataloader/h5dataset.py:508-528 `inp_scaled_cnt`, dataloader/h5dataloader.py:229-231
+sliding windows) and the redistribution API (dataloader/cython_cnt2event/cnt2event_api.py:25-35), with every stage
+on the GPU and no intermediate host round trip:
+
+    host events (pinned) --H2D--> esr_scatter_cnt (LR->HR lift fused) --> frame bank [B*L,2,kH,kW]
+        --> L-2 x esr_net_forward (windows addressed by index into the bank; ConvGRU state carried)
+        --> esr_expand_count / esr_expand_emit on all window outputs --> events [B*(L-2), maxlen, 4] --D2H--> host
+"""
+import torch
+
+from . import encodings
+from .expand import expand
+
+
+class EventSRPipeline:
+    def __init__(self, model, B, L, lr_size, scale, device):
+        self.model, self.B, self.L, self.scale, self.dev = model, B, L, scale, device
+        self.lr_size = (int(lr_size[0]), int(lr_size[1]))
+        self.hr_size = (self.lr_size[0] * scale, self.lr_size[1] * scale)
+        N = 3
+        self.window_index = [
+            torch.tensor([b * L + w + n for b in range(B) for n in range(N)], dtype=torch.int32, device=device)
+            for w in range(L - N + 1)]
+        self.sr_bias = None      # optional synthetic counts added to the SR output before redistribution (bench only)
+
+    @torch.no_grad()
+    def run_device(self, xs, ys, ps, frame_off, n_max_frame, mode=0):
+        """All inputs already on the GPU.  Returns (sr_cnt [B*(L-2),2,kH,kW], events [B*(L-2),maxlen,4]) on the GPU.
+        Sample order of the outputs: window-major (w * B + b)."""
+        bank = encodings.encode_frames(xs, ys, ps, frame_off, lr_size=self.lr_size, hr_size=self.hr_size,
+                                       n_max_frame=n_max_frame)
+        self.model.reset_states()                    # per sequence batch (train_ours_cnt_seq.py:213-216)
+        outs = [self.model(bank, frame_index=idx) for idx in self.window_index]
+        sr = torch.cat(outs, 0)
+        if self.sr_bias is not None:
+            sr = sr + self.sr_bias
+        events = expand(sr, 0, mode)
+        return sr, events
+
+    @torch.no_grad()
+    def run_host(self, xs_h, ys_h, ps_h, off_h, n_max_frame, mode=0):
+        """Pinned host buffers in, host event tensor out (the e2e path: H2D and D2H inside)."""
+        xs = xs_h.to(self.dev, non_blocking=True)
+        ys = ys_h.to(self.dev, non_blocking=True)
+        ps = ps_h.to(self.dev, non_blocking=True)
+        off = off_h.to(self.dev, non_blocking=True)
+        _, events = self.run_device(xs, ys, ps, off, n_max_frame, mode)
+        return events.cpu()

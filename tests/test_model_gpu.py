@@ -61,7 +61,7 @@ def test_reference_fixtures(dev, name):
 @pytest.mark.parametrize("B,H,W,lam", [(1, 64, 64, 0.1), (2, 128, 128, 0.1), (1, 90, 160, 0.3), (3, 40, 72, 1.0)])
 def test_vs_oracle_sequences(dev, B, H, W, lam):
     """4 windows with state carry, incl. the real NFS-syn 2x size 90x160 (pads to 96x160)."""
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
     sd = model_ref.seeded_state_dict(5)
     g = torch.Generator().manual_seed(B * 1000 + H)
     frames = torch.poisson(torch.full((B, 6, 2, H, W), lam), generator=g)
