@@ -84,3 +84,77 @@ int dcn_columns(const SplitTensor &feat, const int *feat_img, const float *om, i
 }
 
 } // namespace esr
+
+// ------------------------------------------------------------------------------------------------
+// `_ext.dcn_v2_forward` operator boundary (models/DCNv2/src/dcn_v2.h:9-27, src/vision.cpp:4-8):
+// fp32 NCHW tensors in the reference's own layout in, fp32 NCHW out.
+// ------------------------------------------------------------------------------------------------
+namespace esr {
+__global__ void __launch_bounds__(256)
+k_om_from_nchw(const float *__restrict__ offset, const float *__restrict__ mask, int B, int HW, float *__restrict__ om)
+{
+    const size_t total = (size_t)B * HW * 216;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % 216);
+        const size_t p = i / 216;
+        const int pix = (int)(p % HW), b = (int)(p / HW);
+        om[i] = c < 144 ? offset[((size_t)b * 144 + c) * HW + pix] : mask[((size_t)b * 72 + (c - 144)) * HW + pix];
+    }
+}
+} // namespace esr
+
+using namespace esr;
+
+static size_t dcn_ws_layout(int B, int H, int W, size_t *o_feat, size_t *o_om, size_t *o_cols, size_t *o_out, size_t *o_w, size_t *o_b)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off = align_up(off + bytes, 1024); return r; };
+    const size_t px = (size_t)B * H * W;
+    *o_feat = take(px * 64 * 4); *o_om = take(px * 216 * 4); *o_cols = take(px * 576 * 4); *o_out = take(px * 64 * 4);
+    *o_w = take(tc_packed_weight_bytes(64, 64, 9)); *o_b = take(64 * 4);
+    return off;
+}
+
+extern "C" size_t esr_dcn_v2_workspace_bytes(int B, int H, int W)
+{
+    size_t a, b, c, d, e, f;
+    return dcn_ws_layout(B, H, W, &a, &b, &c, &d, &e, &f);
+}
+
+extern "C" int esr_dcn_v2_forward(const float *input, const float *weight, const float *bias, const float *offset,
+                                  const float *mask, int B, int C, int H, int W, int Co, int kernel, int stride, int pad,
+                                  int dilation, int deformable_group, float *output, void *workspace, size_t ws_bytes,
+                                  esr_stream_t stream)
+{
+    ESR_REQUIRE(input && weight && bias && offset && mask && output && workspace, "esr_dcn_v2_forward: null pointer");
+    if (!(C == 64 && Co == 64 && kernel == 3 && stride == 1 && pad == 1 && dilation == 1 && deformable_group == 8)) {
+        set_error("esr_dcn_v2_forward: only the configuration ESR uses is implemented (64->64, 3x3, s1 p1 d1, 8 groups; "
+                  "models/model.py:173); got C=%d Co=%d k=%d s=%d p=%d d=%d g=%d", C, Co, kernel, stride, pad, dilation, deformable_group);
+        return ESR_EUNSUPPORTED;
+    }
+    size_t o_feat, o_om, o_cols, o_out, o_w, o_b;
+    const size_t need = dcn_ws_layout(B, H, W, &o_feat, &o_om, &o_cols, &o_out, &o_w, &o_b);
+    if (ws_bytes < need) { set_error("esr_dcn_v2_forward: workspace %zu < %zu", ws_bytes, need); return ESR_EWORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    SplitTensor feat, cols, out;
+    feat.base = (__nv_bfloat16 *)(ws + o_feat); feat.n_img = B; feat.H = H; feat.W = W; feat.C = 64;
+    cols = feat; cols.base = (__nv_bfloat16 *)(ws + o_cols); cols.C = 576;
+    out = feat; out.base = (__nv_bfloat16 *)(ws + o_out);
+    float *om = (float *)(ws + o_om);
+    int rc;
+    if ((rc = split_from_nchw(input, B, 64, H, W, feat.base, st))) return rc;
+    const size_t total = (size_t)B * H * W * 216;
+    k_om_from_nchw<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(offset, mask, B, H * W, om);
+    ESR_LAUNCH_CHECK();
+    if ((rc = dcn_columns(feat, nullptr, om, B, cols, st))) return rc;
+    if ((rc = pack_conv_weight(weight, 64, 64, 3, ws + o_w, st))) return rc;
+    ESR_CUDA_CHECK(cudaMemcpyAsync(ws + o_b, bias, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ConvTCDesc d;
+    d.src[0] = cols; d.n_src = 1; d.ntaps = 1; d.cout = 64; d.wpacked = ws + o_w; d.bias = (const float *)(ws + o_b);
+    d.n_img = B; d.act = ACT_NONE; d.out = out;
+    ConvTCArgs args;
+    if ((rc = conv_tc_prepare(d, &args))) return rc;
+    if ((rc = conv_tc_launch(args, st))) return rc;
+    return split_to_nchw(out.base, B, 64, H, W, output, st);
+}

@@ -153,6 +153,19 @@ int esr_net_forward_profiled(esr_net_t net, const float *input, const int32_t *i
 int esr_net_get_states(esr_net_t net, float *states, esr_stream_t stream);
 int esr_net_set_states(esr_net_t net, const float *states, esr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The `_ext.dcn_v2_forward` operator (modulated deformable 3x3 convolution), reference layouts in and out.
+ * Replaces: models/DCNv2/src/dcn_v2.h:9-27 dcn_v2_forward -> src/cuda/dcn_v2_cuda.cu:20-95 (+ the im2col kernel
+ * src/cuda/dcn_v2_im2col_cuda.cu:125-195), as bound by src/vision.cpp:4-8 and called from models/DCNv2/dcn_v2.py:27.
+ * input [B,C,H,W], weight [Co,C,3,3], bias [Co], offset [B,dg*18,H,W], mask [B,dg*9,H,W], output [B,Co,H,W]; fp32.
+ * Implemented configuration: the one ESR instantiates (C=Co=64, 3x3, stride 1, pad 1, dilation 1, dg=8);
+ * anything else returns ESR_EUNSUPPORTED.
+ * --------------------------------------------------------------------------------------------- */
+size_t esr_dcn_v2_workspace_bytes(int B, int H, int W);
+int esr_dcn_v2_forward(const float *input, const float *weight, const float *bias, const float *offset, const float *mask,
+                       int B, int C, int H, int W, int Co, int kernel, int stride, int pad, int dilation,
+                       int deformable_group, float *output, void *workspace, size_t workspace_bytes, esr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
