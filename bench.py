@@ -88,6 +88,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def usable_cores(cap=32):
+    """Host threads the CPU legs may use: affinity and cgroup quota, capped (torch's small convs stop scaling, and
+    oversubscribing a 128-way box made the oracle ~100x slower when measured)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return max(1, min(n, cap))
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -126,7 +139,7 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     from oracle import model_ref
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     sd = model_ref.seeded_state_dict(0)
     B_sample = 1
@@ -281,10 +294,33 @@ def main():
                 for row in prof_rows:
                     f.write("%d,%d,%.5f,%.0f\n" % row)
 
+    # ---- stage breakdown of one step (device-resident inputs), CUDA events on the launching stream
+    stages = None
+    if rank == 0:
+        from esr_b200 import encodings as enc
+        from esr_b200.expand import expand
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc3 = [0.0, 0.0, 0.0]
+        for _ in range(5):
+            torch.cuda.synchronize()
+            ev[0].record()
+            bank_ = enc.encode_frames(d_xs, d_ys, d_ps, d_off, lr_size=lr, hr_size=hr, n_max_frame=EVENTS_PER_FRAME)
+            ev[1].record()
+            net.reset_states()
+            outs_ = [net(bank_, frame_index=idx) for idx in pipe.window_index]
+            sr_ = torch.cat(outs_, 0) + pipe.sr_bias
+            ev[2].record()
+            expand(sr_, 0, 0)
+            ev[3].record()
+            torch.cuda.synchronize()
+            for i in range(3):
+                acc3[i] += ev[i].elapsed_time(ev[i + 1]) / 5
+        stages = {"encode_ms": acc3[0], "network_ms": acc3[1], "redistribute_ms": acc3[2]}
+
     # ---- CPU baseline (oracle port) on rank 0, N=1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         torch.set_num_threads(cores)
         cpu_oracle_step(wl, 1, sd, 1)
         ts = [cpu_oracle_step(wl, 1, sd, 1)[0] for _ in range(3)]
@@ -311,6 +347,7 @@ def main():
                 "gpu_launches": int(launches),
                 "tensor_roofline_whole_path": {"algorithmic_tflops": FLOP_PER_HR_PIXEL * hr[0] * hr[1] * B * (L - 2) * world /
                                                (ms_dev / args.steps / 1e3) / 1e12},
+                "stages_ms_per_step": stages,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
