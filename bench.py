@@ -304,11 +304,13 @@ def main():
         for _ in range(5):
             torch.cuda.synchronize()
             ev[0].record()
-            bank_ = enc.encode_frames(d_xs, d_ys, d_ps, d_off, lr_size=lr, hr_size=hr, n_max_frame=EVENTS_PER_FRAME)
+            with torch.no_grad():
+                bank_ = enc.encode_frames(d_xs, d_ys, d_ps, d_off, lr_size=lr, hr_size=hr, n_max_frame=EVENTS_PER_FRAME)
             ev[1].record()
-            net.reset_states()
-            outs_ = [net(bank_, frame_index=idx) for idx in pipe.window_index]
-            sr_ = torch.cat(outs_, 0) + pipe.sr_bias
+            with torch.no_grad():
+                net.reset_states()
+                outs_ = [net(bank_, frame_index=idx) for idx in pipe.window_index]
+                sr_ = torch.cat(outs_, 0) + pipe.sr_bias
             ev[2].record()
             expand(sr_, 0, 0)
             ev[3].record()

@@ -1,38 +1,92 @@
-// direct_conv.cu -- CUDA-core 3x3 convolutions for the small-channel, full-resolution layers (HBM/latency bound,
-// Cin <= 64 and Cout <= 64 with too few channels to fill a tensor-core tile):
+// direct_conv.cu -- CUDA-core 3x3 convolutions for the small-channel, full-resolution layers (Cin <= 64 and
+// Cout <= 64 with too few channels to fill a tensor-core tile; HBM / FFMA bound):
 //   head 2->8 (models/model.py:301,330), encoder 8->16->32->64 stride 2 (models/model.py:20-45),
 //   attention maps C->1 sigmoid (models/model.py:195-199,262), decoder bilinear x2 + conv (models/submodules.py:254-299),
 //   tail 8->2 (models/model.py:309,337).
-// One block = 16x16 output pixels, all output channels; the input patch (+halo) is staged in shared memory as
-// [ci][py][px] fp32, weights as [tap][ci][co] fp32 (broadcast reads).  fp32 math throughout.
+// One block = 16x16 output pixels, all output channels.
+//   stage 1: the input patch (+halo) is staged in shared memory as [ci][py][px] fp32 -- 16-byte loads of 8 channels of
+//            the split-bf16 NHWC source per thread (the bilinear x2 upsampling of the decoder is applied on the fly);
+//   stage 2: register tiling -- a thread owns a 2x2 pixel patch x COUT/4 channels (its 4x4 / 5x5 input window is read
+//            once per input channel and reused over the 9 taps; weights are warp-uniform LDS.128 broadcasts);
+//            layers with COUT < 8 use one pixel x all channels per thread;
+//   stage 3: 16-byte split-bf16 stores.
+// fp32 math throughout.
 #include "net.cuh"
 
 namespace esr {
 
 constexpr int DC_T = 16;   // output tile edge
 
+__device__ __forceinline__ void dc_unpack8(const uint4 h, const uint4 l, float (&o)[8])
+{
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        o[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+        o[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void dc_ld8(const __nv_bfloat16 *p, size_t plane, float (&o)[8])
+{
+    dc_unpack8(*reinterpret_cast<const uint4 *>(p), *reinterpret_cast<const uint4 *>(p + plane), o);
+}
+// NV values (2, 4 or 8) -> split-bf16, vector stores
+template <int NV>
+__device__ __forceinline__ void dc_store(__nv_bfloat16 *p, size_t plane, const float *x)
+{
+    uint32_t hw[NV / 2], lw[NV / 2];
+#pragma unroll
+    for (int e = 0; e < NV / 2; ++e) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(x[2 * e], h0, l0);
+        split_bf16(x[2 * e + 1], h1, l1);
+        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    if constexpr (NV == 8) {
+        *reinterpret_cast<uint4 *>(p) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4 *>(p + plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    } else if constexpr (NV == 4) {
+        *reinterpret_cast<uint2 *>(p) = make_uint2(hw[0], hw[1]);
+        *reinterpret_cast<uint2 *>(p + plane) = make_uint2(lw[0], lw[1]);
+    } else {
+        *reinterpret_cast<uint32_t *>(p) = hw[0];
+        *reinterpret_cast<uint32_t *>(p + plane) = lw[0];
+    }
+}
+
+__device__ __forceinline__ float dc_act(float v, int act)
+{
+    if (act == ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    return v;
+}
+
 template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF>
 __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
 {
-    constexpr int PW = (DC_T - 1) * STRIDE + 3;
+    constexpr int PW = (DC_T - 1) * STRIDE + 3;           // patch edge actually needed
+    constexpr int PP = (PW + 3) / 4 * 4;                  // row pitch (floats)
+    constexpr bool TILED = (COUT >= 8);                   // 2x2 pixels x COUT/4 channels per thread
     extern __shared__ float dsm[];
-    float *patch = dsm;                          // [CIN][PW][PW]
-    float *wsm = dsm + CIN * PW * PW;            // [9][CIN][COUT]
-    float *bsm = wsm + 9 * CIN * COUT;           // [COUT]
+    float *patch = dsm;                                   // [CIN][PW][PP]
+    float *wsm = dsm + CIN * PW * PP;                     // [9][CIN][COUT]
+    float *bsm = wsm + 9 * CIN * COUT;                    // [COUT]
 
     const int img = blockIdx.z;
     const int oy0 = blockIdx.y * DC_T, ox0 = blockIdx.x * DC_T;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < 9 * CIN * COUT; i += 256) wsm[i] = a.w[i];
+    for (int i = tid; i < 9 * CIN * COUT / 4; i += 256)
+        reinterpret_cast<float4 *>(wsm)[i] = reinterpret_cast<const float4 *>(a.w)[i];
     if (tid < COUT) bsm[tid] = a.bias[tid];
 
-    // ---- stage the input patch.  Conv input coordinates (virtual, before any upsampling): [0,Hc) x [0,Wc)
+    // ---- stage 1: input patch.  Conv input coordinates (after padding / upsampling): [0,Hc) x [0,Wc)
     const int Hc = UPS ? 2 * a.Hin : a.Hin + a.pad_top + a.pad_bottom;
     const int Wc = UPS ? 2 * a.Win : a.Win + a.pad_left + a.pad_right;
     const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
     const int simg = a.in_img ? a.in_img[img] : img;
-    if (INF == FMT_NCHW_F32) {
+    if constexpr (INF == FMT_NCHW_F32) {
         for (int i = tid; i < CIN * PW * PW; i += 256) {
             const int px = i % PW, py = (i / PW) % PW, ci = i / (PW * PW);
             const int y = iy0 + py, x = ix0 + px;
@@ -42,20 +96,23 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
                 if (sy >= 0 && sy < a.Hin && sx >= 0 && sx < a.Win)
                     v = a.in_f32[(((size_t)simg * CIN + ci) * a.Hin + sy) * a.Win + sx];
             }
-            patch[i] = v;
+            patch[(ci * PW + py) * PP + px] = v;
         }
     } else {
+        static_assert(INF == FMT_NCHW_F32 || CIN % 8 == 0, "split input needs CIN % 8 == 0");
         const __nv_bfloat16 *hi = a.in_split;
         const size_t plane = a.in_plane;
-        for (int i = tid; i < CIN * PW * PW; i += 256) {
-            const int ci = i % CIN, pp = i / CIN;
+        constexpr int Q = CIN / 8;
+        for (int i = tid; i < Q * PW * PW; i += 256) {
+            const int pp = i % (PW * PW), q = i / (PW * PW);            // lanes <-> pixels: conflict-free smem writes
             const int px = pp % PW, py = pp / PW;
             const int y = iy0 + py, x = ix0 + px;
-            float v = 0.0f;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.0f;
             if (y >= 0 && y < Hc && x >= 0 && x < Wc) {
-                if (!UPS) {
-                    const size_t o = (((size_t)simg * a.Hin + y) * a.Win + x) * CIN + ci;
-                    v = join_bf16(hi[o], hi[plane + o]);
+                if constexpr (!UPS) {
+                    dc_ld8(hi + (((size_t)simg * a.Hin + y) * a.Win + x) * CIN + q * 8, plane, v);
                 } else {
                     // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) (submodules.py:290):
                     // src = max(0, (dst + 0.5) * 0.5 - 0.5); neighbours clamped to the image
@@ -65,64 +122,107 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
                     const int y_1 = min(y_0 + 1, a.Hin - 1), x_1 = min(x_0 + 1, a.Win - 1);
                     const float ly = fy - (float)y_0, lx = fx - (float)x_0;
                     const size_t b0 = ((size_t)simg * a.Hin + y_0) * a.Win, b1 = ((size_t)simg * a.Hin + y_1) * a.Win;
-                    const size_t o00 = (b0 + x_0) * CIN + ci, o01 = (b0 + x_1) * CIN + ci;
-                    const size_t o10 = (b1 + x_0) * CIN + ci, o11 = (b1 + x_1) * CIN + ci;
-                    const float v00 = join_bf16(hi[o00], hi[plane + o00]), v01 = join_bf16(hi[o01], hi[plane + o01]);
-                    const float v10 = join_bf16(hi[o10], hi[plane + o10]), v11 = join_bf16(hi[o11], hi[plane + o11]);
-                    // same association as ATen's upsample_bilinear2d: w00*v00 + w01*v01 + w10*v10 + w11*v11
-                    v = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
+                    float v00[8], v01[8], v10[8], v11[8];
+                    dc_ld8(hi + (b0 + x_0) * CIN + q * 8, plane, v00);
+                    dc_ld8(hi + (b0 + x_1) * CIN + q * 8, plane, v01);
+                    dc_ld8(hi + (b1 + x_0) * CIN + q * 8, plane, v10);
+                    dc_ld8(hi + (b1 + x_1) * CIN + q * 8, plane, v11);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)   // ATen: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+                        v[e] = (1.0f - ly) * ((1.0f - lx) * v00[e] + lx * v01[e]) + ly * ((1.0f - lx) * v10[e] + lx * v11[e]);
                 }
             }
-            patch[(ci * PW + py) * PW + px] = v;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) patch[((q * 8 + e) * PW + py) * PP + px] = v[e];
         }
     }
     __syncthreads();
 
-    const int ty = tid / DC_T, tx = tid % DC_T;
-    const int oy = oy0 + ty, ox = ox0 + tx;
-    float acc[COUT];
+    if constexpr (TILED) {
+        // ---- stage 2 (tiled): thread = (cout group cg, pixel group pg): 2x2 pixels x C channels
+        constexpr int C = COUT / 4;
+        constexpr int WIN = STRIDE + 3;                   // input window edge for a 2x2 output patch
+        const int cg = tid >> 6, pg = tid & 63;           // cg is warp-uniform -> weight reads are broadcasts
+        const int gy = pg >> 3, gx = pg & 7;
+        float acc[4][C];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = bsm[co];
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[p][c] = bsm[cg * C + c];
 #pragma unroll 1
-    for (int ci = 0; ci < CIN; ++ci) {
+        for (int ci = 0; ci < CIN; ++ci) {
+            float win[WIN][WIN];
+            const float *pb = patch + (ci * PW + gy * 2 * STRIDE) * PP + gx * 2 * STRIDE;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+            for (int r = 0; r < WIN; ++r)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const float xv = patch[(ci * PW + ty * STRIDE + ky) * PW + tx * STRIDE + kx];
-                const float *wp = wsm + ((ky * 3 + kx) * CIN + ci) * COUT;
+                for (int s = 0; s < WIN; ++s) win[r][s] = pb[r * PP + s];
 #pragma unroll
-                for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, wp[co], acc[co]);
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float *wp = wsm + ((ky * 3 + kx) * CIN + ci) * COUT + cg * C;
+                    float wv[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) wv[c] = wp[c];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float xv = win[(p >> 1) * STRIDE + ky][(p & 1) * STRIDE + kx];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) acc[p][c] = fmaf(xv, wv[c], acc[p][c]);
+                    }
+                }
+        }
+        // ---- stage 3
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int oy = oy0 + gy * 2 + (p >> 1), ox = ox0 + gx * 2 + (p & 1);
+            if (oy >= a.Hout || ox >= a.Wout) continue;
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = dc_act(acc[p][c], a.act);
+            static_assert(OUTF == FMT_SPLIT, "tiled path writes split tensors");
+            __nv_bfloat16 *dst = a.out_split + (((size_t)img * a.Hout + oy) * a.Wout + ox) * COUT + cg * C;
+            if constexpr (C >= 8) {
+#pragma unroll
+                for (int c8 = 0; c8 < C / 8; ++c8) dc_store<8>(dst + c8 * 8, a.out_plane, v + c8 * 8);
+            } else {
+                dc_store<C>(dst, a.out_plane, v);
             }
         }
-    }
-    if (oy >= a.Hout || ox >= a.Wout) return;
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) {
-        float v = acc[co];
-        if (a.act == ACT_RELU) v = fmaxf(v, 0.0f);
-        else if (a.act == ACT_SIGMOID) v = 1.0f / (1.0f + expf(-v));
-        acc[co] = v;
-    }
-    if (OUTF == FMT_SPLIT) {
-        const size_t o = (((size_t)img * a.Hout + oy) * a.Wout + ox) * COUT;
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-            __nv_bfloat16 h, l;
-            split_bf16(acc[co], h, l);
-            a.out_split[o + co] = h;
-            a.out_split[a.out_plane + o + co] = l;
-        }
-    } else if (OUTF == FMT_NHWC_F32) {
-        const size_t o = (((size_t)img * a.Hout + oy) * a.Wout + ox) * COUT;
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) a.out_f32[o + co] = acc[co];
     } else {
-        // NCHW fp32 with the CropSize crop (model_util.py:154-164): only rows/cols inside the crop window are stored
-        const int cy = oy - a.crop_top, cx = ox - a.crop_left;
-        if (cy >= 0 && cy < a.out_H && cx >= 0 && cx < a.out_W) {
+        // ---- stage 2 (narrow): one pixel x all COUT (1 or 2) per thread
+        const int ty = tid / DC_T, tx = tid % DC_T;
+        const int oy = oy0 + ty, ox = ox0 + tx;
+        float acc[COUT];
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) a.out_f32[(((size_t)img * COUT + co) * a.out_H + cy) * a.out_W + cx] = acc[co];
+        for (int co = 0; co < COUT; ++co) acc[co] = bsm[co];
+#pragma unroll 4
+        for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float xv = patch[(ci * PW + ty * STRIDE + ky) * PP + tx * STRIDE + kx];
+                    const float *wp = wsm + ((ky * 3 + kx) * CIN + ci) * COUT;
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, wp[co], acc[co]);
+                }
+        }
+        if (oy >= a.Hout || ox >= a.Wout) return;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = dc_act(acc[co], a.act);
+        if constexpr (OUTF == FMT_NHWC_F32) {
+            const size_t o = (((size_t)img * a.Hout + oy) * a.Wout + ox) * COUT;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) a.out_f32[o + co] = acc[co];
+        } else {
+            // NCHW fp32 with the CropSize crop (model_util.py:154-164): only pixels inside the crop window are stored
+            const int cy = oy - a.crop_top, cx = ox - a.crop_left;
+            if (cy >= 0 && cy < a.out_H && cx >= 0 && cx < a.out_W) {
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) a.out_f32[(((size_t)img * COUT + co) * a.out_H + cy) * a.out_W + cx] = acc[co];
+            }
         }
     }
 }
@@ -131,7 +231,9 @@ template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF>
 static int launch_direct(const DirectArgs &a, cudaStream_t st)
 {
     constexpr int PW = (DC_T - 1) * STRIDE + 3;
-    constexpr size_t smem = sizeof(float) * (size_t)(CIN * PW * PW + 9 * CIN * COUT + COUT);
+    constexpr int PP = (PW + 3) / 4 * 4;
+    constexpr size_t smem = sizeof(float) * (size_t)(CIN * PW * PP + 9 * CIN * COUT + COUT);
+    static_assert(smem <= 227 * 1024, "direct conv tile does not fit in shared memory");
     static bool attr_set = false;
     if (!attr_set) {
         ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_direct<CIN, COUT, STRIDE, UPS, INF, OUTF>,
