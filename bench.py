@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--profile-out", default=None, help="write the per-launch timing table of one window here")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -228,6 +229,9 @@ def main():
     dev_step = lambda: pipe.run_device(d_xs, d_ys, d_ps, d_off, EVENTS_PER_FRAME)
     host_step = lambda: pipe.run_host(h_xs, h_ys, h_ps, h_off, EVENTS_PER_FRAME)
 
+    dev_step()
+    if not args.no_graph:
+        pipe.capture()
     for _ in range(args.warmup):
         dev_step()
         host_step()
@@ -236,7 +240,7 @@ def main():
     barrier()
     l0 = _lib.lib().esr_launch_count()
     ms_dev = timed(dev_step, args.steps)
-    launches = _lib.lib().esr_launch_count() - l0
+    launches = _lib.lib().esr_launch_count() - l0 + args.steps * pipe.graph_launches
     barrier()
     ms_e2e = timed(host_step, args.steps)
     barrier()
@@ -305,12 +309,14 @@ def main():
             torch.cuda.synchronize()
             ev[0].record()
             with torch.no_grad():
-                bank_ = enc.encode_frames(d_xs, d_ys, d_ps, d_off, lr_size=lr, hr_size=hr, n_max_frame=EVENTS_PER_FRAME)
+                enc.encode_frames(d_xs, d_ys, d_ps, d_off, lr_size=lr, hr_size=hr, n_max_frame=EVENTS_PER_FRAME, out=pipe.bank)
             ev[1].record()
             with torch.no_grad():
-                net.reset_states()
-                outs_ = [net(bank_, frame_index=idx) for idx in pipe.window_index]
-                sr_ = torch.cat(outs_, 0) + pipe.sr_bias
+                if pipe._graph is not None:
+                    pipe._graph.replay()
+                    sr_ = pipe._graph_sr
+                else:
+                    sr_ = pipe._windows()
             ev[2].record()
             expand(sr_, 0, 0)
             ev[3].record()
@@ -341,7 +347,8 @@ def main():
                            "events_per_frame": EVENTS_PER_FRAME, "windows_per_sequence": L - 2,
                            "redistribute_input": "model output + Poisson(0.3) synthetic counts",
                            "l2": "256 MiB buffer rewritten between timed steps (outside the timed intervals)",
-                           "parallelism": f"dp{world} (batch shards, no data-path collective)"},
+                           "parallelism": f"dp{world} (batch shards, no data-path collective)",
+                           "cuda_graph": not args.no_graph},
                 "sr_frames_per_s": value * (L - 2) / L,
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,

@@ -69,7 +69,7 @@ def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
     return out if xs.is_cuda else out.cpu()
 
 
-def encode_frames(xs, ys, ps, frame_off, lr_size=None, hr_size=(180, 240), n_max_frame=None):
+def encode_frames(xs, ys, ps, frame_off, lr_size=None, hr_size=(180, 240), n_max_frame=None, out=None):
     """F frames of events -> [F,2,H,W] count images in one launch.
 
     xs, ys, ps: CUDA fp32 [n_total]; frame_off: CUDA int64 [F+1].  With lr_size=(H_lr,W_lr) the coordinates
@@ -77,7 +77,9 @@ def encode_frames(xs, ys, ps, frame_off, lr_size=None, hr_size=(180, 240), n_max
     assert xs.is_cuda and ys.is_cuda and ps.is_cuda and frame_off.is_cuda
     F = frame_off.numel() - 1
     H, W = int(hr_size[0]), int(hr_size[1])
-    out = torch.empty((F, 2, H, W), dtype=torch.float32, device=xs.device)
+    if out is None:
+        out = torch.empty((F, 2, H, W), dtype=torch.float32, device=xs.device)
+    assert out.is_cuda and out.is_contiguous() and tuple(out.shape) == (F, 2, H, W)
     if n_max_frame is None:
         n_max_frame = xs.numel()
     lift = (int(lr_size[1]), W, int(lr_size[0]), H) if lr_size is not None else (0, 0, 0, 0)

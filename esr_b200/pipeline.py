@@ -26,18 +26,49 @@ class EventSRPipeline:
             torch.tensor([b * L + w + n for b in range(B) for n in range(N)], dtype=torch.int32, device=device)
             for w in range(L - N + 1)]
         self.sr_bias = None      # optional synthetic counts added to the SR output before redistribution (bench only)
+        self.bank = torch.zeros((B * L, 2, self.hr_size[0], self.hr_size[1]), dtype=torch.float32, device=device)
+        self._graph = None
+        self._graph_sr = None
+        self.graph_launches = 0
+
+    def _windows(self):
+        self.model.reset_states()                    # per sequence batch (train_ours_cnt_seq.py:213-216)
+        outs = [self.model(self.bank, frame_index=idx) for idx in self.window_index]
+        sr = torch.cat(outs, 0)
+        if self.sr_bias is not None:
+            sr = sr + self.sr_bias
+        return sr
+
+    @torch.no_grad()
+    def capture(self):
+        """Capture the L-2 windows (reset + 45 launches each) into one CUDA graph: the plan allocates nothing and never
+        synchronises, so the whole recurrent chain replays with a single launch from the host."""
+        self._windows()                              # warm-up: packs parameters, builds the plan, sets smem attributes
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._windows()
+        torch.cuda.current_stream().wait_stream(s)
+        from . import _lib
+        c0 = _lib.lib().esr_launch_count()
+        with torch.cuda.graph(g):
+            self._graph_sr = self._windows()
+        self.graph_launches = int(_lib.lib().esr_launch_count() - c0)   # kernels of ours inside one replay
+        self._graph = g
 
     @torch.no_grad()
     def run_device(self, xs, ys, ps, frame_off, n_max_frame, mode=0):
         """All inputs already on the GPU.  Returns (sr_cnt [B*(L-2),2,kH,kW], events [B*(L-2),maxlen,4]) on the GPU.
         Sample order of the outputs: window-major (w * B + b)."""
-        bank = encodings.encode_frames(xs, ys, ps, frame_off, lr_size=self.lr_size, hr_size=self.hr_size,
-                                       n_max_frame=n_max_frame)
-        self.model.reset_states()                    # per sequence batch (train_ours_cnt_seq.py:213-216)
-        outs = [self.model(bank, frame_index=idx) for idx in self.window_index]
-        sr = torch.cat(outs, 0)
-        if self.sr_bias is not None:
-            sr = sr + self.sr_bias
+        encodings.encode_frames(xs, ys, ps, frame_off, lr_size=self.lr_size, hr_size=self.hr_size,
+                                n_max_frame=n_max_frame, out=self.bank)
+        if self._graph is not None:
+            self._graph.replay()
+            sr = self._graph_sr
+        else:
+            sr = self._windows()
         events = expand(sr, 0, mode)
         return sr, events
 
