@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
-    ap.add_argument("--profile-out", default=None, help="write the per-launch timing table of one window here")
+    ap.add_argument("--profile-out", default=None, help="write the per-launch timing table of one step here")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -255,14 +255,14 @@ def main():
     value = frames_per_step * args.steps / (ms_dev / 1e3)
     e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel (k_conv_tc): per-launch CUDA events over one window of the same workload
+    # ---- roofline of the dominant kernel (k_conv_tc): per-launch CUDA events over one sequence batch (all windows) of the same workload
     roofline, prof_rows = None, []
     if rank == 0:
         import ctypes
-        plan = net._plans[(B, 3, hr[0], hr[1])]
+        plan = net._plans[(B, L, hr[0], hr[1])]
         bank = torch.poisson(torch.full((B * L, 2, hr[0], hr[1]), 0.1)).to(dev)
-        out = torch.empty((B, 2, hr[0], hr[1]), device=dev)
-        cap = 128
+        out = torch.empty(((L - 2) * B, 2, hr[0], hr[1]), device=dev)
+        cap = 256
         cls = (ctypes.c_int * cap)()
         ms = (ctypes.c_float * cap)()
         fl = (ctypes.c_double * cap)()
@@ -270,7 +270,7 @@ def main():
         acc = {0: [0.0, 0.0, 0], 1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0]}
         reps = 5
         for r in range(reps + 1):
-            _lib.check(_lib.lib().esr_net_forward_profiled(plan.handle, _lib.ptr(bank), _lib.ptr(pipe.window_index[0]), _lib.ptr(out),
+            _lib.check(_lib.lib().esr_net_forward_profiled(plan.handle, _lib.ptr(bank), None, _lib.ptr(out),
                                                            cap, ctypes.byref(cnt), cls, ms, fl, _lib.stream_ptr()), "profiled forward")
             if r == 0:
                 continue                                             # warm-up
@@ -283,15 +283,15 @@ def main():
         peak_tf, peak_hbm, peak_src = measured_peaks()
         achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         tot_ms = sum(a[0] for a in acc.values())
-        roofline = {"kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, all launches of one window)", "bound": "tensor",
+        roofline = {"kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, all launches of one step)", "bound": "tensor",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "peak_source": peak_src + ", bf16 sustained", "traffic": None,
-                    "launches_per_window": tc_n // reps, "avg_launch_us": tc_ms / max(tc_n, 1) * 1e3,
-                    "algorithmic_gflop_per_window": tc_fl / reps / 1e9,
-                    "share_of_window_time": tc_ms / tot_ms if tot_ms else None,
+                    "launches_per_step": tc_n // reps, "avg_launch_us": tc_ms / max(tc_n, 1) * 1e3,
+                    "algorithmic_gflop_per_step": tc_fl / reps / 1e9,
+                    "share_of_step_kernel_time": tc_ms / tot_ms if tot_ms else None,
                     "note": "algorithmic FLOPs (1x); the fp32-parity 3-pass split-bf16 product issues 3x that on the tensor pipe",
-                    "cuda_core_conv_ms_per_window": acc[1][0] / reps, "elementwise_ms_per_window": acc[2][0] / reps,
-                    "tc_ms_per_window": tc_ms / reps}
+                    "cuda_core_conv_ms_per_step": acc[1][0] / reps, "elementwise_ms_per_step": acc[2][0] / reps,
+                    "tc_ms_per_step": tc_ms / reps}
         if args.profile_out:
             with open(args.profile_out, "w") as f:
                 f.write("idx,class(0=tc,1=direct,2=other),ms,algorithmic_flops\n")
@@ -348,7 +348,8 @@ def main():
                            "redistribute_input": "model output + Poisson(0.3) synthetic counts",
                            "l2": "256 MiB buffer rewritten between timed steps (outside the timed intervals)",
                            "parallelism": f"dp{world} (batch shards, no data-path collective)",
-                           "cuda_graph": not args.no_graph},
+                           "cuda_graph": not args.no_graph,
+                           "plan": "sequence plan: per-frame and state-independent layers batched over all windows, ConvGRU chain serial"},
                 "sr_frames_per_s": value * (L - 2) / L,
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,

@@ -54,8 +54,8 @@ SIGNATURES.update({
 SIGNATURES.update({
     "esr_net_param_bytes": (c_size_t, []),
     "esr_net_pack_params": (c_int, [c_void_p, c_void_p, c_void_p]),
-    "esr_net_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "esr_net_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "esr_net_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "esr_net_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "esr_net_destroy": (c_int, [c_void_p]),
     "esr_net_reset_states": (c_int, [c_void_p, c_void_p]),
     "esr_net_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -176,7 +176,8 @@ int attn_apply(const SplitTensor &aligned, const SplitTensor &mid_src, const int
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_scale_aggregate(const __nv_bfloat16 *__restrict__ x, size_t x_plane, const __nv_bfloat16 *__restrict__ feats, size_t f_plane,
-                  const float *__restrict__ att, int B, int N, int HW, int C, __nv_bfloat16 *__restrict__ out, size_t out_plane)
+                  const float *__restrict__ att, const int *__restrict__ fidx, int B, int N, int HW, int C,
+                  __nv_bfloat16 *__restrict__ out, size_t out_plane)
 {
     const int G = C / 8;
     const size_t total = (size_t)B * HW * G;
@@ -189,7 +190,7 @@ k_scale_aggregate(const __nv_bfloat16 *__restrict__ x, size_t x_plane, const __n
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
         for (int n = 0; n < N; ++n) {
-            const size_t fp = (size_t)(b * N + n) * HW + pix;
+            const size_t fp = (size_t)(fidx ? fidx[b * N + n] : b * N + n) * HW + pix;
             float v[8];
             load8(feats + fp * C + g * 8, f_plane, v);
             const float a = att[fp];
@@ -203,13 +204,13 @@ k_scale_aggregate(const __nv_bfloat16 *__restrict__ x, size_t x_plane, const __n
         store8(out + p * C + g * 8, out_plane, xv);
     }
 }
-int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float *att, int B, int N, const SplitTensor &out,
-                    cudaStream_t st)
+int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float *att, const int *fidx, int B, int N,
+                    const SplitTensor &out, cudaStream_t st)
 {
     const int HW = x.H * x.W, C = x.C;
     const size_t total = (size_t)B * HW * (C / 8);
     k_scale_aggregate<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(x.base, x.plane(), feats.base, feats.plane(),
-                                                                                 att, B, N, HW, C, out.base, out.plane());
+                                                                                 att, fidx, B, N, HW, C, out.base, out.plane());
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

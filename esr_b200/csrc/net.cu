@@ -80,8 +80,12 @@ static const ParamLayout &param_layout()
 }
 
 // ---- the plan ---------------------------------------------------------------------------------------------------
+// Sequence plan: B sequences x L frames, Wn = L-N+1 sliding windows.  Everything that does not depend on the
+// recurrent state is evaluated ONCE for all windows (virtual batch VB = Wn*B, window-major vb = w*B + b), per-frame
+// work (encoder, attention maps) once per bank frame (FR = B*L frames, frame = b*L + l); only the ConvGRU chain runs
+// window after window.  L = N gives the reference's single-window forward.
 struct Net {
-    int B, N, H, W, Hc, Wc, h, w;
+    int B, N, L, Wn, VB, FR, H, W, Hc, Wc, h, w;
     int pad_top, pad_bottom, pad_left, pad_right;
     char *params;   // packed blob
     char *ws;       // workspace
@@ -91,9 +95,9 @@ struct Net {
     SplitTensor t_of0, t_off, cols, aligned, t_cb0, feat, ycat, t_df0, fused, t_dn0, x0, pre0, x1, pre1, x2, pre2, x3;
     float *maps, *zbuf, *om, *sk, *mx, *ck, *att0, *att1, *att2;
     // index maps (device)
-    int *m_pairA, *m_pairB, *m_ltc5, *m_lf3res, *m_f0, *m_fm, *m_dn[3], *m_gf_f, *m_gf_r;
-    std::vector<int *> m_gx, m_gh;     // per GRU step
-    // prepared tensor-core launches, in execution order
+    int *m_fr, *m_pairA, *m_pairB, *m_ltc5, *m_lf3res, *m_f0, *m_fm, *m_dn[3], *m_gf_f, *m_gf_r, *m_gfres;
+    std::vector<int *> m_gx, m_gh;     // per GRU step (Wn * N of them)
+    // prepared tensor-core launches
     ConvTCArgs c_pm0, c_pm1, c_lf1, c_lf2, c_lf3, c_gx, c_gf, c_of0, c_of1, c_com, c_dcn, c_cb0, c_cb1, c_ker, c_df0, c_df1,
         c_dn0, c_dn1, c_at0;
     std::vector<ConvTCArgs> c_gzr, c_go;
@@ -118,23 +122,27 @@ struct Arena {
 static size_t layout(Net &n)
 {
     Arena A(n.ws, n.ws_bytes);
-    const int B = n.B, N = n.N, BN = B * N, h = n.h, w = n.w, Hc = n.Hc, Wc = n.Wc, nf = (N - 1) * B, np = B * (N + 1);
+    const int B = n.B, N = n.N, VB = n.VB, FR = n.FR, VN = VB * N, h = n.h, w = n.w, Hc = n.Hc, Wc = n.Wc;
+    const int nf = (N - 1) * VB, np = VB * (N + 1), nsteps = n.Wn * N;
     // recurrent state first so that its address does not depend on later changes
-    n.hs = A.split((N + 1) * 2 * B, h, w, 64);
-    n.t_head = A.split(BN, Hc, Wc, 8);
-    n.t_e0 = A.split(BN, Hc / 2, Wc / 2, 16);
-    n.t_e1 = A.split(BN, Hc / 4, Wc / 4, 32);
-    n.F = A.split(BN, h, w, 64);
+    n.hs = A.split((nsteps + 1) * 2 * B, h, w, 64);
+    n.t_head = A.split(FR, Hc, Wc, 8);
+    n.t_e0 = A.split(FR, Hc / 2, Wc / 2, 16);
+    n.t_e1 = A.split(FR, Hc / 4, Wc / 4, 32);
+    n.F = A.split(FR, h, w, 64);
+    n.att0 = (float *)A.take(sizeof(float) * FR * h * w);
+    n.att1 = (float *)A.take(sizeof(float) * FR * 4 * h * w);
+    n.att2 = (float *)A.take(sizeof(float) * FR * 16 * h * w);
     n.t_pm0 = A.split(np, h, w, 64);
     n.maps = (float *)A.take(sizeof(float) * np * h * w);
-    n.t_cat = A.split(BN, h, w, 192);
-    n.t_lf1 = A.split(BN, h, w, 192);
-    n.t_lf2 = A.split(BN, h, w, 192);
-    n.ltc = A.split(BN, h, w, 64);
-    n.xc = A.split(BN, h, w, 64);
+    n.t_cat = A.split(VN, h, w, 192);
+    n.t_lf1 = A.split(VN, h, w, 192);
+    n.t_lf2 = A.split(VN, h, w, 192);
+    n.ltc = A.split(VN, h, w, 64);
+    n.xc = A.split(VN, h, w, 64);
     n.rh = A.split(2 * B, h, w, 64);
     n.zbuf = (float *)A.take(sizeof(float) * 2 * B * h * w * 64);
-    n.tp = A.split(BN, h, w, 64);
+    n.tp = A.split(VN, h, w, 64);
     n.t_of0 = A.split(nf, h, w, 64);
     n.t_off = A.split(nf, h, w, 64);
     n.om = (float *)A.take(sizeof(float) * nf * h * w * 216);
@@ -148,25 +156,23 @@ static size_t layout(Net &n)
     n.ycat = A.split(nf, h, w, 128);
     n.t_df0 = A.split(nf, h, w, 64);
     n.fused = A.split(nf, h, w, 64);
-    n.t_dn0 = A.split(B, h, w, 64);
-    n.x0 = A.split(B, h, w, 64);
-    n.att0 = (float *)A.take(sizeof(float) * BN * h * w);
-    n.pre0 = A.split(B, h, w, 64);
-    n.x1 = A.split(B, 2 * h, 2 * w, 32);
-    n.att1 = (float *)A.take(sizeof(float) * BN * 4 * h * w);
-    n.pre1 = A.split(B, 2 * h, 2 * w, 32);
-    n.x2 = A.split(B, 4 * h, 4 * w, 16);
-    n.att2 = (float *)A.take(sizeof(float) * BN * 16 * h * w);
-    n.pre2 = A.split(B, 4 * h, 4 * w, 16);
-    n.x3 = A.split(B, Hc, Wc, 8);
+    n.t_dn0 = A.split(VB, h, w, 64);
+    n.x0 = A.split(VB, h, w, 64);
+    n.pre0 = A.split(VB, h, w, 64);
+    n.x1 = A.split(VB, 2 * h, 2 * w, 32);
+    n.pre1 = A.split(VB, 2 * h, 2 * w, 32);
+    n.x2 = A.split(VB, 4 * h, 4 * w, 16);
+    n.pre2 = A.split(VB, 4 * h, 4 * w, 16);
+    n.x3 = A.split(VB, Hc, Wc, 8);
     // index maps
     auto ints = [&](size_t cnt) { return (int *)A.take(sizeof(int) * cnt); };
-    n.m_pairA = ints(np); n.m_pairB = ints(np); n.m_ltc5 = ints((size_t)BN * 5); n.m_lf3res = ints(BN);
+    n.m_fr = ints(VN);
+    n.m_pairA = ints(np); n.m_pairB = ints(np); n.m_ltc5 = ints((size_t)VN * 5); n.m_lf3res = ints(VN);
     n.m_f0 = ints(nf); n.m_fm = ints(nf);
-    for (int k = 0; k < 3; ++k) n.m_dn[k] = ints(B);
-    n.m_gf_f = ints(BN); n.m_gf_r = ints(BN);
-    n.m_gx.resize(N); n.m_gh.resize(N);
-    for (int s = 0; s < N; ++s) { n.m_gx[s] = ints(2 * B); n.m_gh[s] = ints(2 * B); }
+    for (int k = 0; k < 3; ++k) n.m_dn[k] = ints(VB);
+    n.m_gf_f = ints(VN); n.m_gf_r = ints(VN); n.m_gfres = ints(VN);
+    n.m_gx.resize(nsteps); n.m_gh.resize(nsteps);
+    for (int s = 0; s < nsteps; ++s) { n.m_gx[s] = ints(2 * B); n.m_gh[s] = ints(2 * B); }
     return A.off;
 }
 
@@ -198,89 +204,99 @@ static SplitTensor view_imgs(const SplitTensor &t, int first_img)
 
 static int build(Net &n, cudaStream_t st)
 {
-    const int B = n.B, N = n.N, BN = B * N, nf = (N - 1) * B, np = B * (N + 1), mid = (N - 1) / 2;
+    const int B = n.B, N = n.N, L = n.L, Wn = n.Wn, VB = n.VB, FR = n.FR, VN = VB * N;
+    const int nf = (N - 1) * VB, np = VB * (N + 1), mid = (N - 1) / 2;
     int rc;
+    // bank frame of window slot (vb = w*B + b, n): b*L + w + n
+    auto fr = [&](int vb, int i) { const int w = vb / B, b = vb % B; return b * L + w + i; };
     // ---------------- index maps
     {
-        std::vector<int> a(np), b(np), l5((size_t)BN * 5), r(BN);
-        for (int bb = 0; bb < B; ++bb) {
+        std::vector<int> mfr(VN), a(np), b(np), l5((size_t)VN * 5), r(VN);
+        for (int vb = 0; vb < VB; ++vb) {
             for (int p = 0; p <= N; ++p) {           // pair p: (0,0), (0,1), ..., (N-2,N-1), (N-1,N-1)
                 const int fa = p == 0 ? 0 : p - 1, fb = p == N ? N - 1 : p;
-                a[bb * (N + 1) + p] = bb * N + fa;
-                b[bb * (N + 1) + p] = bb * N + fb;
+                a[vb * (N + 1) + p] = fr(vb, fa);
+                b[vb * (N + 1) + p] = fr(vb, fb);
             }
-            for (int i = 0; i < N; ++i) {            // window i: frames (i-1, i, i+1) edge-replicated (model.py:133-143)
+            for (int i = 0; i < N; ++i) {            // window slot i: frames (i-1, i, i+1) edge-replicated (model.py:133-143)
                 const int i0 = i == 0 ? 0 : i - 1, i2 = i == N - 1 ? N - 1 : i + 1;
-                int *q = &l5[(size_t)(bb * N + i) * 5];
-                q[0] = bb * N + i0; q[1] = bb * N + i; q[2] = bb * N + i2;
-                q[3] = bb * (N + 1) + i;             // map of pair (i0, i)
-                q[4] = bb * (N + 1) + i + 1;         // map of pair (i, i2)
-                r[bb * N + i] = bb * N + i;
+                int *q = &l5[(size_t)(vb * N + i) * 5];
+                q[0] = fr(vb, i0); q[1] = fr(vb, i); q[2] = fr(vb, i2);
+                q[3] = vb * (N + 1) + i;             // map of pair (i0, i)
+                q[4] = vb * (N + 1) + i + 1;         // map of pair (i, i2)
+                r[vb * N + i] = fr(vb, i);
+                mfr[vb * N + i] = fr(vb, i);
             }
         }
-        if ((rc = upload(n.m_pairA, a, st)) || (rc = upload(n.m_pairB, b, st)) || (rc = upload(n.m_ltc5, l5, st)) ||
-            (rc = upload(n.m_lf3res, r, st)))
+        if ((rc = upload(n.m_fr, mfr, st)) || (rc = upload(n.m_pairA, a, st)) || (rc = upload(n.m_pairB, b, st)) ||
+            (rc = upload(n.m_ltc5, l5, st)) || (rc = upload(n.m_lf3res, r, st)) || (rc = upload(n.m_gfres, r, st)))
             return rc;
         std::vector<int> f0(nf), fm(nf);
         int k = 0;
         for (int i = 0; i < N; ++i) {
             if (i == mid) continue;
-            for (int bb = 0; bb < B; ++bb) { f0[k * B + bb] = bb * N + i; fm[k * B + bb] = bb * N + mid; }
+            for (int vb = 0; vb < VB; ++vb) { f0[k * VB + vb] = vb * N + i; fm[k * VB + vb] = vb * N + mid; }
             ++k;
         }
         if ((rc = upload(n.m_f0, f0, st)) || (rc = upload(n.m_fm, fm, st))) return rc;
         for (int kk = 0; kk < 3; ++kk) {
-            std::vector<int> m(B);
-            for (int bb = 0; bb < B; ++bb) m[bb] = kk < N - 1 ? kk * B + bb : bb * N + mid;
+            std::vector<int> m(VB);
+            for (int vb = 0; vb < VB; ++vb) m[vb] = kk < N - 1 ? kk * VB + vb : vb * N + mid;
             if ((rc = upload(n.m_dn[kk], m, st))) return rc;
         }
-        std::vector<int> gf(BN), gr(BN);
-        for (int bb = 0; bb < B; ++bb)
+        // GRU: global step g = w*N + s reads state slot g and writes slot g+1 (slot 0 = carried state)
+        std::vector<int> gf(VN), gr(VN);
+        for (int vb = 0; vb < VB; ++vb) {
+            const int w = vb / B, bb = vb % B;
             for (int i = 0; i < N; ++i) {
-                gf[bb * N + i] = (i + 1) * 2 * B + bb;             // forward output for frame i = GRU step i
-                gr[bb * N + i] = (N - i) * 2 * B + B + bb;         // reverse output for frame i = GRU step N-1-i
+                gf[vb * N + i] = (w * N + i + 1) * 2 * B + bb;             // forward output for frame i = step i of window w
+                gr[vb * N + i] = (w * N + (N - 1 - i) + 1) * 2 * B + B + bb; // reverse output for frame i = step N-1-i
             }
-        if ((rc = upload(n.m_gf_f, gf, st)) || (rc = upload(n.m_gf_r, gr, st))) return rc;
-        for (int s = 0; s < N; ++s) {
-            std::vector<int> gx(2 * B), gh(2 * B);
-            for (int bb = 0; bb < B; ++bb) {
-                gx[bb] = bb * N + s; gx[B + bb] = bb * N + (N - 1 - s);
-                gh[bb] = s * 2 * B + bb; gh[B + bb] = s * 2 * B + B + bb;
-            }
-            if ((rc = upload(n.m_gx[s], gx, st)) || (rc = upload(n.m_gh[s], gh, st))) return rc;
         }
+        if ((rc = upload(n.m_gf_f, gf, st)) || (rc = upload(n.m_gf_r, gr, st))) return rc;
+        for (int w = 0; w < Wn; ++w)
+            for (int s = 0; s < N; ++s) {
+                const int g = w * N + s;
+                std::vector<int> gx(2 * B), gh(2 * B);
+                for (int bb = 0; bb < B; ++bb) {
+                    gx[bb] = (w * B + bb) * N + s; gx[B + bb] = (w * B + bb) * N + (N - 1 - s);
+                    gh[bb] = g * 2 * B + bb; gh[B + bb] = g * 2 * B + B + bb;
+                }
+                if ((rc = upload(n.m_gx[g], gx, st)) || (rc = upload(n.m_gh[g], gh, st))) return rc;
+            }
     }
     // ---------------- tensor-core launches
     ConvTCDesc d;
-    // pred_map on the N+1 unique (frame, frame) pairs
+    // pred_map on the N+1 unique (frame, frame) pairs of every window
     d = mk(n, T_PM0, np, ACT_RELU); d.n_src = 2; d.src[0] = n.F; d.src[1] = n.F; d.src_img[0] = n.m_pairA; d.src_img[1] = n.m_pairB;
     d.out = n.t_pm0;
     if ((rc = conv_tc_prepare(d, &n.c_pm0))) return rc;
     d = mk(n, T_PM1, np, ACT_SIGMOID); d.src[0] = n.t_pm0; d.out_f32 = n.maps; d.out_f32_C = 1;
     if ((rc = conv_tc_prepare(d, &n.c_pm1))) return rc;
     // local_fusion: ResidualBlock(192) + conv 192->64, + feat1
-    d = mk(n, T_LF1, BN, ACT_RELU); d.src[0] = n.t_cat; d.out = n.t_lf1;
+    d = mk(n, T_LF1, VN, ACT_RELU); d.src[0] = n.t_cat; d.out = n.t_lf1;
     if ((rc = conv_tc_prepare(d, &n.c_lf1))) return rc;
-    d = mk(n, T_LF2, BN, ACT_RELU); d.src[0] = n.t_lf1; d.res_mode = RES_PRE_ACT; d.res = n.t_cat; d.out = n.t_lf2;
+    d = mk(n, T_LF2, VN, ACT_RELU); d.src[0] = n.t_lf1; d.res_mode = RES_PRE_ACT; d.res = n.t_cat; d.out = n.t_lf2;
     if ((rc = conv_tc_prepare(d, &n.c_lf2))) return rc;
-    d = mk(n, T_LF3, BN, ACT_NONE); d.src[0] = n.t_lf2; d.res_mode = RES_POST_ACT; d.res = n.F; d.out = n.ltc;
+    d = mk(n, T_LF3, VN, ACT_NONE); d.src[0] = n.t_lf2; d.res_mode = RES_POST_ACT; d.res = n.F; d.res_img = n.m_lf3res; d.out = n.ltc;
     if ((rc = conv_tc_prepare(d, &n.c_lf3))) return rc;
-    // ConvGRU: x-side conv once for all frames (same weights in both directions)
-    d = mk(n, T_GX, BN, ACT_RELU); d.src[0] = n.ltc; d.out = n.xc;
+    // ConvGRU: x-side conv once for all window slots (same weights in both directions)
+    d = mk(n, T_GX, VN, ACT_RELU); d.src[0] = n.ltc; d.out = n.xc;
     if ((rc = conv_tc_prepare(d, &n.c_gx))) return rc;
-    n.c_gzr.resize(N); n.c_go.resize(N);
-    for (int s = 0; s < N; ++s) {
-        d = mk(n, T_GZR, 2 * B, ACT_NONE); d.n_src = 2; d.src[0] = n.xc; d.src_img[0] = n.m_gx[s]; d.src[1] = n.hs; d.src_img[1] = n.m_gh[s];
-        d.epi_mode = EPI_GRU_ZR; d.h_prev = view_imgs(n.hs, s * 2 * B); d.z_buf = n.zbuf; d.out = n.rh;
-        if ((rc = conv_tc_prepare(d, &n.c_gzr[s]))) return rc;
-        d = mk(n, T_GO, 2 * B, ACT_NONE); d.n_src = 2; d.src[0] = n.xc; d.src_img[0] = n.m_gx[s]; d.src[1] = n.rh;
-        d.epi_mode = EPI_GRU_OUT; d.h_prev = view_imgs(n.hs, s * 2 * B); d.z_buf = n.zbuf; d.out = view_imgs(n.hs, (s + 1) * 2 * B);
-        if ((rc = conv_tc_prepare(d, &n.c_go[s]))) return rc;
+    const int nsteps = Wn * N;
+    n.c_gzr.resize(nsteps); n.c_go.resize(nsteps);
+    for (int g = 0; g < nsteps; ++g) {
+        d = mk(n, T_GZR, 2 * B, ACT_NONE); d.n_src = 2; d.src[0] = n.xc; d.src_img[0] = n.m_gx[g]; d.src[1] = n.hs; d.src_img[1] = n.m_gh[g];
+        d.epi_mode = EPI_GRU_ZR; d.h_prev = view_imgs(n.hs, g * 2 * B); d.z_buf = n.zbuf; d.out = n.rh;
+        if ((rc = conv_tc_prepare(d, &n.c_gzr[g]))) return rc;
+        d = mk(n, T_GO, 2 * B, ACT_NONE); d.n_src = 2; d.src[0] = n.xc; d.src_img[0] = n.m_gx[g]; d.src[1] = n.rh;
+        d.epi_mode = EPI_GRU_OUT; d.h_prev = view_imgs(n.hs, g * 2 * B); d.z_buf = n.zbuf; d.out = view_imgs(n.hs, (g + 1) * 2 * B);
+        if ((rc = conv_tc_prepare(d, &n.c_go[g]))) return rc;
     }
-    d = mk(n, T_GF, BN, ACT_RELU); d.n_src = 2; d.src[0] = n.hs; d.src_img[0] = n.m_gf_f; d.src[1] = n.hs; d.src_img[1] = n.m_gf_r;
-    d.res_mode = RES_POST_ACT; d.res = n.F; d.out = n.tp;
+    d = mk(n, T_GF, VN, ACT_RELU); d.n_src = 2; d.src[0] = n.hs; d.src_img[0] = n.m_gf_f; d.src[1] = n.hs; d.src_img[1] = n.m_gf_r;
+    d.res_mode = RES_POST_ACT; d.res = n.F; d.res_img = n.m_gfres; d.out = n.tp;
     if ((rc = conv_tc_prepare(d, &n.c_gf))) return rc;
-    // STFusion.fuse on the N-1 non-middle frames
+    // STFusion.fuse on the N-1 non-middle frames of every window
     d = mk(n, T_OF0, nf, ACT_RELU); d.n_src = 2; d.src[0] = n.tp; d.src_img[0] = n.m_f0; d.src[1] = n.tp; d.src_img[1] = n.m_fm; d.out = n.t_of0;
     if ((rc = conv_tc_prepare(d, &n.c_of0))) return rc;
     d = mk(n, T_OF1, nf, ACT_NONE); d.src[0] = n.t_of0; d.out = n.t_off;
@@ -299,19 +315,19 @@ static int build(Net &n, cudaStream_t st)
     if ((rc = conv_tc_prepare(d, &n.c_df0))) return rc;
     d = mk(n, T_DF1, nf, ACT_NONE); d.src[0] = n.t_df0; d.out = n.fused;
     if ((rc = conv_tc_prepare(d, &n.c_df1))) return rc;
-    d = mk(n, T_DN0, B, ACT_RELU); d.n_src = 3;
+    d = mk(n, T_DN0, VB, ACT_RELU); d.n_src = 3;
     d.src[0] = n.fused; d.src_img[0] = n.m_dn[0]; d.src[1] = n.fused; d.src_img[1] = n.m_dn[1]; d.src[2] = n.tp; d.src_img[2] = n.m_dn[2];
     d.out = n.t_dn0;
     if ((rc = conv_tc_prepare(d, &n.c_dn0))) return rc;
-    d = mk(n, T_DN1, B, ACT_NONE); d.src[0] = n.t_dn0; d.out = n.x0;
+    d = mk(n, T_DN1, VB, ACT_NONE); d.src[0] = n.t_dn0; d.out = n.x0;
     if ((rc = conv_tc_prepare(d, &n.c_dn1))) return rc;
-    d = mk(n, T_AT0, BN, ACT_SIGMOID); d.src[0] = n.F; d.out_f32 = n.att0; d.out_f32_C = 1;
+    d = mk(n, T_AT0, FR, ACT_SIGMOID); d.src[0] = n.F; d.out_f32 = n.att0; d.out_f32_C = 1;
     if ((rc = conv_tc_prepare(d, &n.c_at0))) return rc;
 
     // ---------------- direct launches
-    const ParamLayout &L = param_layout();
+    const ParamLayout &Lp = param_layout();
     auto base = [&](int i, int act) {
-        DirectArgs a; a.w = (const float *)(n.params + L.dw[i]); a.bias = (const float *)(n.params + L.db[i]); a.act = act;
+        DirectArgs a; a.w = (const float *)(n.params + Lp.dw[i]); a.bias = (const float *)(n.params + Lp.db[i]); a.act = act;
         return a;
     };
     auto in_split = [&](DirectArgs &a, const SplitTensor &t) { a.in_split = t.base; a.in_plane = t.plane(); a.Hin = t.H; a.Win = t.W; };
@@ -320,16 +336,16 @@ static int build(Net &n, cudaStream_t st)
     };
     DirectArgs a = base(D_HEAD, ACT_RELU);
     a.Hin = n.H; a.Win = n.W; a.pad_top = n.pad_top; a.pad_bottom = n.pad_bottom; a.pad_left = n.pad_left; a.pad_right = n.pad_right;
-    out_split(a, n.t_head, BN); n.d[D_HEAD] = a;
-    a = base(D_ENC0, ACT_RELU); in_split(a, n.t_head); out_split(a, n.t_e0, BN); n.d[D_ENC0] = a;
-    a = base(D_ENC1, ACT_RELU); in_split(a, n.t_e0); out_split(a, n.t_e1, BN); n.d[D_ENC1] = a;
-    a = base(D_ENC2, ACT_RELU); in_split(a, n.t_e1); out_split(a, n.F, BN); n.d[D_ENC2] = a;
-    a = base(D_AT1, ACT_SIGMOID); in_split(a, n.t_e1); a.out_f32 = n.att1; a.Hout = n.t_e1.H; a.Wout = n.t_e1.W; a.n_img = BN; n.d[D_AT1] = a;
-    a = base(D_AT2, ACT_SIGMOID); in_split(a, n.t_e0); a.out_f32 = n.att2; a.Hout = n.t_e0.H; a.Wout = n.t_e0.W; a.n_img = BN; n.d[D_AT2] = a;
-    a = base(D_RC0, ACT_RELU); in_split(a, n.pre0); out_split(a, n.x1, B); n.d[D_RC0] = a;
-    a = base(D_RC1, ACT_RELU); in_split(a, n.pre1); out_split(a, n.x2, B); n.d[D_RC1] = a;
-    a = base(D_RC2, ACT_RELU); in_split(a, n.pre2); out_split(a, n.x3, B); n.d[D_RC2] = a;
-    a = base(D_TAIL, ACT_RELU); in_split(a, n.x3); a.Hout = n.Hc; a.Wout = n.Wc; a.n_img = B;
+    out_split(a, n.t_head, FR); n.d[D_HEAD] = a;
+    a = base(D_ENC0, ACT_RELU); in_split(a, n.t_head); out_split(a, n.t_e0, FR); n.d[D_ENC0] = a;
+    a = base(D_ENC1, ACT_RELU); in_split(a, n.t_e0); out_split(a, n.t_e1, FR); n.d[D_ENC1] = a;
+    a = base(D_ENC2, ACT_RELU); in_split(a, n.t_e1); out_split(a, n.F, FR); n.d[D_ENC2] = a;
+    a = base(D_AT1, ACT_SIGMOID); in_split(a, n.t_e1); a.out_f32 = n.att1; a.Hout = n.t_e1.H; a.Wout = n.t_e1.W; a.n_img = FR; n.d[D_AT1] = a;
+    a = base(D_AT2, ACT_SIGMOID); in_split(a, n.t_e0); a.out_f32 = n.att2; a.Hout = n.t_e0.H; a.Wout = n.t_e0.W; a.n_img = FR; n.d[D_AT2] = a;
+    a = base(D_RC0, ACT_RELU); in_split(a, n.pre0); out_split(a, n.x1, VB); n.d[D_RC0] = a;
+    a = base(D_RC1, ACT_RELU); in_split(a, n.pre1); out_split(a, n.x2, VB); n.d[D_RC1] = a;
+    a = base(D_RC2, ACT_RELU); in_split(a, n.pre2); out_split(a, n.x3, VB); n.d[D_RC2] = a;
+    a = base(D_TAIL, ACT_RELU); in_split(a, n.x3); a.Hout = n.Hc; a.Wout = n.Wc; a.n_img = VB;
     a.crop_top = n.pad_top; a.crop_left = n.pad_left; a.out_H = n.H; a.out_W = n.W; n.d[D_TAIL] = a;
     return ESR_OK;
 }
@@ -350,8 +366,6 @@ static double direct_flops(int dl, const DirectArgs &a)
 static int forward(Net &n, const float *input, const int *in_img, float *output, cudaStream_t st, Prof *prof = nullptr)
 {
     int rc;
-    auto run = [&](int cls, double flops, int r_unused) { (void)cls; (void)flops; return r_unused; };
-    (void)run;
 #define RUNC(cls_, flops_, x)                                                              \
     do {                                                                                   \
         Prof::Entry pe{};                                                                  \
@@ -367,30 +381,35 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
 #define RUN(x) RUNC(PC_OTHER, 0.0, x)
 #define RUNT(args) RUNC(PC_TC, tc_flops(args), conv_tc_launch(args, st))
 #define RUND(kind, dl, args) RUNC(PC_DIRECT, direct_flops(dl, args), conv_direct(kind, args, st))
-    const int B = n.B, N = n.N, BN = B * N, nf = (N - 1) * B;
+    const int B = n.B, N = n.N, VB = n.VB, VN = VB * N, nf = (N - 1) * VB, nsteps = n.Wn * N;
     const ParamLayout &L = param_layout();
-    // ---- head + encoder (models/model.py:329-331)
+    // ---- per-frame work, once per bank frame: head + encoder (models/model.py:329-331) and the three attention maps
+    //      of scale_aggre (model.py:259-262), which depend on the encoder features only
     DirectArgs a = n.d[D_HEAD]; a.in_f32 = input; a.in_img = in_img;
     RUND(DK_HEAD, D_HEAD, a);
     RUND(DK_ENC0, D_ENC0, n.d[D_ENC0]);
     RUND(DK_ENC1, D_ENC1, n.d[D_ENC1]);
     RUND(DK_ENC2, D_ENC2, n.d[D_ENC2]);
-    // ---- TimePropagation.local_time_corre (model.py:77-89,133-146)
+    RUNT(n.c_at0);
+    RUND(DK_ATT32, D_AT1, n.d[D_AT1]);
+    RUND(DK_ATT16, D_AT2, n.d[D_AT2]);
+    // ---- TimePropagation.local_time_corre for every window (model.py:77-89,133-146)
     RUNT(n.c_pm0);
     RUNT(n.c_pm1);
-    RUN(ltc_cat(n.F, n.maps, n.m_ltc5, BN, n.t_cat, st));
+    RUN(ltc_cat(n.F, n.maps, n.m_ltc5, VN, n.t_cat, st));
     RUNT(n.c_lf1);
     RUNT(n.c_lf2);
     RUNT(n.c_lf3);
-    // ---- TimePropagation.global_time_corre: bidirectional ConvGRU (model.py:91-124)
+    // ---- TimePropagation.global_time_corre: bidirectional ConvGRU (model.py:91-124); the only serial part:
+    //      window after window, step after step, both directions batched as 2B images
     RUNT(n.c_gx);
-    for (int s = 0; s < N; ++s) {
-        RUNT(n.c_gzr[s]);
-        RUNT(n.c_go[s]);
+    for (int g = 0; g < nsteps; ++g) {
+        RUNT(n.c_gzr[g]);
+        RUNT(n.c_go[g]);
     }
     RUNT(n.c_gf);
-    // carried states: slot N (after the last step) becomes slot 0 of the next forward()
-    RUN(copy_split(view_imgs(n.hs, N * 2 * B), nullptr, 2 * B, view_imgs(n.hs, 0), st));
+    // carried states: the last slot becomes slot 0 of the next call
+    RUN(copy_split(view_imgs(n.hs, nsteps * 2 * B), nullptr, 2 * B, view_imgs(n.hs, 0), st));
     // ---- STFusion.fuse for the non-middle frames (model.py:208-231)
     RUNT(n.c_of0);
     RUNT(n.c_of1);
@@ -410,14 +429,11 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     RUNT(n.c_dn0);
     RUNT(n.c_dn1);
     // ---- scale aggregation + reconstruction x3 (model.py:253-291), tail (model.py:337)
-    RUNT(n.c_at0);
-    RUN(scale_aggregate(n.x0, n.F, n.att0, B, N, n.pre0, st));
+    RUN(scale_aggregate(n.x0, n.F, n.att0, n.m_fr, VB, N, n.pre0, st));
     RUND(DK_RECON0, D_RC0, n.d[D_RC0]);
-    RUND(DK_ATT32, D_AT1, n.d[D_AT1]);
-    RUN(scale_aggregate(n.x1, n.t_e1, n.att1, B, N, n.pre1, st));
+    RUN(scale_aggregate(n.x1, n.t_e1, n.att1, n.m_fr, VB, N, n.pre1, st));
     RUND(DK_RECON1, D_RC1, n.d[D_RC1]);
-    RUND(DK_ATT16, D_AT2, n.d[D_AT2]);
-    RUN(scale_aggregate(n.x2, n.t_e0, n.att2, B, N, n.pre2, st));
+    RUN(scale_aggregate(n.x2, n.t_e0, n.att2, n.m_fr, VB, N, n.pre2, st));
     RUND(DK_RECON2, D_RC2, n.d[D_RC2]);
     a = n.d[D_TAIL]; a.out_f32 = output;
     RUND(DK_TAIL, D_TAIL, a);
@@ -435,9 +451,9 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
 // =================================================================================================
 using namespace esr;
 
-static void net_dims(Net &n, int B, int N, int H, int W)
+static void net_dims(Net &n, int B, int N, int L, int H, int W)
 {
-    n.B = B; n.N = N; n.H = H; n.W = W;
+    n.B = B; n.N = N; n.L = L; n.Wn = L - N + 1; n.VB = n.Wn * B; n.FR = B * L; n.H = H; n.W = W;
     n.Hc = (H + 7) / 8 * 8; n.Wc = (W + 7) / 8 * 8; n.h = n.Hc / 8; n.w = n.Wc / 8;
     // CropSize (models/model_util.py:148-151): ceil on top/left, floor on bottom/right
     n.pad_top = (n.Hc - H + 1) / 2; n.pad_bottom = (n.Hc - H) / 2;
@@ -475,22 +491,24 @@ extern "C" int esr_net_pack_params(const float *const *p, void *blob, esr_stream
     return ESR_OK;
 }
 
-extern "C" size_t esr_net_workspace_bytes(int B, int N, int H, int W)
+extern "C" size_t esr_net_workspace_bytes(int B, int N, int L, int H, int W)
 {
+    if (L < N) return 0;
     Net n{};
-    net_dims(n, B, N, H, W);
+    net_dims(n, B, N, L, H, W);
     n.ws = nullptr; n.ws_bytes = 0;
     return layout(n);
 }
 
-extern "C" int esr_net_create(esr_net_t *out, int B, int N, int H, int W, void *params, void *workspace, size_t ws_bytes,
+extern "C" int esr_net_create(esr_net_t *out, int B, int N, int L, int H, int W, void *params, void *workspace, size_t ws_bytes,
                               esr_stream_t stream)
 {
     ESR_REQUIRE(out && params && workspace, "esr_net_create: null pointer");
-    ESR_REQUIRE(B > 0 && H > 0 && W > 0, "esr_net_create: bad dims");
+    ESR_REQUIRE(B > 0 && H > 0 && W > 0 && L >= N, "esr_net_create: bad dims");
+    ESR_REQUIRE(2 * B <= 65535 && (long long)B * L * ((H + 7) / 8) * ((W + 7) / 8) < (1ll << 28), "esr_net_create: batch too large");
     if (N != 3) { set_error("esr_net_create: num_frame=%d (only the shipped num_frame=3 is implemented)", N); return ESR_EUNSUPPORTED; }
     Net *n = new Net();
-    net_dims(*n, B, N, H, W);
+    net_dims(*n, B, N, L, H, W);
     n->params = (char *)params; n->ws = (char *)workspace; n->ws_bytes = ws_bytes;
     const size_t need = layout(*n);
     if (need > ws_bytes) { set_error("esr_net_create: workspace %zu < %zu", ws_bytes, need); delete n; return ESR_EWORKSPACE; }

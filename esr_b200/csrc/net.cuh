@@ -43,9 +43,9 @@ int attn_mlp(const float *mx, int n_img, const float *w0, const float *b0, const
 // y = cat(aligned * sk[...,0] * ck[:64], mid * sk[...,1] * ck[64:])   (models/model.py:224-227)
 int attn_apply(const SplitTensor &aligned, const SplitTensor &mid_src, const int *mid_img, const float *sk, const float *ck,
                int n_img, const SplitTensor &out /*C=128*/, cudaStream_t st);
-// out[b] = x[b] + mean_n(feats[b*N+n] * att[b*N+n])     (models/model.py:259-267)
-int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float *att, int B, int N, const SplitTensor &out,
-                    cudaStream_t st);
+// out[b] = x[b] + mean_n(feats[f] * att[f]), f = fidx[b*N+n] (or b*N+n)     (models/model.py:259-267)
+int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float *att, const int *fidx, int B, int N,
+                    const SplitTensor &out, cudaStream_t st);
 int copy_split(const SplitTensor &src, const int *src_img, int n_img, const SplitTensor &dst, cudaStream_t st);
 
 // ---- deformable sampling (dcn.cu): columns[img][y][x][tap*64 + c] = bilinear(feat[c], y-1+i+off_h, x-1+j+off_w) * mask

@@ -105,16 +105,16 @@ class _STFusion(nn.Module):
 
 
 class _Plan:
-    """One esr_net_t for a (B, N, H, W, device) with its workspace."""
+    """One esr_net_t for a (B, L, H, W, device) with its workspace (L = 3: the reference's single-window forward)."""
 
-    def __init__(self, B, N, H, W, blob, device):
-        L = _lib.lib()
-        self.key = (B, N, H, W)
-        nbytes = L.esr_net_workspace_bytes(B, N, H, W)
+    def __init__(self, B, N, L, H, W, blob, device):
+        lib = _lib.lib()
+        self.key = (B, L, H, W)
+        nbytes = lib.esr_net_workspace_bytes(B, N, L, H, W)
         self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
         self.handle = ctypes.c_void_p()
-        _lib.check(L.esr_net_create(ctypes.byref(self.handle), B, N, H, W, _lib.ptr(blob), _lib.ptr(self.ws), nbytes,
-                                    _lib.stream_ptr()), "esr_net_create")
+        _lib.check(lib.esr_net_create(ctypes.byref(self.handle), B, N, L, H, W, _lib.ptr(blob), _lib.ptr(self.ws), nbytes,
+                                      _lib.stream_ptr()), "esr_net_create")
 
     def close(self):
         if self.handle:
@@ -172,11 +172,11 @@ class DeepRecurrNet(nn.Module):
             self._blob_sig = sig
         return self._blob
 
-    def _plan(self, B, N, H, W, device):
+    def _plan(self, B, L, H, W, device):
         blob = self._packed_params(device)
-        key = (B, N, H, W)
+        key = (B, L, H, W)
         if key not in self._plans:
-            self._plans[key] = _Plan(B, N, H, W, blob, device)
+            self._plans[key] = _Plan(B, self._cfg["num_frame"], L, H, W, blob, device)
         return self._plans[key]
 
     # ------------------------------------------------------------------------------------------
@@ -186,10 +186,10 @@ class DeepRecurrNet(nn.Module):
             with torch.cuda.device(p.ws.device):
                 _lib.check(_lib.lib().esr_net_reset_states(p.handle, _lib.stream_ptr()), "esr_net_reset_states")
 
-    def states(self, B, N, H, W):
+    def states(self, B, L, H, W):
         """The carried states [h_fwd, h_rev] (each Bx64xhxw) of the plan for this shape -- the reference's
         `time_propagate.states`."""
-        p = self._plans[(B, N, H, W)]
+        p = self._plans[(B, L, H, W)]
         h, w = (H + 7) // 8, (W + 7) // 8
         out = torch.empty((2, B, 64, h, w), dtype=torch.float32, device=p.ws.device)
         with torch.cuda.device(p.ws.device):
@@ -220,4 +220,28 @@ class DeepRecurrNet(nn.Module):
             out = torch.empty((B, 2, H, W), dtype=torch.float32, device=x.device)
             _lib.check(_lib.lib().esr_net_forward(plan.handle, _lib.ptr(x), _lib.ptr(frame_index), _lib.ptr(out),
                                                   _lib.stream_ptr()), "esr_net_forward")
+        return out
+
+    def forward_sequence(self, frames):
+        """frames: BxLx2xHxW (L >= num_frame) -> (L-2)*B x 2 x H x W, window-major (w*B + b): the L-2 sliding-window
+        forwards of the reference's loop (train_ours_cnt_seq.py:217-231) in ONE plan -- per-frame layers run once per
+        frame, state-independent layers once for all windows, only the ConvGRU chain is serial.  The carried state is
+        read at the start and left as after the last window, exactly as L-2 successive forward() calls would."""
+        self._check_supported()
+        if not frames.is_cuda:
+            raise _lib.ESRError("esr_b200.DeepRecurrNet.forward_sequence needs a CUDA tensor (there is no CPU path)")
+        if torch.is_grad_enabled() and (frames.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("esr_b200.DeepRecurrNet: backward is not implemented yet (round 1 = inference); "
+                                      "wrap the call in torch.no_grad()")
+        x = frames.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        B, L, C, H, W = x.shape
+        N = self._cfg["num_frame"]
+        assert C == 2 and L >= N
+        with torch.cuda.device(x.device):
+            plan = self._plan(B, L, H, W, x.device)
+            out = torch.empty(((L - N + 1) * B, 2, H, W), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib().esr_net_forward(plan.handle, _lib.ptr(x), None, _lib.ptr(out), _lib.stream_ptr()),
+                       "esr_net_forward")
         return out

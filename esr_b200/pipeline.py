@@ -29,20 +29,23 @@ class EventSRPipeline:
         self.bank = torch.zeros((B * L, 2, self.hr_size[0], self.hr_size[1]), dtype=torch.float32, device=device)
         self._graph = None
         self._graph_sr = None
+        self.sequence_plan = True
         self.graph_launches = 0
 
     def _windows(self):
         self.model.reset_states()                    # per sequence batch (train_ours_cnt_seq.py:213-216)
-        outs = [self.model(self.bank, frame_index=idx) for idx in self.window_index]
-        sr = torch.cat(outs, 0)
+        if self.sequence_plan:
+            sr = self.model.forward_sequence(self.bank.view(self.B, self.L, 2, self.hr_size[0], self.hr_size[1]))
+        else:                                        # the reference's loop: one forward per window
+            sr = torch.cat([self.model(self.bank, frame_index=idx) for idx in self.window_index], 0)
         if self.sr_bias is not None:
             sr = sr + self.sr_bias
         return sr
 
     @torch.no_grad()
     def capture(self):
-        """Capture the L-2 windows (reset + 45 launches each) into one CUDA graph: the plan allocates nothing and never
-        synchronises, so the whole recurrent chain replays with a single launch from the host."""
+        """Capture the whole window chain into one CUDA graph: the plan allocates nothing and never synchronises, so it
+        replays with a single launch from the host."""
         self._windows()                              # warm-up: packs parameters, builds the plan, sets smem attributes
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()

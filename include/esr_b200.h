@@ -128,18 +128,23 @@ int esr_split_to_nchw(const void *src, int n_img, int C, int H, int W, float *ds
  *  params    : 68 device pointers to fp32 tensors in the reference's state_dict order
  *              (head.conv2d.weight, head.conv2d.bias, feat_extract.convblock.0.conv2d.weight, ... tail.conv2d.bias)
  *  blob      : esr_net_param_bytes() bytes; repack whenever the parameters change
- *  workspace : esr_net_workspace_bytes(B,N,H,W) bytes, owned by the caller, must outlive the net; holds all
+ *  workspace : esr_net_workspace_bytes(B,N,L,H,W) bytes, owned by the caller, must outlive the net; holds all
  *              intermediates AND the recurrent states (which persist across esr_net_forward calls)
- *  input     : fp32 [B,N,2,H,W] (the reference layout), or -- with in_img != NULL -- a bank of frames
- *              [n_frames,2,H,W] where in_img[b*N+n] (device int32) selects the frame of window slot (b,n)
- *  output    : fp32 [B,2,H,W]
+ *  L         : frames per sequence handled by one call.  L == N (=3) is the reference's forward: one window,
+ *              input fp32 [B,N,2,H,W], output fp32 [B,2,H,W].  L > N is the sequence form used by the pipeline:
+ *              input fp32 [B,L,2,H,W], output fp32 [(L-N+1)*B,2,H,W] (window-major: w*B+b) = the L-N+1 sliding-window
+ *              forwards the reference would run one after another with the state carried (train_ours_cnt_seq.py:217-231,
+ *              dataloader/h5dataloader.py:229-231).  Per-frame work (encoder, attention maps) is done once per frame
+ *              and all state-independent layers once for all windows; only the ConvGRU chain is serial.  Results are
+ *              identical to L-N+1 single-window calls.
+ *  in_img    : optional device int32 [B*L]: frame (b,l) is read from input image in_img[b*L+l] (frame banks)
  * H, W need not be multiples of 8: the CropSize pad / crop is folded into the first and last kernels.
  * --------------------------------------------------------------------------------------------- */
 typedef void *esr_net_t;
 size_t esr_net_param_bytes(void);
 int esr_net_pack_params(const float *const *params_host_array_of_device_ptrs, void *blob, esr_stream_t stream);
-size_t esr_net_workspace_bytes(int B, int N, int H, int W);
-int esr_net_create(esr_net_t *net, int B, int N, int H, int W, void *blob, void *workspace, size_t workspace_bytes,
+size_t esr_net_workspace_bytes(int B, int N, int L, int H, int W);
+int esr_net_create(esr_net_t *net, int B, int N, int L, int H, int W, void *blob, void *workspace, size_t workspace_bytes,
                    esr_stream_t stream);
 int esr_net_destroy(esr_net_t net);
 int esr_net_reset_states(esr_net_t net, esr_stream_t stream);

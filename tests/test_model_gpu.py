@@ -87,3 +87,21 @@ def test_frame_bank_windows_equal_explicit_windows(dev):
         for w in range(L - 2):
             idx = torch.tensor([b * L + w + n for b in range(B) for n in range(3)], dtype=torch.int32, device=dev)
             assert torch.equal(n1(frames[:, w:w + 3].contiguous()), n2(bank, frame_index=idx))
+
+
+@pytest.mark.parametrize("B,L,H,W", [(2, 5, 32, 48), (1, 8, 64, 64), (3, 4, 36, 44)])
+def test_sequence_plan_equals_window_loop(dev, B, L, H, W):
+    """forward_sequence (per-frame / state-independent layers batched over all windows) must reproduce the reference's
+    loop of single-window forwards with carried state -- bit for bit, including the state left behind."""
+    sd = model_ref.seeded_state_dict(8)
+    g = torch.Generator().manual_seed(B * 31 + L)
+    frames = torch.poisson(torch.full((B, L, 2, H, W), 0.3), generator=g).to(dev)
+    n1, n2 = _net(sd, dev), _net(sd, dev)
+    with torch.no_grad():
+        for rep in range(2):                          # second pass starts from the carried state
+            loop = torch.cat([n1(frames[:, w:w + 3].contiguous()) for w in range(L - 2)], 0)
+            seq = n2.forward_sequence(frames)
+            assert seq.shape == loop.shape
+            assert torch.equal(seq, loop), (rep, (seq - loop).abs().max().item())
+        for a, b in zip(n1.states(B, 3, H, W), n2.states(B, L, H, W)):
+            assert torch.equal(a, b)
