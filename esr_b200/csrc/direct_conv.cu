@@ -3,7 +3,7 @@
 //   head 2->8 (models/model.py:301,330), encoder 8->16->32->64 stride 2 (models/model.py:20-45),
 //   attention maps C->1 sigmoid (models/model.py:195-199,262), decoder bilinear x2 + conv (models/submodules.py:254-299),
 //   tail 8->2 (models/model.py:309,337).
-// One block = 16x16 output pixels, all output channels.
+// One block = a 16x16 / 32x16 / 32x32 output tile (wider for narrower layers), all output channels.
 //   stage 1: the input patch (+halo) is staged in shared memory as [ci][py][px] fp32 -- 16-byte loads of 8 channels of
 //            the split-bf16 NHWC source per thread (the bilinear x2 upsampling of the decoder is applied on the fly);
 //   stage 2: register tiling -- a thread owns a 2x2 pixel patch x COUT/4 channels (its 4x4 / 5x5 input window is read
@@ -15,7 +15,17 @@
 
 namespace esr {
 
-constexpr int DC_T = 16;   // output tile edge
+// Output tile geometry.  Tiled layers: a thread owns 2x2 pixels x C channels, C = 16 (COUT=64) or 8; the COUT/C channel
+// groups are spread over warps, so narrower layers get wider tiles (more pixels per block, 16-byte stores everywhere).
+template <int COUT> struct DcGeom {
+    static constexpr bool TILED = COUT >= 8;
+    static constexpr int C = COUT >= 64 ? 16 : (COUT >= 8 ? 8 : COUT);
+    static constexpr int CG = TILED ? COUT / C : 1;
+    static constexpr int PG = 256 / CG;                         // pixel groups (threads per channel group)
+    static constexpr int TW = TILED ? (CG == 4 ? 16 : 32) : 16; // output tile width
+    static constexpr int TH = TILED ? (CG == 1 ? 32 : 16) : 16; // output tile height
+    static_assert(!TILED || (TW / 2) * (TH / 2) == PG, "tile / thread mapping mismatch");
+};
 
 __device__ __forceinline__ void dc_unpack8(const uint4 h, const uint4 l, float (&o)[8])
 {
@@ -65,16 +75,18 @@ __device__ __forceinline__ float dc_act(float v, int act)
 template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF>
 __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
 {
-    constexpr int PW = (DC_T - 1) * STRIDE + 3;           // patch edge actually needed
+    using G = DcGeom<COUT>;
+    constexpr int PW = (G::TW - 1) * STRIDE + 3;          // patch width actually needed
+    constexpr int PH = (G::TH - 1) * STRIDE + 3;          // patch height
     constexpr int PP = (PW + 3) / 4 * 4;                  // row pitch (floats)
-    constexpr bool TILED = (COUT >= 8);                   // 2x2 pixels x COUT/4 channels per thread
+    constexpr bool TILED = G::TILED;
     extern __shared__ float dsm[];
-    float *patch = dsm;                                   // [CIN][PW][PP]
-    float *wsm = dsm + CIN * PW * PP;                     // [9][CIN][COUT]
+    float *patch = dsm;                                   // [CIN][PH][PP]
+    float *wsm = dsm + CIN * PH * PP;                     // [9][CIN][COUT]
     float *bsm = wsm + 9 * CIN * COUT;                    // [COUT]
 
     const int img = blockIdx.z;
-    const int oy0 = blockIdx.y * DC_T, ox0 = blockIdx.x * DC_T;
+    const int oy0 = blockIdx.y * G::TH, ox0 = blockIdx.x * G::TW;
     const int tid = threadIdx.x;
 
     for (int i = tid; i < 9 * CIN * COUT / 4; i += 256)
@@ -87,8 +99,8 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
     const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
     const int simg = a.in_img ? a.in_img[img] : img;
     if constexpr (INF == FMT_NCHW_F32) {
-        for (int i = tid; i < CIN * PW * PW; i += 256) {
-            const int px = i % PW, py = (i / PW) % PW, ci = i / (PW * PW);
+        for (int i = tid; i < CIN * PW * PH; i += 256) {
+            const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
             const int y = iy0 + py, x = ix0 + px;
             float v = 0.0f;
             if (y >= 0 && y < Hc && x >= 0 && x < Wc) {
@@ -96,15 +108,15 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
                 if (sy >= 0 && sy < a.Hin && sx >= 0 && sx < a.Win)
                     v = a.in_f32[(((size_t)simg * CIN + ci) * a.Hin + sy) * a.Win + sx];
             }
-            patch[(ci * PW + py) * PP + px] = v;
+            patch[(ci * PH + py) * PP + px] = v;
         }
     } else {
         static_assert(INF == FMT_NCHW_F32 || CIN % 8 == 0, "split input needs CIN % 8 == 0");
         const __nv_bfloat16 *hi = a.in_split;
         const size_t plane = a.in_plane;
         constexpr int Q = CIN / 8;
-        for (int i = tid; i < Q * PW * PW; i += 256) {
-            const int pp = i % (PW * PW), q = i / (PW * PW);            // lanes <-> pixels: conflict-free smem writes
+        for (int i = tid; i < Q * PW * PH; i += 256) {
+            const int pp = i % (PW * PH), q = i / (PW * PH);            // lanes <-> pixels: conflict-free smem writes
             const int px = pp % PW, py = pp / PW;
             const int y = iy0 + py, x = ix0 + px;
             float v[8];
@@ -133,17 +145,17 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) patch[((q * 8 + e) * PW + py) * PP + px] = v[e];
+            for (int e = 0; e < 8; ++e) patch[((q * 8 + e) * PH + py) * PP + px] = v[e];
         }
     }
     __syncthreads();
 
     if constexpr (TILED) {
         // ---- stage 2 (tiled): thread = (cout group cg, pixel group pg): 2x2 pixels x C channels
-        constexpr int C = COUT / 4;
+        constexpr int C = G::C;
         constexpr int WIN = STRIDE + 3;                   // input window edge for a 2x2 output patch
-        const int cg = tid >> 6, pg = tid & 63;           // cg is warp-uniform -> weight reads are broadcasts
-        const int gy = pg >> 3, gx = pg & 7;
+        const int cg = tid / G::PG, pg = tid % G::PG;     // cg is warp-uniform -> weight reads are broadcasts
+        const int gy = pg / (G::TW / 2), gx = pg % (G::TW / 2);
         float acc[4][C];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
 #pragma unroll 1
         for (int ci = 0; ci < CIN; ++ci) {
             float win[WIN][WIN];
-            const float *pb = patch + (ci * PW + gy * 2 * STRIDE) * PP + gx * 2 * STRIDE;
+            const float *pb = patch + (ci * PH + gy * 2 * STRIDE) * PP + gx * 2 * STRIDE;
 #pragma unroll
             for (int r = 0; r < WIN; ++r)
 #pragma unroll
@@ -183,16 +195,12 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
             for (int c = 0; c < C; ++c) v[c] = dc_act(acc[p][c], a.act);
             static_assert(OUTF == FMT_SPLIT, "tiled path writes split tensors");
             __nv_bfloat16 *dst = a.out_split + (((size_t)img * a.Hout + oy) * a.Wout + ox) * COUT + cg * C;
-            if constexpr (C >= 8) {
 #pragma unroll
-                for (int c8 = 0; c8 < C / 8; ++c8) dc_store<8>(dst + c8 * 8, a.out_plane, v + c8 * 8);
-            } else {
-                dc_store<C>(dst, a.out_plane, v);
-            }
+            for (int c8 = 0; c8 < C / 8; ++c8) dc_store<8>(dst + c8 * 8, a.out_plane, v + c8 * 8);
         }
     } else {
         // ---- stage 2 (narrow): one pixel x all COUT (1 or 2) per thread
-        const int ty = tid / DC_T, tx = tid % DC_T;
+        const int ty = tid / G::TW, tx = tid % G::TW;
         const int oy = oy0 + ty, ox = ox0 + tx;
         float acc[COUT];
 #pragma unroll
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const float xv = patch[(ci * PW + ty * STRIDE + ky) * PP + tx * STRIDE + kx];
+                    const float xv = patch[(ci * PH + ty * STRIDE + ky) * PP + tx * STRIDE + kx];
                     const float *wp = wsm + ((ky * 3 + kx) * CIN + ci) * COUT;
 #pragma unroll
                     for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, wp[co], acc[co]);
@@ -230,9 +238,11 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
 template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF>
 static int launch_direct(const DirectArgs &a, cudaStream_t st)
 {
-    constexpr int PW = (DC_T - 1) * STRIDE + 3;
+    using G = DcGeom<COUT>;
+    constexpr int PW = (G::TW - 1) * STRIDE + 3;
+    constexpr int PH = (G::TH - 1) * STRIDE + 3;
     constexpr int PP = (PW + 3) / 4 * 4;
-    constexpr size_t smem = sizeof(float) * (size_t)(CIN * PW * PP + 9 * CIN * COUT + COUT);
+    constexpr size_t smem = sizeof(float) * (size_t)(CIN * PH * PP + 9 * CIN * COUT + COUT);
     static_assert(smem <= 227 * 1024, "direct conv tile does not fit in shared memory");
     static bool attr_set = false;
     if (!attr_set) {
@@ -240,7 +250,7 @@ static int launch_direct(const DirectArgs &a, cudaStream_t st)
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((a.Wout + DC_T - 1) / DC_T, (a.Hout + DC_T - 1) / DC_T, a.n_img);
+    dim3 grid((a.Wout + G::TW - 1) / G::TW, (a.Hout + G::TH - 1) / G::TH, a.n_img);
     k_conv_direct<CIN, COUT, STRIDE, UPS, INF, OUTF><<<grid, 256, smem, st>>>(a);
     ESR_LAUNCH_CHECK();
     return ESR_OK;

@@ -162,27 +162,53 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16 *hi_ptr, size_t plan
     }
 }
 
+// activation over 32 values with a warp-uniform selector (no per-element branching)
+__device__ __forceinline__ void act32(float (&v)[32], int act)
+{
+    if (act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    } else if (act == ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+    } else if (act == ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+    }
+}
+
 // One thread's 32 accumulator columns [n0, n0+32) of one valid output pixel -> global memory.
 __device__ __forceinline__ void epilogue_chunk(const ConvTCArgs &a, const uint32_t (&raw)[32], int n0, size_t pix, int img,
                                                int y, int x)
 {
     float v[32];
+    {
+        // bias: 16-byte broadcast loads (npad is a multiple of 16, the blob is 256-byte aligned)
+        const float4 *bp = reinterpret_cast<const float4 *>(a.bias + n0);
+        const int nq = (a.npad - n0 >= 32) ? 8 : 4;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + (n0 + j < a.npad ? a.bias[n0 + j] : 0.0f);
+        for (int q = 0; q < 8; ++q) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < nq) b = bp[q];
+            v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+            v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+            v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+            v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+        }
+    }
 
     if (a.epi_mode == EPI_GRU_ZR) {
         // channels [0,64): update gate z -> fp32; [64,128): reset gate r -> rh = h * r (split)
+        act32(v, ACT_SIGMOID);
         if (n0 < 64) {
             float4 *zp = reinterpret_cast<float4 *>(a.z_buf + pix * 64 + n0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                zp[q] = make_float4(apply_act(v[4 * q], ACT_SIGMOID), apply_act(v[4 * q + 1], ACT_SIGMOID),
-                                    apply_act(v[4 * q + 2], ACT_SIGMOID), apply_act(v[4 * q + 3], ACT_SIGMOID));
+            for (int q = 0; q < 8; ++q) zp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         } else {
             float h[32];
             load_split32(a.h_prev + pix * 64 + (n0 - 64), a.h_plane, h);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = h[j] * apply_act(v[j], ACT_SIGMOID);
+            for (int j = 0; j < 32; ++j) v[j] *= h[j];
             store_split32(a.out + pix * a.out_C + a.out_coff + (n0 - 64), a.out_plane, v);
         }
         return;
@@ -192,48 +218,66 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTCArgs &a, const uint32
         float h[32];
         load_split32(a.h_prev + pix * 64 + n0, a.h_plane, h);
         const float4 *zp = reinterpret_cast<const float4 *>(a.z_buf + pix * 64 + n0);
+        float4 zq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) zq[q] = zp[q];
+        act32(v, ACT_TANH);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const float4 z = zp[q];
-            const float zz[4] = {z.x, z.y, z.z, z.w};
+            const float zz[4] = {zq[q].x, zq[q].y, zq[q].z, zq[q].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int j = 4 * q + e;
-                v[j] = h[j] * (1.0f - zz[e]) + apply_act(v[j], ACT_TANH) * zz[e];
+                v[j] = h[j] * (1.0f - zz[e]) + v[j] * zz[e];
             }
         }
         store_split32(a.out + pix * a.out_C + a.out_coff + n0, a.out_plane, v);
         return;
     }
     // ---- standard epilogue: bias (+ residual before or after the activation)
-    if (a.res_mode != RES_NONE && n0 < a.cout) {
-        float r[32];
+    // activation selector for this chunk: uniform unless act_from falls inside it (conv_offset_mask: 144 = 4.5 chunks)
+    const bool mixed = (a.act_from > n0) && (a.act_from < n0 + 32);
+    const int act = (n0 >= a.act_from) ? a.act : ACT_NONE;
+    float r[32];
+    const bool has_res = a.res_mode != RES_NONE && n0 < a.cout;
+    if (has_res) {
         const size_t rpix = ((size_t)(a.res_img ? a.res_img[img] : img) * a.H + y) * a.W + x;
         load_split32(a.res + rpix * a.res_C + n0, a.res_plane, r);
         if (a.res_mode == RES_PRE_ACT) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + r[j], (n0 + j >= a.act_from) ? a.act : ACT_NONE);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], (n0 + j >= a.act_from) ? a.act : ACT_NONE) + r[j];
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
         }
-    } else {
+    }
+    if (!mixed) act32(v, act);
+    else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], (n0 + j >= a.act_from) ? a.act : ACT_NONE);
+        for (int j = 0; j < 32; ++j)
+            if (n0 + j >= a.act_from) v[j] = apply_act(v[j], a.act);
+    }
+    if (has_res && a.res_mode == RES_POST_ACT) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += r[j];
     }
     if (a.out && n0 + 32 <= a.cout) store_split32(a.out + pix * a.out_C + a.out_coff + n0, a.out_plane, v);
     if (a.out_f32) {
         float *op = a.out_f32 + pix * a.out_f32_C + n0;
+        if ((a.out_f32_C & 3) == 0) {                 // 16-byte stores (conv_offset_mask: 216 channels)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (n0 + j < a.cout) op[j] = v[j];
+            for (int q = 0; q < 8; ++q)
+                if (n0 + 4 * q + 4 <= a.cout)
+                    reinterpret_cast<float4 *>(op)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (n0 + j < a.cout) op[j] = v[j];
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel: one CTA = one tile of 128 output pixels (TH x TW) of one image, all output channels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(const __grid_constant__ ConvTCArgs a)
+__global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const __grid_constant__ ConvTCArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-B alignment
@@ -430,8 +474,17 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     if (rc) return rc;
     a.H = H; a.W = W; a.TW = TW; a.TH = TH;
     a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH; a.n_img = d.n_img;
+    // Pipeline depth.  Grids of more than one wave keep two CTAs resident per SM (<= half the shared memory each) so that
+    // one CTA's prologue / epilogue overlaps the other's main loop; single-wave grids take all the stages that fit.
+    const size_t smem_cap = (size_t)dev_info().max_smem_optin;
+    const int n_tiles = d.n_img * a.tiles_x * a.tiles_y;
     int stages = 6;
-    while (stages > 2 && tc_smem_bytes(a.npad, stages) > (size_t)dev_info().max_smem_optin) --stages;
+    while (stages > 2 && tc_smem_bytes(a.npad, stages) > smem_cap) --stages;
+    if (n_tiles > dev_info().sm_count) {
+        int s2 = stages;
+        while (s2 > 2 && 2 * (tc_smem_bytes(a.npad, s2) + 1024) > smem_cap) --s2;
+        if (2 * (tc_smem_bytes(a.npad, s2) + 1024) <= smem_cap) stages = s2;
+    }
     if (stages > a.nkb) stages = a.nkb < 2 ? 2 : a.nkb;
     a.stages = stages;
     a.bias = d.bias;
