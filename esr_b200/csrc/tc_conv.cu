@@ -15,264 +15,10 @@
 //
 // Reference layers served: every Conv2d of models/model.py at feature resolution (Cin multiple of 64), the ConvGRU
 // gates (models/submodules.py:496-514) and the DCNv2 contraction (models/DCNv2/src/cuda/dcn_v2_cuda.cu:90-92).
-#include "tc_conv.cuh"
+#include "tc_common.cuh"
+#include <cstdlib>
 
 namespace esr {
-
-constexpr int TC_THREADS = 192;
-constexpr int TC_BLOCK_M = 128;
-constexpr int TC_A_BYTES = TC_BLOCK_M * 128;          // one plane of one A tile: 128 rows x 64 bf16
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                            int c3, int c4)
-{
-    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
-                 " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-                 " [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
-                 " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(addr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart).
-// Bits: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;       // SBO = 1024 B
-    d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-    return d;
-}
-// c=F32 [4,6)=1 | a=BF16 [7,10)=1 | b=BF16 [10,13)=1 | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float apply_act(float x, int act)
-{
-    if (act == ACT_RELU) return fmaxf(x, 0.0f);
-    if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
-    if (act == ACT_TANH) return tanhf(x);
-    return x;
-}
-
-// 32 consecutive channels of one pixel of a split tensor -> fp32
-__device__ __forceinline__ void load_split32(const __nv_bfloat16 *hi_ptr, size_t plane, float (&o)[32])
-{
-    const uint4 *ph = reinterpret_cast<const uint4 *>(hi_ptr);
-    const uint4 *pl = reinterpret_cast<const uint4 *>(hi_ptr + plane);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint4 h = ph[q], l = pl[q];
-        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            o[q * 8 + e * 2 + 0] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-            o[q * 8 + e * 2 + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
-        }
-    }
-}
-__device__ __forceinline__ void store_split32(__nv_bfloat16 *hi_ptr, size_t plane, const float (&x)[32])
-{
-    uint32_t hw[16], lw[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(x[2 * e], h0, l0);
-        split_bf16(x[2 * e + 1], h1, l1);
-        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-    uint4 *ph = reinterpret_cast<uint4 *>(hi_ptr);
-    uint4 *pl = reinterpret_cast<uint4 *>(hi_ptr + plane);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        ph[q] = make_uint4(hw[q * 4], hw[q * 4 + 1], hw[q * 4 + 2], hw[q * 4 + 3]);
-        pl[q] = make_uint4(lw[q * 4], lw[q * 4 + 1], lw[q * 4 + 2], lw[q * 4 + 3]);
-    }
-}
-
-// activation over 32 values with a warp-uniform selector (no per-element branching)
-__device__ __forceinline__ void act32(float (&v)[32], int act)
-{
-    if (act == ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-    } else if (act == ACT_SIGMOID) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
-    } else if (act == ACT_TANH) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-    }
-}
-
-// One thread's 32 accumulator columns [n0, n0+32) of one valid output pixel -> global memory.
-__device__ __forceinline__ void epilogue_chunk(const ConvTCArgs &a, const uint32_t (&raw)[32], int n0, size_t pix, int img,
-                                               int y, int x)
-{
-    float v[32];
-    {
-        // bias: 16-byte broadcast loads (npad is a multiple of 16, the blob is 256-byte aligned)
-        const float4 *bp = reinterpret_cast<const float4 *>(a.bias + n0);
-        const int nq = (a.npad - n0 >= 32) ? 8 : 4;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (q < nq) b = bp[q];
-            v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
-            v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
-            v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
-            v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
-        }
-    }
-
-    if (a.epi_mode == EPI_GRU_ZR) {
-        // channels [0,64): update gate z -> fp32; [64,128): reset gate r -> rh = h * r (split)
-        act32(v, ACT_SIGMOID);
-        if (n0 < 64) {
-            float4 *zp = reinterpret_cast<float4 *>(a.z_buf + pix * 64 + n0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) zp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-            float h[32];
-            load_split32(a.h_prev + pix * 64 + (n0 - 64), a.h_plane, h);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= h[j];
-            store_split32(a.out + pix * a.out_C + a.out_coff + (n0 - 64), a.out_plane, v);
-        }
-        return;
-    }
-    if (a.epi_mode == EPI_GRU_OUT) {
-        // h' = h (1 - z) + tanh(.) z        (models/submodules.py:511-512)
-        float h[32];
-        load_split32(a.h_prev + pix * 64 + n0, a.h_plane, h);
-        const float4 *zp = reinterpret_cast<const float4 *>(a.z_buf + pix * 64 + n0);
-        float4 zq[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) zq[q] = zp[q];
-        act32(v, ACT_TANH);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float zz[4] = {zq[q].x, zq[q].y, zq[q].z, zq[q].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = 4 * q + e;
-                v[j] = h[j] * (1.0f - zz[e]) + v[j] * zz[e];
-            }
-        }
-        store_split32(a.out + pix * a.out_C + a.out_coff + n0, a.out_plane, v);
-        return;
-    }
-    // ---- standard epilogue: bias (+ residual before or after the activation)
-    // activation selector for this chunk: uniform unless act_from falls inside it (conv_offset_mask: 144 = 4.5 chunks)
-    const bool mixed = (a.act_from > n0) && (a.act_from < n0 + 32);
-    const int act = (n0 >= a.act_from) ? a.act : ACT_NONE;
-    float r[32];
-    const bool has_res = a.res_mode != RES_NONE && n0 < a.cout;
-    if (has_res) {
-        const size_t rpix = ((size_t)(a.res_img ? a.res_img[img] : img) * a.H + y) * a.W + x;
-        load_split32(a.res + rpix * a.res_C + n0, a.res_plane, r);
-        if (a.res_mode == RES_PRE_ACT) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += r[j];
-        }
-    }
-    if (!mixed) act32(v, act);
-    else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (n0 + j >= a.act_from) v[j] = apply_act(v[j], a.act);
-    }
-    if (has_res && a.res_mode == RES_POST_ACT) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += r[j];
-    }
-    if (a.out && n0 + 32 <= a.cout) store_split32(a.out + pix * a.out_C + a.out_coff + n0, a.out_plane, v);
-    if (a.out_f32) {
-        float *op = a.out_f32 + pix * a.out_f32_C + n0;
-        if ((a.out_f32_C & 3) == 0) {                 // 16-byte stores (conv_offset_mask: 216 channels)
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (n0 + 4 * q + 4 <= a.cout)
-                    reinterpret_cast<float4 *>(op)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < a.cout) op[j] = v[j];
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // the kernel: one CTA = one tile of 128 output pixels (TH x TW) of one image, all output channels
@@ -410,14 +156,14 @@ static PFN_tmapEncodeTiled get_encode()
     return fn;
 }
 
-static int make_amap(const SplitTensor &t, int TW, int TH, CUtensorMap *out)
+static int make_amap(const SplitTensor &t, int BW, int BH, CUtensorMap *out)
 {
     PFN_tmapEncodeTiled enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ESR_ECUDA; }
     const cuuint64_t C = t.C, W = t.W, H = t.H, N = t.n_img;
     cuuint64_t gdim[5] = {C, W, H, N, 2};
     cuuint64_t gstr[4] = {C * 2, W * C * 2, H * W * C * 2, N * H * W * C * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)BW, (cuuint32_t)BH, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -425,13 +171,13 @@ static int make_amap(const SplitTensor &t, int TW, int TH, CUtensorMap *out)
     return ESR_OK;
 }
 
-static int make_bmap(const void *w, int npad, int nkb, CUtensorMap *out)
+static int make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap *out)
 {
     PFN_tmapEncodeTiled enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ESR_ECUDA; }
     cuuint64_t gdim[3] = {64, (cuuint64_t)npad, (cuuint64_t)2 * nkb};
     cuuint64_t gstr[2] = {128, (cuuint64_t)npad * 128};
-    cuuint32_t box[3] = {64, (cuuint32_t)npad, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(w), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -455,23 +201,31 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     int chunks = 0;
     // tile shape: 128 pixels; prefer wide tiles, but do not waste more than half a tile on narrow images
     int TW = W >= 24 ? 32 : (W >= 12 ? 16 : 8);
-    if (H <= 128 / TW / 2 && TW > 8) { /* very flat image: keep TW */ }
     int TH = TC_BLOCK_M / TW;
+    // 3x3 convs use the halo-reuse kernel (8 x 16 tiles, 16 x 18 halo boxes) unless ESR_TC_V1 is set (debug aid)
+    static const bool force_v1 = getenv("ESR_TC_V1") != nullptr;
+    const int npad_ = tc_npad(d.cout);
+    int a_st = 0, b_st = 0;
+    const bool v3 = d.ntaps == 9 && !force_v1 && conv_tc3_plan(npad_, &a_st, &b_st);
+    int BW = TW, BH = TH;
+    if (v3) { TW = 8; TH = 16; BW = 16; BH = 18; }
     for (int s = 0; s < d.n_src; ++s) {
         const SplitTensor &t = d.src[s];
         ESR_REQUIRE(t.base && t.C % 64 == 0 && t.H == H && t.W == W, "conv_tc: source %d has C=%d H=%d W=%d", s, t.C, t.H, t.W);
         chunks += t.C / 64;
         a.chunk_end[s] = chunks;
         a.src_img[s] = d.src_img[s];
-        int rc = make_amap(t, TW, TH, &a.amap[s]);
+        int rc = make_amap(t, BW, BH, &a.amap[s]);
         if (rc) return rc;
     }
     for (int s = d.n_src; s < TC_MAX_SRC; ++s) a.chunk_end[s] = 1 << 30;
     a.n_src = d.n_src; a.ntaps = d.ntaps; a.nkb = chunks * d.ntaps;
     a.npad = tc_npad(d.cout); a.cout = d.cout;
     ESR_REQUIRE(a.npad <= 256, "conv_tc: cout=%d too large", d.cout);
-    int rc = make_bmap(d.wpacked, a.npad, a.nkb, &a.bmap);
+    int rc = make_bmap(d.wpacked, a.npad, a.nkb, a.npad, &a.bmap);
     if (rc) return rc;
+    a.kernel_ver = v3 ? 3 : 1;
+    a.cluster = 1; a.a_stages = a_st;
     a.H = H; a.W = W; a.TW = TW; a.TH = TH;
     a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH; a.n_img = d.n_img;
     // Pipeline depth.  Grids of more than one wave keep two CTAs resident per SM (<= half the shared memory each) so that
@@ -487,6 +241,12 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     }
     if (stages > a.nkb) stages = a.nkb < 2 ? 2 : a.nkb;
     a.stages = stages;
+    if (v3) {
+        static const bool no_mc = getenv("ESR_TC_NO_MULTICAST") != nullptr;
+        a.stages = b_st;
+        a.cluster = (!no_mc && n_tiles >= 2) ? 2 : 1;
+        if (a.cluster == 2 && (rc = make_bmap(d.wpacked, a.npad, a.nkb, a.npad / 2, &a.bmap_half))) return rc;
+    }
     a.bias = d.bias;
     a.act = d.act; a.act_from = d.act_from; a.res_mode = d.res_mode; a.epi_mode = d.epi_mode;
     if (d.res_mode != RES_NONE) {
@@ -511,6 +271,7 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
 
 int conv_tc_launch(const ConvTCArgs &a, cudaStream_t st)
 {
+    if (a.kernel_ver == 3) return conv_tc3_launch(a, st);
     static int max_set = 0;
     const size_t smem = tc_smem_bytes(a.npad, a.stages);
     if ((int)smem > max_set) {

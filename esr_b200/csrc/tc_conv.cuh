@@ -24,6 +24,9 @@ constexpr int TC_MAX_SRC = 3;
 struct ConvTCArgs {
     CUtensorMap amap[TC_MAX_SRC];   // 5-D maps over the source split tensors (C, W, H, img, plane), box (64, TW, TH, 1, 1)
     CUtensorMap bmap;               // 3-D map over packed weights (64, npad, 2*nkb), box (64, npad, 1)
+    CUtensorMap bmap_half;          // same tensor, box (64, npad/2, 1): the half a CTA multicasts in a 2-CTA cluster
+    int kernel_ver;                 // 1: tc_conv.cu (tap-shifted tiles), 3: tc_conv3.cu (halo reuse + weight multicast)
+    int a_stages, cluster;          // v3 only: halo ring depth, cluster size (1 or 2)
     const int *src_img[TC_MAX_SRC]; // output image -> source image (nullptr = identity)
     int chunk_end[TC_MAX_SRC];      // cumulative number of 64-channel chunks after source s
     int n_src, ntaps, nkb, npad, cout;
@@ -67,6 +70,9 @@ static inline size_t tc_packed_weight_bytes(int cout, int cin_total, int ntaps)
 // Builds tensor maps + launch geometry.  H, W taken from src[0].
 int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args);
 int conv_tc_launch(const ConvTCArgs &args, cudaStream_t st);
+// tc_conv3.cu
+bool conv_tc3_plan(int npad, int *a_stages, int *b_stages);
+int conv_tc3_launch(const ConvTCArgs &args, cudaStream_t st);
 
 // w: fp32 [cout, cin, k, k] (device) -> packed split bf16 [2][nkb][npad][64]; kb = chunk*ntaps + tap
 int pack_conv_weight(const float *w, int cout, int cin, int ksz, void *dst, cudaStream_t st);
