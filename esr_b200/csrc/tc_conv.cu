@@ -202,11 +202,13 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     // tile shape: 128 pixels; prefer wide tiles, but do not waste more than half a tile on narrow images
     int TW = W >= 24 ? 32 : (W >= 12 ? 16 : 8);
     int TH = TC_BLOCK_M / TW;
-    // 3x3 convs use the halo-reuse kernel (8 x 16 tiles, 16 x 18 halo boxes) unless ESR_TC_V1 is set (debug aid)
-    static const bool force_v1 = getenv("ESR_TC_V1") != nullptr;
+    // The halo-reuse + weight-multicast kernel (tc_conv3.cu: 8 x 16 tiles, 16 x 18 halo boxes) is opt-in (ESR_TC_V3=1):
+    // measured on B200 it is 5-50 % SLOWER than this kernel with two co-resident CTAs per SM (profiles/r1_notes.md) --
+    // the main loop turned out to be latency / shared-memory-port bound, not L2-bandwidth bound.
+    static const bool use_v3 = getenv("ESR_TC_V3") != nullptr;
     const int npad_ = tc_npad(d.cout);
     int a_st = 0, b_st = 0;
-    const bool v3 = d.ntaps == 9 && !force_v1 && conv_tc3_plan(npad_, &a_st, &b_st);
+    const bool v3 = d.ntaps == 9 && use_v3 && conv_tc3_plan(npad_, &a_st, &b_st);
     int BW = TW, BH = TH;
     if (v3) { TW = 8; TH = 16; BW = 16; BH = 18; }
     for (int s = 0; s < d.n_src; ++s) {

@@ -6,13 +6,15 @@
 //   * A: per 64-channel chunk ONE TMA box of the (16+2) x 16 pixel halo tile (hi and lo planes, 2 x 36 KB).  The tile is
 //     8 pixels wide and 16 tall, the halo rows are 16 pixels (2048 B) apart, so the 128 rows of tap (dy,dx) are the
 //     canonical 128B-swizzled K-major layout starting at halo pixel (dy,dx): 8-row groups 2048 B apart (SBO), start
-//     address advanced by (dy*16+dx)*128 B with the descriptor's base-offset field set to the start's row phase
-//     ((addr >> 7) & 7).  All 9 taps x 4 K-steps x 3 split products run from the same shared-memory tile.
+//     address advanced by (dy*16+dx)*128 B (the swizzle is a function of the absolute shared-memory address, so the
+//     shifted view stays consistent with what TMA wrote).  All 9 taps x 4 K-steps x 3 split products run from the
+//     same shared-memory tile.
 //   * B: thread-block clusters of 2 CTAs (adjacent tiles); each CTA loads half of every weight tile and TMA-multicasts it
 //     into both CTAs, so the per-CTA weight traffic halves.  Stage release is cluster-wide (tcgen05.commit multicast).
 // Epilogue, operand precision (3-pass split bf16, fp32 accumulate in TMEM) and tensor formats are those of tc_conv.cu.
 // Warp roles: 0 = A (halo) producer, 1 = MMA issuer + TMEM owner, 2 = B (weights) producer, 3..6 = epilogue.
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace esr {
 
@@ -44,8 +46,10 @@ __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// K-major SWIZZLE_128B descriptor whose start is not 1024-byte aligned: SBO = 2048 B (16-pixel halo rows),
-// base offset (bits 49-51) = row phase of the start address inside the 8-row swizzle pattern.
+// K-major SWIZZLE_128B descriptor whose start is NOT 1024-byte aligned: SBO = 2048 B (16-pixel halo rows).
+// Measured on B200 (tools/diag_halo.py): the tensor core applies the 128B swizzle to the absolute shared-memory address
+// (start + row offset), exactly like TMA does when it writes the box, so a start advanced by whole 128-byte rows needs
+// NO base-offset correction (setting bits 49-51 to the start's row phase breaks every tap with dx != 0).
 __device__ __forceinline__ uint64_t umma_smem_desc_halo(uint32_t smem_addr)
 {
     uint64_t d = 0;
@@ -53,7 +57,6 @@ __device__ __forceinline__ uint64_t umma_smem_desc_halo(uint32_t smem_addr)
     d |= (uint64_t)1 << 16;
     d |= (uint64_t)(2048 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
     d |= (uint64_t)2 << 61;
     return d;
 }
@@ -222,6 +225,7 @@ bool conv_tc3_plan(int npad, int *a_stages, int *b_stages)
 int conv_tc3_launch(const ConvTCArgs &a, cudaStream_t st)
 {
     static int max_set = 0;
+
     const size_t smem = t3_smem_bytes(a.npad, a.a_stages, a.stages);
     if ((int)smem > max_set) {
         ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

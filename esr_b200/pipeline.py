@@ -29,6 +29,7 @@ class EventSRPipeline:
         self.bank = torch.zeros((B * L, 2, self.hr_size[0], self.hr_size[1]), dtype=torch.float32, device=device)
         self._graph = None
         self._graph_sr = None
+        self._host_events = None
         self.sequence_plan = True
         self.graph_launches = 0
 
@@ -83,4 +84,11 @@ class EventSRPipeline:
         ps = ps_h.to(self.dev, non_blocking=True)
         off = off_h.to(self.dev, non_blocking=True)
         _, events = self.run_device(xs, ys, ps, off, n_max_frame, mode)
-        return events.cpu()
+        # D2H into a reusable pinned buffer (pageable `.cpu()` copies run at a fraction of the link rate)
+        n = events.numel()
+        if self._host_events is None or self._host_events.numel() < n:
+            self._host_events = torch.empty((int(n * 1.25) + 1024,), dtype=torch.float32).pin_memory()
+        host = self._host_events[:n].view(events.shape)
+        host.copy_(events, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
