@@ -65,6 +65,62 @@ k_scatter_image(float *__restrict__ xs, float *__restrict__ ys, float *__restric
     }
 }
 
+// time-bin slice bounds of events_to_stack_no_polarity (encodings.py:204-240) with the reference's own
+// binary_search_torch_tensor (encodings.py:77-99) -- including its early exits on exact matches, which decide which of
+// several equal timestamps ends a bin.  One thread per bin; fp32 arithmetic rounded step by step like torch's.
+__global__ void k_time_bin_bounds(const float *__restrict__ ts, long long n, int B, long long *__restrict__ out)
+{
+    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= B) return;
+    const float t0 = ts[0];
+    const float dt = __fadd_rn(__fsub_rn(ts[n - 1], t0), 1e-6f);            // ts[-1]-ts[0] + 1e-6
+    const float delta = __fdiv_rn(dt, (float)B);
+    const float tstart = __fadd_rn(t0, __fmul_rn(delta, (float)bi));
+    const float tend = __fadd_rn(tstart, delta);
+    for (int side = 0; side < 2; ++side) {
+        const float x = side == 0 ? tstart : tend;
+        long long l = 0, r = n - 1, res = 0;
+        bool found = false;
+        while (l <= r) {
+            if (ts[l] == x) { res = l; found = true; break; }
+            if (ts[r] == x) { res = r; found = true; break; }
+            const long long mid = l + (r - l) / 2;
+            const float mv = ts[mid];
+            if (mv == x) { res = mid; found = true; break; }
+            else if (mv < x) l = mid + 1;
+            else r = mid - 1;
+        }
+        if (!found) res = side == 0 ? l : r;
+        out[2 * bi + side] = side == 0 ? res : res + 1;                      // end = search(..., side='right') + 1
+    }
+}
+
+// events_to_voxel (encodings.py:271-286): bin b accumulates ps * max(0, 1 - |ts*(nb-1) - b|) through events_to_image.
+// Quirk kept: the first bin's call zeroes out-of-range xs/ys in place, so in bins >= 1 those events are no longer
+// out of range and their weight lands on pixel (0,0).
+__global__ void __launch_bounds__(256)
+k_scatter_voxel(float *__restrict__ xs, float *__restrict__ ys, const float *__restrict__ ts, const float *__restrict__ ps,
+                long long n, int nb, int H, int W, int writeback, float *__restrict__ out)
+{
+    const float fW = (float)W, fH = (float)H;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float x = xs[i], y = ys[i];
+        const float p = ps[i];
+        const float tt = __fmul_rn(ts[i], (float)(nb - 1));
+        const bool oor = (x >= fW) | (x < 0.0f) | (y >= fH) | (y < 0.0f);
+        if (oor) { x = 0.0f; y = 0.0f; }
+        const size_t pix = (size_t)(long long)y * W + (size_t)(long long)x;
+        for (int b = 0; b < nb; ++b) {
+            const float w = fmaxf(0.0f, __fsub_rn(1.0f, fabsf(__fsub_rn(tt, (float)b))));
+            const float v = __fmul_rn(p, w);
+            if (oor && b == 0) continue;                                     // dropped only in the first bin
+            if (v != 0.0f) atomicAdd(out + (size_t)b * H * W + pix, v);
+        }
+        if (writeback && oor) { xs[i] = 0.0f; ys[i] = 0.0f; }
+    }
+}
+
 // =============================================================================================
 // 2. exclusive scan of uint32 (multi-level, tile = 1024 threads x 4)
 // =============================================================================================
@@ -386,6 +442,30 @@ extern "C" int esr_scatter_image(float *xs, float *ys, float *ps, int64_t n, int
     const int64_t cap = (int64_t)dev_info().sm_count * 16;
     if (bx > cap) bx = cap;
     k_scatter_image<<<(unsigned)bx, 256, 0, st>>>(xs, ys, ps, n, H, W, writeback, out);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+extern "C" int esr_time_bin_bounds(const float *ts, int64_t n, int B, int64_t *bounds, esr_stream_t stream)
+{
+    ESR_REQUIRE(ts && bounds && n > 0 && B > 0, "esr_time_bin_bounds: bad arguments");
+    k_time_bin_bounds<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ts, (long long)n, B, (long long *)bounds);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+extern "C" int esr_scatter_voxel(float *xs, float *ys, const float *ts, const float *ps, int64_t n, int num_bins, int H, int W,
+                                 int writeback, float *out, esr_stream_t stream)
+{
+    ESR_REQUIRE(H > 0 && W > 0 && num_bins > 0 && out && n >= 0, "esr_scatter_voxel: bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)num_bins * H * W, st));
+    if (n == 0) return ESR_OK;
+    ESR_REQUIRE(xs && ys && ts && ps, "esr_scatter_voxel: null event arrays");
+    int64_t bx = ceil_div64(n, 256 * 4);
+    const int64_t cap = (int64_t)dev_info().sm_count * 16;
+    if (bx > cap) bx = cap;
+    k_scatter_voxel<<<(unsigned)bx, 256, 0, st>>>(xs, ys, ts, ps, (long long)n, num_bins, H, W, writeback, out);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

@@ -3,6 +3,8 @@
 Same names, positional arguments and side effects as the reference:
   events_to_image(xs, ys, ps, sensor_size)        encodings.py:243-268
   events_to_channels(xs, ys, ps, sensor_size)     encodings.py:289-304
+  events_to_stack_no_polarity(xs, ys, ts, ps, B, device, sensor_size)   encodings.py:204-240 (+ :77-99)
+  events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size)                encodings.py:271-286
   cython_event_redistribute(event_stack, mode)    encodings.py:466-484
   multiprocess_cython(event_stack, mode)          encodings.py:495-533 (per-sample calls, no process pool)
   stack2cnt(stack)                                encodings.py:652-670
@@ -45,6 +47,60 @@ def events_to_image(xs, ys, ps, sensor_size=(180, 240)):
     for src, d, cb in ((xs, dx, cbx), (ys, dy, cby), (ps, dp, cbp)):
         if cb and src.dtype == torch.float32:
             src.copy_(d)
+    return out if xs.is_cuda else out.cpu()
+
+
+def events_to_stack_no_polarity(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)):
+    """Signed per-time-bin event sums [B,H,W] (encodings.py:204-240).  Bin edges come from the reference's own binary
+    search semantics (esr_time_bin_bounds); each bin is one events_to_image pass over its slice, so the slices of the
+    caller's xs/ys/ps are modified in place exactly as in the reference."""
+    dev = xs.device if xs.is_cuda else _dev()
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    n = len(ts)
+    if n <= 3 or float(ts.sum()) == 0:
+        z = torch.zeros([B, H, W], device=dev)
+        return z if xs.is_cuda else z.cpu()
+    assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
+    dx, cbx = _to_dev_f32(xs, dev)
+    dy, cby = _to_dev_f32(ys, dev)
+    dp, cbp = _to_dev_f32(ps, dev)
+    dt, _ = _to_dev_f32(ts, dev)
+    L = _lib.lib()
+    bounds = torch.empty((B, 2), dtype=torch.int64, device=dev)
+    out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.esr_time_bin_bounds(_lib.ptr(dt), n, int(B), _lib.ptr(bounds), _lib.stream_ptr()), "esr_time_bin_bounds")
+        bh = bounds.cpu().tolist()
+        for bi, (beg, end) in enumerate(bh):
+            beg, end = max(0, min(beg, n)), max(0, min(end, n))          # python slice clamping
+            cnt = max(0, end - beg)
+            _lib.check(L.esr_scatter_image(_lib.ptr(dx[beg:]) if cnt else None, _lib.ptr(dy[beg:]) if cnt else None,
+                                           _lib.ptr(dp[beg:]) if cnt else None, cnt, H, W, 1, _lib.ptr(out[bi]),
+                                           _lib.stream_ptr()), "esr_scatter_image")
+    for src, d, cb in ((xs, dx, cbx), (ys, dy, cby), (ps, dp, cbp)):
+        if cb and src.dtype == torch.float32:
+            src.copy_(d)
+    return out if xs.is_cuda else out.cpu()
+
+
+def events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size=(180, 240)):
+    """Voxel grid with temporal bilinear interpolation [num_bins,H,W] (encodings.py:271-286); xs, ys are modified in
+    place for out-of-range events like the reference (and, like it, such events then land on pixel (0,0) of bins >= 1)."""
+    assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
+    dev = xs.device if xs.is_cuda else _dev()
+    dx, cbx = _to_dev_f32(xs, dev)
+    dy, cby = _to_dev_f32(ys, dev)
+    dp, _ = _to_dev_f32(ps, dev)
+    dt, _ = _to_dev_f32(ts, dev)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    out = torch.empty((int(num_bins), H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().esr_scatter_voxel(_lib.ptr(dx), _lib.ptr(dy), _lib.ptr(dt), _lib.ptr(dp), dx.numel(), int(num_bins),
+                                                H, W, 1, _lib.ptr(out), _lib.stream_ptr()), "esr_scatter_voxel")
+    if cbx and xs.dtype == torch.float32:
+        xs.copy_(dx)
+    if cby and ys.dtype == torch.float32:
+        ys.copy_(dy)
     return out if xs.is_cuda else out.cpu()
 
 

@@ -53,6 +53,17 @@ int esr_scatter_cnt(float *xs, float *ys, const float *ps, const int64_t *frame_
 int esr_scatter_image(float *xs, float *ys, float *ps, int64_t n, int H, int W, int writeback, float *out,
                       esr_stream_t stream);
 
+/* Replaces: the slicing of dataloader/encodings.py:204-240 events_to_stack_no_polarity, i.e. its calls to
+ * binary_search_torch_tensor (encodings.py:77-99).  ts: sorted fp32 [n]; bounds: int64 [B,2] = (beg, end) of every time
+ * bin, identical to the reference's search (incl. which of several equal timestamps it stops on). */
+int esr_time_bin_bounds(const float *ts, int64_t n, int B, int64_t *bounds, esr_stream_t stream);
+
+/* Replaces: dataloader/encodings.py:271-286 events_to_voxel (temporal bilinear voxel grid through events_to_image).
+ * out: fp32 [num_bins,H,W], overwritten.  Keeps the reference's side effect (xs, ys zeroed in place for out-of-range
+ * events) and its consequence (those events land on pixel (0,0) in bins >= 1). */
+int esr_scatter_voxel(float *xs, float *ys, const float *ts, const float *ps, int64_t n, int num_bins, int H, int W,
+                      int writeback, float *out, esr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * dense counts / time-bin stacks -> time-sorted event lists
  * Replaces: dataloader/cython_cnt2event/cnt2event.pyx:18-116 (kind 0: vals = [B,2,H,W], P=2, C=1) and

@@ -100,3 +100,31 @@ def event_redistribute(event_stack, mode=0):
     else:
         raise Exception("wrong event stack")
     return _expand(lib().oracle_event_redistribute, event_stack, (B, P, C, H, W), mode)
+
+
+def events_to_stack_no_polarity(xs, ys, ts, ps, B, sensor_size):
+    """float32 numpy arrays (xs, ys, ps MUTATED in place like the reference) -> float32 [B,H,W]"""
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    n = len(ts)
+    out = np.zeros((B, H, W), dtype=np.float32)
+    if n <= 3 or float(ts.sum()) == 0:
+        return out
+    bounds = np.zeros(2 * B, dtype=np.int64)
+    lib().oracle_time_bin_bounds(_p(np.ascontiguousarray(ts, np.float32), _f32p), ctypes.c_int64(n), int(B), _p(bounds, _i64p))
+    for b in range(B):
+        beg, end = int(bounds[2 * b]), int(bounds[2 * b + 1])
+        sx, sy, sp = xs[beg:end], ys[beg:end], ps[beg:end]           # views: in-place side effects reach the caller
+        lib().oracle_events_to_image_inplace(_p(sx, _f32p), _p(sy, _f32p), _p(sp, _f32p), ctypes.c_int64(len(sx)), H, W,
+                                             _p(out[b], _f32p))
+    return out
+
+
+def events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size):
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    out = np.zeros((num_bins, H, W), dtype=np.float32)
+    ts = np.ascontiguousarray(ts, np.float32)
+    ps = np.ascontiguousarray(ps, np.float32)
+    rc = lib().oracle_events_to_voxel(_p(xs, _f32p), _p(ys, _f32p), _p(ts, _f32p), _p(ps, _f32p), ctypes.c_int64(len(xs)),
+                                      int(num_bins), H, W, _p(out, _f32p))
+    assert rc == 0
+    return out

@@ -72,6 +72,32 @@ def main():
         out[f"lift{i}_dims"] = np.array([H, W, k])
         out[f"lift{i}_out"] = img.numpy()
 
+    # --- events_to_stack_no_polarity (+ binary_search_torch_tensor) and events_to_voxel
+    tcases = []
+    for (n, H, W, TB) in [(2, 4, 4, 3), (50, 8, 10, 1), (3000, 24, 32, 5), (4000, 45, 80, 1), (2500, 16, 16, 4)]:
+        xs = (rng.random(n) * (W + 4) - 2).astype(np.float32)
+        ys = (rng.random(n) * (H + 4) - 2).astype(np.float32)
+        ps = rng.choice(np.array([-1, 1], np.float32), n)
+        ts = np.sort(rng.random(n)).astype(np.float32)
+        if n >= 2500:
+            ts = np.round(ts * 40) / 40            # many equal timestamps: exercises the search's early exits
+            ts = np.sort(ts).astype(np.float32)
+        if n > 3:
+            ts = ((ts - ts[0]) / (ts[-1] - ts[0] + np.float32(1e-6))).astype(np.float32)   # event_formatting normalisation
+        tcases.append((xs, ys, ts, ps, H, W, TB))
+    out["n_stack"] = len(tcases)
+    for i, (xs, ys, ts, ps, H, W, TB) in enumerate(tcases):
+        tx, ty, tt, tp = (torch.from_numpy(a.copy()) for a in (xs, ys, ts, ps))
+        st = ref_enc.events_to_stack_no_polarity(tx, ty, tt, tp, TB, sensor_size=(H, W))
+        out[f"stk{i}_xs"], out[f"stk{i}_ys"], out[f"stk{i}_ts"], out[f"stk{i}_ps"] = xs, ys, ts, ps
+        out[f"stk{i}_dims"] = np.array([H, W, TB])
+        out[f"stk{i}_out"] = st.numpy()
+        out[f"stk{i}_xs_after"], out[f"stk{i}_ps_after"] = tx.numpy(), tp.numpy()
+        tx, ty, tt, tp = (torch.from_numpy(a.copy()) for a in (xs, ys, ts, ps))
+        vx = ref_enc.events_to_voxel(tx, ty, tt, tp, max(TB, 2), sensor_size=(H, W))
+        out[f"stk{i}_voxel"] = vx.numpy()
+        out[f"stk{i}_voxel_xs_after"] = tx.numpy()
+
     # --- cnt2event
     c = np.zeros((1, 2, 2, 3), np.float32)
     c[0, 0, 0, 1], c[0, 0, 1, 2], c[0, 1, 0, 0], c[0, 1, 1, 1] = 2.5, 3.0, 1.0, 3.5

@@ -146,3 +146,27 @@ def test_empty_and_error_cases(dev):
         c2e.cnt2event(c, 0)
     with pytest.raises(ValueError):
         c2e.cnt2event(z.astype(np.float64), 0)
+
+
+def test_stack_and_voxel_golden(golden_events, dev):
+    """Row 3 of the scope table: events_to_stack_no_polarity with the reference's binary-search bin edges, and
+    events_to_voxel.  The stack is bit-exact (per-bin sums of +-1); voxel weights are fp32 sums accumulated with
+    atomics, so they are compared to 1e-5 relative (summation order differs)."""
+    from esr_b200 import encodings as enc
+    g = golden_events
+    for i in range(int(g["n_stack"])):
+        H, W, TB = (int(v) for v in g[f"stk{i}_dims"])
+        for on_gpu in (False, True):
+            xs, ys, ts, ps = (torch.from_numpy(g[f"stk{i}_{k}"].copy()) for k in ("xs", "ys", "ts", "ps"))
+            if on_gpu:
+                xs, ys, ts, ps = (t.to(dev) for t in (xs, ys, ts, ps))
+            out = enc.events_to_stack_no_polarity(xs, ys, ts, ps, TB, sensor_size=(H, W))
+            assert out.is_cuda == on_gpu
+            assert np.array_equal(out.cpu().numpy(), g[f"stk{i}_out"]), (i, on_gpu)
+            assert np.array_equal(xs.cpu().numpy(), g[f"stk{i}_xs_after"])
+            assert np.array_equal(ps.cpu().numpy(), g[f"stk{i}_ps_after"])
+        xs, ys, ts, ps = (torch.from_numpy(g[f"stk{i}_{k}"].copy()) for k in ("xs", "ys", "ts", "ps"))
+        vox = enc.events_to_voxel(xs, ys, ts, ps, max(TB, 2), sensor_size=(H, W)).numpy()
+        want = g[f"stk{i}_voxel"]
+        assert np.abs(vox - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), i
+        assert np.array_equal(xs.numpy(), g[f"stk{i}_voxel_xs_after"])

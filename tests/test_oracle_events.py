@@ -79,3 +79,18 @@ def test_cnt2event_negative_raises():
     c[0, 0, 0, 0], c[0, 1, 1, 1] = 3, -1
     with pytest.raises(ValueError):
         oe.cnt2event(c, 0)
+
+
+def test_stack_and_voxel_golden(golden_events):
+    """events_to_stack_no_polarity (+ the reference's own binary search) and events_to_voxel, incl. in-place effects."""
+    g = golden_events
+    for i in range(int(g["n_stack"])):
+        H, W, TB = (int(v) for v in g[f"stk{i}_dims"])
+        xs, ys, ts, ps = (g[f"stk{i}_{k}"].copy() for k in ("xs", "ys", "ts", "ps"))
+        out = oe.events_to_stack_no_polarity(xs, ys, ts, ps, TB, (H, W))
+        assert np.array_equal(out, g[f"stk{i}_out"]), i
+        assert np.array_equal(xs, g[f"stk{i}_xs_after"]) and np.array_equal(ps, g[f"stk{i}_ps_after"])
+        xs, ys, ts, ps = (g[f"stk{i}_{k}"].copy() for k in ("xs", "ys", "ts", "ps"))
+        vox = oe.events_to_voxel(xs, ys, ts, ps, max(TB, 2), (H, W))
+        assert np.array_equal(vox, g[f"stk{i}_voxel"]), i
+        assert np.array_equal(xs, g[f"stk{i}_voxel_xs_after"])
