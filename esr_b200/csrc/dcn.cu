@@ -25,16 +25,26 @@ __device__ __forceinline__ void ld8(const __nv_bfloat16 *hi, size_t plane, float
     }
 }
 
+constexpr int DCN_PIX = 32;    // pixels per block
+
 __global__ void __launch_bounds__(256)
 k_dcn_columns(const __nv_bfloat16 *__restrict__ feat, size_t f_plane, const int *__restrict__ feat_img,
               const float *__restrict__ om, int n_img, int H, int W, __nv_bfloat16 *__restrict__ cols, size_t c_plane)
 {
-    const size_t total = (size_t)n_img * H * W * 72;          // 9 taps x 8 groups
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % 8), k = (int)((i / 8) % 9);
-        const size_t p = i / 72;
+    // the 216 offset/mask values of DCN_PIX consecutive pixels, staged with coalesced 16-byte loads
+    __shared__ float4 s_om4[DCN_PIX * 54];
+    const float *s_om = reinterpret_cast<const float *>(s_om4);
+    const size_t npix = (size_t)n_img * H * W;
+    const size_t p0 = (size_t)blockIdx.x * DCN_PIX;
+    const int cnt = (int)min((size_t)DCN_PIX, npix - p0);
+    const float4 *src = reinterpret_cast<const float4 *>(om + p0 * 216);
+    for (int i = threadIdx.x; i < cnt * 54; i += 256) s_om4[i] = src[i];
+    __syncthreads();
+    for (int it = threadIdx.x; it < cnt * 72; it += 256) {
+        const int g = it % 8, k = (it / 8) % 9, lp = it / 72;
+        const size_t p = p0 + lp;
         const int x = (int)(p % W), y = (int)((p / W) % H), img = (int)(p / ((size_t)W * H));
-        const float *o = om + p * 216;
+        const float *o = s_om + lp * 216;
         const float off_h = o[g * 18 + 2 * k], off_w = o[g * 18 + 2 * k + 1], m = o[144 + g * 9 + k];
         const float h_im = (float)(y - 1 + k / 3) + off_h;
         const float w_im = (float)(x - 1 + k % 3) + off_w;
@@ -76,8 +86,8 @@ k_dcn_columns(const __nv_bfloat16 *__restrict__ feat, size_t f_plane, const int 
 int dcn_columns(const SplitTensor &feat, const int *feat_img, const float *om, int n_img, const SplitTensor &cols, cudaStream_t st)
 {
     ESR_REQUIRE(feat.C == 64 && cols.C == 576 && cols.H == feat.H && cols.W == feat.W, "dcn_columns: bad shapes");
-    const size_t total = (size_t)n_img * feat.H * feat.W * 72;
-    k_dcn_columns<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(feat.base, feat.plane(), feat_img, om, n_img, feat.H,
+    const size_t npix = (size_t)n_img * feat.H * feat.W;
+    k_dcn_columns<<<(unsigned)ceil_div64((int64_t)npix, DCN_PIX), 256, 0, st>>>(feat.base, feat.plane(), feat_img, om, n_img, feat.H,
                                                                              feat.W, cols.base, cols.plane());
     ESR_LAUNCH_CHECK();
     return ESR_OK;

@@ -84,6 +84,9 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
     float *patch = dsm;                                   // [CIN][PH][PP]
     float *wsm = dsm + CIN * PH * PP;                     // [9][CIN][COUT]
     float *bsm = wsm + 9 * CIN * COUT;                    // [COUT]
+    constexpr int IPP = (PW + 2 + 3) / 4 * 4;             // fused head: input patch pitch
+    float *inp = bsm + ((COUT + 3) / 4 * 4);              // fused head: [2][PH+2][IPP] input patch, then [9][2][8] + [8]
+    float *w0s = inp + 2 * (PH + 2) * IPP;
 
     const int img = blockIdx.z;
     const int oy0 = blockIdx.y * G::TH, ox0 = blockIdx.x * G::TW;
@@ -98,7 +101,43 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
     const int Wc = UPS ? 2 * a.Win : a.Win + a.pad_left + a.pad_right;
     const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
     const int simg = a.in_img ? a.in_img[img] : img;
-    if constexpr (INF == FMT_NCHW_F32) {
+    if constexpr (INF == FMT_HEAD_FUSED) {
+        // head (2 -> 8, relu; models/model.py:301,330) evaluated on the fly for the (PH x PW) patch this tile needs:
+        // the full-resolution 8-channel tensor (the largest activation of the network) never goes to HBM.
+        static_assert(INF != FMT_HEAD_FUSED || CIN == 8, "fused head feeds the 8-channel encoder layer");
+        for (int i = tid; i < 9 * 2 * 8 + 8; i += 256) w0s[i] = i < 144 ? a.w0[i] : a.b0[i - 144];
+        for (int i = tid; i < 2 * (PH + 2) * (PW + 2); i += 256) {
+            const int px = i % (PW + 2), py = (i / (PW + 2)) % (PH + 2), ci = i / ((PW + 2) * (PH + 2));
+            const int y = iy0 - 1 + py, x = ix0 - 1 + px;                 // head-input coordinates (padded frame)
+            float v = 0.0f;
+            const int sy = y - a.pad_top, sx = x - a.pad_left;           // CropSize zero padding (model_util.py:148-152)
+            if (sy >= 0 && sy < a.Hin && sx >= 0 && sx < a.Win)
+                v = a.in_f32[(((size_t)simg * 2 + ci) * a.Hin + sy) * a.Win + sx];
+            inp[(ci * (PH + 2) + py) * IPP + px] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < PH * PW; i += 256) {
+            const int px = i % PW, py = i / PW;
+            const int y = iy0 + py, x = ix0 + px;
+            float o[8];
+            const bool inside = (y >= 0 && y < Hc && x >= 0 && x < Wc);   // outside = the encoder conv's zero padding
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = w0s[144 + c];
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float xv = inp[(ci * (PH + 2) + py + ky) * IPP + px + kx];
+                        const float *wp = w0s + ((ky * 3 + kx) * 2 + ci) * 8;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) o[c] = fmaf(xv, wp[c], o[c]);
+                    }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) patch[(c * PH + py) * PP + px] = inside ? fmaxf(o[c], 0.0f) : 0.0f;
+        }
+    } else if constexpr (INF == FMT_NCHW_F32) {
         for (int i = tid; i < CIN * PW * PH; i += 256) {
             const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
             const int y = iy0 + py, x = ix0 + px;
@@ -111,7 +150,7 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
             patch[(ci * PH + py) * PP + px] = v;
         }
     } else {
-        static_assert(INF == FMT_NCHW_F32 || CIN % 8 == 0, "split input needs CIN % 8 == 0");
+        static_assert(INF != FMT_SPLIT || CIN % 8 == 0, "split input needs CIN % 8 == 0");
         const __nv_bfloat16 *hi = a.in_split;
         const size_t plane = a.in_plane;
         constexpr int Q = CIN / 8;
@@ -242,7 +281,9 @@ static int launch_direct(const DirectArgs &a, cudaStream_t st)
     constexpr int PW = (G::TW - 1) * STRIDE + 3;
     constexpr int PH = (G::TH - 1) * STRIDE + 3;
     constexpr int PP = (PW + 3) / 4 * 4;
-    constexpr size_t smem = sizeof(float) * (size_t)(CIN * PH * PP + 9 * CIN * COUT + COUT);
+    constexpr int IPP = (PW + 2 + 3) / 4 * 4;
+    constexpr size_t extra = INF == FMT_HEAD_FUSED ? (size_t)(2 * (PH + 2) * IPP + 9 * 2 * 8 + 8) : 0;
+    constexpr size_t smem = sizeof(float) * ((size_t)(CIN * PH * PP + 9 * CIN * COUT + (COUT + 3) / 4 * 4) + extra);
     static_assert(smem <= 227 * 1024, "direct conv tile does not fit in shared memory");
     static bool attr_set = false;
     if (!attr_set) {
@@ -260,6 +301,7 @@ int conv_direct(DirectKind kind, const DirectArgs &a, cudaStream_t st)
 {
     switch (kind) {
     case DK_HEAD:    return launch_direct<2, 8, 1, false, FMT_NCHW_F32, FMT_SPLIT>(a, st);
+    case DK_HEAD_ENC0: return launch_direct<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT>(a, st);
     case DK_ENC0:    return launch_direct<8, 16, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);
     case DK_ENC1:    return launch_direct<16, 32, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);
     case DK_ENC2:    return launch_direct<32, 64, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);

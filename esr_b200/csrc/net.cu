@@ -91,7 +91,7 @@ struct Net {
     char *ws;       // workspace
     size_t ws_bytes;
     // tensors
-    SplitTensor t_head, t_e0, t_e1, F, t_pm0, t_cat, t_lf1, t_lf2, ltc, xc, hs, rh, tp;
+    SplitTensor t_e0, t_e1, F, t_pm0, t_cat, t_lf1, t_lf2, ltc, xc, hs, rh, tp;
     SplitTensor t_of0, t_off, cols, aligned, t_cb0, feat, ycat, t_df0, fused, t_dn0, x0, pre0, x1, pre1, x2, pre2, x3;
     float *maps, *zbuf, *om, *sk, *mx, *ck, *att0, *att1, *att2;
     // index maps (device)
@@ -126,7 +126,6 @@ static size_t layout(Net &n)
     const int nf = (N - 1) * VB, np = VB * (N + 1), nsteps = n.Wn * N;
     // recurrent state first so that its address does not depend on later changes
     n.hs = A.split((nsteps + 1) * 2 * B, h, w, 64);
-    n.t_head = A.split(FR, Hc, Wc, 8);
     n.t_e0 = A.split(FR, Hc / 2, Wc / 2, 16);
     n.t_e1 = A.split(FR, Hc / 4, Wc / 4, 32);
     n.F = A.split(FR, h, w, 64);
@@ -334,10 +333,12 @@ static int build(Net &n, cudaStream_t st)
     auto out_split = [&](DirectArgs &a, const SplitTensor &t, int n_img) {
         a.out_split = t.base; a.out_plane = t.plane(); a.Hout = t.H; a.Wout = t.W; a.n_img = n_img;
     };
-    DirectArgs a = base(D_HEAD, ACT_RELU);
+    // head (2->8 @HR) is fused into the first encoder layer (8->16, stride 2): its 8-channel full-resolution output is
+    // recomputed per tile in shared memory instead of taking a round trip through HBM
+    DirectArgs a = base(D_ENC0, ACT_RELU);
+    a.w0 = (const float *)(n.params + Lp.dw[D_HEAD]); a.b0 = (const float *)(n.params + Lp.db[D_HEAD]);
     a.Hin = n.H; a.Win = n.W; a.pad_top = n.pad_top; a.pad_bottom = n.pad_bottom; a.pad_left = n.pad_left; a.pad_right = n.pad_right;
-    out_split(a, n.t_head, FR); n.d[D_HEAD] = a;
-    a = base(D_ENC0, ACT_RELU); in_split(a, n.t_head); out_split(a, n.t_e0, FR); n.d[D_ENC0] = a;
+    out_split(a, n.t_e0, FR); n.d[D_ENC0] = a;
     a = base(D_ENC1, ACT_RELU); in_split(a, n.t_e0); out_split(a, n.t_e1, FR); n.d[D_ENC1] = a;
     a = base(D_ENC2, ACT_RELU); in_split(a, n.t_e1); out_split(a, n.F, FR); n.d[D_ENC2] = a;
     a = base(D_AT1, ACT_SIGMOID); in_split(a, n.t_e1); a.out_f32 = n.att1; a.Hout = n.t_e1.H; a.Wout = n.t_e1.W; a.n_img = FR; n.d[D_AT1] = a;
@@ -385,9 +386,8 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     const ParamLayout &L = param_layout();
     // ---- per-frame work, once per bank frame: head + encoder (models/model.py:329-331) and the three attention maps
     //      of scale_aggre (model.py:259-262), which depend on the encoder features only
-    DirectArgs a = n.d[D_HEAD]; a.in_f32 = input; a.in_img = in_img;
-    RUND(DK_HEAD, D_HEAD, a);
-    RUND(DK_ENC0, D_ENC0, n.d[D_ENC0]);
+    DirectArgs a = n.d[D_ENC0]; a.in_f32 = input; a.in_img = in_img;
+    RUNC(PC_DIRECT, direct_flops(D_ENC0, a) + 2.0 * a.n_img * n.Hc * n.Wc * 8.0 * 2.0 * 9.0, conv_direct(DK_HEAD_ENC0, a, st));
     RUND(DK_ENC1, D_ENC1, n.d[D_ENC1]);
     RUND(DK_ENC2, D_ENC2, n.d[D_ENC2]);
     RUNT(n.c_at0);

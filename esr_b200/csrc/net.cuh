@@ -4,9 +4,9 @@
 
 namespace esr {
 
-enum Fmt : int { FMT_NCHW_F32 = 0, FMT_SPLIT = 1, FMT_NHWC_F32 = 2 };
+enum Fmt : int { FMT_NCHW_F32 = 0, FMT_SPLIT = 1, FMT_NHWC_F32 = 2, FMT_HEAD_FUSED = 3 };
 
-enum DirectKind : int { DK_HEAD, DK_ENC0, DK_ENC1, DK_ENC2, DK_ATT32, DK_ATT16, DK_RECON0, DK_RECON1, DK_RECON2, DK_TAIL };
+enum DirectKind : int { DK_HEAD, DK_HEAD_ENC0, DK_ENC0, DK_ENC1, DK_ENC2, DK_ATT32, DK_ATT16, DK_RECON0, DK_RECON1, DK_RECON2, DK_TAIL };
 
 struct DirectArgs {
     // input
@@ -19,6 +19,7 @@ struct DirectArgs {
     // weights
     const float *w = nullptr;                   // [9][CIN][COUT]
     const float *bias = nullptr;                // [COUT]
+    const float *w0 = nullptr, *b0 = nullptr;   // fused head (2->8): [9][2][8], [8]
     int act = ACT_NONE;
     // output
     int n_img = 0, Hout = 0, Wout = 0;
