@@ -216,6 +216,45 @@ int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float 
 }
 
 // ---------------------------------------------------------------------------------------------
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) (models/submodules.py:290) on a split tensor:
+// src index = max(0, (dst + 0.5) / 2 - 0.5), neighbours clamped; same association as ATen's upsample_bilinear2d.
+__global__ void __launch_bounds__(256)
+k_upsample2x(const __nv_bfloat16 *__restrict__ src, size_t s_plane, int n_img, int H, int W, int C,
+             __nv_bfloat16 *__restrict__ dst, size_t d_plane)
+{
+    const int G = C / 8, H2 = 2 * H, W2 = 2 * W;
+    const size_t total = (size_t)n_img * H2 * W2 * G;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % G);
+        const size_t p = i / G;
+        const int x = (int)(p % W2), y = (int)((p / W2) % H2), img = (int)(p / ((size_t)W2 * H2));
+        const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f), fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const size_t b0 = ((size_t)img * H + y0) * W, b1 = ((size_t)img * H + y1) * W;
+        float v00[8], v01[8], v10[8], v11[8], o[8];
+        load8(src + (b0 + x0) * C + g * 8, s_plane, v00);
+        load8(src + (b0 + x1) * C + g * 8, s_plane, v01);
+        load8(src + (b1 + x0) * C + g * 8, s_plane, v10);
+        load8(src + (b1 + x1) * C + g * 8, s_plane, v11);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            o[e] = (1.0f - ly) * ((1.0f - lx) * v00[e] + lx * v01[e]) + ly * ((1.0f - lx) * v10[e] + lx * v11[e]);
+        store8(dst + p * C + g * 8, d_plane, o);
+    }
+}
+int upsample2x(const SplitTensor &src, int n_img, const SplitTensor &dst, cudaStream_t st)
+{
+    ESR_REQUIRE(dst.H == 2 * src.H && dst.W == 2 * src.W && dst.C == src.C && src.C % 8 == 0, "upsample2x: bad shapes");
+    const size_t total = (size_t)n_img * dst.H * dst.W * (src.C / 8);
+    k_upsample2x<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(src.base, src.plane(), n_img, src.H, src.W, src.C,
+                                                                            dst.base, dst.plane());
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_copy_split(const __nv_bfloat16 *__restrict__ src, size_t s_plane, const int *__restrict__ src_img, int n_img, size_t per_img8,
              __nv_bfloat16 *__restrict__ dst, size_t d_plane)

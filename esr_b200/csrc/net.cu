@@ -29,7 +29,7 @@ static_assert(P_COUNT == 68, "reference state_dict has 68 tensors");
 
 // tensor-core layers
 enum TL : int { T_PM0, T_PM1, T_LF1, T_LF2, T_LF3, T_GX, T_GZR, T_GO, T_GF, T_OF0, T_OF1, T_COM, T_DCN, T_CB0, T_CB1,
-                T_KER, T_DF0, T_DF1, T_DN0, T_DN1, T_AT0, T_COUNT };
+                T_KER, T_DF0, T_DF1, T_DN0, T_DN1, T_AT0, T_RC0, T_COUNT };
 struct TLInfo { int w, b, w2, b2, cout, cin, k; };
 static const TLInfo TLS[T_COUNT] = {
     {P_PM0_W, P_PM0_B, -1, -1, 64, 128, 3}, {P_PM1_W, P_PM1_B, -1, -1, 1, 64, 3},
@@ -39,7 +39,7 @@ static const TLInfo TLS[T_COUNT] = {
     {P_COM_W, P_COM_B, -1, -1, 216, 64, 3}, {P_DCN_W, P_DCN_B, -1, -1, 64, 64, 3}, {P_CB0_W, P_CB0_B, -1, -1, 64, 128, 3},
     {P_CB1_W, P_CB1_B, -1, -1, 64, 64, 3}, {P_KER_W, P_KER_B, -1, -1, 2, 64, 1}, {P_DF0_W, P_DF0_B, -1, -1, 64, 128, 3},
     {P_DF1_W, P_DF1_B, -1, -1, 64, 64, 3}, {P_DN0_W, P_DN0_B, -1, -1, 64, 192, 3}, {P_DN1_W, P_DN1_B, -1, -1, 64, 64, 3},
-    {P_AT0_W, P_AT0_B, -1, -1, 1, 64, 3},
+    {P_AT0_W, P_AT0_B, -1, -1, 1, 64, 3}, {P_RC0_W, P_RC0_B, -1, -1, 32, 64, 3},
 };
 // direct (CUDA-core) layers
 enum DL : int { D_HEAD, D_ENC0, D_ENC1, D_ENC2, D_AT1, D_AT2, D_RC0, D_RC1, D_RC2, D_TAIL, D_COUNT };
@@ -92,14 +92,14 @@ struct Net {
     size_t ws_bytes;
     // tensors
     SplitTensor t_e0, t_e1, F, t_pm0, t_cat, t_lf1, t_lf2, ltc, xc, hs, rh, tp;
-    SplitTensor t_of0, t_off, cols, aligned, t_cb0, feat, ycat, t_df0, fused, t_dn0, x0, pre0, x1, pre1, x2, pre2, x3;
+    SplitTensor t_of0, t_off, cols, aligned, t_cb0, feat, ycat, t_df0, fused, t_dn0, x0, pre0, up0, x1, pre1, x2, pre2, x3;
     float *maps, *zbuf, *om, *sk, *mx, *ck, *att0, *att1, *att2;
     // index maps (device)
     int *m_fr, *m_pairA, *m_pairB, *m_ltc5, *m_lf3res, *m_f0, *m_fm, *m_dn[3], *m_gf_f, *m_gf_r, *m_gfres;
     std::vector<int *> m_gx, m_gh;     // per GRU step (Wn * N of them)
     // prepared tensor-core launches
     ConvTCArgs c_pm0, c_pm1, c_lf1, c_lf2, c_lf3, c_gx, c_gf, c_of0, c_of1, c_com, c_dcn, c_cb0, c_cb1, c_ker, c_df0, c_df1,
-        c_dn0, c_dn1, c_at0;
+        c_dn0, c_dn1, c_at0, c_rc0;
     std::vector<ConvTCArgs> c_gzr, c_go;
     DirectArgs d[D_COUNT];
 };
@@ -158,6 +158,7 @@ static size_t layout(Net &n)
     n.t_dn0 = A.split(VB, h, w, 64);
     n.x0 = A.split(VB, h, w, 64);
     n.pre0 = A.split(VB, h, w, 64);
+    n.up0 = A.split(VB, 2 * h, 2 * w, 64);
     n.x1 = A.split(VB, 2 * h, 2 * w, 32);
     n.pre1 = A.split(VB, 2 * h, 2 * w, 32);
     n.x2 = A.split(VB, 4 * h, 4 * w, 16);
@@ -322,6 +323,9 @@ static int build(Net &n, cudaStream_t st)
     if ((rc = conv_tc_prepare(d, &n.c_dn1))) return rc;
     d = mk(n, T_AT0, FR, ACT_SIGMOID); d.src[0] = n.F; d.out_f32 = n.att0; d.out_f32_C = 1;
     if ((rc = conv_tc_prepare(d, &n.c_at0))) return rc;
+    // recons[0] (64 -> 32 at 2h x 2w) on the tensor cores: bilinear x2 is materialised once, then a plain 3x3 conv
+    d = mk(n, T_RC0, VB, ACT_RELU); d.src[0] = n.up0; d.out = n.x1;
+    if ((rc = conv_tc_prepare(d, &n.c_rc0))) return rc;
 
     // ---------------- direct launches
     const ParamLayout &Lp = param_layout();
@@ -430,7 +434,8 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     RUNT(n.c_dn1);
     // ---- scale aggregation + reconstruction x3 (model.py:253-291), tail (model.py:337)
     RUN(scale_aggregate(n.x0, n.F, n.att0, n.m_fr, VB, N, n.pre0, st));
-    RUND(DK_RECON0, D_RC0, n.d[D_RC0]);
+    RUN(upsample2x(n.pre0, VB, n.up0, st));
+    RUNT(n.c_rc0);
     RUN(scale_aggregate(n.x1, n.t_e1, n.att1, n.m_fr, VB, N, n.pre1, st));
     RUND(DK_RECON1, D_RC1, n.d[D_RC1]);
     RUN(scale_aggregate(n.x2, n.t_e0, n.att2, n.m_fr, VB, N, n.pre2, st));

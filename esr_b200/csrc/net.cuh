@@ -47,6 +47,8 @@ int attn_apply(const SplitTensor &aligned, const SplitTensor &mid_src, const int
 // out[b] = x[b] + mean_n(feats[f] * att[f]), f = fidx[b*N+n] (or b*N+n)     (models/model.py:259-267)
 int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float *att, const int *fidx, int B, int N,
                     const SplitTensor &out, cudaStream_t st);
+// bilinear x2 (align_corners=False) of a split tensor (models/submodules.py:290)
+int upsample2x(const SplitTensor &src, int n_img, const SplitTensor &dst, cudaStream_t st);
 int copy_split(const SplitTensor &src, const int *src_img, int n_img, const SplitTensor &dst, cudaStream_t st);
 
 // ---- deformable sampling (dcn.cu): columns[img][y][x][tap*64 + c] = bilinear(feat[c], y-1+i+off_h, x-1+j+off_w) * mask
