@@ -15,16 +15,18 @@
 
 namespace esr {
 
-// Output tile geometry.  Tiled layers: a thread owns 2x2 pixels x C channels, C = 16 (COUT=64) or 8; the COUT/C channel
-// groups are spread over warps, so narrower layers get wider tiles (more pixels per block, 16-byte stores everywhere).
-template <int COUT> struct DcGeom {
+// Output tile geometry.  Tiled layers: a thread owns TPW x 2 pixels x C channels, C = 16 (COUT=64) or 8; the COUT/C
+// channel groups are spread over warps, so narrower layers get wider tiles (more pixels per block, 16-byte stores
+// everywhere).  TPW = 4 doubles the reuse of every weight read where the larger patch still fits in shared memory.
+template <int COUT, int TPW> struct DcGeom {
     static constexpr bool TILED = COUT >= 8;
     static constexpr int C = COUT >= 64 ? 16 : (COUT >= 8 ? 8 : COUT);
     static constexpr int CG = TILED ? COUT / C : 1;
     static constexpr int PG = 256 / CG;                         // pixel groups (threads per channel group)
-    static constexpr int TW = TILED ? (CG == 4 ? 16 : 32) : 16; // output tile width
-    static constexpr int TH = TILED ? (CG == 1 ? 32 : 16) : 16; // output tile height
-    static_assert(!TILED || (TW / 2) * (TH / 2) == PG, "tile / thread mapping mismatch");
+    static constexpr int GW = PG == 64 ? 8 : 16;                // pixel groups along x
+    static constexpr int GH = PG / GW;
+    static constexpr int TW = TILED ? GW * TPW : 16;            // output tile width
+    static constexpr int TH = TILED ? GH * 2 : 16;              // output tile height
 };
 
 __device__ __forceinline__ void dc_unpack8(const uint4 h, const uint4 l, float (&o)[8])
@@ -72,10 +74,10 @@ __device__ __forceinline__ float dc_act(float v, int act)
     return v;
 }
 
-template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF>
+template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF, int TPW>
 __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
 {
-    using G = DcGeom<COUT>;
+    using G = DcGeom<COUT, TPW>;
     constexpr int PW = (G::TW - 1) * STRIDE + 3;          // patch width actually needed
     constexpr int PH = (G::TH - 1) * STRIDE + 3;          // patch height
     constexpr int PP = (PW + 3) / 4 * 4;                  // row pitch (floats)
@@ -190,24 +192,26 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
     __syncthreads();
 
     if constexpr (TILED) {
-        // ---- stage 2 (tiled): thread = (cout group cg, pixel group pg): 2x2 pixels x C channels
+        // ---- stage 2 (tiled): thread = (cout group cg, pixel group pg): TPW x 2 pixels x C channels
         constexpr int C = G::C;
-        constexpr int WIN = STRIDE + 3;                   // input window edge for a 2x2 output patch
+        constexpr int NP = TPW * 2;                       // pixels per thread
+        constexpr int WINW = (TPW - 1) * STRIDE + 3;      // input window of the thread's pixel patch
+        constexpr int WINH = STRIDE + 3;
         const int cg = tid / G::PG, pg = tid % G::PG;     // cg is warp-uniform -> weight reads are broadcasts
-        const int gy = pg / (G::TW / 2), gx = pg % (G::TW / 2);
-        float acc[4][C];
+        const int gy = pg / G::GW, gx = pg % G::GW;
+        float acc[NP][C];
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int p = 0; p < NP; ++p)
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[p][c] = bsm[cg * C + c];
 #pragma unroll 1
         for (int ci = 0; ci < CIN; ++ci) {
-            float win[WIN][WIN];
-            const float *pb = patch + (ci * PH + gy * 2 * STRIDE) * PP + gx * 2 * STRIDE;
+            float win[WINH][WINW];
+            const float *pb = patch + (ci * PH + gy * 2 * STRIDE) * PP + gx * TPW * STRIDE;
 #pragma unroll
-            for (int r = 0; r < WIN; ++r)
+            for (int r = 0; r < WINH; ++r)
 #pragma unroll
-                for (int s = 0; s < WIN; ++s) win[r][s] = pb[r * PP + s];
+                for (int s = 0; s < WINW; ++s) win[r][s] = pb[r * PP + s];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -217,8 +221,8 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
 #pragma unroll
                     for (int c = 0; c < C; ++c) wv[c] = wp[c];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const float xv = win[(p >> 1) * STRIDE + ky][(p & 1) * STRIDE + kx];
+                    for (int p = 0; p < NP; ++p) {
+                        const float xv = win[(p / TPW) * STRIDE + ky][(p % TPW) * STRIDE + kx];
 #pragma unroll
                         for (int c = 0; c < C; ++c) acc[p][c] = fmaf(xv, wv[c], acc[p][c]);
                     }
@@ -226,8 +230,8 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
         }
         // ---- stage 3
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int oy = oy0 + gy * 2 + (p >> 1), ox = ox0 + gx * 2 + (p & 1);
+        for (int p = 0; p < NP; ++p) {
+            const int oy = oy0 + gy * 2 + p / TPW, ox = ox0 + gx * TPW + p % TPW;
             if (oy >= a.Hout || ox >= a.Wout) continue;
             float v[C];
 #pragma unroll
@@ -274,10 +278,10 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
     }
 }
 
-template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF>
+template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF, int TPW = 2>
 static int launch_direct(const DirectArgs &a, cudaStream_t st)
 {
-    using G = DcGeom<COUT>;
+    using G = DcGeom<COUT, TPW>;
     constexpr int PW = (G::TW - 1) * STRIDE + 3;
     constexpr int PH = (G::TH - 1) * STRIDE + 3;
     constexpr int PP = (PW + 3) / 4 * 4;
@@ -287,12 +291,12 @@ static int launch_direct(const DirectArgs &a, cudaStream_t st)
     static_assert(smem <= 227 * 1024, "direct conv tile does not fit in shared memory");
     static bool attr_set = false;
     if (!attr_set) {
-        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_direct<CIN, COUT, STRIDE, UPS, INF, OUTF>,
+        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_direct<CIN, COUT, STRIDE, UPS, INF, OUTF, TPW>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     dim3 grid((a.Wout + G::TW - 1) / G::TW, (a.Hout + G::TH - 1) / G::TH, a.n_img);
-    k_conv_direct<CIN, COUT, STRIDE, UPS, INF, OUTF><<<grid, 256, smem, st>>>(a);
+    k_conv_direct<CIN, COUT, STRIDE, UPS, INF, OUTF, TPW><<<grid, 256, smem, st>>>(a);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
@@ -303,13 +307,13 @@ int conv_direct(DirectKind kind, const DirectArgs &a, cudaStream_t st)
     case DK_HEAD:    return launch_direct<2, 8, 1, false, FMT_NCHW_F32, FMT_SPLIT>(a, st);
     case DK_HEAD_ENC0: return launch_direct<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT>(a, st);
     case DK_ENC0:    return launch_direct<8, 16, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);
-    case DK_ENC1:    return launch_direct<16, 32, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);
+    case DK_ENC1:    return launch_direct<16, 32, 2, false, FMT_SPLIT, FMT_SPLIT, 4>(a, st);
     case DK_ENC2:    return launch_direct<32, 64, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);
     case DK_ATT32:   return launch_direct<32, 1, 1, false, FMT_SPLIT, FMT_NHWC_F32>(a, st);
     case DK_ATT16:   return launch_direct<16, 1, 1, false, FMT_SPLIT, FMT_NHWC_F32>(a, st);
     case DK_RECON0:  return launch_direct<64, 32, 1, true, FMT_SPLIT, FMT_SPLIT>(a, st);
-    case DK_RECON1:  return launch_direct<32, 16, 1, true, FMT_SPLIT, FMT_SPLIT>(a, st);
-    case DK_RECON2:  return launch_direct<16, 8, 1, true, FMT_SPLIT, FMT_SPLIT>(a, st);
+    case DK_RECON1:  return launch_direct<32, 16, 1, true, FMT_SPLIT, FMT_SPLIT, 4>(a, st);
+    case DK_RECON2:  return launch_direct<16, 8, 1, true, FMT_SPLIT, FMT_SPLIT, 4>(a, st);
     case DK_TAIL:    return launch_direct<8, 2, 1, false, FMT_SPLIT, FMT_NCHW_F32>(a, st);
     }
     set_error("conv_direct: unknown kind %d", (int)kind);
