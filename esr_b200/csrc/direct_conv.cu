@@ -17,7 +17,8 @@ namespace esr {
 
 // Output tile geometry.  Tiled layers: a thread owns TPW x 2 pixels x C channels, C = 16 (COUT=64) or 8; the COUT/C
 // channel groups are spread over warps, so narrower layers get wider tiles (more pixels per block, 16-byte stores
-// everywhere).  TPW = 4 doubles the reuse of every weight read where the larger patch still fits in shared memory.
+// everywhere).  TPW = 4 (more weight reuse per thread) is implemented but measured SLOWER on B200 for enc1 / recons[1,2]
+// (fewer resident blocks per SM), so every layer currently uses TPW = 2.
 template <int COUT, int TPW> struct DcGeom {
     static constexpr bool TILED = COUT >= 8;
     static constexpr int C = COUT >= 64 ? 16 : (COUT >= 8 ? 8 : COUT);
@@ -307,13 +308,13 @@ int conv_direct(DirectKind kind, const DirectArgs &a, cudaStream_t st)
     case DK_HEAD:    return launch_direct<2, 8, 1, false, FMT_NCHW_F32, FMT_SPLIT>(a, st);
     case DK_HEAD_ENC0: return launch_direct<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT>(a, st);
     case DK_ENC0:    return launch_direct<8, 16, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);
-    case DK_ENC1:    return launch_direct<16, 32, 2, false, FMT_SPLIT, FMT_SPLIT, 4>(a, st);
+    case DK_ENC1:    return launch_direct<16, 32, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);
     case DK_ENC2:    return launch_direct<32, 64, 2, false, FMT_SPLIT, FMT_SPLIT>(a, st);
     case DK_ATT32:   return launch_direct<32, 1, 1, false, FMT_SPLIT, FMT_NHWC_F32>(a, st);
     case DK_ATT16:   return launch_direct<16, 1, 1, false, FMT_SPLIT, FMT_NHWC_F32>(a, st);
     case DK_RECON0:  return launch_direct<64, 32, 1, true, FMT_SPLIT, FMT_SPLIT>(a, st);
-    case DK_RECON1:  return launch_direct<32, 16, 1, true, FMT_SPLIT, FMT_SPLIT, 4>(a, st);
-    case DK_RECON2:  return launch_direct<16, 8, 1, true, FMT_SPLIT, FMT_SPLIT, 4>(a, st);
+    case DK_RECON1:  return launch_direct<32, 16, 1, true, FMT_SPLIT, FMT_SPLIT>(a, st);
+    case DK_RECON2:  return launch_direct<16, 8, 1, true, FMT_SPLIT, FMT_SPLIT>(a, st);
     case DK_TAIL:    return launch_direct<8, 2, 1, false, FMT_SPLIT, FMT_NCHW_F32>(a, st);
     }
     set_error("conv_direct: unknown kind %d", (int)kind);
