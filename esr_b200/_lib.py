@@ -70,6 +70,8 @@ SIGNATURES.update({
 
 SIGNATURES.update({
     "esr_dcn_v2_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "esr_dcn_v2_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "esr_dcn_v2_backward": (c_int, [c_void_p] * 6 + [c_int] * 10 + [c_void_p] * 6 + [c_size_t, c_void_p]),
     "esr_dcn_v2_forward": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p, c_void_p, c_size_t, c_void_p]),
 })
 

@@ -111,6 +111,13 @@ k_om_from_nchw(const float *__restrict__ offset, const float *__restrict__ mask,
         om[i] = c < 144 ? offset[((size_t)b * 144 + c) * HW + pix] : mask[((size_t)b * 72 + (c - 144)) * HW + pix];
     }
 }
+int om_from_nchw(const float *offset, const float *mask, int B, int HW, float *om, cudaStream_t st)
+{
+    const size_t total = (size_t)B * HW * 216;
+    k_om_from_nchw<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(offset, mask, B, HW, om);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
 } // namespace esr
 
 using namespace esr;
@@ -154,9 +161,7 @@ extern "C" int esr_dcn_v2_forward(const float *input, const float *weight, const
     float *om = (float *)(ws + o_om);
     int rc;
     if ((rc = split_from_nchw(input, B, 64, H, W, feat.base, st))) return rc;
-    const size_t total = (size_t)B * H * W * 216;
-    k_om_from_nchw<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(offset, mask, B, H * W, om);
-    ESR_LAUNCH_CHECK();
+    if ((rc = om_from_nchw(offset, mask, B, H * W, om, st))) return rc;
     if ((rc = dcn_columns(feat, nullptr, om, B, cols, st))) return rc;
     if ((rc = pack_conv_weight(weight, 64, 64, 3, ws + o_w, st))) return rc;
     ESR_CUDA_CHECK(cudaMemcpyAsync(ws + o_b, bias, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));

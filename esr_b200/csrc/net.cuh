@@ -56,4 +56,7 @@ int copy_split(const SplitTensor &src, const int *src_img, int n_img, const Spli
 int dcn_columns(const SplitTensor &feat, const int *feat_img, const float *om, int n_img, const SplitTensor &cols /*C=576*/,
                 cudaStream_t st);
 
+// offset [B,144,HW] + mask [B,72,HW] (reference NCHW) -> om [B*HW, 216]
+int om_from_nchw(const float *offset, const float *mask, int B, int HW, float *om, cudaStream_t st);
+
 } // namespace esr

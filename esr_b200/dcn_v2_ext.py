@@ -4,7 +4,7 @@
 
 dcn_v2_forward keeps the reference's 14-argument signature (models/DCNv2/dcn_v2.py:27-42) and its behaviour:
 contiguous fp32 CUDA tensors in the NCHW layout, a freshly allocated output, errors as RuntimeError.
-dcn_v2_backward is not implemented in round 1 (inference only) and raises.
+dcn_v2_backward returns the reference's five gradients (fp32 atomics for grad_input, like the reference).
 """
 import torch
 
@@ -40,5 +40,25 @@ def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride
     return out
 
 
-def dcn_v2_backward(*args):
-    raise NotImplementedError("esr_b200: dcn_v2_backward is not implemented yet (round 1 covers inference)")
+def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                    dilation_h, dilation_w, deformable_group):
+    """-> [grad_input, grad_offset, grad_mask, grad_weight, grad_bias]  (models/DCNv2/dcn_v2.py:50-66)"""
+    if not input.is_cuda:
+        raise RuntimeError("Not compiled with CPU support")
+    for t in (input, weight, bias, offset, mask, grad_output):
+        if t.dtype != torch.float32:
+            raise RuntimeError("dcn_v2_backward: expected float32 tensors")
+    B, C, H, W = input.shape
+    Co = weight.shape[0]
+    L = _lib.lib()
+    args = [t.contiguous() for t in (input, weight, bias, offset, mask, grad_output)]
+    outs = [torch.empty_like(args[0]), torch.empty_like(args[3]), torch.empty_like(args[4]), torch.empty_like(args[1]),
+            torch.empty_like(args[2])]
+    with torch.cuda.device(input.device):
+        nbytes = L.esr_dcn_v2_backward_workspace_bytes(B, H, W)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=input.device)
+        rc = L.esr_dcn_v2_backward(*[_lib.ptr(t) for t in args], B, C, H, W, Co, kernel_h, stride_h, pad_h, dilation_h,
+                                   deformable_group, *[_lib.ptr(t) for t in outs], _lib.ptr(ws), nbytes, _lib.stream_ptr())
+    if rc != 0:
+        raise RuntimeError("dcn_v2_backward: " + L.esr_last_error().decode())
+    return outs

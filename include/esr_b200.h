@@ -178,6 +178,15 @@ int esr_net_set_states(esr_net_t net, const float *states, esr_stream_t stream);
  * anything else returns ESR_EUNSUPPORTED.
  * --------------------------------------------------------------------------------------------- */
 size_t esr_dcn_v2_workspace_bytes(int B, int H, int W);
+/* Replaces: models/DCNv2/src/dcn_v2.h:29-50 dcn_v2_backward -> src/cuda/dcn_v2_cuda.cu:97-216 (+ the col2im / coord kernels
+ * src/cuda/dcn_v2_im2col_cuda.cu:197-327), called from models/DCNv2/dcn_v2.py:50.  Same five gradients, reference layouts:
+ * grad_input [B,C,H,W], grad_offset [B,dg*18,H,W], grad_mask [B,dg*9,H,W], grad_weight [Co,C,3,3], grad_bias [Co].
+ * grad_input uses fp32 atomics like the reference (summation order is not deterministic). */
+size_t esr_dcn_v2_backward_workspace_bytes(int B, int H, int W);
+int esr_dcn_v2_backward(const float *input, const float *weight, const float *bias, const float *offset, const float *mask,
+                        const float *grad_output, int B, int C, int H, int W, int Co, int kernel, int stride, int pad,
+                        int dilation, int deformable_group, float *grad_input, float *grad_offset, float *grad_mask,
+                        float *grad_weight, float *grad_bias, void *workspace, size_t workspace_bytes, esr_stream_t stream);
 int esr_dcn_v2_forward(const float *input, const float *weight, const float *bias, const float *offset, const float *mask,
                        int B, int C, int H, int W, int Co, int kernel, int stride, int pad, int dilation,
                        int deformable_group, float *output, void *workspace, size_t workspace_bytes, esr_stream_t stream);
