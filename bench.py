@@ -33,6 +33,8 @@ WORKLOADS = {
     "cfg2": dict(scale=2, L=8, lr=(128, 128), B=8, desc="2x SR, seq_len=8, LR 128x128 synthetic events, batch=8/GPU"),
     # BASELINE.json configs[2]: 4x SR, seq_len=8, LR 128x128, batch=32 over 8 GPUs = 4 per GPU
     "cfg3": dict(scale=4, L=8, lr=(128, 128), B=4, desc="4x SR, seq_len=8, LR 128x128 synthetic events, batch=4/GPU"),
+    # BASELINE.json configs[3]: 4x SR, seq_len=16, LR 256x256, batch=16 over 8 GPUs = 2 per GPU (long-sequence stress)
+    "cfg4": dict(scale=4, L=16, lr=(256, 256), B=2, desc="4x SR, seq_len=16, LR 256x256 synthetic events, batch=2/GPU"),
 }
 EVENTS_PER_FRAME = 2048          # shipped WINDOW (config/train_ours_enfssyn.yml:9)
 FLOP_PER_HR_PIXEL = 184.7e3

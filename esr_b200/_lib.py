@@ -28,6 +28,7 @@ SIGNATURES = {
     "esr_expand_count": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "esr_expand_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_i64]),
     "esr_expand_emit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p, c_int, c_int,
                                 c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

@@ -266,10 +266,14 @@ __device__ __forceinline__ float linspace_f32(double t0, double t1, unsigned int
     return (float)__dadd_rn(__dmul_rn((double)j, step), t0);
 }
 
+// Compact keys (cnt2event, linear timestamps, max count <= 255): the timestamp of event (n, j) is one of the few values
+// float32(linspace(0,1,n)[j]); `rank[n*rank_m + j]` is its index among the sorted distinct values, so the sort key is
+// ceil(log2(#distinct)) bits instead of 30 and one or two radix passes replace four.  The item then carries
+// rank | j << 16 | negative << 31 and the timestamp is re-derived from (n, j) when the row is written.
 __global__ void __launch_bounds__(256)
 k_expand_emit(const float *__restrict__ vals, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offs,
               int64_t total_slots, int C, int HW, int kind, int mode, const double *__restrict__ rnd,
-              Item *__restrict__ items)
+              const uint16_t *__restrict__ rank, int rank_m, Item *__restrict__ items)
 {
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total_slots;
          s += (int64_t)gridDim.x * blockDim.x) {
@@ -288,6 +292,16 @@ k_expand_emit(const float *__restrict__ vals, const uint32_t *__restrict__ count
             t0f = (float)__dadd_rn(__ddiv_rn((double)c, (double)C), __ddiv_rn(1.0, (double)(100 * C)));
             t1f = (float)__ddiv_rn((double)(c + 1), (double)C);
             t0 = (double)t0f; t1 = (double)t1f;
+        }
+        if (rank) {                                                   // compact-key path (kind 0, mode 0, n <= rank_m)
+            const uint16_t *rk = rank + (size_t)n * rank_m;
+            for (uint32_t j = 0; j < n; ++j) {
+                Item it;
+                it.tkey = (uint32_t)rk[j] | (j << 16) | (negbit << 31);
+                it.slot = (uint32_t)s;
+                items[(size_t)off + j] = it;
+            }
+            continue;
         }
         for (uint32_t j = 0; j < n; ++j) {
             float t;
@@ -313,14 +327,15 @@ constexpr int RS_WARPS = 8;
 constexpr int RS_IPT = 8;                                  // rounds of 32 consecutive items per warp
 constexpr int RS_TILE = RS_WARPS * 32 * RS_IPT;            // 2048 items per block
 
-__device__ __forceinline__ uint32_t rs_digit(const Item &it, int pass, uint32_t slots_per_sample)
+// key_passes = 4 for raw fp32 timestamp bits, 1 or 2 for compact ranks (low 16 bits of tkey)
+__device__ __forceinline__ uint32_t rs_digit(const Item &it, int pass, int key_passes, uint32_t slots_per_sample)
 {
-    if (pass < 4) return ((it.tkey & 0x7fffffffu) >> (8 * pass)) & 255u;
+    if (pass < key_passes) return ((it.tkey & 0x7fffffffu) >> (8 * pass)) & 255u;
     return (it.slot / slots_per_sample) & 255u;
 }
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
-k_radix_hist(const Item *__restrict__ items, int64_t n, int pass, uint32_t slots_per_sample,
+k_radix_hist(const Item *__restrict__ items, int64_t n, int pass, int key_passes, uint32_t slots_per_sample,
              uint32_t *__restrict__ hist /*[256][nblocks]*/)
 {
     __shared__ uint32_t h[256];
@@ -329,7 +344,7 @@ k_radix_hist(const Item *__restrict__ items, int64_t n, int pass, uint32_t slots
     const int64_t base = (int64_t)blockIdx.x * RS_TILE;
     for (int k = threadIdx.x; k < RS_TILE; k += RS_WARPS * 32) {
         const int64_t i = base + k;
-        if (i < n) atomicAdd(&h[rs_digit(items[i], pass, slots_per_sample)], 1u);
+        if (i < n) atomicAdd(&h[rs_digit(items[i], pass, key_passes, slots_per_sample)], 1u);
     }
     __syncthreads();
     hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
@@ -337,10 +352,10 @@ k_radix_hist(const Item *__restrict__ items, int64_t n, int pass, uint32_t slots
 
 // Final pass writes the padded [B, maxlen, 4] rows directly instead of items.
 __global__ void __launch_bounds__(RS_WARPS * 32)
-k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, int64_t n, int pass, uint32_t slots_per_sample,
+k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, int64_t n, int pass, int key_passes, uint32_t slots_per_sample,
                 const uint32_t *__restrict__ hist_scanned /*[256][nblocks] exclusive*/,
                 int final_pass, float *__restrict__ rows, const int64_t *__restrict__ sample_start, int64_t maxlen,
-                int W, int H)
+                int W, int H, const uint32_t *__restrict__ counts /*non-null: compact keys*/)
 {
     __shared__ uint32_t cnt[RS_WARPS][256];     // per-warp digit counters -> then per-warp bases
     __shared__ uint32_t gbase[256];
@@ -357,7 +372,7 @@ k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, int64_t n, 
         const int64_t i = wbase + r * 32 + lane;
         const bool valid = i < n;
         if (valid) it[r] = in[i];
-        dig[r] = valid ? rs_digit(it[r], pass, slots_per_sample) : 0xffffffffu;
+        dig[r] = valid ? rs_digit(it[r], pass, key_passes, slots_per_sample) : 0xffffffffu;
         // rank among the lanes of this round holding the same digit
         const uint32_t peers = __match_any_sync(0xffffffffu, dig[r]);
         const uint32_t before = __popc(peers & ((1u << lane) - 1u));
@@ -391,7 +406,8 @@ k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, int64_t n, 
         const uint32_t x = in_s % (uint32_t)W, y = (in_s / (uint32_t)W) % (uint32_t)H;
         float4 row;
         row.x = (float)x; row.y = (float)y;
-        row.z = __uint_as_float(it[r].tkey & 0x7fffffffu);
+        row.z = counts ? linspace_f32(0.0, 1.0, counts[slot], (it[r].tkey >> 16) & 255u)
+                       : __uint_as_float(it[r].tkey & 0x7fffffffu);
         row.w = (it[r].tkey >> 31) ? -1.0f : 1.0f;
         const int64_t local = (int64_t)pos - sample_start[b];
         reinterpret_cast<float4 *>(rows)[(size_t)b * maxlen + local] = row;
@@ -513,10 +529,13 @@ extern "C" size_t esr_expand_workspace_bytes(int B, int P, int C, int H, int W, 
 }
 
 extern "C" int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P, int C, int H, int W, int kind,
-                               int mode, const double *rnd, const int32_t *active_host, const int64_t *start_host,
+                               int mode, const double *rnd, const uint16_t *rank_table, int rank_m, int rank_bits,
+                               const int32_t *active_host, const int64_t *start_host,
                                int64_t total_events, int64_t maxlen, float *out, void *workspace,
                                size_t workspace_bytes, esr_stream_t stream)
 {
+    ESR_REQUIRE(!rank_table || (kind == 0 && mode == 0 && rank_m >= 1 && rank_m <= 255 && rank_bits >= 1 && rank_bits <= 16),
+                "esr_expand_emit: compact keys need cnt2event, linear timestamps and max count <= 255");
     ESR_REQUIRE(vals && counts && active_host && start_host && out && workspace, "esr_expand_emit: null pointer");
     ESR_REQUIRE(B > 0 && B <= 256 && (mode == 0 || mode == 1), "esr_expand_emit: bad B/mode");
     ESR_REQUIRE(mode == 0 || rnd, "esr_expand_emit: mode 1 needs the random stream");
@@ -544,20 +563,21 @@ extern "C" int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P
         int64_t bx = ceil_div64(slots, 256 * 2);
         const int64_t cap = (int64_t)dev_info().sm_count * 32;
         if (bx > cap) bx = cap;
-        k_expand_emit<<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, slots, C, H * W, kind, mode, rnd, items[0]);
+        k_expand_emit<<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, slots, C, H * W, kind, mode, rnd, rank_table, rank_m, items[0]);
         ESR_LAUNCH_CHECK();
     }
     const int64_t nblk = ceil_div64(total_events, RS_TILE);
-    const int npass = B > 1 ? 5 : 4;
+    const int key_passes = rank_table ? (rank_bits + 7) / 8 : 4;
+    const int npass = key_passes + (B > 1 ? 1 : 0);
     int cur = 0;
     for (int p = 0; p < npass; ++p) {
-        k_radix_hist<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], total_events, p, (uint32_t)S, hist);
+        k_radix_hist<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], total_events, p, key_passes, (uint32_t)S, hist);
         ESR_LAUNCH_CHECK();
         rc = exclusive_scan_u32(hist, hist, 256 * nblk, histws, st);
         if (rc) return rc;
         const int fin = p == npass - 1;
-        k_radix_scatter<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], items[cur ^ 1], total_events, p, (uint32_t)S,
-                                                                  hist, fin, out, d_start, maxlen, W, H);
+        k_radix_scatter<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], items[cur ^ 1], total_events, p, key_passes, (uint32_t)S,
+                                                                  hist, fin, out, d_start, maxlen, W, H, rank_table ? counts : nullptr);
         ESR_LAUNCH_CHECK();
         cur ^= 1;
     }

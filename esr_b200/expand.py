@@ -19,6 +19,24 @@ def _numpy_stream(n):
     return np.random.random([int(n)])
 
 
+_RANK_CACHE = {}
+
+
+def _rank_table(m, dev):
+    """Compact sort keys for cnt2event/linear timestamps: rank of float32(np.linspace(0,1,n)[j]) among all distinct
+    timestamps that counts 1..m can produce (numpy's own linspace = the reference's arithmetic).  Cached per (m, device)."""
+    key = (m, str(dev))
+    if key not in _RANK_CACHE:
+        vals = [np.linspace(0, 1, n).astype(np.float32) for n in range(1, m + 1)]
+        uniq = np.unique(np.concatenate(vals))
+        table = np.zeros((m + 1, m), dtype=np.uint16)
+        for n in range(1, m + 1):
+            table[n, :n] = np.searchsorted(uniq, vals[n - 1])
+        bits = max(1, int(np.ceil(np.log2(max(2, len(uniq))))))
+        _RANK_CACHE[key] = (torch.from_numpy(table.view(np.int16)).to(dev), bits)
+    return _RANK_CACHE[key]
+
+
 def expand(vals, kind, mode):
     """vals: CUDA fp32 tensor [B,2,H,W] (kind 0) or [B,P,C,H,W] / [B,C,H,W] (kind 1) -> CUDA fp32 [B,maxlen,4]."""
     if not vals.is_cuda:
@@ -72,10 +90,17 @@ def expand(vals, kind, mode):
             rnd = torch.from_numpy(_numpy_stream(total)).to(dev)
         else:
             np.random.seed(123)                     # visible side effect of every reference call
+        rank, rank_m, rank_bits = None, 0, 0
+        mx = int(h[:, 3][active].max()) if active.any() else 0
+        if kind == 0 and mode == 0 and 1 <= mx <= 255:
+            rank_m = 1 << max(0, (mx - 1).bit_length())            # few distinct table sizes: 1, 2, 4, ... 256
+            rank_m = min(rank_m, 255)
+            rank, rank_bits = _rank_table(rank_m, dev)
         nbytes = L.esr_expand_workspace_bytes(B, P, C, H, W, total)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         act32 = np.ascontiguousarray(active.astype(np.int32))
         _lib.check(L.esr_expand_emit(_lib.ptr(vals), _lib.ptr(counts), B, P, C, H, W, kind, int(mode), _lib.ptr(rnd),
+                                     _lib.ptr(rank), rank_m, rank_bits,
                                      act32.ctypes.data_as(ctypes.c_void_p), start.ctypes.data_as(ctypes.c_void_p),
                                      total, maxlen, _lib.ptr(out), _lib.ptr(ws), nbytes, st), "esr_expand_emit")
     return out

@@ -83,9 +83,13 @@ int esr_scatter_voxel(float *xs, float *ys, const float *ts, const float *ps, in
 int esr_expand_count(const float *vals, int B, int P, int C, int H, int W, int kind, int64_t *stats, uint32_t *counts,
                      esr_stream_t stream);
 size_t esr_expand_workspace_bytes(int B, int P, int C, int H, int W, int64_t total_events);
+/* rank_table (optional, device uint16 [(rank_m+1) * rank_m]): compact sort keys for cnt2event with linear timestamps and
+ * max per-pixel count rank_m <= 255 -- rank_table[n*rank_m + j] = index of float32(linspace(0,1,n)[j]) among the sorted
+ * distinct timestamps, rank_bits = bits needed; NULL = sort on the raw fp32 timestamp bits (always valid). */
 int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P, int C, int H, int W, int kind, int mode,
-                    const double *rnd, const int32_t *active_host, const int64_t *start_host, int64_t total_events,
-                    int64_t maxlen, float *out, void *workspace, size_t workspace_bytes, esr_stream_t stream);
+                    const double *rnd, const uint16_t *rank_table, int rank_m, int rank_bits, const int32_t *active_host,
+                    const int64_t *start_host, int64_t total_events, int64_t maxlen, float *out, void *workspace,
+                    size_t workspace_bytes, esr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core convolution (tcgen05, TMA-tiled implicit GEMM), layer-level entry point.

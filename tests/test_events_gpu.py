@@ -170,3 +170,17 @@ def test_stack_and_voxel_golden(golden_events, dev):
         want = g[f"stk{i}_voxel"]
         assert np.abs(vox - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), i
         assert np.array_equal(xs.numpy(), g[f"stk{i}_voxel_xs_after"])
+
+
+@pytest.mark.parametrize("peak", [1, 2, 3, 16, 17, 128, 255, 256, 300])
+def test_cnt2event_compact_and_raw_sort_keys(dev, peak):
+    """Counts up to 255 take the compact-rank sort keys, larger ones the raw fp32 timestamp bits; both must equal the
+    oracle bit for bit (ties between pixels with different counts are where a wrong rank table would show)."""
+    from esr_b200 import cnt2event as c2e
+    from oracle import events as oe
+    rng = np.random.default_rng(peak)
+    cnt = rng.integers(0, min(peak, 6) + 1, (2, 2, 12, 10)).astype(np.float32)
+    cnt[0, 0, 3, 4] = peak
+    cnt[1, 1, 0, 0] = max(1, peak - 1)
+    got = c2e.cnt2event_cuda(torch.from_numpy(cnt).to(dev), 0).cpu().numpy()
+    assert np.array_equal(got, oe.cnt2event(cnt, 0))
