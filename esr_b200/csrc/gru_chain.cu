@@ -1,0 +1,260 @@
+// gru_chain.cu -- the whole bidirectional ConvGRU recurrence of a sequence batch in ONE cooperative kernel.
+//
+// Reference: TimePropagation.global_time_corre (models/model.py:91-124) calling RecurrentConvLayer / ConvGRU
+// (models/submodules.py:340-344, 496-514) once per frame and direction, window after window with the state carried.
+// Per step:  z, r = sigmoid(conv3x3(cat(x, h)))   (update | reset gates, one N = 128 GEMM)
+//            o    = tanh(conv3x3(cat(x, h * r)))  (N = 64 GEMM),   h' = h (1 - z) + o z
+// The two convolutions of a step and consecutive steps are separated by true grid-wide dependencies (3x3 halos), so
+// the per-launch version (tc_conv.cu, 2 launches per step) spends most of each ~25 us launch on launch latency,
+// TMEM allocation, barrier set-up, pipeline fill and drain.  Here the CTAs stay resident: TMEM, mbarriers and tensor
+// maps are set up once, every phase (2 per step) is a tcgen05 implicit GEMM over the CTA's tile(s) followed by the
+// fused gate epilogue, and phases are separated by a grid barrier (co-residency guaranteed by the cooperative launch).
+//
+// Memory ordering across a phase boundary: the epilogue writes h*r / h' with generic-proxy stores; the next phase reads
+// them through TMA (async proxy) from OTHER CTAs.  Writers: stores -> fence.proxy.async -> __threadfence -> barrier
+// arrive (release); readers: barrier wait (acquire) -> fence.proxy.async -> TMA.  z and h are re-read only by the thread
+// that wrote them (same tile -> same CTA -> same TMEM lane in every phase).
+#include "tc_common.cuh"
+#include "net.cuh"
+
+namespace esr {
+
+constexpr int GC_THREADS = 192;
+
+struct GruChainArgs {
+    CUtensorMap amap_xc, amap_hs, amap_rh;      // 5-D maps (64 ch, W, H, img, plane), box (64, TW, TH, 1, 1)
+    CUtensorMap bmap_zr, bmap_go;               // packed weights: update|reset (N=128), out gate (N=64); 18 K-blocks each
+    const float *bias_zr, *bias_go;             // [128], [64]
+    __nv_bfloat16 *hs; size_t hs_plane;         // state slots: image = slot * 2B + j
+    __nv_bfloat16 *rh; size_t rh_plane;         // h * r, [2B, H, W, 64]
+    float *zbuf;                                // update gate, fp32 [2B, H, W, 64]
+    unsigned int *barrier;                      // grid barrier counter (zeroed before the launch)
+    int B, N, nsteps, H, W, TW, TH, tiles_x, tiles_y, stages;
+};
+
+__device__ __forceinline__ void gc_grid_barrier(unsigned int *counter, unsigned int target)
+{
+    asm volatile("fence.proxy.async;" ::: "memory");      // this thread's generic stores before later async-proxy reads
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_constant__ GruChainArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t B_MAX = 128u * 128u;                               // one plane of the N = 128 weight tile
+    constexpr uint32_t STAGE = 2u * TC_A_BYTES + 2u * B_MAX;              // 64 KB
+    const uint32_t bar_base = smem_base + (uint32_t)a.stages * STAGE;
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages, bar_accum = bar_base + 16u * a.stages;
+    const uint32_t tmem_slot = bar_accum + 8u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B2 = 2 * a.B;
+    const int tiles_per_img = a.tiles_x * a.tiles_y, n_tiles = B2 * tiles_per_img;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // pipeline state, private to each role, identical sequences on every role
+    uint32_t ps = 0, pph = 0;          // producer stage / phase bit
+    uint32_t ms = 0, mph = 0;          // MMA stage / phase bit
+    uint32_t acc_ph = 0;               // accumulator barrier parity (flips once per tile)
+
+    for (int p = 0; p < 2 * a.nsteps; ++p) {
+        const int g = p >> 1, which = p & 1;              // which: 0 = update|reset gates, 1 = candidate + blend
+        const int w_idx = g / a.N, s_idx = g - w_idx * a.N;
+        const int npad = which == 0 ? 128 : 64;
+        const uint32_t b_bytes = (uint32_t)npad * 128u;
+        const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+        const CUtensorMap *bmap = which == 0 ? &a.bmap_zr : &a.bmap_go;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int img = tile / tiles_per_img;         // j in [0, 2B): j < B forward direction, else time-reversed
+            const int trem = tile - img * tiles_per_img;
+            const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+            // frame of this image at this step: forward reads window slot s, reverse reads slot N-1-s (model.py:95-96,107-108)
+            const int bb = img < a.B ? img : img - a.B;
+            const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
+            const int hs_img = g * B2 + img;
+            if (warp == 0) {
+                if (lane == 0) {
+                    for (int kb = 0; kb < 18; ++kb) {
+                        const int src = kb / 9, tap = kb - src * 9;
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
+                        mbar_expect_tx(bar_full + 8u * ps, stage_bytes);
+                        const uint32_t st = smem_base + ps * STAGE;
+                        const CUtensorMap *am = src == 0 ? &a.amap_xc : (which == 0 ? &a.amap_hs : &a.amap_rh);
+                        const int simg = src == 0 ? xc_img : (which == 0 ? hs_img : img);
+                        tma_load_5d(am, bar_full + 8u * ps, st, 0, x0 + dx, y0 + dy, simg, 0);
+                        tma_load_5d(am, bar_full + 8u * ps, st + TC_A_BYTES, 0, x0 + dx, y0 + dy, simg, 1);
+                        tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, 0, kb);
+                        tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + kb);
+                        if (++ps == (uint32_t)a.stages) { ps = 0; pph ^= 1u; }
+                    }
+                }
+            } else if (warp == 1) {
+                if (lane == 0) {
+                    const uint32_t idesc = umma_idesc(TC_BLOCK_M, npad);
+                    for (int kb = 0; kb < 18; ++kb) {
+                        mbar_wait(bar_full + 8u * ms, mph);
+                        tc_fence_after();
+                        const uint32_t st = smem_base + ms * STAGE;
+                        const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                            const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                            umma_bf16(tmem_base, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+                            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+                        }
+                        umma_commit(bar_empty + 8u * ms);
+                        if (++ms == (uint32_t)a.stages) { ms = 0; mph ^= 1u; }
+                    }
+                    umma_commit(bar_accum);
+                }
+            } else {
+                const int quad = warp & 3;
+                const int m = quad * 32 + lane;
+                const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+                const bool valid = (y < a.H) && (x < a.W);
+                const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);   // within a 2B-image tensor
+                const __nv_bfloat16 *h_prev = a.hs + ((size_t)g * B2 * a.H * a.W + pix) * 64;
+                mbar_wait(bar_accum, acc_ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+                for (int n0 = 0; n0 < npad; n0 += 32) {
+                    uint32_t raw[32];
+                    tmem_ld32(taddr + (uint32_t)n0, raw);
+                    if (valid) {
+                        float v[32];
+                        const float4 *bp = reinterpret_cast<const float4 *>((which == 0 ? a.bias_zr : a.bias_go) + n0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b = bp[q];
+                            v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+                            v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+                            v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+                            v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+                        }
+                        if (which == 0) {
+                            act32(v, ACT_SIGMOID);
+                            if (n0 < 64) {                                      // update gate z (fp32)
+                                float4 *zp = reinterpret_cast<float4 *>(a.zbuf + pix * 64 + n0);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) zp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            } else {                                            // reset gate r -> h * r
+                                float h[32];
+                                load_split32(h_prev + (n0 - 64), a.hs_plane, h);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] *= h[j];
+                                store_split32(a.rh + pix * 64 + (n0 - 64), a.rh_plane, v);
+                            }
+                        } else {                                                // h' = h (1 - z) + tanh(.) z
+                            float h[32];
+                            load_split32(h_prev + n0, a.hs_plane, h);
+                            const float4 *zp = reinterpret_cast<const float4 *>(a.zbuf + pix * 64 + n0);
+                            float4 zq[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) zq[q] = zp[q];
+                            act32(v, ACT_TANH);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float zz[4] = {zq[q].x, zq[q].y, zq[q].z, zq[q].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int j = 4 * q + e;
+                                    v[j] = h[j] * (1.0f - zz[e]) + v[j] * zz[e];
+                                }
+                            }
+                            __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64;
+                            store_split32(h_new + n0, a.hs_plane, v);
+                        }
+                    }
+                    __syncwarp();
+                }
+                tc_fence_before();
+            }
+            acc_ph ^= 1u;
+            // the next tile's MMAs overwrite the accumulator: wait until this tile's epilogue has read it
+            __syncthreads();
+            tc_fence_after();
+        }
+        gc_grid_barrier(a.barrier, (unsigned int)(p + 1) * gridDim.x);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct GruChainPlan {
+    GruChainArgs args;
+    int grid;
+    size_t smem;
+};
+
+int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const void *w_zr,
+                      const float *b_zr, const void *w_go, const float *b_go, unsigned int *barrier, int B, int N,
+                      int nsteps, void **plan_out)
+{
+    GruChainPlan *p = new GruChainPlan();
+    GruChainArgs &a = p->args;
+    memset(&a, 0, sizeof(a));
+    const int H = xc.H, W = xc.W;
+    int TW = W >= 24 ? 32 : (W >= 12 ? 16 : 8);
+    int TH = TC_BLOCK_M / TW;
+    int rc;
+    if ((rc = tc_make_amap(xc, TW, TH, &a.amap_xc)) || (rc = tc_make_amap(hs, TW, TH, &a.amap_hs)) ||
+        (rc = tc_make_amap(rh, TW, TH, &a.amap_rh)) || (rc = tc_make_bmap(w_zr, 128, 18, 128, &a.bmap_zr)) ||
+        (rc = tc_make_bmap(w_go, 64, 18, 64, &a.bmap_go))) { delete p; return rc; }
+    a.bias_zr = b_zr; a.bias_go = b_go;
+    a.hs = hs.base; a.hs_plane = hs.plane(); a.rh = rh.base; a.rh_plane = rh.plane(); a.zbuf = zbuf; a.barrier = barrier;
+    a.B = B; a.N = N; a.nsteps = nsteps; a.H = H; a.W = W; a.TW = TW; a.TH = TH;
+    a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH;
+    a.stages = 3;
+    p->smem = 1024 + (size_t)a.stages * (2 * TC_A_BYTES + 2 * 128 * 128) + 16 * a.stages + 64;
+    ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    int per_sm = 0;
+    ESR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gru_chain, GC_THREADS, p->smem));
+    if (per_sm < 1) { set_error("gru_chain: kernel does not fit on an SM"); delete p; return ESR_EUNSUPPORTED; }
+    const int n_tiles = 2 * B * a.tiles_x * a.tiles_y;
+    const int max_grid = dev_info().sm_count * per_sm;
+    p->grid = n_tiles < max_grid ? n_tiles : max_grid;
+    *plan_out = p;
+    return ESR_OK;
+}
+
+int gru_chain_launch(void *plan, cudaStream_t st)
+{
+    GruChainPlan *p = (GruChainPlan *)plan;
+    ESR_CUDA_CHECK(cudaMemsetAsync(p->args.barrier, 0, sizeof(unsigned int), st));
+    void *kargs[] = {(void *)&p->args};
+    ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain, dim3(p->grid), dim3(GC_THREADS), kargs, p->smem, st));
+    esr::count_launch();
+    return ESR_OK;
+}
+
+void gru_chain_destroy(void *plan) { delete (GruChainPlan *)plan; }
+
+} // namespace esr

@@ -9,6 +9,7 @@
 // Frame/image ordering everywhere: image = b * N + n.  Fuse images: j = k * B + b (k-th non-middle frame).
 // GRU step images: j < B forward direction (sample j), j >= B time-reversed direction (sample j - B).
 #include "net.cuh"
+#include <cstdlib>
 #include <vector>
 #include <string>
 
@@ -101,6 +102,8 @@ struct Net {
     ConvTCArgs c_pm0, c_pm1, c_lf1, c_lf2, c_lf3, c_gx, c_gf, c_of0, c_of1, c_com, c_dcn, c_cb0, c_cb1, c_ker, c_df0, c_df1,
         c_dn0, c_dn1, c_at0, c_rc0;
     std::vector<ConvTCArgs> c_gzr, c_go;
+    void *gru_plan = nullptr;          // cooperative whole-chain kernel (gru_chain.cu); nullptr = per-step launches
+    unsigned int *gru_barrier = nullptr;
     DirectArgs d[D_COUNT];
 };
 
@@ -173,6 +176,7 @@ static size_t layout(Net &n)
     n.m_gf_f = ints(VN); n.m_gf_r = ints(VN); n.m_gfres = ints(VN);
     n.m_gx.resize(nsteps); n.m_gh.resize(nsteps);
     for (int s = 0; s < nsteps; ++s) { n.m_gx[s] = ints(2 * B); n.m_gh[s] = ints(2 * B); }
+    n.gru_barrier = (unsigned int *)A.take(256);
     return A.off;
 }
 
@@ -293,6 +297,13 @@ static int build(Net &n, cudaStream_t st)
         d.epi_mode = EPI_GRU_OUT; d.h_prev = view_imgs(n.hs, g * 2 * B); d.z_buf = n.zbuf; d.out = view_imgs(n.hs, (g + 1) * 2 * B);
         if ((rc = conv_tc_prepare(d, &n.c_go[g]))) return rc;
     }
+    // the same chain as ONE cooperative kernel (default); ESR_GRU_PER_STEP=1 keeps the two-launches-per-step path
+    static const bool per_step = getenv("ESR_GRU_PER_STEP") != nullptr;
+    if (!per_step) {
+        if ((rc = gru_chain_prepare(n.xc, n.hs, n.rh, n.zbuf, pw(n, T_GZR), pb(n, T_GZR), pw(n, T_GO), pb(n, T_GO), n.gru_barrier,
+                                    B, N, nsteps, &n.gru_plan)))
+            return rc;
+    }
     d = mk(n, T_GF, VN, ACT_RELU); d.n_src = 2; d.src[0] = n.hs; d.src_img[0] = n.m_gf_f; d.src[1] = n.hs; d.src_img[1] = n.m_gf_r;
     d.res_mode = RES_POST_ACT; d.res = n.F; d.res_img = n.m_gfres; d.out = n.tp;
     if ((rc = conv_tc_prepare(d, &n.c_gf))) return rc;
@@ -407,9 +418,15 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     // ---- TimePropagation.global_time_corre: bidirectional ConvGRU (model.py:91-124); the only serial part:
     //      window after window, step after step, both directions batched as 2B images
     RUNT(n.c_gx);
-    for (int g = 0; g < nsteps; ++g) {
-        RUNT(n.c_gzr[g]);
-        RUNT(n.c_go[g]);
+    if (n.gru_plan) {
+        double fl = 0.0;
+        for (int g = 0; g < nsteps; ++g) fl += tc_flops(n.c_gzr[g]) + tc_flops(n.c_go[g]);
+        RUNC(PC_TC, fl, gru_chain_launch(n.gru_plan, st));
+    } else {
+        for (int g = 0; g < nsteps; ++g) {
+            RUNT(n.c_gzr[g]);
+            RUNT(n.c_go[g]);
+        }
     }
     RUNT(n.c_gf);
     // carried states: the last slot becomes slot 0 of the next call
@@ -528,6 +545,7 @@ extern "C" int esr_net_create(esr_net_t *out, int B, int N, int L, int H, int W,
 
 extern "C" int esr_net_destroy(esr_net_t net)
 {
+    if (net && ((Net *)net)->gru_plan) gru_chain_destroy(((Net *)net)->gru_plan);
     delete (Net *)net;
     return ESR_OK;
 }

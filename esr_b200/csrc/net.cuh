@@ -56,6 +56,13 @@ int copy_split(const SplitTensor &src, const int *src_img, int n_img, const Spli
 int dcn_columns(const SplitTensor &feat, const int *feat_img, const float *om, int n_img, const SplitTensor &cols /*C=576*/,
                 cudaStream_t st);
 
+// ---- the ConvGRU recurrence of a whole sequence batch in one cooperative kernel (gru_chain.cu)
+int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const void *w_zr,
+                      const float *b_zr, const void *w_go, const float *b_go, unsigned int *barrier, int B, int N,
+                      int nsteps, void **plan_out);
+int gru_chain_launch(void *plan, cudaStream_t st);
+void gru_chain_destroy(void *plan);
+
 // offset [B,144,HW] + mask [B,72,HW] (reference NCHW) -> om [B*HW, 216]
 int om_from_nchw(const float *offset, const float *mask, int B, int HW, float *om, cudaStream_t st);
 

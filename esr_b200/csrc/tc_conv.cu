@@ -186,6 +186,9 @@ static int make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap
     return ESR_OK;
 }
 
+int tc_make_amap(const SplitTensor &t, int BW, int BH, CUtensorMap *out) { return make_amap(t, BW, BH, out); }
+int tc_make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap *out) { return make_bmap(w, npad, nkb, box_rows, out); }
+
 static size_t tc_smem_bytes(int npad, int stages)
 {
     return 1024 + (size_t)stages * (2 * TC_A_BYTES + 2 * (size_t)npad * 128) + 16 * (size_t)stages + 64;

@@ -70,6 +70,9 @@ static inline size_t tc_packed_weight_bytes(int cout, int cin_total, int ntaps)
 // Builds tensor maps + launch geometry.  H, W taken from src[0].
 int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args);
 int conv_tc_launch(const ConvTCArgs &args, cudaStream_t st);
+// tensor-map builders (shared with gru_chain.cu)
+int tc_make_amap(const SplitTensor &t, int box_w, int box_h, CUtensorMap *out);
+int tc_make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap *out);
 // tc_conv3.cu
 bool conv_tc3_plan(int npad, int *a_stages, int *b_stages);
 int conv_tc3_launch(const ConvTCArgs &args, cudaStream_t st);
