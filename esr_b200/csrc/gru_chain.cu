@@ -19,7 +19,7 @@
 
 namespace esr {
 
-constexpr int GC_THREADS = 192;
+constexpr int GC_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quadrant)
 
 struct GruChainArgs {
     CUtensorMap amap_xc, amap_hs, amap_rh;      // 5-D maps (64 ch, W, H, img, plane), box (64, TW, TH, 1, 1)
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
                     umma_commit(bar_accum);
                 }
             } else {
-                const int quad = warp & 3;
+                const int quad = warp & 3, half = (warp - 2) >> 2;   // two warps share a lane quadrant and split the columns
                 const int m = quad * 32 + lane;
                 const int y = y0 + m / a.TW, x = x0 + m % a.TW;
                 const bool valid = (y < a.H) && (x < a.W);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
                 mbar_wait(bar_accum, acc_ph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-                for (int n0 = 0; n0 < npad; n0 += 32) {
+                for (int n0 = half * (npad / 2); n0 < (half + 1) * (npad / 2); n0 += 32) {
                     uint32_t raw[32];
                     tmem_ld32(taddr + (uint32_t)n0, raw);
                     if (valid) {
