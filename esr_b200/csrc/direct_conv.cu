@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
     constexpr int IPP = (PW + 2 + 3) / 4 * 4;             // fused head: input patch pitch
     float *inp = bsm + ((COUT + 3) / 4 * 4);              // fused head: [2][PH+2][IPP] input patch, then [9][2][8] + [8]
     float *w0s = inp + 2 * (PH + 2) * IPP;
-    float *lrs = inp;                                     // upsampling layers: low-resolution source patch (same region)
 
     const int img = blockIdx.z;
     const int oy0 = blockIdx.y * G::TH, ox0 = blockIdx.x * G::TW;
@@ -158,54 +157,37 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
         const __nv_bfloat16 *hi = a.in_split;
         const size_t plane = a.in_plane;
         constexpr int Q = CIN / 8;
-        if constexpr (!UPS) {
-            for (int i = tid; i < Q * PW * PH; i += 256) {
-                const int pp = i % (PW * PH), q = i / (PW * PH);        // lanes <-> pixels: conflict-free smem writes
-                const int px = pp % PW, py = pp / PW;
-                const int y = iy0 + py, x = ix0 + px;
-                float v[8];
+        for (int i = tid; i < Q * PW * PH; i += 256) {
+            const int pp = i % (PW * PH), q = i / (PW * PH);            // lanes <-> pixels: conflict-free smem writes
+            const int px = pp % PW, py = pp / PW;
+            const int y = iy0 + py, x = ix0 + px;
+            float v[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.0f;
-                if (y >= 0 && y < Hc && x >= 0 && x < Wc)
+            for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+            if (y >= 0 && y < Hc && x >= 0 && x < Wc) {
+                if constexpr (!UPS) {
                     dc_ld8(hi + (((size_t)simg * a.Hin + y) * a.Win + x) * CIN + q * 8, plane, v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) patch[((q * 8 + e) * PH + py) * PP + px] = v[e];
-            }
-        } else {
-            // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) (submodules.py:290) fused into the
-            // patch fill: src = max(0, (dst + 0.5) * 0.5 - 0.5), neighbours clamped to the image.  The low-resolution
-            // source patch is staged once (one 16-byte load per source pixel and channel octet, rows/cols clamped to
-            // the image), then the upsampled patch is interpolated from shared memory.
-            constexpr int LH = PH / 2 + 2, LW = PW / 2 + 2, LP = (LW + 3) / 4 * 4;
-            float *lr = lrs;                                             // [CIN][LH][LP]
-            const int by = (int)floorf(((float)iy0 + 0.5f) * 0.5f - 0.5f), bx = (int)floorf(((float)ix0 + 0.5f) * 0.5f - 0.5f);
-            for (int i = tid; i < Q * LW * LH; i += 256) {
-                const int pp = i % (LW * LH), q = i / (LW * LH);
-                const int lx = pp % LW, ly = pp / LW;
-                const int sy = min(max(by + ly, 0), a.Hin - 1), sx = min(max(bx + lx, 0), a.Win - 1);
-                float v[8];
-                dc_ld8(hi + (((size_t)simg * a.Hin + sy) * a.Win + sx) * CIN + q * 8, plane, v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) lr[((q * 8 + e) * LH + ly) * LP + lx] = v[e];
-            }
-            __syncthreads();
-            for (int i = tid; i < CIN * PW * PH; i += 256) {
-                const int px = i % PW, py = (i / PW) % PH, ci = i / (PW * PH);
-                const int y = iy0 + py, x = ix0 + px;
-                float v = 0.0f;
-                if (y >= 0 && y < Hc && x >= 0 && x < Wc) {
+                } else {
+                    // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) (submodules.py:290):
+                    // src = max(0, (dst + 0.5) * 0.5 - 0.5); neighbours clamped to the image
                     const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f);
                     const float fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
                     const int y_0 = (int)fy, x_0 = (int)fx;
                     const int y_1 = min(y_0 + 1, a.Hin - 1), x_1 = min(x_0 + 1, a.Win - 1);
-                    const float wy = fy - (float)y_0, wx = fx - (float)x_0;
-                    const float *l0 = lr + (ci * LH + (y_0 - by)) * LP, *l1 = lr + (ci * LH + (y_1 - by)) * LP;
-                    // ATen: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
-                    v = (1.0f - wy) * ((1.0f - wx) * l0[x_0 - bx] + wx * l0[x_1 - bx]) +
-                        wy * ((1.0f - wx) * l1[x_0 - bx] + wx * l1[x_1 - bx]);
+                    const float ly = fy - (float)y_0, lx = fx - (float)x_0;
+                    const size_t b0 = ((size_t)simg * a.Hin + y_0) * a.Win, b1 = ((size_t)simg * a.Hin + y_1) * a.Win;
+                    float v00[8], v01[8], v10[8], v11[8];
+                    dc_ld8(hi + (b0 + x_0) * CIN + q * 8, plane, v00);
+                    dc_ld8(hi + (b0 + x_1) * CIN + q * 8, plane, v01);
+                    dc_ld8(hi + (b1 + x_0) * CIN + q * 8, plane, v10);
+                    dc_ld8(hi + (b1 + x_1) * CIN + q * 8, plane, v11);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)   // ATen: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11)
+                        v[e] = (1.0f - ly) * ((1.0f - lx) * v00[e] + lx * v01[e]) + ly * ((1.0f - lx) * v10[e] + lx * v11[e]);
                 }
-                patch[(ci * PH + py) * PP + px] = v;
             }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) patch[((q * 8 + e) * PH + py) * PP + px] = v[e];
         }
     }
     __syncthreads();
@@ -305,8 +287,7 @@ static int launch_direct(const DirectArgs &a, cudaStream_t st)
     constexpr int PH = (G::TH - 1) * STRIDE + 3;
     constexpr int PP = (PW + 3) / 4 * 4;
     constexpr int IPP = (PW + 2 + 3) / 4 * 4;
-    constexpr int LH = PH / 2 + 2, LW = PW / 2 + 2, LP = (LW + 3) / 4 * 4;
-    constexpr size_t extra = INF == FMT_HEAD_FUSED ? (size_t)(2 * (PH + 2) * IPP + 9 * 2 * 8 + 8) : (UPS ? (size_t)CIN * LH * LP : 0);
+    constexpr size_t extra = INF == FMT_HEAD_FUSED ? (size_t)(2 * (PH + 2) * IPP + 9 * 2 * 8 + 8) : 0;
     constexpr size_t smem = sizeof(float) * ((size_t)(CIN * PH * PP + 9 * CIN * COUT + (COUT + 3) / 4 * 4) + extra);
     static_assert(smem <= 227 * 1024, "direct conv tile does not fit in shared memory");
     static bool attr_set = false;
