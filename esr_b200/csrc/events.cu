@@ -47,71 +47,9 @@ k_scatter_cnt(float *__restrict__ xs, float *__restrict__ ys, const float *__res
     }
 }
 
-// Cluster variant for frames with many more events than pixels: the 2xHxW image of a frame is tiled over the shared
-// memory of a thread-block cluster (CS CTAs, slice = ceil(2HW / CS) floats each).  Every CTA streams its share of the
-// events with coalesced loads and routes each contribution to the owning CTA's shared-memory tile with a distributed-
-// shared-memory reduction (red.shared::cluster.add.f32) instead of an L2 atomic; after a cluster barrier each CTA adds
-// its tile to the global image (one atomic per non-zero pixel and cluster).  Same arithmetic and quirks as above.
-// Shared-memory fp32 adds compile to compare-and-swap loops, far too slow across the cluster, so the tiles hold uint32
-// and take the (overwhelmingly common) integer contributions -- ps = +-1 gives ps*ps = 1 -- with a native integer
-// reduction; the rare non-integer contribution goes straight to the global image with the usual fp32 atomic.
-__device__ __forceinline__ void dsm_red_add(uint32_t local_smem_addr, uint32_t cta_rank, uint32_t v)
-{
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
-    asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
-}
-__device__ __forceinline__ bool small_int(float v) { return v == floorf(v) && v <= 1024.0f; }
-
-__global__ void __launch_bounds__(512)
-k_scatter_cnt_dsm(float *__restrict__ xs, float *__restrict__ ys, const float *__restrict__ ps,
-                  const int64_t *__restrict__ frame_off, int64_t n_single, int H, int W, float w_lr, float w_hr, float h_lr,
-                  float h_hr, int do_lift, int writeback, float *__restrict__ out, int cs, int slice, int clusters_per_frame)
-{
-    extern __shared__ uint32_t tile[];
-    uint32_t crank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const int cluster_id = blockIdx.x / cs;
-    const int f = cluster_id / clusters_per_frame, cidx = cluster_id % clusters_per_frame;
-    for (int i = threadIdx.x; i < slice; i += blockDim.x) tile[i] = 0u;
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-
-    const int64_t beg = frame_off ? frame_off[f] : 0, end = frame_off ? frame_off[f + 1] : n_single;
-    const float fW = (float)W, fH = (float)H;
-    const int HW = H * W;
-    const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
-    const int64_t stride = (int64_t)clusters_per_frame * cs * blockDim.x;
-    for (int64_t i = beg + ((int64_t)cidx * cs + crank) * blockDim.x + threadIdx.x; i < end; i += stride) {
-        float x = xs[i], y = ys[i];
-        const float p = ps[i];
-        if (do_lift) {
-            x = __fmul_rn(__fdiv_rn(x, w_lr), w_hr);
-            y = __fmul_rn(__fdiv_rn(y, h_lr), h_hr);
-        }
-        const bool oor = (x >= fW) | (x < 0.0f) | (y >= fH) | (y < 0.0f);
-        float vpos = __fmul_rn(p, p < 0.0f ? 0.0f : p);
-        const float vneg = __fmul_rn(p, p > 0.0f ? 0.0f : p);
-        if (oor) { x = 0.0f; y = 0.0f; vpos = 0.0f; }
-        const int pix = (int)((long long)y * W + (long long)x);
-        if (vpos != 0.0f) {
-            if (small_int(vpos)) { const int o = pix / slice; dsm_red_add(tile_base + 4u * (uint32_t)(pix - o * slice), (uint32_t)o, (uint32_t)vpos); }
-            else atomicAdd(out + (size_t)f * 2 * HW + pix, vpos);
-        }
-        if (vneg != 0.0f) {
-            const int q = HW + pix;
-            if (small_int(vneg)) { const int o = q / slice; dsm_red_add(tile_base + 4u * (uint32_t)(q - o * slice), (uint32_t)o, (uint32_t)vneg); }
-            else atomicAdd(out + (size_t)f * 2 * HW + q, vneg);
-        }
-        if (writeback && oor) { xs[i] = 0.0f; ys[i] = 0.0f; }
-    }
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    float *img = out + (size_t)f * 2 * HW;
-    const int base = (int)crank * slice;
-    for (int i = threadIdx.x; i < slice && base + i < 2 * HW; i += blockDim.x) {
-        const uint32_t v = tile[i];
-        if (v != 0u) atomicAdd(img + base + i, (float)v);
-    }
-}
+// Measured dead end (profiles/r1_notes.md): tiling the image over the shared memory of an 8/16-CTA cluster and routing
+// the contributions with distributed-shared-memory reductions (red.shared::cluster.add.u32) is exact but 3x SLOWER than
+// the L2 atomics above (48 vs 142 G events/s at 1e8 events onto 256x256); shared-memory fp32 adds compile to CAS loops.
 
 // events_to_image (encodings.py:243-268): one image, raw weights ps, out-of-range events dropped and
 // xs/ys/ps zeroed in place when writeback is set.
@@ -506,37 +444,6 @@ extern "C" int esr_scatter_cnt(float *xs, float *ys, const float *ps, const int6
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     ESR_REQUIRE(F <= 65535, "esr_scatter_cnt: at most 65535 frames per call");
-    // Dense frames (>= 8 events per image cell on average): distributed-shared-memory tiles instead of L2 atomics.
-    {
-        static const bool no_dsm = getenv("ESR_SCATTER_NO_DSM") != nullptr;
-        const int64_t cells = 2ll * H * W;
-        int cs = cells <= 8 * 49152 ? 8 : 16;                       // 8 x 192 KB portable, 16 needs the non-portable size
-        const int64_t slice = (cells + cs - 1) / cs;
-        if (!no_dsm && n_max_frame >= 8 * cells && slice * 4 <= 200 * 1024) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                ESR_CUDA_CHECK(cudaFuncSetAttribute(k_scatter_cnt_dsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                ESR_CUDA_CHECK(cudaFuncSetAttribute(k_scatter_cnt_dsm, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-                attr_set = true;
-            }
-            int cpf = dev_info().sm_count / cs / F;                // clusters per frame: fill the GPU once
-            if (cpf < 1) cpf = 1;
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)(F * cpf * cs));
-            cfg.blockDim = dim3(512);
-            cfg.dynamicSmemBytes = (size_t)slice * 4;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            ESR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_scatter_cnt_dsm, xs, ys, ps, frame_off, n_max_frame, H, W, (float)lift_w_lr,
-                                              (float)lift_w_hr, (float)lift_h_lr, (float)lift_h_hr, do_lift,
-                                              (int)(writeback && !do_lift), out, cs, (int)slice, cpf));
-            esr::count_launch();
-            return ESR_OK;
-        }
-    }
     dim3 grid((unsigned)bx, (unsigned)F);
     k_scatter_cnt<<<grid, 256, 0, st>>>(xs, ys, ps, frame_off, n_max_frame, H, W, (float)lift_w_lr, (float)lift_w_hr,
                                          (float)lift_h_lr, (float)lift_h_hr, do_lift, writeback && !do_lift, out);

@@ -184,3 +184,28 @@ def test_cnt2event_compact_and_raw_sort_keys(dev, peak):
     cnt[1, 1, 0, 0] = max(1, peak - 1)
     got = c2e.cnt2event_cuda(torch.from_numpy(cnt).to(dev), 0).cpu().numpy()
     assert np.array_equal(got, oe.cnt2event(cnt, 0))
+
+
+@pytest.mark.parametrize("H,W,n", [(32, 32, 60000), (64, 48, 200000), (128, 128, 400000)])
+def test_dense_frames_scatter_vs_oracle(dev, H, W, n):
+    """Dense frames (many events per image cell, heavy atomic contention): unit polarities are integer sums and must be
+    bit-exact; non-integer weights are fp32 atomics in arbitrary order (tolerance)."""
+    from esr_b200 import encodings as enc
+    from oracle import events as oe
+    rng = np.random.default_rng(H + n)
+    xs = rng.integers(-3, W + 3, n).astype(np.float32)
+    ys = rng.integers(-3, H + 3, n).astype(np.float32)
+    ps = rng.choice(np.array([-1, 1], np.float32), n)
+    off = np.array([0, n // 3, n], np.int64)                     # two frames, both dense
+    got = enc.encode_frames(torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev), torch.from_numpy(ps).to(dev),
+                            torch.from_numpy(off).to(dev), hr_size=(H, W), n_max_frame=int(n - n // 3)).cpu().numpy()
+    for f in range(2):
+        a, b = off[f], off[f + 1]
+        want = oe.events_to_channels(xs[a:b].copy(), ys[a:b].copy(), ps[a:b], (H, W))
+        assert np.array_equal(got[f], want), f
+    ps2 = ps.copy()
+    ps2[::5] *= 1.5                                              # ps*ps = 2.25: not an integer
+    got = enc.encode_frames(torch.from_numpy(xs).to(dev), torch.from_numpy(ys).to(dev), torch.from_numpy(ps2).to(dev),
+                            torch.from_numpy(off).to(dev), hr_size=(H, W), n_max_frame=int(n - n // 3)).cpu().numpy()
+    want = oe.events_to_channels(xs[:off[1]].copy(), ys[:off[1]].copy(), ps2[:off[1]], (H, W))
+    np.testing.assert_allclose(got[0], want, rtol=1e-5, atol=1e-3)
