@@ -30,6 +30,7 @@ class EventSRPipeline:
         self._graph = None
         self._graph_sr = None
         self._host_events = None
+        self._copy_stream = None
         self.sequence_plan = True
         self.graph_launches = 0
 
@@ -75,6 +76,45 @@ class EventSRPipeline:
             sr = self._windows()
         events = expand(sr, 0, mode)
         return sr, events
+
+    # ---- asynchronous end-to-end API: the D2H of step i overlaps the H2D + compute of step i+1 --------------------
+    @torch.no_grad()
+    def submit_host(self, xs_h, ys_h, ps_h, off_h, n_max_frame, mode=0):
+        """Enqueue one batch (pinned host buffers in) and return a handle; `collect(handle)` yields the host event
+        tensor.  Compute runs on the current stream; the result is copied out on a side stream into one of two pinned
+        buffers, so up to two batches can be in flight."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._host_pool = [None, None]
+            self._slot = 0
+        xs = xs_h.to(self.dev, non_blocking=True)
+        ys = ys_h.to(self.dev, non_blocking=True)
+        ps = ps_h.to(self.dev, non_blocking=True)
+        off = off_h.to(self.dev, non_blocking=True)
+        _, events = self.run_device(xs, ys, ps, off, n_max_frame, mode)
+        slot = self._slot
+        self._slot ^= 1
+        n = events.numel()
+        buf = self._host_pool[slot]
+        if buf is None or buf.numel() < n:
+            buf = torch.empty((int(n * 1.25) + 1024,), dtype=torch.float32).pin_memory()
+            self._host_pool[slot] = buf
+        host = buf[:n].view(events.shape)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            host.copy_(events, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        events.record_stream(self._copy_stream)
+        return (host, done)
+
+    @staticmethod
+    def collect(handle):
+        host, done = handle
+        done.synchronize()
+        return host
 
     @torch.no_grad()
     def run_host(self, xs_h, ys_h, ps_h, off_h, n_max_frame, mode=0):
