@@ -51,6 +51,25 @@ def synth_events(B, L, lr, seed):
     return xs, ys, ps, off
 
 
+def synth_weights(seed=0):
+    """Random-init weights of the shipped architecture (fan-in scaled normal; non-zero conv_offset_mask so that the
+    deformable sampling is exercised), keyed like the reference state_dict.  No checkpoint exists offline."""
+    from esr_b200.model import DeepRecurrNet
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in DeepRecurrNet(inch=2, basech=8, num_frame=3).state_dict().items():
+        shp = tuple(v.shape)
+        if k.endswith(".weight"):
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            std = 0.02 if "conv_offset_mask" in k else (1.0 / fan_in) ** 0.5
+            sd[k] = torch.randn(shp, generator=g) * std
+        else:
+            sd[k] = torch.randn(shp, generator=g) * (0.3 if "conv_offset_mask" in k else 0.05)
+    return sd
+
+
 def synth_sr_bias(B, L, hr, seed):
     """A random-init network's output rounds to zero events, so the redistribution stage is fed
     `model output + Poisson(0.3)` synthetic counts to do representative work."""
@@ -140,10 +159,9 @@ def cpu_oracle_step(wl, B_sample, sd, seed):
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    from oracle import model_ref
     cores = usable_cores()
     torch.set_num_threads(cores)
-    sd = model_ref.seeded_state_dict(0)
+    sd = synth_weights(0)
     B_sample = 1
     for _ in range(max(1, min(args.warmup, 2))):
         cpu_oracle_step(wl, B_sample, sd, 1)
@@ -187,7 +205,6 @@ def main():
     from esr_b200 import _lib
     from esr_b200.model import DeepRecurrNet
     from esr_b200.pipeline import EventSRPipeline
-    from oracle import model_ref    # only for the seeded weights + the cpu_baseline leg
 
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
@@ -197,7 +214,7 @@ def main():
 
     scale, L, lr, B = wl["scale"], wl["L"], wl["lr"], wl["B"]
     hr = (lr[0] * scale, lr[1] * scale)
-    sd = model_ref.seeded_state_dict(0)
+    sd = synth_weights(0)
     net = DeepRecurrNet(inch=2, basech=8, num_frame=3)
     net.load_state_dict(sd)
     net = net.to(dev).eval()

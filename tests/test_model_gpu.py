@@ -105,3 +105,19 @@ def test_sequence_plan_equals_window_loop(dev, B, L, H, W):
             assert torch.equal(seq, loop), (rep, (seq - loop).abs().max().item())
         for a, b in zip(n1.states(B, 3, H, W), n2.states(B, L, H, W)):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,L,H,W", [(1, 3, 8, 8), (1, 4, 16, 24), (2, 3, 20, 300), (1, 5, 130, 70), (5, 3, 24, 24)])
+def test_edge_shapes_vs_oracle(dev, B, L, H, W):
+    """Tiny feature maps (1x1 at 8x8 input), very flat / odd sizes that need the CropSize pad, odd batch sizes: the TMA
+    boxes then reach far outside the tensors and most tile rows are masked."""
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    sd = model_ref.seeded_state_dict(9)
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    frames = torch.poisson(torch.full((B, L, 2, H, W), 0.5), generator=g)
+    net, ora = _net(sd, dev), model_ref.OracleNet(sd)
+    with torch.no_grad():
+        got = net.forward_sequence(frames.to(dev)).cpu()
+        want = torch.cat([ora(frames[:, w:w + 3].contiguous()) for w in range(L - 2)], 0)
+    assert got.shape == want.shape
+    assert _rel(got, want) < REL, _rel(got, want)

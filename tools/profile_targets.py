@@ -11,7 +11,7 @@ from esr_b200 import encodings as enc                     # noqa: E402
 from esr_b200.expand import expand                         # noqa: E402
 from esr_b200.model import DeepRecurrNet                   # noqa: E402
 from esr_b200.pipeline import EventSRPipeline              # noqa: E402
-from oracle import model_ref                               # noqa: E402  (seeded weights only)
+import bench                                                  # noqa: E402  (synthetic weights)
 
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(1)
@@ -28,7 +28,7 @@ for _ in range(2):
 
 B, L, lr, scale = 8, 8, (128, 128), 2
 net = DeepRecurrNet(inch=2, basech=8, num_frame=3)
-net.load_state_dict(model_ref.seeded_state_dict(0))
+net.load_state_dict(bench.synth_weights(0))
 net = net.to(dev).eval()
 pipe = EventSRPipeline(net, B, L, lr, scale, dev)
 ne = B * L * 2048
