@@ -16,6 +16,7 @@
 // that wrote them (same tile -> same CTA -> same TMEM lane in every phase).
 #include "tc_common.cuh"
 #include "net.cuh"
+#include <cstdlib>
 
 namespace esr {
 
@@ -47,6 +48,72 @@ __device__ __forceinline__ void gc_grid_barrier(unsigned int *counter, unsigned 
     }
     __syncthreads();
     asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// Fused gate epilogue of one tile: TMEM -> registers -> sigmoid / tanh / blend -> z (fp32), h*r or h' (split bf16).
+// Eight warps: two per TMEM lane quadrant, each taking half of the columns.
+__device__ __forceinline__ void gc_epilogue(const GruChainArgs &a, int which, int g, int img, int y0, int x0, int warp, int lane,
+                                            uint32_t tmem_acc)
+{
+    const int B2 = 2 * a.B;
+    const int npad = which == 0 ? 128 : 64;
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;
+    const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+    const bool valid = (y < a.H) && (x < a.W);
+    const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);   // within a 2B-image tensor
+    const __nv_bfloat16 *h_prev = a.hs + ((size_t)g * B2 * a.H * a.W + pix) * 64;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16);
+    for (int n0 = half * (npad / 2); n0 < (half + 1) * (npad / 2); n0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32(taddr + (uint32_t)n0, raw);
+        if (valid) {
+            float v[32];
+            const float4 *bp = reinterpret_cast<const float4 *>((which == 0 ? a.bias_zr : a.bias_go) + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b = bp[q];
+                v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+                v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+                v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+                v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+            }
+            if (which == 0) {
+                act32(v, ACT_SIGMOID);
+                if (n0 < 64) {                                      // update gate z (fp32)
+                    float4 *zp = reinterpret_cast<float4 *>(a.zbuf + pix * 64 + n0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) zp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else {                                            // reset gate r -> h * r
+                    float h[32];
+                    load_split32(h_prev + (n0 - 64), a.hs_plane, h);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= h[j];
+                    store_split32(a.rh + pix * 64 + (n0 - 64), a.rh_plane, v);
+                }
+            } else {                                                // h' = h (1 - z) + tanh(.) z
+                float h[32];
+                load_split32(h_prev + n0, a.hs_plane, h);
+                const float4 *zp = reinterpret_cast<const float4 *>(a.zbuf + pix * 64 + n0);
+                float4 zq[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) zq[q] = zp[q];
+                act32(v, ACT_TANH);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float zz[4] = {zq[q].x, zq[q].y, zq[q].z, zq[q].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * q + e;
+                        v[j] = h[j] * (1.0f - zz[e]) + v[j] * zz[e];
+                    }
+                }
+                __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64;
+                store_split32(h_new + n0, a.hs_plane, v);
+            }
+        }
+        __syncwarp();
+    }
 }
 
 __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_constant__ GruChainArgs a)
@@ -133,65 +200,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
                     umma_commit(bar_accum);
                 }
             } else {
-                const int quad = warp & 3, half = (warp - 2) >> 2;   // two warps share a lane quadrant and split the columns
-                const int m = quad * 32 + lane;
-                const int y = y0 + m / a.TW, x = x0 + m % a.TW;
-                const bool valid = (y < a.H) && (x < a.W);
-                const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);   // within a 2B-image tensor
-                const __nv_bfloat16 *h_prev = a.hs + ((size_t)g * B2 * a.H * a.W + pix) * 64;
                 mbar_wait(bar_accum, acc_ph);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-                for (int n0 = half * (npad / 2); n0 < (half + 1) * (npad / 2); n0 += 32) {
-                    uint32_t raw[32];
-                    tmem_ld32(taddr + (uint32_t)n0, raw);
-                    if (valid) {
-                        float v[32];
-                        const float4 *bp = reinterpret_cast<const float4 *>((which == 0 ? a.bias_zr : a.bias_go) + n0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b = bp[q];
-                            v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
-                            v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
-                            v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
-                            v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
-                        }
-                        if (which == 0) {
-                            act32(v, ACT_SIGMOID);
-                            if (n0 < 64) {                                      // update gate z (fp32)
-                                float4 *zp = reinterpret_cast<float4 *>(a.zbuf + pix * 64 + n0);
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) zp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                            } else {                                            // reset gate r -> h * r
-                                float h[32];
-                                load_split32(h_prev + (n0 - 64), a.hs_plane, h);
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] *= h[j];
-                                store_split32(a.rh + pix * 64 + (n0 - 64), a.rh_plane, v);
-                            }
-                        } else {                                                // h' = h (1 - z) + tanh(.) z
-                            float h[32];
-                            load_split32(h_prev + n0, a.hs_plane, h);
-                            const float4 *zp = reinterpret_cast<const float4 *>(a.zbuf + pix * 64 + n0);
-                            float4 zq[8];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) zq[q] = zp[q];
-                            act32(v, ACT_TANH);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float zz[4] = {zq[q].x, zq[q].y, zq[q].z, zq[q].w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int j = 4 * q + e;
-                                    v[j] = h[j] * (1.0f - zz[e]) + v[j] * zz[e];
-                                }
-                            }
-                            __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64;
-                            store_split32(h_new + n0, a.hs_plane, v);
-                        }
-                    }
-                    __syncwarp();
-                }
+                gc_epilogue(a, which, g, img, y0, x0, warp, lane, tmem_base);
                 tc_fence_before();
             }
             acc_ph ^= 1u;
@@ -207,11 +218,133 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined variant (one tile per CTA, the usual case): the x-side half of a phase's K loop (9 of 18 K-blocks: taps over
+// the step's input features) does not depend on the previous phase, so the producer and the MMA thread run it BEFORE the
+// grid barrier, into the second of two TMEM accumulators, while the epilogue warps are still finishing the previous
+// phase.  Only the 9 state-side K-blocks (h, or h*r) wait for the barrier.  The barrier is split: the epilogue warps
+// arrive (after their stores and fences), the producer thread alone waits.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_constant__ GruChainArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t B_MAX = 128u * 128u;
+    constexpr uint32_t STAGE = 2u * TC_A_BYTES + 2u * B_MAX;
+    const uint32_t bar_base = smem_base + (uint32_t)a.stages * STAGE;
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages, bar_accum = bar_base + 16u * a.stages;   // 2 accum barriers
+    const uint32_t tmem_slot = bar_accum + 16u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B2 = 2 * a.B;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int tile = blockIdx.x;                                  // grid == number of tiles
+    const int img = tile / tiles_per_img;
+    const int trem = tile - img * tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+    const int bb = img < a.B ? img : img - a.B;
+    const int n_phases = 2 * a.nsteps;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        mbar_init(bar_accum, 1); mbar_init(bar_accum + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);                    // two 128-column accumulators
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ps = 0, pph = 0;
+            for (int p = 0; p < n_phases; ++p) {
+                const int g = p >> 1, which = p & 1;
+                const int w_idx = g / a.N, s_idx = g - w_idx * a.N;
+                const uint32_t b_bytes = (which == 0 ? 128u : 64u) * 128u;
+                const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+                const CUtensorMap *bmap = which == 0 ? &a.bmap_zr : &a.bmap_go;
+                const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
+                for (int kb = 0; kb < 18; ++kb) {
+                    const int src = kb / 9, tap = kb - src * 9;
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    if (kb == 9 && p > 0) {
+                        // state-side operands are written by every CTA's epilogue of phase p-1: wait for all of them
+                        const unsigned int target = (unsigned int)p * gridDim.x;
+                        unsigned int v;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barrier) : "memory");
+                        } while (v < target);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
+                    mbar_expect_tx(bar_full + 8u * ps, stage_bytes);
+                    const uint32_t st = smem_base + ps * STAGE;
+                    const CUtensorMap *am = src == 0 ? &a.amap_xc : (which == 0 ? &a.amap_hs : &a.amap_rh);
+                    const int simg = src == 0 ? xc_img : (which == 0 ? g * B2 + img : img);
+                    tma_load_5d(am, bar_full + 8u * ps, st, 0, x0 + dx, y0 + dy, simg, 0);
+                    tma_load_5d(am, bar_full + 8u * ps, st + TC_A_BYTES, 0, x0 + dx, y0 + dy, simg, 1);
+                    tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, 0, kb);
+                    tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + kb);
+                    if (++ps == (uint32_t)a.stages) { ps = 0; pph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t ms = 0, mph = 0;
+            for (int p = 0; p < n_phases; ++p) {
+                const int npad = (p & 1) == 0 ? 128 : 64;
+                const uint32_t b_bytes = (uint32_t)npad * 128u;
+                const uint32_t idesc = umma_idesc(TC_BLOCK_M, npad);
+                const uint32_t acc = tmem_base + (uint32_t)(p & 1) * 128u;   // phase p's epilogue reads this one while p+1 fills the other
+                for (int kb = 0; kb < 18; ++kb) {
+                    mbar_wait(bar_full + 8u * ms, mph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + ms * STAGE;
+                    const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                        const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                        umma_bf16(acc, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(acc, dah, dbl, idesc, 1u);
+                        umma_bf16(acc, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(bar_empty + 8u * ms);
+                    if (++ms == (uint32_t)a.stages) { ms = 0; mph ^= 1u; }
+                }
+                umma_commit(bar_accum + 8u * (uint32_t)(p & 1));
+            }
+        }
+    } else {
+        // accumulator p&1 is overwritten by phase p+2, whose MMAs only start after phase p+1's state-side loads, i.e.
+        // after the grid barrier that this CTA's epilogue of phase p has already arrived on: no extra hand-shake needed
+        for (int p = 0; p < n_phases; ++p) {
+            mbar_wait(bar_accum + 8u * (uint32_t)(p & 1), (uint32_t)((p >> 1) & 1));
+            tc_fence_after();
+            gc_epilogue(a, p & 1, p >> 1, img, y0, x0, warp, lane, tmem_base + (uint32_t)(p & 1) * 128u);
+            tc_fence_before();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps
+            if (warp == 2 && lane == 0) atomicAdd(a.barrier, 1u);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct GruChainPlan {
     GruChainArgs args;
     int grid;
     size_t smem;
+    bool pipelined;
 };
 
 int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const void *w_zr,
@@ -238,9 +371,12 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
     int per_sm = 0;
     ESR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gru_chain, GC_THREADS, p->smem));
     if (per_sm < 1) { set_error("gru_chain: kernel does not fit on an SM"); delete p; return ESR_EUNSUPPORTED; }
+    ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     const int n_tiles = 2 * B * a.tiles_x * a.tiles_y;
     const int max_grid = dev_info().sm_count * per_sm;
     p->grid = n_tiles < max_grid ? n_tiles : max_grid;
+    static const bool no_pipe = getenv("ESR_GRU_NO_PIPE") != nullptr;
+    p->pipelined = !no_pipe && n_tiles <= max_grid;            // one tile per CTA: overlap the x-side K-blocks with the epilogue
     *plan_out = p;
     return ESR_OK;
 }
@@ -250,7 +386,8 @@ int gru_chain_launch(void *plan, cudaStream_t st)
     GruChainPlan *p = (GruChainPlan *)plan;
     ESR_CUDA_CHECK(cudaMemsetAsync(p->args.barrier, 0, sizeof(unsigned int), st));
     void *kargs[] = {(void *)&p->args};
-    ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain, dim3(p->grid), dim3(GC_THREADS), kargs, p->smem, st));
+    ESR_CUDA_CHECK(cudaLaunchCooperativeKernel(p->pipelined ? (void *)k_gru_chain_pipe : (void *)k_gru_chain, dim3(p->grid),
+                                               dim3(GC_THREADS), kargs, p->smem, st));
     esr::count_launch();
     return ESR_OK;
 }

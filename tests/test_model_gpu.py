@@ -121,3 +121,25 @@ def test_edge_shapes_vs_oracle(dev, B, L, H, W):
         want = torch.cat([ora(frames[:, w:w + 3].contiguous()) for w in range(L - 2)], 0)
     assert got.shape == want.shape
     assert _rel(got, want) < REL, _rel(got, want)
+
+
+def test_full_size_properties_cfg2(dev):
+    """BASELINE.json configs[1] at full size (B=8, L=8, HR 256x256), where the CPU oracle would take minutes:
+    size-independent properties instead -- (1) the sequence plan equals the reference's loop of single-window forwards
+    bit for bit, (2) determinism across runs, (3) the batch is independent (a sample alone gives the same output),
+    (4) outputs are non-negative (final ReLU) and finite."""
+    sd = model_ref.seeded_state_dict(11)
+    g = torch.Generator().manual_seed(4242)
+    B, L, H, W = 8, 8, 256, 256
+    frames = torch.poisson(torch.full((B, L, 2, H, W), 0.1), generator=g).to(dev)
+    n1, n2, n3 = _net(sd, dev), _net(sd, dev), _net(sd, dev)
+    with torch.no_grad():
+        seq = n1.forward_sequence(frames)
+        n1.reset_states()
+        seq2 = n1.forward_sequence(frames)
+        loop = torch.cat([n2(frames[:, w:w + 3].contiguous()) for w in range(L - 2)], 0)
+        solo = n3.forward_sequence(frames[3:4].contiguous())
+    assert torch.equal(seq, loop)
+    assert torch.equal(seq, seq2)
+    assert torch.equal(solo, seq.view(L - 2, B, 2, H, W)[:, 3])
+    assert bool(torch.isfinite(seq).all()) and float(seq.min()) >= 0.0
