@@ -23,6 +23,7 @@ SIGNATURES = {
     "esr_scatter_cnt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_int,
                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "esr_scatter_image": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "esr_scatter_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "esr_time_bin_bounds": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "esr_scatter_voxel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "esr_expand_count": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

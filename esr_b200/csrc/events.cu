@@ -126,6 +126,36 @@ k_scatter_voxel(float *__restrict__ xs, float *__restrict__ ys, const float *__r
     }
 }
 
+// events_to_mask (encodings.py:307-331): mask[(long)y,(long)x] = |ps| with accumulate=False, i.e. the LAST event that
+// hits a pixel decides (torch's CPU index_put_ walks the indices in order).  Out-of-range events are zeroed in place
+// first, so they write 0 to pixel (0,0) when they come last.  Two passes: atomicMax of the event index per pixel, then
+// the winning event writes its |ps|.
+__global__ void __launch_bounds__(256)
+k_mask_last_index(float *__restrict__ xs, float *__restrict__ ys, float *__restrict__ ps, long long n, int H, int W,
+                  int writeback, int *__restrict__ last)
+{
+    const float fW = (float)W, fH = (float)H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float x = xs[i], y = ys[i];
+        const bool oor = (x >= fW) | (x < 0.0f) | (y >= fH) | (y < 0.0f);
+        if (oor) { x = 0.0f; y = 0.0f; if (writeback) { xs[i] = 0.0f; ys[i] = 0.0f; ps[i] = 0.0f; } }
+        atomicMax(last + (size_t)(long long)y * W + (size_t)(long long)x, (int)i);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_mask_write(const float *__restrict__ xs, const float *__restrict__ ys, const float *__restrict__ ps, long long n, int H, int W,
+             const int *__restrict__ last, float *__restrict__ out)
+{
+    const float fW = (float)W, fH = (float)H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float x = xs[i], y = ys[i], p = ps[i];
+        const bool oor = (x >= fW) | (x < 0.0f) | (y >= fH) | (y < 0.0f);
+        if (oor) { x = 0.0f; y = 0.0f; p = 0.0f; }
+        const size_t pix = (size_t)(long long)y * W + (size_t)(long long)x;
+        if (last[pix] == (int)i) out[pix] = fabsf(p);
+    }
+}
+
 // =============================================================================================
 // 2. exclusive scan of uint32 (multi-level, tile = 1024 threads x 4)
 // =============================================================================================
@@ -463,6 +493,27 @@ extern "C" int esr_scatter_image(float *xs, float *ys, float *ps, int64_t n, int
     const int64_t cap = (int64_t)dev_info().sm_count * 16;
     if (bx > cap) bx = cap;
     k_scatter_image<<<(unsigned)bx, 256, 0, st>>>(xs, ys, ps, n, H, W, writeback, out);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+extern "C" int esr_scatter_mask(float *xs, float *ys, float *ps, int64_t n, int H, int W, int writeback, int32_t *last_tmp,
+                                float *out, esr_stream_t stream)
+{
+    ESR_REQUIRE(H > 0 && W > 0 && out && last_tmp && n >= 0 && n < (1ll << 31), "esr_scatter_mask: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)H * W, st));
+    if (n == 0) return ESR_OK;
+    ESR_REQUIRE(xs && ys && ps, "esr_scatter_mask: null event arrays");
+    ESR_CUDA_CHECK(cudaMemsetAsync(last_tmp, 0xff, sizeof(int32_t) * (size_t)H * W, st));     // -1
+    int64_t bx = ceil_div64(n, 256 * 4);
+    const int64_t cap = (int64_t)dev_info().sm_count * 16;
+    if (bx > cap) bx = cap;
+    // pass 2 must see the ORIGINAL coordinates: with writeback the first pass zeroes them, which maps to the same pixel
+    // (0,0) and weight 0 as the recomputed out-of-range case, so reading the mutated arrays is equivalent
+    k_mask_last_index<<<(unsigned)bx, 256, 0, st>>>(xs, ys, ps, (long long)n, H, W, writeback, last_tmp);
+    ESR_LAUNCH_CHECK();
+    k_mask_write<<<(unsigned)bx, 256, 0, st>>>(xs, ys, ps, (long long)n, H, W, last_tmp, out);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

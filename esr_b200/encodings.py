@@ -5,6 +5,7 @@ Same names, positional arguments and side effects as the reference:
   events_to_channels(xs, ys, ps, sensor_size)     encodings.py:289-304
   events_to_stack_no_polarity(xs, ys, ts, ps, B, device, sensor_size)   encodings.py:204-240 (+ :77-99)
   events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size)                encodings.py:271-286
+  events_to_mask(xs, ys, ps, sensor_size)                               encodings.py:307-331
   cython_event_redistribute(event_stack, mode)    encodings.py:466-484
   multiprocess_cython(event_stack, mode)          encodings.py:495-533 (per-sample calls, no process pool)
   stack2cnt(stack)                                encodings.py:652-670
@@ -44,6 +45,25 @@ def events_to_image(xs, ys, ps, sensor_size=(180, 240)):
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().esr_scatter_image(_lib.ptr(dx), _lib.ptr(dy), _lib.ptr(dp), dx.numel(), H, W, 1,
                                                 _lib.ptr(out), _lib.stream_ptr()), "esr_scatter_image")
+    for src, d, cb in ((xs, dx, cbx), (ys, dy, cby), (ps, dp, cbp)):
+        if cb and src.dtype == torch.float32:
+            src.copy_(d)
+    return out if xs.is_cuda else out.cpu()
+
+
+def events_to_mask(xs, ys, ps, sensor_size=(180, 240)):
+    """Binary-style mask (encodings.py:307-331): mask[y,x] = |ps| of the last event on the pixel; xs, ys, ps are modified
+    in place for out-of-range events like the reference."""
+    dev = xs.device if xs.is_cuda else _dev()
+    dx, cbx = _to_dev_f32(xs, dev)
+    dy, cby = _to_dev_f32(ys, dev)
+    dp, cbp = _to_dev_f32(ps, dev)
+    H, W = int(sensor_size[0]), int(sensor_size[1])
+    out = torch.empty((H, W), dtype=torch.float32, device=dev)
+    tmp = torch.empty((H * W,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().esr_scatter_mask(_lib.ptr(dx), _lib.ptr(dy), _lib.ptr(dp), dx.numel(), H, W, 1, _lib.ptr(tmp),
+                                               _lib.ptr(out), _lib.stream_ptr()), "esr_scatter_mask")
     for src, d, cb in ((xs, dx, cbx), (ys, dy, cby), (ps, dp, cbp)):
         if cb and src.dtype == torch.float32:
             src.copy_(d)

@@ -53,6 +53,11 @@ int esr_scatter_cnt(float *xs, float *ys, const float *ps, const int64_t *frame_
 int esr_scatter_image(float *xs, float *ys, float *ps, int64_t n, int H, int W, int writeback, float *out,
                       esr_stream_t stream);
 
+/* Replaces: dataloader/encodings.py:307-331 events_to_mask (index_put_ with accumulate=False: the last event hitting a
+ * pixel writes |ps|; out-of-range events are zeroed in place and then write 0 to pixel (0,0)).  last_tmp: int32 [H*W]. */
+int esr_scatter_mask(float *xs, float *ys, float *ps, int64_t n, int H, int W, int writeback, int32_t *last_tmp, float *out,
+                     esr_stream_t stream);
+
 /* Replaces: the slicing of dataloader/encodings.py:204-240 events_to_stack_no_polarity, i.e. its calls to
  * binary_search_torch_tensor (encodings.py:77-99).  ts: sorted fp32 [n]; bounds: int64 [B,2] = (beg, end) of every time
  * bin, identical to the reference's search (incl. which of several equal timestamps it stops on). */

@@ -97,6 +97,11 @@ def main():
         vx = ref_enc.events_to_voxel(tx, ty, tt, tp, max(TB, 2), sensor_size=(H, W))
         out[f"stk{i}_voxel"] = vx.numpy()
         out[f"stk{i}_voxel_xs_after"] = tx.numpy()
+        tx, ty, tp = (torch.from_numpy(a.copy()) for a in (xs, ys, ps))
+        pm = tp.clone(); pm[::9] = 0.5                                  # non-unit weights: the LAST writer decides
+        out[f"stk{i}_mask_ps"] = pm.numpy().copy()
+        out[f"stk{i}_mask"] = ref_enc.events_to_mask(tx, ty, pm, sensor_size=(H, W)).numpy()
+        out[f"stk{i}_mask_ps_after"] = pm.numpy()
 
     # --- cnt2event
     c = np.zeros((1, 2, 2, 3), np.float32)

@@ -209,3 +209,15 @@ def test_dense_frames_scatter_vs_oracle(dev, H, W, n):
                             torch.from_numpy(off).to(dev), hr_size=(H, W), n_max_frame=int(n - n // 3)).cpu().numpy()
     want = oe.events_to_channels(xs[:off[1]].copy(), ys[:off[1]].copy(), ps2[:off[1]], (H, W))
     np.testing.assert_allclose(got[0], want, rtol=1e-5, atol=1e-3)
+
+
+def test_events_to_mask_golden(golden_events, dev):
+    """accumulate=False: the last event on a pixel wins (reference: sequential CPU index_put_)."""
+    from esr_b200 import encodings as enc
+    g = golden_events
+    for i in range(int(g["n_stack"])):
+        H, W, _ = (int(v) for v in g[f"stk{i}_dims"])
+        xs, ys, ps = (torch.from_numpy(g[f"stk{i}_{k}"].copy()) for k in ("xs", "ys", "mask_ps"))
+        out = enc.events_to_mask(xs, ys, ps, sensor_size=(H, W))
+        assert np.array_equal(out.numpy(), g[f"stk{i}_mask"]), i
+        assert np.array_equal(ps.numpy(), g[f"stk{i}_mask_ps_after"])
