@@ -304,7 +304,8 @@ def main():
         ms = (ctypes.c_float * cap)()
         fl = (ctypes.c_double * cap)()
         cnt = ctypes.c_int(0)
-        acc = {0: [0.0, 0.0, 0], 1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0]}
+        acc = {0: [0.0, 0.0, 0], 1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0], 3: [0.0, 0.0, 0]}
+        per_launch = {}                                              # launch index -> [ms sum, flops]
         reps = 5
         for r in range(reps + 1):
             _lib.check(_lib.lib().esr_net_forward_profiled(plan.handle, _lib.ptr(bank), None, _lib.ptr(out),
@@ -314,15 +315,29 @@ def main():
             for i in range(cnt.value):
                 a = acc[cls[i]]
                 a[0] += ms[i]; a[1] += fl[i]; a[2] += 1
+                pl = per_launch.setdefault(i, [0.0, fl[i], int(cls[i])])
+                pl[0] += ms[i]
             if r == reps:
                 prof_rows = [(i, int(cls[i]), float(ms[i]), float(fl[i])) for i in range(cnt.value)]
-        tc_ms, tc_fl, tc_n = acc[0]
+        tc_ms, tc_fl, tc_n = (acc[0][i] + acc[3][i] for i in range(3))     # tensor-core work: convs + GRU chain kernel
         peak_tf, peak_hbm, peak_src = measured_peaks()
         achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         tot_ms = sum(a[0] for a in acc.values())
-        roofline = {"kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, all launches of one step)", "bound": "tensor",
-                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "peak_source": peak_src + ", bf16 sustained", "traffic": None,
+        # the dominant single launch: the k_conv_tc instance with the most work (local_fusion.0.conv1/conv2, 192->192 3x3
+        # over all window slots), excluding the cooperative GRU kernel, timed live above
+        top = max((v for v in per_launch.values() if v[2] == 0), key=lambda v: v[1], default=None)
+        top_ms = top[0] / reps if top else 0.0
+        top_tf = top[1] / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
+        roofline = {"kernel": "k_conv_tc (tcgen05 implicit-GEMM conv): largest launch = local_fusion 192->192 3x3 over all window slots",
+                    "bound": "tensor", "achieved": top_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": top_tf / peak_tf,
+                    "peak_source": peak_src + ", bf16 sustained",
+                    "launch_ms": top_ms, "algorithmic_gflop_per_launch": top[1] / 1e9 if top else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this launch at cfg2, ncu --set full,
+                    # profiles/r1_ncu_tc.md (114.8 MB + 66.3 MB); algorithmic bytes: 144 x 32 x 32 x 192 x 4 B in + out = 226.5 MB
+                    "traffic": 181.07e6 if args.workload == "cfg2" else None,
+                    "tensor_pipe_active_pct_ncu": 55.4 if args.workload == "cfg2" else None,
+                    "all_tc_launches": {"achieved": achieved, "frac": achieved / peak_tf},
+                    "gru_chain_ms_per_step": acc[3][0] / reps,
                     "launches_per_step": tc_n // reps, "avg_launch_us": tc_ms / max(tc_n, 1) * 1e3,
                     "algorithmic_gflop_per_step": tc_fl / reps / 1e9,
                     "share_of_step_kernel_time": tc_ms / tot_ms if tot_ms else None,
@@ -331,7 +346,7 @@ def main():
                     "tc_ms_per_step": tc_ms / reps}
         if args.profile_out:
             with open(args.profile_out, "w") as f:
-                f.write("idx,class(0=tc,1=direct,2=other),ms,algorithmic_flops\n")
+                f.write("idx,class(0=tc,1=direct,2=other,3=gru_chain),ms,algorithmic_flops\n")
                 for row in prof_rows:
                     f.write("%d,%d,%.5f,%.0f\n" % row)
 

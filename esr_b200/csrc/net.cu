@@ -371,7 +371,7 @@ struct Prof {
     struct Entry { cudaEvent_t e0, e1; int cls; double flops; };
     std::vector<Entry> entries;
 };
-enum ProfClass : int { PC_TC = 0, PC_DIRECT = 1, PC_OTHER = 2 };
+enum ProfClass : int { PC_TC = 0, PC_DIRECT = 1, PC_OTHER = 2, PC_GRU = 3 };
 
 static double tc_flops(const ConvTCArgs &a) { return 2.0 * a.n_img * a.H * a.W * (double)a.cout * (double)a.nkb * 64.0; }
 static double direct_flops(int dl, const DirectArgs &a)
@@ -421,7 +421,7 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     if (n.gru_plan) {
         double fl = 0.0;
         for (int g = 0; g < nsteps; ++g) fl += tc_flops(n.c_gzr[g]) + tc_flops(n.c_go[g]);
-        RUNC(PC_TC, fl, gru_chain_launch(n.gru_plan, st));
+        RUNC(PC_GRU, fl, gru_chain_launch(n.gru_plan, st));
     } else {
         for (int g = 0; g < nsteps; ++g) {
             RUNT(n.c_gzr[g]);

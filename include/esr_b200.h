@@ -170,7 +170,8 @@ int esr_net_destroy(esr_net_t net);
 int esr_net_reset_states(esr_net_t net, esr_stream_t stream);
 int esr_net_forward(esr_net_t net, const float *input, const int32_t *in_img, float *output, esr_stream_t stream);
 /* Same as esr_net_forward, but brackets every kernel launch with CUDA events on `stream`, synchronises, and reports
- * per-launch {class (0 tensor-core conv, 1 CUDA-core conv, 2 element-wise/sampling), milliseconds, algorithmic FLOPs}
+ * per-launch {class (0 tensor-core conv, 1 CUDA-core conv, 2 element-wise/sampling, 3 cooperative ConvGRU chain),
+ * milliseconds, algorithmic FLOPs}
  * into host arrays (measurement aid for bench.py's roofline object; not on the production path). */
 int esr_net_forward_profiled(esr_net_t net, const float *input, const int32_t *in_img, float *output, int max_entries,
                              int *n_entries_host, int *cls_host, float *ms_host, double *flops_host, esr_stream_t stream);
