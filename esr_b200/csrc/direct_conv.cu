@@ -209,10 +209,16 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
         for (int ci = 0; ci < CIN; ++ci) {
             float win[WINH][WINW];
             const float *pb = patch + (ci * PH + gy * 2 * STRIDE) * PP + gx * TPW * STRIDE;
+            // the window starts at an even float offset (PP % 4 == 0, gx * TPW * STRIDE even): 8-byte shared loads
 #pragma unroll
-            for (int r = 0; r < WINH; ++r)
+            for (int r = 0; r < WINH; ++r) {
 #pragma unroll
-                for (int s = 0; s < WINW; ++s) win[r][s] = pb[r * PP + s];
+                for (int s2 = 0; s2 + 1 < WINW; s2 += 2) {
+                    const float2 t = *reinterpret_cast<const float2 *>(pb + r * PP + s2);
+                    win[r][s2] = t.x; win[r][s2 + 1] = t.y;
+                }
+                if (WINW & 1) win[r][WINW - 1] = pb[r * PP + WINW - 1];
+            }
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -220,7 +226,10 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
                     const float *wp = wsm + ((ky * 3 + kx) * CIN + ci) * COUT + cg * C;
                     float wv[C];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) wv[c] = wp[c];
+                    for (int c4 = 0; c4 < C / 4; ++c4) {                 // warp-uniform 16-byte broadcast loads
+                        const float4 t = reinterpret_cast<const float4 *>(wp)[c4];
+                        wv[4 * c4] = t.x; wv[4 * c4 + 1] = t.y; wv[4 * c4 + 2] = t.z; wv[4 * c4 + 3] = t.w;
+                    }
 #pragma unroll
                     for (int p = 0; p < NP; ++p) {
                         const float xv = win[(p / TPW) * STRIDE + ky][(p % TPW) * STRIDE + kx];
