@@ -221,3 +221,21 @@ def test_events_to_mask_golden(golden_events, dev):
         out = enc.events_to_mask(xs, ys, ps, sensor_size=(H, W))
         assert np.array_equal(out.numpy(), g[f"stk{i}_mask"]), i
         assert np.array_equal(ps.numpy(), g[f"stk{i}_mask_ps_after"])
+
+
+def test_dataset_glue_matches_reference_semantics(dev, golden_events):
+    """event_formatting / create_normalized_events / create_scaled_encoding('cnt') = the lift fixtures of the reference."""
+    from esr_b200 import dataset as ds
+    g = golden_events
+    for i in range(int(g["n_lift"])):
+        H, W, k = (int(v) for v in g[f"lift{i}_dims"])
+        xs, ys, ps = g[f"lift{i}_xs"], g[f"lift{i}_ys"], g[f"lift{i}_ps"]
+        ts = np.linspace(5.0, 6.0, len(xs))
+        ev = ds.event_formatting(np.stack([xs, ys, ts, ps]), device=dev)
+        assert ev.is_cuda and ev.dtype == torch.float32 and float(ev[2, 0]) == 0.0 and float(ev[2, -1]) < 1.0
+        norm = ds.create_normalized_events(ev, (H, W))
+        cnt = ds.create_scaled_encoding(norm, (H * k, W * k), 'cnt')
+        assert np.array_equal(cnt.cpu().numpy(), g[f"lift{i}_out"]), i
+    fr = torch.arange(2 * 5 * 3, device=dev).view(2, 5, 3)
+    wins = ds.sliding_windows(fr)
+    assert len(wins) == 3 and torch.equal(wins[1], fr[:, 1:4])
