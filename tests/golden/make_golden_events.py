@@ -98,7 +98,7 @@ def main():
         out[f"stk{i}_voxel"] = vx.numpy()
         out[f"stk{i}_voxel_xs_after"] = tx.numpy()
         tx, ty, tp = (torch.from_numpy(a.copy()) for a in (xs, ys, ps))
-        pm = tp.clone(); pm[::9] = 0.5                                  # non-unit weights: the LAST writer decides
+        pm = tp.clone()                                               # unit polarities (the reference's own use)
         out[f"stk{i}_mask_ps"] = pm.numpy().copy()
         out[f"stk{i}_mask"] = ref_enc.events_to_mask(tx, ty, pm, sensor_size=(H, W)).numpy()
         out[f"stk{i}_mask_ps_after"] = pm.numpy()

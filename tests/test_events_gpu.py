@@ -212,14 +212,20 @@ def test_dense_frames_scatter_vs_oracle(dev, H, W, n):
 
 
 def test_events_to_mask_golden(golden_events, dev):
-    """accumulate=False: the last event on a pixel wins (reference: sequential CPU index_put_)."""
+    """accumulate=False: the last event on a pixel wins.  torch's CPU index_put_ is sequential only for small inputs
+    (larger ones are split over threads, so WHICH duplicate wins is not defined by the reference itself); with unit
+    polarities every in-range writer stores 1, and only pixel (0,0) -- where zeroed out-of-range events also land -- is
+    order dependent, so it is checked for membership instead of equality."""
     from esr_b200 import encodings as enc
     g = golden_events
     for i in range(int(g["n_stack"])):
         H, W, _ = (int(v) for v in g[f"stk{i}_dims"])
         xs, ys, ps = (torch.from_numpy(g[f"stk{i}_{k}"].copy()) for k in ("xs", "ys", "mask_ps"))
         out = enc.events_to_mask(xs, ys, ps, sensor_size=(H, W))
-        assert np.array_equal(out.numpy(), g[f"stk{i}_mask"]), i
+        got, want = out.numpy().copy(), g[f"stk{i}_mask"].copy()
+        assert got[0, 0] in (0.0, 1.0)
+        got[0, 0] = want[0, 0] = 0.0
+        assert np.array_equal(got, want), i
         assert np.array_equal(ps.numpy(), g[f"stk{i}_mask_ps_after"])
 
 
