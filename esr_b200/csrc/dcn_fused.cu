@@ -1,0 +1,227 @@
+// dcn_fused.cu -- DCNv2 forward with the deformable sampling fused into the tensor-core contraction.
+//
+// Reference: modulated_deformable_im2col (models/DCNv2/src/cuda/dcn_v2_im2col_cuda.cu:125-195) writes columns[B, Ci*9, h*w]
+// to HBM and dcn_v2_cuda.cu:90-92 multiplies them by W[Co, Ci*9].  Here the columns never exist in HBM: per CTA (128
+// output pixels) and tap, eight sampler warps evaluate the bilinear sample x mask for the tile's 128 pixels x 64
+// channels and write it as split bf16 directly in the 128-byte-swizzled K-major shared-memory layout that tcgen05.mma
+// reads (hi and lo planes, chunk = deformable group, chunk index XOR (row & 7)); fence.proxy.async + an mbarrier hand the
+// stage to the MMA thread, the tap's weight tile arrives by TMA, and the accumulator stays in TMEM across the 9 taps.
+// The sampler warps then run the epilogue (bias + ReLU of STFusion.fuse, models/model.py:217) and store split bf16.
+// Warps: 0 = weight TMA, 1 = MMA + TMEM, 2..9 = samplers / epilogue.  Two A stages + two B stages (96 KB): 2 CTAs per SM.
+#include "tc_common.cuh"
+#include "net.cuh"
+
+namespace esr {
+
+constexpr int DF_THREADS = 320;
+constexpr uint32_t DF_B_BYTES = 64u * 128u;                       // one plane of the 64 x 64 weight tile
+constexpr uint32_t DF_A_STAGE = 2u * TC_A_BYTES, DF_B_STAGE = 2u * DF_B_BYTES;
+
+struct DcnFusedArgs {
+    CUtensorMap bmap;                          // packed DCN weight: (64, 64, 2*9), box (64, 64, 1)
+    const __nv_bfloat16 *feat; size_t f_plane; // features to sample (split, 64 ch), indexed through feat_img
+    const int *feat_img;
+    const float *om;                           // [n_img, H, W, 216]: 144 offsets, 72 masks (sigmoid applied)
+    const float *bias;
+    __nv_bfloat16 *out; size_t out_plane;      // [n_img, H, W, 64] split
+    int n_img, H, W, TW, TH, tiles_x, tiles_y, act;
+};
+
+__device__ __forceinline__ void df_ld8(const __nv_bfloat16 *hi, size_t plane, float (&o)[8])
+{
+    const uint4 h = *reinterpret_cast<const uint4 *>(hi);
+    const uint4 l = *reinterpret_cast<const uint4 *>(hi + plane);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        o[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+        o[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+    }
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_constant__ DcnFusedArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
+    const uint32_t a_ring = smem_base, b_ring = smem_base + 2u * DF_A_STAGE;
+    const uint32_t bar_base = b_ring + 2u * DF_B_STAGE;
+    const uint32_t bar_afull = bar_base, bar_aempty = bar_base + 16u, bar_bfull = bar_base + 32u, bar_bempty = bar_base + 48u;
+    const uint32_t bar_accum = bar_base + 64u, tmem_slot = bar_base + 72u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_afull + 8u * s, 256); mbar_init(bar_aempty + 8u * s, 1);
+            mbar_init(bar_bfull + 8u * s, 1); mbar_init(bar_bempty + 8u * s, 1);
+        }
+        mbar_init(bar_accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int t = 0; t < 9; ++t) {
+                const uint32_t s = t & 1, ph = (t >> 1) & 1;
+                mbar_wait(bar_bempty + 8u * s, ph ^ 1u);
+                mbar_expect_tx(bar_bfull + 8u * s, DF_B_STAGE);
+                tma_load_3d(&a.bmap, bar_bfull + 8u * s, b_ring + s * DF_B_STAGE, 0, 0, t);
+                tma_load_3d(&a.bmap, bar_bfull + 8u * s, b_ring + s * DF_B_STAGE + DF_B_BYTES, 0, 0, 9 + t);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64);
+            for (int t = 0; t < 9; ++t) {
+                const uint32_t s = t & 1, ph = (t >> 1) & 1;
+                mbar_wait(bar_afull + 8u * s, ph);
+                mbar_wait(bar_bfull + 8u * s, ph);
+                tc_fence_after();
+                const uint32_t a_hi = a_ring + s * DF_A_STAGE, a_lo = a_hi + TC_A_BYTES;
+                const uint32_t b_hi = b_ring + s * DF_B_STAGE, b_lo = b_hi + DF_B_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                    umma_bf16(tmem_base, dal, dbh, idesc, (t | k) != 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+                    umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+                }
+                umma_commit(bar_aempty + 8u * s);
+                umma_commit(bar_bempty + 8u * s);
+            }
+            umma_commit(bar_accum);
+        }
+    } else {
+        // ===================== samplers: 256 threads, 4 (pixel, group) items each per tap =====================
+        const int st = threadIdx.x - 64;                       // 0..255
+        const size_t fbase = (size_t)(a.feat_img ? a.feat_img[img] : img) * a.H * a.W;
+        for (int t = 0; t < 9; ++t) {
+            const uint32_t s = t & 1, ph = (t >> 1) & 1;
+            mbar_wait(bar_aempty + 8u * s, ph ^ 1u);
+            uint8_t *stage = smem_gen + (size_t)s * DF_A_STAGE;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                const int item = j * 256 + st;
+                const int m = item >> 3, g = item & 7;         // tile row (pixel) and deformable group
+                const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+                if (y < a.H && x < a.W) {
+                    const float *o = a.om + (((size_t)img * a.H + y) * a.W + x) * 216;
+                    const float off_h = o[g * 18 + 2 * t], off_w = o[g * 18 + 2 * t + 1], mk = o[144 + g * 9 + t];
+                    const float h_im = (float)(y - 1 + t / 3) + off_h;
+                    const float w_im = (float)(x - 1 + t % 3) + off_w;
+                    if (h_im > -1.0f && w_im > -1.0f && h_im < (float)a.H && w_im < (float)a.W) {
+                        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                        const int h_high = h_low + 1, w_high = w_low + 1;
+                        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+                        const float hh = 1.0f - lh, hw = 1.0f - lw;
+                        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+                        float c1[8], c2[8], c3[8], c4[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) c1[e] = c2[e] = c3[e] = c4[e] = 0.0f;
+                        const __nv_bfloat16 *f0 = a.feat + (fbase * 64) + g * 8;
+                        if (h_low >= 0 && w_low >= 0) df_ld8(f0 + ((size_t)h_low * a.W + w_low) * 64, a.f_plane, c1);
+                        if (h_low >= 0 && w_high <= a.W - 1) df_ld8(f0 + ((size_t)h_low * a.W + w_high) * 64, a.f_plane, c2);
+                        if (h_high <= a.H - 1 && w_low >= 0) df_ld8(f0 + ((size_t)h_high * a.W + w_low) * 64, a.f_plane, c3);
+                        if (h_high <= a.H - 1 && w_high <= a.W - 1) df_ld8(f0 + ((size_t)h_high * a.W + w_high) * 64, a.f_plane, c4);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = (w1 * c1[e] + w2 * c2[e] + w3 * c3[e] + w4 * c4[e]) * mk;
+                    }
+                }
+                uint32_t hw_[4], lw_[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(v[2 * e], h0, l0);
+                    split_bf16(v[2 * e + 1], h1, l1);
+                    hw_[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lw_[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                // K-major SWIZZLE_128B: row m at m*128, 16-byte chunk g stored at chunk (g ^ (m & 7))
+                const uint32_t off = (uint32_t)m * 128u + (uint32_t)((g ^ (m & 7)) << 4);
+                *reinterpret_cast<uint4 *>(stage + off) = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);
+                *reinterpret_cast<uint4 *>(stage + TC_A_BYTES + off) = make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_afull + 8u * s) : "memory");
+        }
+        // ===================== epilogue: two warps per TMEM lane quadrant, 32 columns each =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int m = quad * 32 + lane;
+        const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+        const bool valid = (y < a.H) && (x < a.W);
+        mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), raw);
+        if (valid) {
+            float v[32];
+            const float4 *bp = reinterpret_cast<const float4 *>(a.bias + half * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b = bp[q];
+                v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+                v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+                v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+                v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+            }
+            act32(v, a.act);
+            const size_t pix = ((size_t)img * a.H + y) * a.W + x;
+            store_split32(a.out + pix * 64 + half * 32, a.out_plane, v);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+struct DcnFusedPlan { DcnFusedArgs args; unsigned grid; size_t smem; };
+
+int dcn_fused_prepare(const SplitTensor &feat, const int *feat_img, const float *om, const void *wpacked, const float *bias,
+                      int n_img, int act, const SplitTensor &out, void **plan_out)
+{
+    ESR_REQUIRE(feat.C == 64 && out.C == 64 && out.H == feat.H && out.W == feat.W, "dcn_fused: bad shapes");
+    DcnFusedPlan *p = new DcnFusedPlan();
+    DcnFusedArgs &a = p->args;
+    memset(&a, 0, sizeof(a));
+    int rc = tc_make_bmap(wpacked, 64, 9, 64, &a.bmap);
+    if (rc) { delete p; return rc; }
+    const int H = feat.H, W = feat.W;
+    a.feat = feat.base; a.f_plane = feat.plane(); a.feat_img = feat_img; a.om = om; a.bias = bias;
+    a.out = out.base; a.out_plane = out.plane(); a.n_img = n_img; a.H = H; a.W = W; a.act = act;
+    a.TW = W >= 12 ? 16 : 8; a.TH = TC_BLOCK_M / a.TW;
+    a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
+    p->grid = (unsigned)(n_img * a.tiles_x * a.tiles_y);
+    p->smem = 1024 + 2 * DF_A_STAGE + 2 * DF_B_STAGE + 128;
+    cudaError_t e = cudaFuncSetAttribute(k_dcn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+    if (e != cudaSuccess) { set_error("dcn_fused: %s", cudaGetErrorString(e)); delete p; return ESR_ECUDA; }
+    *plan_out = p;
+    return ESR_OK;
+}
+
+int dcn_fused_launch(void *plan, cudaStream_t st)
+{
+    DcnFusedPlan *p = (DcnFusedPlan *)plan;
+    k_dcn_fused<<<p->grid, DF_THREADS, p->smem, st>>>(p->args);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+void dcn_fused_destroy(void *plan) { delete (DcnFusedPlan *)plan; }
+
+} // namespace esr

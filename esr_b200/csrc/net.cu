@@ -102,6 +102,7 @@ struct Net {
     ConvTCArgs c_pm0, c_pm1, c_lf1, c_lf2, c_lf3, c_gx, c_gf, c_of0, c_of1, c_com, c_dcn, c_cb0, c_cb1, c_ker, c_df0, c_df1,
         c_dn0, c_dn1, c_at0, c_rc0;
     std::vector<ConvTCArgs> c_gzr, c_go;
+    void *dcn_plan = nullptr;          // fused sampling + contraction (dcn_fused.cu); nullptr = columns + 1x1 GEMM
     void *gru_plan = nullptr;          // cooperative whole-chain kernel (gru_chain.cu); nullptr = per-step launches
     unsigned int *gru_barrier = nullptr;
     DirectArgs d[D_COUNT];
@@ -316,6 +317,12 @@ static int build(Net &n, cudaStream_t st)
     if ((rc = conv_tc_prepare(d, &n.c_com))) return rc;
     d = mk(n, T_DCN, nf, ACT_RELU); d.ntaps = 1; d.src[0] = n.cols; d.out = n.aligned;
     if ((rc = conv_tc_prepare(d, &n.c_dcn))) return rc;
+    // default: the sampler writes the swizzled A tiles straight into shared memory (no columns tensor);
+    // ESR_DCN_COLUMNS=1 keeps the two-kernel path (columns in HBM + 1x1 GEMM) for comparison
+    static const bool dcn_cols = getenv("ESR_DCN_COLUMNS") != nullptr;
+    if (!dcn_cols) {
+        if ((rc = dcn_fused_prepare(n.tp, n.m_f0, n.om, pw(n, T_DCN), pb(n, T_DCN), nf, ACT_RELU, n.aligned, &n.dcn_plan))) return rc;
+    }
     d = mk(n, T_CB0, nf, ACT_RELU); d.n_src = 2; d.src[0] = n.aligned; d.src[1] = n.tp; d.src_img[1] = n.m_fm; d.out = n.t_cb0;
     if ((rc = conv_tc_prepare(d, &n.c_cb0))) return rc;
     d = mk(n, T_CB1, nf, ACT_NONE); d.src[0] = n.t_cb0; d.out = n.feat;
@@ -435,8 +442,12 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     RUNT(n.c_of0);
     RUNT(n.c_of1);
     RUNT(n.c_com);
-    RUN(dcn_columns(n.tp, n.m_f0, n.om, nf, n.cols, st));
-    RUNT(n.c_dcn);
+    if (n.dcn_plan) {
+        RUNC(PC_TC, 2.0 * 64 * 576 * (double)nf * n.h * n.w, dcn_fused_launch(n.dcn_plan, st));
+    } else {
+        RUN(dcn_columns(n.tp, n.m_f0, n.om, nf, n.cols, st));
+        RUNT(n.c_dcn);
+    }
     RUNT(n.c_cb0);
     RUNT(n.c_cb1);
     RUNT(n.c_ker);
@@ -546,6 +557,7 @@ extern "C" int esr_net_create(esr_net_t *out, int B, int N, int L, int H, int W,
 extern "C" int esr_net_destroy(esr_net_t net)
 {
     if (net && ((Net *)net)->gru_plan) gru_chain_destroy(((Net *)net)->gru_plan);
+    if (net && ((Net *)net)->dcn_plan) dcn_fused_destroy(((Net *)net)->dcn_plan);
     delete (Net *)net;
     return ESR_OK;
 }

@@ -56,6 +56,12 @@ int copy_split(const SplitTensor &src, const int *src_img, int n_img, const Spli
 int dcn_columns(const SplitTensor &feat, const int *feat_img, const float *om, int n_img, const SplitTensor &cols /*C=576*/,
                 cudaStream_t st);
 
+// ---- DCNv2 with the sampling fused into the tcgen05 contraction (dcn_fused.cu): no columns tensor in HBM
+int dcn_fused_prepare(const SplitTensor &feat, const int *feat_img, const float *om, const void *wpacked, const float *bias,
+                      int n_img, int act, const SplitTensor &out, void **plan_out);
+int dcn_fused_launch(void *plan, cudaStream_t st);
+void dcn_fused_destroy(void *plan);
+
 // ---- the ConvGRU recurrence of a whole sequence batch in one cooperative kernel (gru_chain.cu)
 int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const void *w_zr,
                       const float *b_zr, const void *w_go, const float *b_go, unsigned int *barrier, int B, int N,

@@ -25,13 +25,17 @@ def event_formatting(events, device=None):
     ys = torch.from_numpy(np.asarray(events[1]).astype(np.float32)).to(device)
     ts = torch.from_numpy(np.asarray(events[2]).astype(np.float32)).to(device)
     ps = torch.from_numpy(np.asarray(events[3]).astype(np.float32)).to(device)
-    ts = (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)
+    ts = (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)      # tensor / tensor: IEEE division on the device too
     return torch.stack([xs, ys, ts, ps])
 
 
 def create_normalized_events(events, sensor_resolution):
     xs, ys, ts, ps = events[0], events[1], events[2], events[3]
-    xs, ys = xs / sensor_resolution[1], ys / sensor_resolution[0]
+    # divisors as device tensors: torch's CUDA `tensor / python_scalar` multiplies by the reciprocal, which is not the
+    # IEEE division the reference's CPU tensors get (differs for non-power-of-two sensor sizes)
+    dw = torch.tensor(float(sensor_resolution[1]), dtype=torch.float32, device=xs.device)
+    dh = torch.tensor(float(sensor_resolution[0]), dtype=torch.float32, device=xs.device)
+    xs, ys = xs / dw, ys / dh
     return torch.stack([xs, ys, ts, ps]).float()
 
 
