@@ -14,6 +14,7 @@ c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
 c_i64 = ctypes.c_int64
 c_size_t = ctypes.c_size_t
+c_float = ctypes.c_float
 
 # name -> (restype, argtypes); must list every symbol of include/esr_b200.h (tests/test_capi_symbols.py checks)
 SIGNATURES = {
@@ -75,6 +76,11 @@ SIGNATURES.update({
     "esr_dcn_v2_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "esr_dcn_v2_backward": (c_int, [c_void_p] * 6 + [c_int] * 10 + [c_void_p] * 6 + [c_size_t, c_void_p]),
     "esr_dcn_v2_forward": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "esr_conv2d_workspace_bytes": (c_size_t, [c_int] * 7),
+    "esr_conv2d_forward": (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "esr_conv2d_backward": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "esr_mse_loss": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_float, c_void_p]),
+    "esr_adam_step": (c_int, [c_void_p] * 5 + [c_size_t, c_int] + [c_float] * 5 + [c_void_p]),
 })
 
 

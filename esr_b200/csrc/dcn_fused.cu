@@ -111,7 +111,19 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
             const uint32_t s = t & 1, ph = (t >> 1) & 1;
             mbar_wait(bar_aempty + 8u * s, ph ^ 1u);
             uint8_t *stage = smem_gen + (size_t)s * DF_A_STAGE;
-#pragma unroll 1
+            // the offsets / masks of this thread's 4 items first: one L2 round trip instead of one per item
+            float oh[4], ow[4], omk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = (j * 256 + st) >> 3, g = st & 7;
+                const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+                oh[j] = ow[j] = omk[j] = 0.0f;
+                if (y < a.H && x < a.W) {
+                    const float *o = a.om + (((size_t)img * a.H + y) * a.W + x) * 216;
+                    oh[j] = __ldg(o + g * 18 + 2 * t); ow[j] = __ldg(o + g * 18 + 2 * t + 1); omk[j] = __ldg(o + 144 + g * 9 + t);
+                }
+            }
+#pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int item = j * 256 + st;
                 const int m = item >> 3, g = item & 7;         // tile row (pixel) and deformable group
@@ -120,8 +132,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = 0.0f;
                 if (y < a.H && x < a.W) {
-                    const float *o = a.om + (((size_t)img * a.H + y) * a.W + x) * 216;
-                    const float off_h = o[g * 18 + 2 * t], off_w = o[g * 18 + 2 * t + 1], mk = o[144 + g * 9 + t];
+                    const float off_h = oh[j], off_w = ow[j], mk = omk[j];
                     const float h_im = (float)(y - 1 + t / 3) + off_h;
                     const float w_im = (float)(x - 1 + t % 3) + off_w;
                     if (h_im > -1.0f && w_im > -1.0f && h_im < (float)a.H && w_im < (float)a.W) {

@@ -319,7 +319,7 @@ static int build(Net &n, cudaStream_t st)
     if ((rc = conv_tc_prepare(d, &n.c_dcn))) return rc;
     // default: the sampler writes the swizzled A tiles straight into shared memory (no columns tensor);
     // ESR_DCN_COLUMNS=1 keeps the two-kernel path (columns in HBM + 1x1 GEMM) for comparison
-    static const bool dcn_cols = getenv("ESR_DCN_COLUMNS") != nullptr;
+    const bool dcn_cols = getenv("ESR_DCN_COLUMNS") != nullptr;      // read per net, so a test can build both
     if (!dcn_cols) {
         if ((rc = dcn_fused_prepare(n.tp, n.m_f0, n.om, pw(n, T_DCN), pb(n, T_DCN), nf, ACT_RELU, n.aligned, &n.dcn_plan))) return rc;
     }

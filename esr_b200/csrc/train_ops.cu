@@ -1,0 +1,525 @@
+// train_ops.cu -- operators of the training step (train_ours_cnt_seq.py:206-235, 767-782).
+//
+// The reference's step is  sum over windows of MSELoss(forward(window), gt)  ->  one backward  ->  Adam(amsgrad).  Its
+// backward is ATen's conv2d backward for every ConvLayer (models/submodules.py:159-200) plus `_ext.dcn_v2_backward`
+// (dcn_bwd.cu here).  This file holds the convolution operator pair in the reference's own tensor layout (fp32 NCHW, the
+// layout autograd hands over) and the loss / optimizer kernels:
+//
+//   esr_conv2d_forward   y = act(conv(x, w) + b)            3x3 pad 1 or 1x1 pad 0, stride 1 or 2
+//   esr_conv2d_backward  g = dy * act'(y);  db = sum g;  dw = x (*) g;  dx = g (*) rot180(w)^T
+//   esr_mse_loss         mean((p - t)^2) and its gradient
+//   esr_adam_step        torch.optim.Adam semantics (L2 weight decay folded into the gradient, optional amsgrad)
+//
+// Stride-1 layers with 64-multiple input channels run on the tcgen05 implicit-GEMM kernel of tc_conv.cu (fp32 -> split
+// bf16, 3-pass product, fp32 accumulate): the forward directly, dx as the same kernel over g with the weights transposed
+// and rotated, and dw as a tensor-core reduction over pixels (k_wgrad_tc below, MN-major operands).  Every other shape
+// (the <= 32-channel full-resolution layers, stride-2 encoder convs, 1- and 2-channel heads) uses the CUDA-core kernels
+// in this file.  dw / db / dx-by-atomics accumulate in fp32; summation order over pixels is not deterministic (neither is
+// the reference's cuDNN / atomicAdd backward).
+#include "tc_common.cuh"
+#include "net.cuh"
+
+namespace esr {
+
+// ------------------------------------------------------------------------------------------------------------------
+// elementwise pieces
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(float v, int act)
+{
+    if (act == ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-v));
+    if (act == ACT_TANH) return tanhf(v);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_act_bwd(const float *__restrict__ dy, const float *__restrict__ y, float *__restrict__ g,
+                                                 size_t n, int act)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float o = y[i];
+        float d = 1.0f;
+        if (act == ACT_RELU) d = o > 0.0f ? 1.0f : 0.0f;
+        else if (act == ACT_SIGMOID) d = o * (1.0f - o);
+        else if (act == ACT_TANH) d = 1.0f - o * o;
+        g[i] = dy[i] * d;
+    }
+}
+
+// db[co] += sum over (n, pixel) of g[n, co, pixel]; grid (Cout, chunks)
+__global__ void __launch_bounds__(256) k_bias_grad(const float *__restrict__ g, int B, int Cout, int HW, float *__restrict__ db)
+{
+    const int co = blockIdx.x;
+    const size_t total = (size_t)B * HW;
+    float s = 0.0f;
+    for (size_t i = (size_t)blockIdx.y * 256 + threadIdx.x; i < total; i += (size_t)gridDim.y * 256) {
+        const size_t n = i / HW, p = i - n * HW;
+        s += g[(n * Cout + co) * HW + p];
+    }
+    __shared__ float red[8];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        s = red[threadIdx.x];
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(db + co, s);
+    }
+}
+
+// wT[ci][co][K-1-ky][K-1-kx] = w[co][ci][ky][kx]: the weights of the convolution that maps g to dx
+__global__ void k_weight_rot_t(const float *__restrict__ w, int Cout, int Cin, int KK, float *__restrict__ wt)
+{
+    const int total = Cout * Cin * KK;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int t = i % KK, ci = (i / KK) % Cin, co = i / (KK * Cin);
+        wt[((size_t)ci * Cout + co) * KK + (KK - 1 - t)] = w[i];
+    }
+}
+
+// fp32 NHWC [n][HW][C] -> NCHW [n][C][HW] (the tensor-core kernel's fp32 output -> the layout autograd expects)
+__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float *__restrict__ src, int C, int HW, float *__restrict__ dst)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int p = p0 + r, c = c0 + tx;
+        tile[r][tx] = (p < HW && c < C) ? src[((size_t)n * HW + p) * C + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, p = p0 + tx;
+        if (c < C && p < HW) dst[((size_t)n * C + c) * HW + p] = tile[tx][r];
+    }
+}
+
+static int nhwc_to_nchw(const float *src, int B, int C, int HW, float *dst, cudaStream_t st)
+{
+    k_nhwc_to_nchw<<<dim3((HW + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(src, C, HW, dst);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CUDA-core convolution, fp32 NCHW.  Block = 16 x 16 output pixels x 8 output channels; input channels in chunks of 8.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int G_T = 16, G_C = 8;
+
+template <int KS>
+__global__ void __launch_bounds__(256) k_conv_fwd_g(const float *__restrict__ x, const float *__restrict__ w,
+                                                    const float *__restrict__ bias, float *__restrict__ y, int Cin, int H, int W,
+                                                    int Cout, int Ho, int Wo, int stride, int act)
+{
+    extern __shared__ float sm[];
+    const int PD = (G_T - 1) * stride + KS;                        // patch edge
+    float *patch = sm;                                             // [G_C][PD][PD]
+    float *wsm = sm + G_C * PD * PD;                               // [G_C co][G_C ci][KS*KS]
+    constexpr int KK = KS * KS, pad = KS / 2;
+    const int tiles_x = (Wo + G_T - 1) / G_T;
+    const int ty0 = (blockIdx.x / tiles_x) * G_T, tx0 = (blockIdx.x % tiles_x) * G_T;
+    const int co0 = blockIdx.y * G_C, n = blockIdx.z;
+    const int tid = threadIdx.y * G_T + threadIdx.x;
+    const int oy = ty0 + threadIdx.y, ox = tx0 + threadIdx.x;
+    float acc[G_C];
+#pragma unroll
+    for (int c = 0; c < G_C; ++c) acc[c] = (co0 + c < Cout) ? bias[co0 + c] : 0.0f;
+    for (int ci0 = 0; ci0 < Cin; ci0 += G_C) {
+        for (int i = tid; i < G_C * PD * PD; i += 256) {
+            const int ci = i / (PD * PD), r = i - ci * PD * PD;
+            const int iy = ty0 * stride - pad + r / PD, ix = tx0 * stride - pad + r % PD;
+            float v = 0.0f;
+            if (ci0 + ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)n * Cin + ci0 + ci) * H + iy) * W + ix];
+            patch[i] = v;
+        }
+        for (int i = tid; i < G_C * G_C * KK; i += 256) {
+            const int t = i % KK, ci = (i / KK) % G_C, co = i / (KK * G_C);
+            wsm[i] = (co0 + co < Cout && ci0 + ci < Cin) ? w[((size_t)(co0 + co) * Cin + ci0 + ci) * KK + t] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int ci = 0; ci < G_C; ++ci) {
+#pragma unroll
+            for (int t = 0; t < KK; ++t) {
+                const float v = patch[(ci * PD + threadIdx.y * stride + t / KS) * PD + threadIdx.x * stride + t % KS];
+#pragma unroll
+                for (int c = 0; c < G_C; ++c) acc[c] = fmaf(v, wsm[(c * G_C + ci) * KK + t], acc[c]);
+            }
+        }
+        __syncthreads();
+    }
+    if (oy < Ho && ox < Wo) {
+#pragma unroll
+        for (int c = 0; c < G_C; ++c)
+            if (co0 + c < Cout) y[(((size_t)n * Cout + co0 + c) * Ho + oy) * Wo + ox] = act_fwd(acc[c], act);
+    }
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// dx[n, ci, y, x] = sum over co, taps of g[n, co, (y + pad - ky) / s, (x + pad - kx) / s] * w[co, ci, ky, kx]  (when divisible)
+template <int KS>
+__global__ void __launch_bounds__(256) k_conv_dgrad_g(const float *__restrict__ g, const float *__restrict__ w, float *__restrict__ dx,
+                                                      int Cin, int H, int W, int Cout, int Ho, int Wo, int stride)
+{
+    extern __shared__ float sm[];
+    constexpr int KK = KS * KS, pad = KS / 2;
+    const int GP = (G_T - 1 + KS - 1) / stride + 2;                // g patch edge
+    float *patch = sm;                                             // [G_C co][GP][GP]
+    float *wsm = sm + G_C * GP * GP;                               // [G_C co][G_C ci][KK]
+    const int tiles_x = (W + G_T - 1) / G_T;
+    const int ty0 = (blockIdx.x / tiles_x) * G_T, tx0 = (blockIdx.x % tiles_x) * G_T;
+    const int ci0 = blockIdx.y * G_C, n = blockIdx.z;
+    const int tid = threadIdx.y * G_T + threadIdx.x;
+    const int yy = ty0 + threadIdx.y, xx = tx0 + threadIdx.x;
+    const int gy0 = floor_div(ty0 + pad - (KS - 1), stride), gx0 = floor_div(tx0 + pad - (KS - 1), stride);
+    float acc[G_C];
+#pragma unroll
+    for (int c = 0; c < G_C; ++c) acc[c] = 0.0f;
+    for (int co0 = 0; co0 < Cout; co0 += G_C) {
+        for (int i = tid; i < G_C * GP * GP; i += 256) {
+            const int co = i / (GP * GP), r = i - co * GP * GP;
+            const int gy = gy0 + r / GP, gx = gx0 + r % GP;
+            float v = 0.0f;
+            if (co0 + co < Cout && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo) v = g[(((size_t)n * Cout + co0 + co) * Ho + gy) * Wo + gx];
+            patch[i] = v;
+        }
+        for (int i = tid; i < G_C * G_C * KK; i += 256) {
+            const int t = i % KK, ci = (i / KK) % G_C, co = i / (KK * G_C);
+            wsm[i] = (co0 + co < Cout && ci0 + ci < Cin) ? w[((size_t)(co0 + co) * Cin + ci0 + ci) * KK + t] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < KK; ++t) {
+            const int ty = yy + pad - t / KS, tx = xx + pad - t % KS;
+            if (ty < 0 || tx < 0 || ty % stride != 0 || tx % stride != 0) continue;
+            const int py = ty / stride - gy0, px = tx / stride - gx0;
+            if (py >= GP || px >= GP) continue;
+            for (int co = 0; co < G_C; ++co) {
+                const float v = patch[(co * GP + py) * GP + px];
+#pragma unroll
+                for (int c = 0; c < G_C; ++c) acc[c] = fmaf(v, wsm[(co * G_C + c) * KK + t], acc[c]);
+            }
+        }
+        __syncthreads();
+    }
+    if (yy < H && xx < W) {
+#pragma unroll
+        for (int c = 0; c < G_C; ++c)
+            if (ci0 + c < Cin) dx[(((size_t)n * Cin + ci0 + c) * H + yy) * W + xx] = acc[c];
+    }
+}
+
+// dw[co, ci, ky, kx] += sum over (n, oy, ox) of g[n, co, oy, ox] * x[n, ci, oy*s + ky - pad, ox*s + kx - pad]
+// grid (co-tiles * ci-tiles, work slices); each block walks (image, 16x16 output tile) items with stride gridDim.y
+template <int KS>
+__global__ void __launch_bounds__(256) k_conv_wgrad_g(const float *__restrict__ x, const float *__restrict__ g, float *__restrict__ dw,
+                                                      int B, int Cin, int H, int W, int Cout, int Ho, int Wo, int stride)
+{
+    extern __shared__ float sm[];
+    constexpr int KK = KS * KS, pad = KS / 2, NP = G_C * KK;       // (ci, tap) pairs per block
+    constexpr int NSPLIT = 256 / NP;                               // pixel splits
+    const int PD = (G_T - 1) * stride + KS;
+    float *gs = sm;                                                // [256 px][G_C co]
+    float *xs = sm + 256 * G_C;                                    // [G_C ci][PD][PD]
+    const int ci_tiles = (Cin + G_C - 1) / G_C;
+    const int co0 = (blockIdx.x / ci_tiles) * G_C, ci0 = (blockIdx.x % ci_tiles) * G_C;
+    const int tiles_x = (Wo + G_T - 1) / G_T, tiles_y = (Ho + G_T - 1) / G_T;
+    const int items = B * tiles_x * tiles_y;
+    const int tid = threadIdx.x;
+    const int pair = tid % NP, split = tid / NP;
+    const int pci = pair / KK, pt = pair % KK;
+    const bool active = split < NSPLIT;
+    float acc[G_C];
+#pragma unroll
+    for (int c = 0; c < G_C; ++c) acc[c] = 0.0f;
+    for (int it = blockIdx.y; it < items; it += gridDim.y) {
+        const int n = it / (tiles_x * tiles_y), tr = it % (tiles_x * tiles_y);
+        const int ty0 = (tr / tiles_x) * G_T, tx0 = (tr % tiles_x) * G_T;
+        for (int i = tid; i < 256 * G_C; i += 256) {
+            const int co = i / 256, p = i % 256;                   // coalesced along pixels
+            const int oy = ty0 + p / G_T, ox = tx0 + p % G_T;
+            float v = 0.0f;
+            if (co0 + co < Cout && oy < Ho && ox < Wo) v = g[(((size_t)n * Cout + co0 + co) * Ho + oy) * Wo + ox];
+            gs[p * G_C + co] = v;
+        }
+        for (int i = tid; i < G_C * PD * PD; i += 256) {
+            const int ci = i / (PD * PD), r = i - ci * PD * PD;
+            const int iy = ty0 * stride - pad + r / PD, ix = tx0 * stride - pad + r % PD;
+            float v = 0.0f;
+            if (ci0 + ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)n * Cin + ci0 + ci) * H + iy) * W + ix];
+            xs[i] = v;
+        }
+        __syncthreads();
+        if (active) {
+            for (int p = split; p < 256; p += NSPLIT) {
+                const float xv = xs[(pci * PD + (p / G_T) * stride + pt / KS) * PD + (p % G_T) * stride + pt % KS];
+                const float4 g0 = *reinterpret_cast<const float4 *>(gs + p * G_C), g1 = *reinterpret_cast<const float4 *>(gs + p * G_C + 4);
+                acc[0] = fmaf(xv, g0.x, acc[0]); acc[1] = fmaf(xv, g0.y, acc[1]); acc[2] = fmaf(xv, g0.z, acc[2]); acc[3] = fmaf(xv, g0.w, acc[3]);
+                acc[4] = fmaf(xv, g1.x, acc[4]); acc[5] = fmaf(xv, g1.y, acc[5]); acc[6] = fmaf(xv, g1.z, acc[6]); acc[7] = fmaf(xv, g1.w, acc[7]);
+            }
+        }
+        __syncthreads();
+    }
+    if (active && ci0 + pci < Cin) {
+#pragma unroll
+        for (int c = 0; c < G_C; ++c)
+            if (co0 + c < Cout) atomicAdd(dw + ((size_t)(co0 + c) * Cin + ci0 + pci) * KK + pt, acc[c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// loss and optimizer
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mse(const float *__restrict__ p, const float *__restrict__ t, size_t n, float inv_n,
+                                             float *__restrict__ loss, float *__restrict__ grad, float grad_scale)
+{
+    float s = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float d = p[i] - t[i];
+        s = fmaf(d, d, s);
+        if (grad) grad[i] = 2.0f * d * inv_n * grad_scale;
+    }
+    __shared__ float red[8];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        s = red[threadIdx.x];
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(loss, s * inv_n);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                              float *__restrict__ v, float *__restrict__ vmax, size_t n, float lr, float b1, float b2,
+                                              float eps, float wd, float bc1, float bc2_sqrt)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float pi = p[i];
+        const float gi = fmaf(wd, pi, g[i]);                       // torch.optim.Adam: L2 term added to the gradient
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        float vh = vi;
+        if (vmax) { vh = fmaxf(vmax[i], vi); vmax[i] = vh; }       // amsgrad
+        const float denom = sqrtf(vh) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static inline bool tc_fwd_ok(int Cin, int Cout, int ksz, int stride) { return stride == 1 && Cin % 64 == 0 && Cout <= 256 && (ksz == 3 || ksz == 1); }
+static inline bool tc_dgrad_ok(int Cin, int Cout, int ksz, int stride) { return stride == 1 && Cout % 64 == 0 && Cin <= 256 && (ksz == 3 || ksz == 1); }
+
+struct Bump {
+    uint8_t *base; size_t off, cap;
+    void *take(size_t bytes) { void *p = base ? base + off : nullptr; off = align_up(off + bytes, 256); return p; }
+};
+
+static size_t conv2d_ws(int B, int Cin, int H, int W, int Cout, int ksz, int stride)
+{
+    const int Ho = (H + 2 * (ksz / 2) - ksz) / stride + 1, Wo = (W + 2 * (ksz / 2) - ksz) / stride + 1;
+    Bump f{nullptr, 0, 0}, b{nullptr, 0, 0};
+    if (tc_fwd_ok(Cin, Cout, ksz, stride)) {
+        f.take((size_t)B * Cin * H * W * 4); f.take(tc_packed_weight_bytes(Cout, Cin, ksz * ksz)); f.take(256 * 4);
+        f.take((size_t)B * tc_npad(Cout) * H * W * 4);
+    }
+    b.take((size_t)B * Cout * Ho * Wo * 4);
+    if (tc_dgrad_ok(Cin, Cout, ksz, stride)) {
+        b.take((size_t)B * Cout * Ho * Wo * 4); b.take((size_t)Cout * Cin * ksz * ksz * 4);
+        b.take(tc_packed_weight_bytes(Cin, Cout, ksz * ksz)); b.take(256 * 4); b.take((size_t)B * tc_npad(Cin) * H * W * 4);
+    }
+    return (f.off > b.off ? f.off : b.off) + 1024;
+}
+
+// y = act(conv(x)) on the tensor cores: fp32 NCHW -> split NHWC -> k_conv_tc -> fp32 NCHW
+static int conv_tc_nchw(const float *x, const float *w, const float *bias, int B, int Cin, int H, int W, int Cout, int ksz, int act,
+                        float *y, Bump &ws, cudaStream_t st)
+{
+    int rc;
+    SplitTensor xs; xs.base = (__nv_bfloat16 *)ws.take((size_t)B * Cin * H * W * 4); xs.n_img = B; xs.H = H; xs.W = W; xs.C = Cin;
+    void *wp = ws.take(tc_packed_weight_bytes(Cout, Cin, ksz * ksz));
+    float *bp = (float *)ws.take(256 * 4);
+    float *yt = (float *)ws.take((size_t)B * Cout * H * W * 4);           // fp32 NHWC
+    ESR_REQUIRE(ws.off <= ws.cap, "conv2d: workspace too small (%zu > %zu)", ws.off, ws.cap);
+    if ((rc = split_from_nchw(x, B, Cin, H, W, xs.base, st))) return rc;
+    if ((rc = pack_conv_weight(w, Cout, Cin, ksz, wp, st))) return rc;
+    ESR_CUDA_CHECK(cudaMemsetAsync(bp, 0, 256 * 4, st));
+    if (bias) ESR_CUDA_CHECK(cudaMemcpyAsync(bp, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, st));
+    ConvTCDesc d;
+    d.src[0] = xs; d.n_src = 1; d.ntaps = ksz * ksz; d.cout = Cout; d.wpacked = wp; d.bias = bp; d.n_img = B; d.act = act;
+    d.out_f32 = yt; d.out_f32_C = Cout;
+    ConvTCArgs a;
+    if ((rc = conv_tc_prepare(d, &a))) return rc;
+    if ((rc = conv_tc_launch(a, st))) return rc;
+    return nhwc_to_nchw(yt, B, Cout, H * W, y, st);
+}
+
+template <int KS>
+static int launch_generic(int which, const float *x, const float *w, const float *bias, const float *g, float *out, int B, int Cin,
+                          int H, int W, int Cout, int Ho, int Wo, int stride, int act, cudaStream_t st)
+{
+    constexpr int KK = KS * KS;
+    const dim3 blk(G_T, G_T);
+    if (which == 0) {
+        const int PD = (G_T - 1) * stride + KS;
+        const size_t smem = (size_t)(G_C * PD * PD + G_C * G_C * KK) * 4;
+        const dim3 grid(((Wo + G_T - 1) / G_T) * ((Ho + G_T - 1) / G_T), (Cout + G_C - 1) / G_C, B);
+        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_fwd_g<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_conv_fwd_g<KS><<<grid, blk, smem, st>>>(x, w, bias, out, Cin, H, W, Cout, Ho, Wo, stride, act);
+    } else if (which == 1) {
+        const int GP = (G_T - 1 + KS - 1) / stride + 2;
+        const size_t smem = (size_t)(G_C * GP * GP + G_C * G_C * KK) * 4;
+        const dim3 grid(((W + G_T - 1) / G_T) * ((H + G_T - 1) / G_T), (Cin + G_C - 1) / G_C, B);
+        k_conv_dgrad_g<KS><<<grid, blk, smem, st>>>(g, w, out, Cin, H, W, Cout, Ho, Wo, stride);
+    } else {
+        const int PD = (G_T - 1) * stride + KS;
+        const size_t smem = (size_t)(256 * G_C + G_C * PD * PD) * 4;
+        const int pairs = ((Cout + G_C - 1) / G_C) * ((Cin + G_C - 1) / G_C);
+        const int items = B * ((Wo + G_T - 1) / G_T) * ((Ho + G_T - 1) / G_T);
+        int slices = (dev_info().sm_count * 8 + pairs - 1) / pairs;
+        if (slices > items) slices = items;
+        if (slices < 1) slices = 1;
+        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_wgrad_g<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_conv_wgrad_g<KS><<<dim3(pairs, slices), 256, smem, st>>>(x, g, out, B, Cin, H, W, Cout, Ho, Wo, stride);
+    }
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+static int generic(int which, int ksz, const float *x, const float *w, const float *bias, const float *g, float *out, int B, int Cin,
+                   int H, int W, int Cout, int Ho, int Wo, int stride, int act, cudaStream_t st)
+{
+    return ksz == 3 ? launch_generic<3>(which, x, w, bias, g, out, B, Cin, H, W, Cout, Ho, Wo, stride, act, st)
+                    : launch_generic<1>(which, x, w, bias, g, out, B, Cin, H, W, Cout, Ho, Wo, stride, act, st);
+}
+
+int wgrad_tc(const float *x, const __nv_bfloat16 *g_split, int B, int Cin, int H, int W, int Cout, int ksz, float *dw, Bump &ws,
+             cudaStream_t st);   // wgrad_tc.cu (optional; returns ESR_EINVAL when the shape is not supported)
+
+} // namespace esr
+
+using namespace esr;
+
+extern "C" {
+
+size_t esr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ksz, int stride)
+{
+    return conv2d_ws(B, Cin, H, W, Cout, ksz, stride);
+}
+
+int esr_conv2d_forward(const float *x, const float *w, const float *bias, int B, int Cin, int H, int W, int Cout, int ksz, int stride,
+                       int act, float *y, void *workspace, size_t workspace_bytes, esr_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_REQUIRE(x && w && bias && y, "conv2d_forward: null pointer");
+    ESR_REQUIRE((ksz == 3 || ksz == 1) && (stride == 1 || stride == 2) && act >= 0 && act <= 3, "conv2d_forward: ksz=%d stride=%d act=%d", ksz,
+                stride, act);
+    ESR_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "conv2d_forward: bad shape");
+    const int pad = ksz / 2, Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
+    if (tc_fwd_ok(Cin, Cout, ksz, stride)) {
+        ESR_REQUIRE(workspace, "conv2d_forward: workspace required");
+        Bump ws{(uint8_t *)workspace, 0, workspace_bytes};
+        return conv_tc_nchw(x, w, bias, B, Cin, H, W, Cout, ksz, act, y, ws, st);
+    }
+    return generic(0, ksz, x, w, bias, nullptr, y, B, Cin, H, W, Cout, Ho, Wo, stride, act, st);
+}
+
+int esr_conv2d_backward(const float *x, const float *w, const float *y, const float *dy, int B, int Cin, int H, int W, int Cout, int ksz,
+                        int stride, int act, float *dx, float *dw, float *db, void *workspace, size_t workspace_bytes,
+                        esr_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_REQUIRE(x && w && dy && dw && db && workspace, "conv2d_backward: null pointer");
+    ESR_REQUIRE(act == ACT_NONE || y, "conv2d_backward: the forward output is needed for the activation derivative");
+    ESR_REQUIRE((ksz == 3 || ksz == 1) && (stride == 1 || stride == 2) && act >= 0 && act <= 3, "conv2d_backward: ksz=%d stride=%d act=%d", ksz,
+                stride, act);
+    const int pad = ksz / 2, Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
+    Bump ws{(uint8_t *)workspace, 0, workspace_bytes};
+    int rc;
+    const size_t ng = (size_t)B * Cout * Ho * Wo;
+    float *g = (float *)ws.take(ng * 4);
+    ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
+    if (act == ACT_NONE) {
+        ESR_CUDA_CHECK(cudaMemcpyAsync(g, dy, ng * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        k_act_bwd<<<(unsigned)min((size_t)4096, (ng + 255) / 256), 256, 0, st>>>(dy, y, g, ng, act);
+        ESR_LAUNCH_CHECK();
+    }
+    ESR_CUDA_CHECK(cudaMemsetAsync(db, 0, (size_t)Cout * 4, st));
+    {
+        const size_t total = (size_t)B * Ho * Wo;
+        int chunks = (int)min((size_t)64, (total + 4095) / 4096);
+        k_bias_grad<<<dim3(Cout, chunks < 1 ? 1 : chunks), 256, 0, st>>>(g, B, Cout, Ho * Wo, db);
+        ESR_LAUNCH_CHECK();
+    }
+    ESR_CUDA_CHECK(cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * ksz * ksz * 4, st));
+    const bool tcd = tc_dgrad_ok(Cin, Cout, ksz, stride);
+    __nv_bfloat16 *gsplit = nullptr;
+    if (tcd) {
+        gsplit = (__nv_bfloat16 *)ws.take(ng * 4);
+        ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
+        if ((rc = split_from_nchw(g, B, Cout, Ho, Wo, gsplit, st))) return rc;
+    }
+    // ---- dw
+    static const bool no_tc_wgrad = getenv("ESR_WGRAD_GENERIC") != nullptr;
+    bool dw_done = false;
+    if (tcd && !no_tc_wgrad && Cin % 64 == 0 && stride == 1) {
+        Bump ws2 = ws;
+        rc = wgrad_tc(x, gsplit, B, Cin, H, W, Cout, ksz, dw, ws2, st);
+        if (rc == ESR_OK) dw_done = true;
+        else if (rc != ESR_EINVAL) return rc;
+    }
+    if (!dw_done && (rc = generic(2, ksz, x, nullptr, nullptr, g, dw, B, Cin, H, W, Cout, Ho, Wo, stride, 0, st))) return rc;
+    // ---- dx
+    if (dx) {
+        if (tcd) {
+            float *wt = (float *)ws.take((size_t)Cout * Cin * ksz * ksz * 4);
+            void *wp = ws.take(tc_packed_weight_bytes(Cin, Cout, ksz * ksz));
+            float *bp = (float *)ws.take(256 * 4);
+            float *dt = (float *)ws.take((size_t)B * Cin * H * W * 4);       // fp32 NHWC
+            ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small (%zu > %zu)", ws.off, ws.cap);
+            k_weight_rot_t<<<(Cout * Cin * ksz * ksz + 255) / 256, 256, 0, st>>>(w, Cout, Cin, ksz * ksz, wt);
+            ESR_LAUNCH_CHECK();
+            if ((rc = pack_conv_weight(wt, Cin, Cout, ksz, wp, st))) return rc;
+            ESR_CUDA_CHECK(cudaMemsetAsync(bp, 0, 256 * 4, st));
+            SplitTensor gsrc; gsrc.base = gsplit; gsrc.n_img = B; gsrc.H = Ho; gsrc.W = Wo; gsrc.C = Cout;
+            ConvTCDesc d;
+            d.src[0] = gsrc; d.n_src = 1; d.ntaps = ksz * ksz; d.cout = Cin; d.wpacked = wp; d.bias = bp; d.n_img = B; d.act = ACT_NONE;
+            d.out_f32 = dt; d.out_f32_C = Cin;
+            ConvTCArgs a;
+            if ((rc = conv_tc_prepare(d, &a))) return rc;
+            if ((rc = conv_tc_launch(a, st))) return rc;
+            if ((rc = nhwc_to_nchw(dt, B, Cin, H * W, dx, st))) return rc;
+        } else {
+            if ((rc = generic(1, ksz, nullptr, w, nullptr, g, dx, B, Cin, H, W, Cout, Ho, Wo, stride, 0, st))) return rc;
+        }
+    }
+    return ESR_OK;
+}
+
+int esr_mse_loss(const float *pred, const float *target, size_t n, float *loss, float *grad, float grad_scale, esr_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_REQUIRE(pred && target && loss && n > 0, "mse_loss: bad arguments");
+    ESR_CUDA_CHECK(cudaMemsetAsync(loss, 0, 4, st));
+    k_mse<<<(unsigned)min((size_t)1024, (n + 255) / 256), 256, 0, st>>>(pred, target, n, 1.0f / (float)n, loss, grad, grad_scale);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n, int step, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, esr_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    k_adam<<<(unsigned)min((size_t)2048, (n + 255) / 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                        weight_decay, (float)bc1, (float)sqrt(bc2));
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+} // extern "C"

@@ -6,8 +6,11 @@ state_dict key names (models/model.py:294-344; 68 tensors), so a refe
 The parameters are ordinary `nn.Parameter`s (DDP-wrappable); the forward pass is the C++/CUDA plan behind
 `esr_net_*` (include/esr_b200.h).  There is no PyTorch/CPU fallback: a CPU tensor or a missing library raises.
 
-Round-1 scope: inference (forward only).  Autograd through the CUDA plan is not implemented yet; calling forward
-with gradients enabled raises so that a training script cannot silently train nothing.
+Two execution paths, both sm_100a kernels behind the C ABI:
+  * torch.no_grad(): the fused inference plan (esr_net_*), states kept inside the plan's workspace;
+  * gradients enabled (training, train_ours_cnt_seq.py:217-232): esr_b200.train.forward_window -- the same network
+    composed from differentiable operators (esr_conv2d_forward/backward, esr_dcn_v2_forward/backward), with the
+    carried ConvGRU states kept as graph tensors so that backward runs through time like the reference's.
 """
 import ctypes
 import math
@@ -144,6 +147,7 @@ class DeepRecurrNet(nn.Module):
         self._plans = {}
         self._blob = None
         self._blob_sig = None
+        self._train_states = None          # [h_fwd, h_rev] with autograd history (training path)
 
     # ------------------------------------------------------------------------------------------
     def _check_supported(self):
@@ -182,6 +186,7 @@ class DeepRecurrNet(nn.Module):
     # ------------------------------------------------------------------------------------------
     def reset_states(self):
         """models/model.py:311-312: forget the carried ConvGRU states (of every cached shape)."""
+        self._train_states = None
         for p in self._plans.values():
             with torch.cuda.device(p.ws.device):
                 _lib.check(_lib.lib().esr_net_reset_states(p.handle, _lib.stream_ptr()), "esr_net_reset_states")
@@ -203,8 +208,11 @@ class DeepRecurrNet(nn.Module):
         if not input.is_cuda:
             raise _lib.ESRError("esr_b200.DeepRecurrNet.forward needs a CUDA tensor (there is no CPU path)")
         if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("esr_b200.DeepRecurrNet: backward is not implemented yet (round 1 = inference); "
-                                      "wrap the call in torch.no_grad()")
+            if frame_index is not None:
+                raise _lib.ESRError("esr_b200.DeepRecurrNet: frame banks are an inference feature")
+            from . import train
+            out, self._train_states = train.forward_window(self, input, self._train_states)
+            return out
         x = input.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
@@ -231,8 +239,8 @@ class DeepRecurrNet(nn.Module):
         if not frames.is_cuda:
             raise _lib.ESRError("esr_b200.DeepRecurrNet.forward_sequence needs a CUDA tensor (there is no CPU path)")
         if torch.is_grad_enabled() and (frames.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("esr_b200.DeepRecurrNet: backward is not implemented yet (round 1 = inference); "
-                                      "wrap the call in torch.no_grad()")
+            n = self._cfg["num_frame"]
+            return torch.cat([self.forward(frames[:, w:w + n]) for w in range(frames.shape[1] - n + 1)], 0)
         x = frames.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()

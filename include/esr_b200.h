@@ -201,6 +201,29 @@ int esr_dcn_v2_forward(const float *input, const float *weight, const float *bia
                        int B, int C, int H, int W, int Co, int kernel, int stride, int pad, int dilation,
                        int deformable_group, float *output, void *workspace, size_t workspace_bytes, esr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step operators.
+ * Replaces, for one ConvLayer (models/submodules.py:159-200: Conv2d(bias) -> activation), ATen's conv2d forward and
+ * backward as autograd calls them inside train_ours_cnt_seq.py:217-231 (forward) and :232 (loss.backward()); and
+ * nn.MSELoss (:774) and torch.optim.Adam(lr, weight_decay, amsgrad) (:781, config/train_ours_enfssyn.yml optimizer).
+ * Tensors are fp32 NCHW (x [B,Cin,H,W], w [Cout,Cin,k,k], y/dy [B,Cout,Ho,Wo]); k = 3 (pad 1) or 1 (pad 0); stride 1|2;
+ * act: 0 none, 1 relu, 2 sigmoid, 3 tanh (fused into the forward; backward multiplies dy by act'(y)).
+ * backward: dx may be NULL (first layer); dw [Cout,Cin,k,k] and db [Cout] are overwritten (not accumulated).
+ * workspace: esr_conv2d_workspace_bytes() bytes of device memory owned by the caller.
+ * --------------------------------------------------------------------------------------------- */
+size_t esr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ksz, int stride);
+int esr_conv2d_forward(const float *x, const float *w, const float *bias, int B, int Cin, int H, int W, int Cout, int ksz,
+                       int stride, int act, float *y, void *workspace, size_t workspace_bytes, esr_stream_t stream);
+int esr_conv2d_backward(const float *x, const float *w, const float *y, const float *dy, int B, int Cin, int H, int W, int Cout,
+                        int ksz, int stride, int act, float *dx, float *dw, float *db, void *workspace, size_t workspace_bytes,
+                        esr_stream_t stream);
+/* loss[0] = mean((pred - target)^2); grad (optional) = grad_scale * 2 (pred - target) / n */
+int esr_mse_loss(const float *pred, const float *target, size_t n, float *loss, float *grad, float grad_scale,
+                 esr_stream_t stream);
+/* One torch.optim.Adam step over a flat fp32 parameter buffer; step counts from 1; max_exp_avg_sq != NULL = amsgrad. */
+int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n, int step,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, esr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,22 @@ def test_sequence_plan_equals_window_loop(dev, B, L, H, W):
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("B,L,H,W", [(1, 3, 16, 16), (2, 4, 36, 44), (1, 3, 72, 130)])
+def test_fused_dcn_equals_columns_path(dev, B, L, H, W, monkeypatch):
+    """The DCN kernel that samples straight into the swizzled tcgen05 operand tiles must give the same bits as the
+    two-kernel path (columns tensor in HBM + 1x1 GEMM): same sampling arithmetic, same MMA order."""
+    sd = model_ref.seeded_state_dict(9)
+    g = torch.Generator().manual_seed(L * 7 + H)
+    frames = torch.poisson(torch.full((B, L, 2, H, W), 0.4), generator=g).to(dev)
+    n1 = _net(sd, dev)
+    with torch.no_grad():
+        fused = n1.forward_sequence(frames)
+        monkeypatch.setenv("ESR_DCN_COLUMNS", "1")
+        n2 = _net(sd, dev)
+        cols = n2.forward_sequence(frames)
+    assert torch.equal(fused, cols), (fused - cols).abs().max().item()
+
+
 @pytest.mark.parametrize("B,L,H,W", [(1, 3, 8, 8), (1, 4, 16, 24), (2, 3, 20, 300), (1, 5, 130, 70), (5, 3, 24, 24)])
 def test_edge_shapes_vs_oracle(dev, B, L, H, W):
     """Tiny feature maps (1x1 at 8x8 input), very flat / odd sizes that need the CropSize pad, odd batch sizes: the TMA

@@ -1,0 +1,200 @@
+"""GPU parity of the training-step operators: esr_conv2d_forward/backward, esr_mse_loss,
+esr_adam_step and the differentiable window forward, against torch CPU fp32 autograd of the same maths (for the whole
+network: autograd through the oracle restatement of models/model.py).
+
+Tolerance: max |got - want| <= 1e-3 * max |want| per tensor (BASELINE.json north_star's fp32 bar), a little wider for
+whole-network gradients where it says so.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import model_ref
+
+pytestmark = pytest.mark.gpu
+REL = 1e-3
+torch.set_num_threads(min(16, torch.get_num_threads()))
+
+
+def _rel(got, want):
+    return ((got.cpu() - want).abs().max() / want.abs().max().clamp_min(1e-20)).item()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+ACTS = {None: lambda v: v, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}
+
+CONV_CASES = [
+    # B, Cin, Cout, k, stride, act, H, W
+    (2, 64, 64, 3, 1, "relu", 20, 28),          # tensor-core forward, dx and dw
+    (1, 128, 64, 3, 1, "sigmoid", 17, 23),      # ConvGRU gates (ragged tile edges)
+    (2, 128, 64, 3, 1, "tanh", 16, 16),
+    (1, 192, 192, 3, 1, None, 16, 24),          # local_fusion residual convs
+    (1, 192, 64, 3, 1, None, 12, 40),
+    (2, 64, 216, 3, 1, None, 16, 16),           # conv_offset_mask: Cout not a multiple of 64 -> CUDA-core dx
+    (2, 64, 1, 3, 1, "sigmoid", 20, 20),        # pred_map[1], attens[0]
+    (2, 64, 2, 1, 1, "sigmoid", 20, 20),        # STFusion.kernel (1x1)
+    (2, 128, 64, 1, 1, "relu", 20, 20),         # global_fusion (1x1)
+    (2, 64, 32, 3, 1, "relu", 24, 24),          # recons[0]
+    (2, 2, 8, 3, 1, "relu", 40, 56),            # head
+    (2, 8, 16, 3, 2, "relu", 40, 56),           # encoder, stride 2
+    (2, 16, 32, 3, 2, "relu", 20, 28),
+    (1, 32, 64, 3, 2, "relu", 18, 26),
+    (2, 32, 16, 3, 1, "relu", 33, 47),          # recons[1] (odd sizes)
+    (2, 16, 8, 3, 1, "relu", 40, 40),
+    (3, 8, 2, 3, 1, "relu", 31, 17),            # tail
+    (1, 32, 1, 3, 1, "sigmoid", 24, 24),        # attens[1]
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,k,stride,act,H,W", CONV_CASES)
+def test_conv2d_forward_backward_vs_torch(dev, B, Cin, Cout, k, stride, act, H, W):
+    from esr_b200 import train
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout * 7 + H)
+    x = torch.randn(B, Cin, H, W, generator=g, requires_grad=True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).requires_grad_()
+    b = (0.1 * torch.randn(Cout, generator=g)).requires_grad_()
+    want = ACTS[act](F.conv2d(x, w, b, stride=stride, padding=k // 2))
+    dy = torch.randn(want.shape, generator=g)
+    want.backward(dy)
+    xg, wg, bg = (t.detach().to(dev).requires_grad_() for t in (x, w, b))
+    got = train.conv2d(xg, wg, bg, stride, act)
+    assert got.shape == want.shape
+    assert _rel(got.detach(), want.detach()) <= REL
+    got.backward(dy.to(dev))
+    assert _rel(xg.grad, x.grad) <= REL, "dx"
+    assert _rel(wg.grad, w.grad) <= REL, "dw"
+    assert _rel(bg.grad, b.grad) <= REL, "db"
+
+
+def test_conv2d_first_layer_needs_no_dx(dev):
+    from esr_b200 import train
+    x = torch.randn(1, 2, 16, 16, device=dev)
+    w = torch.randn(8, 2, 3, 3, device=dev, requires_grad=True)
+    b = torch.zeros(8, device=dev, requires_grad=True)
+    train.conv2d(x, w, b, 1, "relu").sum().backward()
+    assert w.grad is not None and b.grad is not None
+
+
+def test_mse_loss_and_adam_vs_torch(dev):
+    from esr_b200 import train
+    g = torch.Generator().manual_seed(5)
+    p0, t0 = torch.randn(3, 2, 33, 17, generator=g), torch.randn(3, 2, 33, 17, generator=g)
+    pr = p0.clone().requires_grad_()
+    want = F.mse_loss(pr, t0)
+    want.backward()
+    pg = p0.to(dev).requires_grad_()
+    got = train.mse_loss(pg, t0.to(dev))
+    (3.0 * got).backward()
+    assert abs(got.item() - want.item()) <= 1e-6 * abs(want.item()) + 1e-9
+    assert _rel(pg.grad, 3.0 * pr.grad) <= 1e-6
+    # Adam(lr 1e-3, weight_decay 1e-4, amsgrad) = config/train_ours_enfssyn.yml optimizer
+    shapes = [(8, 2, 3, 3), (8,), (64, 128, 3, 3), (5,)]
+    ref = [torch.randn(s, generator=g).requires_grad_() for s in shapes]
+    mine = [r.detach().clone().to(dev).requires_grad_() for r in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    o_mine = train.Adam(mine, lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    for step in range(6):
+        o_mine.zero_grad()
+        for r, m in zip(ref, mine):
+            gr = torch.randn(r.shape, generator=g) * (0.1 if step % 2 else 10.0)
+            r.grad = gr.clone()
+            m.grad.copy_(gr.to(dev))
+        o_ref.step()
+        o_mine.step()
+        for r, m in zip(ref, mine):
+            assert torch.allclose(m.detach().cpu(), r.detach(), rtol=2e-6, atol=2e-7), step
+
+
+def _frames(B, L, H, W, seed, lam=0.3):
+    g = torch.Generator().manual_seed(seed)
+    return torch.poisson(torch.full((B, L, 2, H, W), lam), generator=g), torch.poisson(torch.full((B, L, 2, H, W), lam), generator=g)
+
+
+def _net(sd, dev):
+    from esr_b200.model import DeepRecurrNet
+    net = DeepRecurrNet(inch=2, basech=8, num_frame=3)
+    net.load_state_dict(sd)
+    return net.to(dev)
+
+
+def test_training_forward_matches_inference_plan(dev):
+    """The differentiable composition and the fused no_grad plan are the same function (incl. the carried state)."""
+    sd = model_ref.seeded_state_dict(21)
+    frames, _ = _frames(2, 5, 36, 44, 3)
+    frames = frames.to(dev)
+    a, b = _net(sd, dev), _net(sd, dev)
+    for w in range(3):
+        with torch.no_grad():
+            want = a(frames[:, w:w + 3].contiguous())
+        got = b(frames[:, w:w + 3])
+        assert got.requires_grad
+        assert _rel(got.detach().cpu(), want.cpu()) <= REL, w
+
+
+@pytest.mark.parametrize("B,L,H,W", [(1, 4, 32, 32), (2, 5, 24, 40), (1, 3, 20, 28)])
+def test_sequence_gradients_vs_oracle_autograd(dev, B, L, H, W):
+    """Loss = sum over windows of MSE(pred, gt[mid]) with the ConvGRU state carried (train_ours_cnt_seq.py:209-232):
+    loss value and all 68 parameter gradients vs autograd through the oracle on the CPU."""
+    from esr_b200 import train
+    sd = model_ref.seeded_state_dict(31 + L)
+    frames, gt = _frames(B, L, H, W, 11 + H)
+    ref = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    states, loss_ref = None, 0
+    for w in range(L - 2):
+        pred, states = model_ref.forward(ref, frames[:, w:w + 3], states)
+        loss_ref = loss_ref + F.mse_loss(pred, gt[:, w + 1])
+    loss_ref.backward()
+
+    net = _net(sd, dev)
+    net.reset_states()
+    fd, gd = frames.to(dev), gt.to(dev)
+    loss = 0
+    for w in range(L - 2):
+        loss = loss + train.mse_loss(net(fd[:, w:w + 3]), gd[:, w + 1])
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= REL * abs(loss_ref.item())
+    worst = {}
+    for name, p in net.named_parameters():
+        want = ref[name].grad
+        assert p.grad is not None, name
+        worst[name] = _rel(p.grad, want)
+    bad = {k: v for k, v in worst.items() if v > 3 * REL}
+    assert not bad, bad
+
+
+def test_train_step_tracks_oracle_losses(dev):
+    """Four full iterations (zero_grad, reset_states, windows, backward, Adam amsgrad): the loss trajectory follows the
+    oracle trained with torch.optim.Adam, and the loss goes down."""
+    from esr_b200 import train
+    sd = model_ref.seeded_state_dict(41)
+    frames, gt = _frames(2, 5, 32, 32, 77)
+    ref = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    opt_ref = torch.optim.Adam(list(ref.values()), lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    net = _net(sd, dev)
+    opt = train.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    fd, gd = frames.to(dev), gt.to(dev)
+    losses, losses_ref = [], []
+    for it in range(4):
+        opt_ref.zero_grad()
+        states, lr_ = None, 0
+        for w in range(3):
+            pred, states = model_ref.forward(ref, frames[:, w:w + 3], states)
+            lr_ = lr_ + F.mse_loss(pred, gt[:, w + 1])
+        lr_.backward()
+        opt_ref.step()
+        losses_ref.append(lr_.item())
+        losses.append(train.train_step(net, opt, fd, gd).item())
+    assert losses[-1] < losses[0]
+    for a, b in zip(losses, losses_ref):
+        assert abs(a - b) <= 5e-3 * abs(b), (losses, losses_ref)
+    # the inference plan sees the updated parameters (cached blob repacked after the in-place optimizer step)
+    with torch.no_grad():
+        net.reset_states()
+        out = net(fd[:, 0:3].contiguous())
+        want, _ = model_ref.forward({k: v.detach() for k, v in ref.items()}, frames[:, 0:3], None)
+    assert _rel(out.cpu(), want) <= 2e-2
