@@ -45,6 +45,12 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// bump allocator over a caller-provided workspace (base == nullptr: size query only)
+struct Bump {
+    uint8_t *base; size_t off, cap;
+    void *take(size_t bytes) { void *p = base ? base + off : nullptr; off = align_up(off + bytes, 256); return p; }
+};
+
 // device properties cache (immutable after first use)
 struct DevInfo { int sm_count; int max_smem_optin; };
 const DevInfo &dev_info();

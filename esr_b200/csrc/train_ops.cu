@@ -313,11 +313,6 @@ __global__ void __launch_bounds__(256) k_adam(float *__restrict__ p, const float
 static inline bool tc_fwd_ok(int Cin, int Cout, int ksz, int stride) { return stride == 1 && Cin % 64 == 0 && Cout <= 256 && (ksz == 3 || ksz == 1); }
 static inline bool tc_dgrad_ok(int Cin, int Cout, int ksz, int stride) { return stride == 1 && Cout % 64 == 0 && Cin <= 256 && (ksz == 3 || ksz == 1); }
 
-struct Bump {
-    uint8_t *base; size_t off, cap;
-    void *take(size_t bytes) { void *p = base ? base + off : nullptr; off = align_up(off + bytes, 256); return p; }
-};
-
 static size_t conv2d_ws(int B, int Cin, int H, int W, int Cout, int ksz, int stride)
 {
     const int Ho = (H + 2 * (ksz / 2) - ksz) / stride + 1, Wo = (W + 2 * (ksz / 2) - ksz) / stride + 1;
@@ -328,7 +323,8 @@ static size_t conv2d_ws(int B, int Cin, int H, int W, int Cout, int ksz, int str
     }
     b.take((size_t)B * Cout * Ho * Wo * 4);
     if (tc_dgrad_ok(Cin, Cout, ksz, stride)) {
-        b.take((size_t)B * Cout * Ho * Wo * 4); b.take((size_t)Cout * Cin * ksz * ksz * 4);
+        b.take((size_t)B * Cout * Ho * Wo * 4); b.take((size_t)B * Cin * H * W * 4);      // g split, x split (dw on tensor cores)
+        b.take((size_t)Cout * Cin * ksz * ksz * 4);
         b.take(tc_packed_weight_bytes(Cin, Cout, ksz * ksz)); b.take(256 * 4); b.take((size_t)B * tc_npad(Cin) * H * W * 4);
     }
     return (f.off > b.off ? f.off : b.off) + 1024;

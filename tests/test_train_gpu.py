@@ -169,7 +169,7 @@ def test_sequence_gradients_vs_oracle_autograd(dev, B, L, H, W):
 
 def test_train_step_tracks_oracle_losses(dev):
     """Four full iterations (zero_grad, reset_states, windows, backward, Adam amsgrad): the loss trajectory follows the
-    oracle trained with torch.optim.Adam, and the loss goes down."""
+    oracle trained with torch.optim.Adam step for step."""
     from esr_b200 import train
     sd = model_ref.seeded_state_dict(41)
     frames, gt = _frames(2, 5, 32, 32, 77)
@@ -189,9 +189,9 @@ def test_train_step_tracks_oracle_losses(dev):
         opt_ref.step()
         losses_ref.append(lr_.item())
         losses.append(train.train_step(net, opt, fd, gd).item())
-    assert losses[-1] < losses[0]
     for a, b in zip(losses, losses_ref):
-        assert abs(a - b) <= 5e-3 * abs(b), (losses, losses_ref)
+        assert abs(a - b) <= 1e-3 * abs(b), (losses, losses_ref)
+    assert abs((losses[-1] - losses[0]) - (losses_ref[-1] - losses_ref[0])) <= 0.05 * abs(losses_ref[-1] - losses_ref[0]) + 1e-6
     # the inference plan sees the updated parameters (cached blob repacked after the in-place optimizer step)
     with torch.no_grad():
         net.reset_states()
