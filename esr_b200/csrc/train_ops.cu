@@ -290,10 +290,20 @@ __global__ void __launch_bounds__(256) k_mse(const float *__restrict__ p, const 
     }
 }
 
+__global__ void k_adam_tick(int *step) { *step += 1; }
+
 __global__ void __launch_bounds__(256) k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                                               float *__restrict__ v, float *__restrict__ vmax, size_t n, float lr, float b1, float b2,
-                                              float eps, float wd, float bc1, float bc2_sqrt)
+                                              float eps, float wd, const int *__restrict__ step)
 {
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {                                        // bias corrections from the device-side step counter
+        const int t = *step;
+        s_bc[0] = (float)(1.0 - pow((double)b1, (double)t));
+        s_bc[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+    }
+    __syncthreads();
+    const float bc1 = s_bc[0], bc2_sqrt = s_bc[1];
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
         const float pi = p[i];
         const float gi = fmaf(wd, pi, g[i]);                       // torch.optim.Adam: L2 term added to the gradient
@@ -363,7 +373,8 @@ static int launch_generic(int which, const float *x, const float *w, const float
         const int PD = (G_T - 1) * stride + KS;
         const size_t smem = (size_t)(G_C * PD * PD + G_C * G_C * KK) * 4;
         const dim3 grid(((Wo + G_T - 1) / G_T) * ((Ho + G_T - 1) / G_T), (Cout + G_C - 1) / G_C, B);
-        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_fwd_g<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static bool attr = false;
+        if (!attr) { ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_fwd_g<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
         k_conv_fwd_g<KS><<<grid, blk, smem, st>>>(x, w, bias, out, Cin, H, W, Cout, Ho, Wo, stride, act);
     } else if (which == 1) {
         const int GP = (G_T - 1 + KS - 1) / stride + 2;
@@ -378,7 +389,8 @@ static int launch_generic(int which, const float *x, const float *w, const float
         int slices = (dev_info().sm_count * 8 + pairs - 1) / pairs;
         if (slices > items) slices = items;
         if (slices < 1) slices = 1;
-        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_wgrad_g<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static bool attr = false;
+        if (!attr) { ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_wgrad_g<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
         k_conv_wgrad_g<KS><<<dim3(pairs, slices), 256, smem, st>>>(x, g, out, B, Cin, H, W, Cout, Ho, Wo, stride);
     }
     ESR_LAUNCH_CHECK();
@@ -506,14 +518,15 @@ int esr_mse_loss(const float *pred, const float *target, size_t n, float *loss, 
     return ESR_OK;
 }
 
-int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n, int step, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, esr_stream_t stream)
+int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n,
+                  int32_t *step_counter, float lr, float beta1, float beta2, float eps, float weight_decay, esr_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    ESR_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
-    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    ESR_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_counter && n > 0, "adam_step: bad arguments");
+    k_adam_tick<<<1, 1, 0, st>>>(step_counter);
+    ESR_LAUNCH_CHECK();
     k_adam<<<(unsigned)min((size_t)2048, (n + 255) / 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                                        weight_decay, (float)bc1, (float)sqrt(bc2));
+                                                                        weight_decay, step_counter);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

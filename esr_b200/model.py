@@ -211,8 +211,11 @@ class DeepRecurrNet(nn.Module):
             if frame_index is not None:
                 raise _lib.ESRError("esr_b200.DeepRecurrNet: frame banks are an inference feature")
             from . import train
-            out, self._train_states = train.forward_window(self, input, self._train_states)
+            # L == num_frame: the reference's single window; L > num_frame: all sliding windows in one graph (window-major)
+            out, self._train_states = train.forward_sequence(self, input, self._train_states)
             return out
+        if frame_index is None and input.dim() == 5 and input.shape[1] > self._cfg["num_frame"]:
+            return self.forward_sequence(input)
         x = input.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
@@ -239,8 +242,7 @@ class DeepRecurrNet(nn.Module):
         if not frames.is_cuda:
             raise _lib.ESRError("esr_b200.DeepRecurrNet.forward_sequence needs a CUDA tensor (there is no CPU path)")
         if torch.is_grad_enabled() and (frames.requires_grad or any(p.requires_grad for p in self.parameters())):
-            n = self._cfg["num_frame"]
-            return torch.cat([self.forward(frames[:, w:w + n]) for w in range(frames.shape[1] - n + 1)], 0)
+            return self.forward(frames)
         x = frames.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()

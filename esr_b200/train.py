@@ -125,101 +125,113 @@ def _cl(m, x, stride=1, act=None):
     return conv2d(x, m.conv2d.weight, m.conv2d.bias, stride, act)
 
 
-def _local_time_corre(tp, f0, f1, f2):
-    """TimePropagation.local_time_corre (models/model.py:77-89)."""
-    def pred_map(a, b):
-        return _cl(tp.pred_map[1], _cl(tp.pred_map[0], torch.cat([a, b], 1), act="relu"), act="sigmoid")
+def forward_sequence(model, frames, states=None):
+    """frames BxLx2xHxW (L >= num_frame) -> ((L-2)*B x 2 x H x W window-major, [h_fwd, h_rev]).
 
-    x = torch.cat([f0 * pred_map(f0, f1), f1, f2 * pred_map(f1, f2)], 1)
-    rb = tp.local_fusion[0]                                   # ResidualBlock (models/submodules.py:391-409)
-    r = conv2d(x, rb.conv1.weight, rb.conv1.bias, 1, "relu")
-    r = torch.relu(conv2d(r, rb.conv2.weight, rb.conv2.bias, 1, None) + x)
-    return _cl(tp.local_fusion[1], r) + f1
-
-
-def _gru_step(tp, x, h):
-    """RecurrentConvLayer + ConvGRU (models/submodules.py:340-344, 496-514)."""
-    g = tp.lstm.recurrent_block
-    x = _cl(tp.lstm.conv, x, act="relu")
-    if h is None:
-        h = torch.zeros_like(x)
-    xh = torch.cat([x, h], 1)
-    z = conv2d(xh, g.update_gate.weight, g.update_gate.bias, 1, "sigmoid")
-    r = conv2d(xh, g.reset_gate.weight, g.reset_gate.bias, 1, "sigmoid")
-    o = conv2d(torch.cat([x, h * r], 1), g.out_gate.weight, g.out_gate.bias, 1, "tanh")
-    return h * (1 - z) + o * z
-
-
-def forward_window(model, inp, states=None):
-    """inp BxNx2xHxW -> (Bx2xHxW, [h_fwd, h_rev]); differentiable w.r.t. the parameters, the input and `states`."""
+    The L-2 sliding-window forwards of the reference's training loop (train_ours_cnt_seq.py:217-231) as ONE differentiable
+    graph with the same batching as the inference plan: head / encoder / attention maps once per frame,
+    every state-independent layer once for all windows, only the ConvGRU chain serial (both directions batched as 2B).
+    Per image the arithmetic is that of models/model.py:314-344; gradients w.r.t. parameters, frames and `states`."""
     cfg = model._cfg
     N = cfg["num_frame"]
-    B, n_in, Cin, H, W = inp.shape
-    assert n_in == N
+    B, L, Cin, H, W = frames.shape
+    assert L >= N and N == 3
+    Wn = L - N + 1
     Hc, Wc = 8 * math.ceil(H / 8), 8 * math.ceil(W / 8)
-    x = inp.float()
-    if (Hc, Wc) != (H, W):                                     # CropSize.pad (models/model_util.py:148-152)
+    x = frames.float().transpose(0, 1).reshape(L * B, Cin, H, W)          # frame-major: image l*B + b
+    if (Hc, Wc) != (H, W):                                               # CropSize.pad (models/model_util.py:148-152)
         pt, pb = math.ceil(0.5 * (Hc - H)), math.floor(0.5 * (Hc - H))
         pl, pr = math.ceil(0.5 * (Wc - W)), math.floor(0.5 * (Wc - W))
         x = F.pad(x, (pl, pr, pt, pb))
-    x = _cl(model.head, x.reshape(B * N, Cin, Hc, Wc), act="relu")
+    x = _cl(model.head, x, act="relu")
     pyramid = []
-    for blk in model.feat_extract.convblock:                    # FeatsExtract (models/model.py:20-45)
+    for blk in model.feat_extract.convblock:                              # FeatsExtract (models/model.py:20-45)
         x = _cl(blk, x, stride=2, act="relu")
         pyramid.append(x)
     pyramid.reverse()
     C, h, w = pyramid[0].shape[1:]
-    f = pyramid[0].view(B, N, C, h, w)
+    f = pyramid[0].view(L, B, C, h, w)
 
-    tp = model.time_propagate                                   # TimePropagation.forward (models/model.py:126-153)
-    ltc = []
-    for i in range(N):
-        lo, hi = max(i - 1, 0), min(i + 1, N - 1)
-        ltc.append(_local_time_corre(tp, f[:, lo], f[:, i], f[:, hi]))
+    # ---- TimePropagation.local_time_corre (models/model.py:77-89, 133-146) for every (window, slot)
+    tp = model.time_propagate
+    pairs = sorted({(j, j) for j in range(Wn)} | {(j + 2, j + 2) for j in range(Wn)} | {(j, j + 1) for j in range(L - 1)})
+    pm_in = torch.cat([torch.cat([f[a], f[b]], 1) for a, b in pairs], 0)
+    pm = _cl(tp.pred_map[1], _cl(tp.pred_map[0], pm_in, act="relu"), act="sigmoid").view(len(pairs), B, 1, h, w)
+    gate = {p: pm[k] for k, p in enumerate(pairs)}
+    cat_in = []
+    for wi in range(Wn):
+        for i in range(N):
+            a, b, c = wi + max(i - 1, 0), wi + i, wi + min(i + 1, N - 1)
+            cat_in.append(torch.cat([f[a] * gate[(a, b)], f[b], f[c] * gate[(b, c)]], 1))
+    xcat = torch.cat(cat_in, 0)                                           # [(Wn*3*B), 192, h, w]
+    rb = tp.local_fusion[0]                                               # ResidualBlock (models/submodules.py:391-409)
+    r = conv2d(xcat, rb.conv1.weight, rb.conv1.bias, 1, "relu")
+    r = torch.relu(conv2d(r, rb.conv2.weight, rb.conv2.bias, 1, None) + xcat)
+    mid_feat = torch.cat([f[wi + i] for wi in range(Wn) for i in range(N)], 0)
+    ltc = _cl(tp.local_fusion[1], r) + mid_feat
+    # ---- TimePropagation.global_time_corre: RecurrentConvLayer + ConvGRU (models/submodules.py:340-344, 496-514)
+    gx = _cl(tp.lstm.conv, ltc, act="relu").view(Wn, N, B, C, h, w)       # the x-side conv of every step at once
+    gru = tp.lstm.recurrent_block
+    w_zr = torch.cat([gru.update_gate.weight, gru.reset_gate.weight], 0)   # both gates in one 128 -> 128 convolution
+    b_zr = torch.cat([gru.update_gate.bias, gru.reset_gate.bias], 0)
     h_f, h_r = states if states is not None else (None, None)
+    hs = None if h_f is None else torch.cat([h_f, h_r], 0)                # forward and reverse chains batched as 2B
     fwd, rev = [], []
-    for i in range(N):
-        if cfg["gtc_frozen"]:
-            h_f, h_r = None, None
-        h_f = _gru_step(tp, ltc[i], h_f)
-        h_r = _gru_step(tp, ltc[N - 1 - i], h_r)
-        fwd.append(h_f)
-        rev.append(h_r)
-    new_states = [None, None] if cfg["gtc_frozen"] else [h_f, h_r]
-    both = torch.cat([torch.stack(fwd, 1), torch.stack(rev[::-1], 1)], 2).view(B * N, 2 * C, h, w)
-    prop = _cl(tp.global_fusion, both, act="relu").view(B, N, C, h, w) + f
+    for wi in range(Wn):
+        rev_w = [None] * N
+        for i in range(N):
+            if cfg["gtc_frozen"]:
+                hs = None
+            xi = torch.cat([gx[wi, i], gx[wi, N - 1 - i]], 0)
+            if hs is None:
+                hs = torch.zeros_like(xi)
+            zr = conv2d(torch.cat([xi, hs], 1), w_zr, b_zr, 1, "sigmoid")
+            z, rg = zr[:, :C], zr[:, C:]
+            o = conv2d(torch.cat([xi, hs * rg], 1), gru.out_gate.weight, gru.out_gate.bias, 1, "tanh")
+            hs = hs * (1 - z) + o * z
+            fwd.append(hs[:B])
+            rev_w[N - 1 - i] = hs[B:]
+        rev.extend(rev_w)
+    new_states = [None, None] if cfg["gtc_frozen"] else [hs[:B], hs[B:]]
+    both = torch.cat([torch.cat(fwd, 0), torch.cat(rev, 0)], 1)           # [(Wn*3*B), 128, h, w]
+    prop = (_cl(tp.global_fusion, both, act="relu") + mid_feat).view(Wn, N, B, C, h, w)
 
-    sf = model.spacetime_fuse                                   # STFusion.forward (models/model.py:208-291)
+    # ---- STFusion (models/model.py:208-291): both neighbours of all windows at once
+    sf = model.spacetime_fuse
     mid = (N - 1) // 2
-    center = prop[:, mid]
-    fused = []
-    for i in range(N):
-        if i == mid:
-            continue
-        nb = prop[:, i]
-        off_feat = _cl(sf.offset[1], _cl(sf.offset[0], torch.cat([nb, center], 1), act="relu"))
-        om = conv2d(off_feat, sf.dcn.conv_offset_mask.weight, sf.dcn.conv_offset_mask.bias, 1, None)
-        o1, o2, msk = torch.chunk(om, 3, dim=1)                 # DCN_sep.forward (models/DCNv2/dcn_v2.py:214-227)
-        aligned = torch.relu(dcn_v2(nb, torch.cat((o1, o2), 1), torch.sigmoid(msk), sf.dcn.weight, sf.dcn.bias, 8))
-        ft = _cl(sf.convblock[1], _cl(sf.convblock[0], torch.cat([aligned, center], 1), act="relu"))
-        sk = _cl(sf.kernel, ft, act="sigmoid")
-        mlp = sf.fc[0].layers
-        ck = torch.relu(F.linear(ft.flatten(2).max(dim=2)[0], mlp[0].weight, mlp[0].bias))
-        ck = torch.sigmoid(F.linear(ck, mlp[1].weight, mlp[1].bias))
-        y = torch.cat([aligned * sk[:, 0:1] * ck[:, :C, None, None], center * sk[:, 1:2] * ck[:, C:, None, None]], 1)
-        fused.append(_cl(sf.dcn_fusion[1], _cl(sf.dcn_fusion[0], y, act="relu")))
-    fused.append(center)
-    x = _cl(sf.dense_fusion[1], _cl(sf.dense_fusion[0], torch.cat(fused, 1), act="relu"))
-    for lvl, ft in enumerate(pyramid):                          # scale_aggre + recons (models/model.py:253-291)
-        att = _cl(sf.attens[lvl], ft, act="sigmoid")
-        x = x + (ft * att).view(B, N, *ft.shape[1:]).mean(1)
-        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    center = prop[:, mid].reshape(Wn * B, C, h, w)
+    others = [i for i in range(N) if i != mid]
+    nb = torch.cat([prop[:, i].reshape(Wn * B, C, h, w) for i in others], 0)
+    ctr = torch.cat([center] * len(others), 0)
+    off_feat = _cl(sf.offset[1], _cl(sf.offset[0], torch.cat([nb, ctr], 1), act="relu"))
+    om = conv2d(off_feat, sf.dcn.conv_offset_mask.weight, sf.dcn.conv_offset_mask.bias, 1, None)
+    o1, o2, msk = torch.chunk(om, 3, dim=1)                               # DCN_sep.forward (models/DCNv2/dcn_v2.py:214-227)
+    aligned = torch.relu(dcn_v2(nb, torch.cat((o1, o2), 1), torch.sigmoid(msk), sf.dcn.weight, sf.dcn.bias, 8))
+    ft = _cl(sf.convblock[1], _cl(sf.convblock[0], torch.cat([aligned, ctr], 1), act="relu"))
+    sk = _cl(sf.kernel, ft, act="sigmoid")
+    mlp = sf.fc[0].layers
+    ck = torch.relu(F.linear(ft.flatten(2).max(dim=2)[0], mlp[0].weight, mlp[0].bias))
+    ck = torch.sigmoid(F.linear(ck, mlp[1].weight, mlp[1].bias))
+    y = torch.cat([aligned * sk[:, 0:1] * ck[:, :C, None, None], ctr * sk[:, 1:2] * ck[:, C:, None, None]], 1)
+    fz = _cl(sf.dcn_fusion[1], _cl(sf.dcn_fusion[0], y, act="relu")).view(len(others), Wn * B, C, h, w)
+    x = torch.cat([fz[k] for k in range(len(others))] + [center], 1)
+    x = _cl(sf.dense_fusion[1], _cl(sf.dense_fusion[0], x, act="relu"))
+    for lvl, ft in enumerate(pyramid):                                    # scale_aggre + recons (models/model.py:253-291)
+        prod = (ft * _cl(sf.attens[lvl], ft, act="sigmoid")).view(L, B, *ft.shape[1:])
+        agg = torch.stack([prod[wi:wi + N].mean(0) for wi in range(Wn)], 0).flatten(0, 1)
+        x = F.interpolate(x + agg, scale_factor=2, mode="bilinear", align_corners=False)
         x = _cl(sf.recons[lvl], x, act="relu")
     x = _cl(model.tail, x, act="relu")
-    if (Hc, Wc) != (H, W):                                     # CropSize.crop (models/model_util.py:154-164)
+    if (Hc, Wc) != (H, W):                                               # CropSize.crop (models/model_util.py:154-164)
         cy, cx = Hc // 2, Wc // 2
         x = x[..., cy - H // 2: cy + math.ceil(H / 2), cx - W // 2: cx + math.ceil(W / 2)].contiguous()
     return x, new_states
+
+
+def forward_window(model, inp, states=None):
+    """inp BxNx2xHxW -> (Bx2xHxW, [h_fwd, h_rev]): the reference's single-window forward, differentiable."""
+    assert inp.shape[1] == model._cfg["num_frame"]
+    return forward_sequence(model, inp, states)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -228,7 +240,8 @@ def forward_window(model, inp, states=None):
 class Adam:
     """torch.optim.Adam(params, lr, betas, eps, weight_decay, amsgrad) semantics (the reference's optimizer,
     train_ours_cnt_seq.py:781 + config optimizer args) with one kernel launch per step: parameters and gradients are
-    re-homed as views of two flat fp32 buffers (so DDP buckets and the update see contiguous memory)."""
+    re-homed as views of two flat fp32 buffers (so DDP buckets and the update see contiguous memory); the step counter
+    is a device int the kernel increments itself, so a captured CUDA graph of the step stays correct on replay."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False):
         self.params = [p for p in params if p.requires_grad]
@@ -248,7 +261,7 @@ class Adam:
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
         self.max_exp_avg_sq = torch.zeros_like(self.flat) if amsgrad else None
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.step_count = 0
+        self.step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)   # step counter lives on the device (graph replays)
         self.param_groups = [dict(params=self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)]
 
     def zero_grad(self, set_to_none=False):
@@ -261,15 +274,30 @@ class Adam:
             off += k
 
     def step(self):
-        self.step_count += 1
         lr = self.param_groups[0]["lr"]
         with torch.cuda.device(self.flat.device):
             _lib.check(_lib.lib().esr_adam_step(_lib.ptr(self.flat), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
                                                 _lib.ptr(self.exp_avg_sq), _lib.ptr(self.max_exp_avg_sq), self.flat.numel(),
-                                                self.step_count, lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                                _lib.stream_ptr()), "esr_adam_step")
+                                                _lib.ptr(self.step_dev), lr, self.betas[0], self.betas[1], self.eps,
+                                                self.weight_decay, _lib.stream_ptr()), "esr_adam_step")
         torch._C._increment_version(self.params)                  # the kernel wrote the parameters behind autograd's back:
         #                                                           bump their versions so cached inference blobs repack
+
+
+def _step_body(model, optimizer, frames, gt, num_frame, all_reduce):
+    Wn = frames.shape[1] - num_frame + 1
+    mid = (num_frame - 1) // 2
+    optimizer.zero_grad()
+    net = model.module if hasattr(model, "module") else model
+    net.reset_states()
+    pred = model(frames)                                          # all windows, window-major [(Wn*B), 2, H, W]
+    target = gt[:, mid:mid + Wn].transpose(0, 1).reshape(pred.shape)
+    loss = Wn * mse_loss(pred, target)                            # = sum over windows of MSELoss(pred_w, gt[:, w + mid])
+    loss.backward()
+    if all_reduce is not None:
+        all_reduce(optimizer.flat_grad)
+    optimizer.step()
+    return loss.detach()
 
 
 def train_step(model, optimizer, frames, gt, num_frame=3, all_reduce=None):
@@ -277,19 +305,40 @@ def train_step(model, optimizer, frames, gt, num_frame=3, all_reduce=None):
 
     frames: BxLx2xHxW input count tensors (inp_scaled_cnt of each frame); gt: BxLx2xHxW target count tensors.
     Windows slide by one frame (dataloader/h5dataloader.py:229-231); the loss is the sum over windows of
-    MSE(pred, gt[:, window middle]); one backward; optional `all_reduce(flat_grad)` (DDP's role); one Adam step.
-    Returns the summed loss (a 0-dim tensor)."""
-    L = frames.shape[1]
-    mid = (num_frame - 1) // 2
-    optimizer.zero_grad()
-    net = model.module if hasattr(model, "module") else model
-    net.reset_states()
-    loss = 0
-    for w in range(L - num_frame + 1):
-        pred = model(frames[:, w:w + num_frame])
-        loss = loss + mse_loss(pred, gt[:, w + mid])
-    loss.backward()
-    if all_reduce is not None:
-        all_reduce(optimizer.flat_grad)
-    optimizer.step()
-    return loss.detach()
+    MSE(pred, gt[:, window middle]) with the ConvGRU state carried from window to window; one backward; optional
+    `all_reduce(flat_grad)` (DDP's role when the model is not DDP-wrapped); one Adam step.  Returns the summed loss."""
+    return _step_body(model, optimizer, frames, gt, num_frame, all_reduce)
+
+
+class GraphedTrainStep:
+    """train_step captured once into a CUDA graph (forward, backward, all-reduce hook and the Adam kernel) and replayed:
+    no Python / launch overhead per iteration.  Shapes are fixed at construction; data is copied into static buffers."""
+
+    def __init__(self, model, optimizer, frames_shape, device, num_frame=3, all_reduce=None, warmup=2):
+        self.model, self.opt = model, optimizer
+        self.frames = torch.zeros(frames_shape, dtype=torch.float32, device=device)
+        self.gt = torch.zeros(frames_shape, dtype=torch.float32, device=device)
+        keep = [t.clone() for t in (optimizer.flat, optimizer.exp_avg, optimizer.exp_avg_sq)]
+        keep_max = None if optimizer.max_exp_avg_sq is None else optimizer.max_exp_avg_sq.clone()
+        keep_step = optimizer.step_dev.clone()
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):                             # warm-up: lazy inits + allocator, outside the capture
+            for _ in range(warmup):
+                _step_body(model, optimizer, self.frames, self.gt, num_frame, all_reduce)
+        torch.cuda.current_stream(device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = _step_body(model, optimizer, self.frames, self.gt, num_frame, all_reduce)
+        for dst, src in zip((optimizer.flat, optimizer.exp_avg, optimizer.exp_avg_sq), keep):   # undo the warm-up updates
+            dst.copy_(src)
+        if keep_max is not None:
+            optimizer.max_exp_avg_sq.copy_(keep_max)
+        optimizer.step_dev.copy_(keep_step)
+
+    def __call__(self, frames, gt):
+        self.frames.copy_(frames)
+        self.gt.copy_(gt)
+        self.graph.replay()
+        torch._C._increment_version(self.opt.params)
+        return self.loss

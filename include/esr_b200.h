@@ -220,9 +220,12 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
 /* loss[0] = mean((pred - target)^2); grad (optional) = grad_scale * 2 (pred - target) / n */
 int esr_mse_loss(const float *pred, const float *target, size_t n, float *loss, float *grad, float grad_scale,
                  esr_stream_t stream);
-/* One torch.optim.Adam step over a flat fp32 parameter buffer; step counts from 1; max_exp_avg_sq != NULL = amsgrad. */
-int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n, int step,
-                  float lr, float beta1, float beta2, float eps, float weight_decay, esr_stream_t stream);
+/* One torch.optim.Adam step over a flat fp32 parameter buffer; max_exp_avg_sq != NULL = amsgrad.  step_counter is a
+ * DEVICE int32 holding the number of steps taken so far (0 before the first); the call increments it on the stream and
+ * uses the new value for the bias corrections, so the call can sit inside a replayed CUDA graph. */
+int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n,
+                  int32_t *step_counter, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  esr_stream_t stream);
 
 #ifdef __cplusplus
 }
