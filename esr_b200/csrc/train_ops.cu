@@ -66,13 +66,13 @@ __global__ void __launch_bounds__(256) k_bias_grad(const float *__restrict__ g, 
     }
 }
 
-// wT[ci][co][K-1-ky][K-1-kx] = w[co][ci][ky][kx]: the weights of the convolution that maps g to dx
-__global__ void k_weight_rot_t(const float *__restrict__ w, int Cout, int Cin, int KK, float *__restrict__ wt)
+// wT[ci][co][K-1-ky][K-1-kx] = w[co][ci][ky][kx]: the weights of the convolution that maps g to dx (co padded to CoutPad)
+__global__ void k_weight_rot_t(const float *__restrict__ w, int Cout, int CoutPad, int Cin, int KK, float *__restrict__ wt)
 {
     const int total = Cout * Cin * KK;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int t = i % KK, ci = (i / KK) % Cin, co = i / (KK * Cin);
-        wt[((size_t)ci * Cout + co) * KK + (KK - 1 - t)] = w[i];
+        wt[((size_t)ci * CoutPad + co) * KK + (KK - 1 - t)] = w[i];
     }
 }
 
@@ -91,6 +91,38 @@ __global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float *__restrict__ 
         const int c = c0 + r, p = p0 + tx;
         if (c < C && p < HW) dst[((size_t)n * C + c) * HW + p] = tile[tx][r];
     }
+}
+
+// fp32 NCHW -> split bf16 NHWC with the channel count padded to Cpad (extra channels zero): smem-tiled transpose, coalesced
+// on both sides.  Padding lets Cout = 216 (conv_offset_mask) use the 64-channel tensor-core tiles in dx and dw.
+__global__ void __launch_bounds__(256) k_split_from_nchw_t(const float *__restrict__ src, int C, int Cpad, int HW,
+                                                           __nv_bfloat16 *__restrict__ dst, size_t plane)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, p = p0 + tx;
+        tile[r][tx] = (c < C && p < HW) ? src[((size_t)n * C + c) * HW + p] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int p = p0 + r, c = c0 + tx;
+        if (p < HW && c < Cpad) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(tile[tx][r], hi, lo);
+            const size_t o = ((size_t)n * HW + p) * Cpad + c;
+            dst[o] = hi;
+            dst[plane + o] = lo;
+        }
+    }
+}
+
+static int split_from_nchw_pad(const float *src, int B, int C, int Cpad, int HW, __nv_bfloat16 *dst, cudaStream_t st)
+{
+    k_split_from_nchw_t<<<dim3((HW + 31) / 32, (Cpad + 31) / 32, B), 256, 0, st>>>(src, C, Cpad, HW, dst, (size_t)B * HW * Cpad);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
 }
 
 static int nhwc_to_nchw(const float *src, int B, int C, int HW, float *dst, cudaStream_t st)
@@ -321,7 +353,9 @@ __global__ void __launch_bounds__(256) k_adam(float *__restrict__ p, const float
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 static inline bool tc_fwd_ok(int Cin, int Cout, int ksz, int stride) { return stride == 1 && Cin % 64 == 0 && Cout <= 256 && (ksz == 3 || ksz == 1); }
-static inline bool tc_dgrad_ok(int Cin, int Cout, int ksz, int stride) { return stride == 1 && Cout % 64 == 0 && Cin <= 256 && (ksz == 3 || ksz == 1); }
+// dx / dw on the tensor cores: g is padded to a 64-multiple of channels; not worth it for the 1-, 2-, 8- and 16-channel layers
+static inline bool tc_dgrad_ok(int Cin, int Cout, int ksz, int stride) { return stride == 1 && Cout >= 32 && Cout <= 256 && Cin <= 256 && (ksz == 3 || ksz == 1); }
+static inline int pad64(int c) { return (c + 63) / 64 * 64; }
 
 static size_t conv2d_ws(int B, int Cin, int H, int W, int Cout, int ksz, int stride)
 {
@@ -333,9 +367,9 @@ static size_t conv2d_ws(int B, int Cin, int H, int W, int Cout, int ksz, int str
     }
     b.take((size_t)B * Cout * Ho * Wo * 4);
     if (tc_dgrad_ok(Cin, Cout, ksz, stride)) {
-        b.take((size_t)B * Cout * Ho * Wo * 4); b.take((size_t)B * Cin * H * W * 4);      // g split, x split (dw on tensor cores)
-        b.take((size_t)Cout * Cin * ksz * ksz * 4);
-        b.take(tc_packed_weight_bytes(Cin, Cout, ksz * ksz)); b.take(256 * 4); b.take((size_t)B * tc_npad(Cin) * H * W * 4);
+        b.take((size_t)B * pad64(Cout) * Ho * Wo * 4); b.take((size_t)B * Cin * H * W * 4);      // g split, x split (dw on tensor cores)
+        b.take((size_t)pad64(Cout) * Cin * ksz * ksz * 4);
+        b.take(tc_packed_weight_bytes(Cin, pad64(Cout), ksz * ksz)); b.take(256 * 4); b.take((size_t)B * tc_npad(Cin) * H * W * 4);
     }
     return (f.off > b.off ? f.off : b.off) + 1024;
 }
@@ -350,7 +384,7 @@ static int conv_tc_nchw(const float *x, const float *w, const float *bias, int B
     float *bp = (float *)ws.take(256 * 4);
     float *yt = (float *)ws.take((size_t)B * Cout * H * W * 4);           // fp32 NHWC
     ESR_REQUIRE(ws.off <= ws.cap, "conv2d: workspace too small (%zu > %zu)", ws.off, ws.cap);
-    if ((rc = split_from_nchw(x, B, Cin, H, W, xs.base, st))) return rc;
+    if ((rc = split_from_nchw_pad(x, B, Cin, Cin, H * W, xs.base, st))) return rc;
     if ((rc = pack_conv_weight(w, Cout, Cin, ksz, wp, st))) return rc;
     ESR_CUDA_CHECK(cudaMemsetAsync(bp, 0, 256 * 4, st));
     if (bias) ESR_CUDA_CHECK(cudaMemcpyAsync(bp, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, st));
@@ -404,8 +438,8 @@ static int generic(int which, int ksz, const float *x, const float *w, const flo
                     : launch_generic<1>(which, x, w, bias, g, out, B, Cin, H, W, Cout, Ho, Wo, stride, act, st);
 }
 
-int wgrad_tc(const float *x, const __nv_bfloat16 *g_split, int B, int Cin, int H, int W, int Cout, int ksz, float *dw, Bump &ws,
-             cudaStream_t st);   // wgrad_tc.cu (optional; returns ESR_EINVAL when the shape is not supported)
+int wgrad_tc(const __nv_bfloat16 *x_split, const __nv_bfloat16 *g_split, int B, int Cin, int H, int W, int Cout, int CoutPad, int ksz,
+             float *dw, cudaStream_t st);   // wgrad_tc.cu (returns ESR_EINVAL when the shape is not supported)
 
 } // namespace esr
 
@@ -465,18 +499,22 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
     }
     ESR_CUDA_CHECK(cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * ksz * ksz * 4, st));
     const bool tcd = tc_dgrad_ok(Cin, Cout, ksz, stride);
+    const int gC = pad64(Cout);
     __nv_bfloat16 *gsplit = nullptr;
     if (tcd) {
-        gsplit = (__nv_bfloat16 *)ws.take(ng * 4);
+        gsplit = (__nv_bfloat16 *)ws.take((size_t)B * gC * Ho * Wo * 4);
         ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
-        if ((rc = split_from_nchw(g, B, Cout, Ho, Wo, gsplit, st))) return rc;
+        if ((rc = split_from_nchw_pad(g, B, Cout, gC, Ho * Wo, gsplit, st))) return rc;
     }
     // ---- dw
     static const bool no_tc_wgrad = getenv("ESR_WGRAD_GENERIC") != nullptr;
     bool dw_done = false;
-    if (tcd && !no_tc_wgrad && Cin % 64 == 0 && stride == 1) {
-        Bump ws2 = ws;
-        rc = wgrad_tc(x, gsplit, B, Cin, H, W, Cout, ksz, dw, ws2, st);
+    if (tcd && !no_tc_wgrad && Cin % 64 == 0) {
+        Bump ws2 = ws;                                               // x split is dead after the kernel: dx reuses the space
+        __nv_bfloat16 *xsplit = (__nv_bfloat16 *)ws2.take((size_t)B * Cin * H * W * 4);
+        ESR_REQUIRE(ws2.off <= ws2.cap, "conv2d_backward: workspace too small");
+        if ((rc = split_from_nchw_pad(x, B, Cin, Cin, H * W, xsplit, st))) return rc;
+        rc = wgrad_tc(xsplit, gsplit, B, Cin, H, W, Cout, gC, ksz, dw, st);
         if (rc == ESR_OK) dw_done = true;
         else if (rc != ESR_EINVAL) return rc;
     }
@@ -484,16 +522,17 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
     // ---- dx
     if (dx) {
         if (tcd) {
-            float *wt = (float *)ws.take((size_t)Cout * Cin * ksz * ksz * 4);
-            void *wp = ws.take(tc_packed_weight_bytes(Cin, Cout, ksz * ksz));
+            float *wt = (float *)ws.take((size_t)gC * Cin * ksz * ksz * 4);
+            void *wp = ws.take(tc_packed_weight_bytes(Cin, gC, ksz * ksz));
             float *bp = (float *)ws.take(256 * 4);
             float *dt = (float *)ws.take((size_t)B * Cin * H * W * 4);       // fp32 NHWC
             ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small (%zu > %zu)", ws.off, ws.cap);
-            k_weight_rot_t<<<(Cout * Cin * ksz * ksz + 255) / 256, 256, 0, st>>>(w, Cout, Cin, ksz * ksz, wt);
+            if (gC != Cout) ESR_CUDA_CHECK(cudaMemsetAsync(wt, 0, (size_t)gC * Cin * ksz * ksz * 4, st));
+            k_weight_rot_t<<<(Cout * Cin * ksz * ksz + 255) / 256, 256, 0, st>>>(w, Cout, gC, Cin, ksz * ksz, wt);
             ESR_LAUNCH_CHECK();
-            if ((rc = pack_conv_weight(wt, Cin, Cout, ksz, wp, st))) return rc;
+            if ((rc = pack_conv_weight(wt, Cin, gC, ksz, wp, st))) return rc;
             ESR_CUDA_CHECK(cudaMemsetAsync(bp, 0, 256 * 4, st));
-            SplitTensor gsrc; gsrc.base = gsplit; gsrc.n_img = B; gsrc.H = Ho; gsrc.W = Wo; gsrc.C = Cout;
+            SplitTensor gsrc; gsrc.base = gsplit; gsrc.n_img = B; gsrc.H = Ho; gsrc.W = Wo; gsrc.C = gC;
             ConvTCDesc d;
             d.src[0] = gsrc; d.n_src = 1; d.ntaps = ksz * ksz; d.cout = Cin; d.wpacked = wp; d.bias = bp; d.n_img = B; d.act = ACT_NONE;
             d.out_f32 = dt; d.out_f32_C = Cin;

@@ -27,7 +27,7 @@ constexpr uint32_t WG_TILE = TC_BLOCK_M * 128u;       // one 64-channel x 128-pi
 struct WgradArgs {
     CUtensorMap gmap, xmap;           // 5-D (C, W, H, img, plane), box (64, TW, TH, 1, 1)
     float *dw;                        // [Cout][Cin][KK]
-    int Cout, Cin, KK;
+    int Cout, CoutPad, Cin, KK;       // g has CoutPad (64-multiple) channels, the first Cout are real
     int a_is_x;                       // 1: M side = x channels (shifted per tap), N side = g; 0: M side = g, N side = x
     int m_blocks, n_chunks, groups;   // grid decomposition
     int n_img, H, W, TW, TH, tiles_x, tiles_y, slices;
@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
     const int nch = bid % a.n_chunks; const int mblk = bid / a.n_chunks;
     const int tap0 = grp == 0 ? 0 : 5;
     const int ntap = a.KK == 1 ? 1 : (grp == 0 ? 5 : 4);
-    const int m_ch = a.a_is_x ? a.Cin : a.Cout;
+ const int m_ch = a.a_is_x ? a.Cin : a.CoutPad;               // channels of the M-side tensor as stored
+    const int m_real = a.a_is_x ? a.Cin : a.Cout;
     const int m0 = mblk * 128;
     const bool m_dup = m0 + 64 >= m_ch;                                  // only 64 channels left on the M side
     const int n0 = nch * 64;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
         // ===================== epilogue: TMEM -> fp32 atomics into dw =====================
         const int quad = warp & 3;
         const int m = quad * 32 + lane;                                  // accumulator row = M-side channel
-        const bool row_ok = (m < 64 || !m_dup) && (m0 + m < m_ch);
+        const bool row_ok = (m < 64 || !m_dup) && (m0 + m < m_real);
         mbar_wait(bar_accum, 0);
         tc_fence_after();
         for (int j = 0; j < ntap; ++j) {
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
                     for (int c = 0; c < 32; ++c) {
                         const int nc = n0 + half * 32 + c;
                         const int co = a.a_is_x ? nc : m0 + m, ci = a.a_is_x ? m0 + m : nc;
-                        atomicAdd(a.dw + ((size_t)co * a.Cin + ci) * a.KK + tap, __uint_as_float(raw[c]));
+                        if (co < a.Cout) atomicAdd(a.dw + ((size_t)co * a.Cin + ci) * a.KK + tap, __uint_as_float(raw[c]));
                     }
                 }
             }
@@ -192,16 +193,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// x: fp32 NCHW (converted to split NHWC in the workspace); g_split: split NHWC [2][B][H][W][Cout]; dw pre-zeroed.
-int wgrad_tc(const float *x, const __nv_bfloat16 *g_split, int B, int Cin, int H, int W, int Cout, int ksz, float *dw, Bump &ws,
-             cudaStream_t st)
+// x_split: split NHWC [2][B][H][W][Cin]; g_split: split NHWC [2][B][H][W][CoutPad] (channels >= Cout zero); dw pre-zeroed.
+int wgrad_tc(const __nv_bfloat16 *x_split, const __nv_bfloat16 *g_split, int B, int Cin, int H, int W, int Cout, int CoutPad, int ksz,
+             float *dw, cudaStream_t st)
 {
-    if (Cin % 64 != 0 || Cout % 64 != 0 || (ksz != 3 && ksz != 1)) return ESR_EINVAL;
+    if (Cin % 64 != 0 || CoutPad % 64 != 0 || CoutPad < Cout || (ksz != 3 && ksz != 1)) return ESR_EINVAL;
     int rc;
-    SplitTensor xs; xs.base = (__nv_bfloat16 *)ws.take((size_t)B * Cin * H * W * 4); xs.n_img = B; xs.H = H; xs.W = W; xs.C = Cin;
-    ESR_REQUIRE(ws.off <= ws.cap, "wgrad_tc: workspace too small (%zu > %zu)", ws.off, ws.cap);
-    if ((rc = split_from_nchw(x, B, Cin, H, W, xs.base, st))) return rc;
-    SplitTensor gs; gs.base = const_cast<__nv_bfloat16 *>(g_split); gs.n_img = B; gs.H = H; gs.W = W; gs.C = Cout;
+    SplitTensor xs; xs.base = const_cast<__nv_bfloat16 *>(x_split); xs.n_img = B; xs.H = H; xs.W = W; xs.C = Cin;
+    SplitTensor gs; gs.base = const_cast<__nv_bfloat16 *>(g_split); gs.n_img = B; gs.H = H; gs.W = W; gs.C = CoutPad;
     WgradArgs a;
     memset(&a, 0, sizeof(a));
     a.TW = W >= 24 ? 32 : (W >= 12 ? 16 : 8); a.TH = TC_BLOCK_M / a.TW;
@@ -209,7 +208,8 @@ int wgrad_tc(const float *x, const __nv_bfloat16 *g_split, int B, int Cin, int H
     if ((rc = tc_make_amap(xs, a.TW, a.TH, &a.xmap))) return rc;
     a.dw = dw; a.Cout = Cout; a.Cin = Cin; a.KK = ksz * ksz;
     a.a_is_x = (Cout == 64 && Cin >= 128) ? 1 : 0;
-    const int m_ch = a.a_is_x ? Cin : Cout, n_ch = a.a_is_x ? Cout : Cin;
+    const int m_ch = a.a_is_x ? Cin : CoutPad, n_ch = a.a_is_x ? CoutPad : Cin;
+    a.CoutPad = CoutPad;
     a.m_blocks = (m_ch + 127) / 128; a.n_chunks = n_ch / 64; a.groups = ksz == 3 ? 2 : 1;
     a.n_img = B; a.H = H; a.W = W;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
