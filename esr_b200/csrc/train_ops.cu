@@ -186,6 +186,149 @@ __global__ void __launch_bounds__(256) k_conv_fwd_g(const float *__restrict__ x,
     }
 }
 
+// Register-tiled variant for stride 1, 3x3: block = 64 x 16 output pixels, thread = 4 pixels along x  x  8 output channels.
+// Per input channel a thread reads its 3 x 6 patch values with 16-/8-byte loads and the 9 x 8 weights as broadcast
+// float4 pairs: 24 shared-memory instructions per 288 FMAs (the simple kernel above: 9 per 8).
+constexpr int R_TW = 64, R_TH = 16, R_PW = 72, R_PH = 18;          // patch: image columns tx0-4 .. tx0+67, pitch 72 floats
+
+__global__ void __launch_bounds__(256) k_conv_fwd_r(const float *__restrict__ x, const float *__restrict__ w,
+                                                    const float *__restrict__ bias, float *__restrict__ y, int Cin, int H, int W,
+                                                    int Cout, int act)
+{
+    extern __shared__ float sm[];
+    float *patch = sm;                                             // [G_C ci][R_PH][R_PW], col j <-> image x0 - 1 + j ... shifted by 3
+    float *wsm = sm + G_C * R_PH * R_PW;                           // [G_C ci][9][G_C co]
+    const int tiles_x = (W + R_TW - 1) / R_TW;
+    const int ty0 = (blockIdx.x / tiles_x) * R_TH, tx0 = (blockIdx.x % tiles_x) * R_TW;
+    const int co0 = blockIdx.y * G_C, n = blockIdx.z;
+    const int tid = threadIdx.x, lx = tid & 15, ly = tid >> 4;
+    float acc[4][G_C];
+#pragma unroll
+    for (int c = 0; c < G_C; ++c) {
+        const float b = (bias && co0 + c < Cout) ? bias[co0 + c] : 0.0f;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][c] = b;
+    }
+    // patch column jc holds image column tx0 - 4 + jc (so that a thread's first needed column 4*lx + 3 ... is 16-byte
+    // aligned at 4*lx + 0 after loading [4*lx, 4*lx+8)): columns needed by thread lx: tx0 + 4*lx - 1 .. + 4 = jc 4*lx+3 .. 4*lx+8
+    for (int ci0 = 0; ci0 < Cin; ci0 += G_C) {
+        for (int i = tid; i < G_C * R_PH * R_PW; i += 256) {
+            const int ci = i / (R_PH * R_PW), r = i - ci * R_PH * R_PW;
+            const int iy = ty0 - 1 + r / R_PW, ix = tx0 - 4 + r % R_PW;
+            float v = 0.0f;
+            if (ci0 + ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)n * Cin + ci0 + ci) * H + iy) * W + ix];
+            patch[i] = v;
+        }
+        for (int i = tid; i < G_C * 9 * G_C; i += 256) {
+            const int co = i % G_C, t = (i / G_C) % 9, ci = i / (G_C * 9);
+            wsm[i] = (co0 + co < Cout && ci0 + ci < Cin) ? w[((size_t)(co0 + co) * Cin + ci0 + ci) * 9 + t] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int ci = 0; ci < G_C; ++ci) {
+            float v[3][6];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float *row = patch + (ci * R_PH + ly + r) * R_PW + 4 * lx;
+                const float4 a = *reinterpret_cast<const float4 *>(row), b = *reinterpret_cast<const float4 *>(row + 4);
+                const float2 c = *reinterpret_cast<const float2 *>(row + 8);
+                // needed: columns 3..8 of this 10-wide window
+                v[r][0] = a.w; v[r][1] = b.x; v[r][2] = b.y; v[r][3] = b.z; v[r][4] = b.w; v[r][5] = c.x;
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(wsm + (ci * 9 + t) * G_C);
+                const float4 w1 = *reinterpret_cast<const float4 *>(wsm + (ci * 9 + t) * G_C + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float xv = v[t / 3][p + t % 3];
+#pragma unroll
+                    for (int c = 0; c < G_C; ++c) acc[p][c] = fmaf(xv, wv[c], acc[p][c]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int oy = ty0 + ly;
+    if (oy < H) {
+#pragma unroll
+        for (int c = 0; c < G_C; ++c) {
+            if (co0 + c >= Cout) continue;
+            float *dst = y + (((size_t)n * Cout + co0 + c) * H + oy) * W + tx0 + 4 * lx;
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (tx0 + 4 * lx + p < W) dst[p] = act_fwd(acc[p][c], act);
+        }
+    }
+}
+
+// dw for 3x3: thread = (input channel, kernel row) x 3 kernel columns x 8 output channels (24 accumulators), pixels of the
+// 16x16 tile split over 10 thread groups; 5 shared-memory instructions per 24 FMAs.
+__global__ void __launch_bounds__(256) k_conv_wgrad_r(const float *__restrict__ x, const float *__restrict__ g, float *__restrict__ dw,
+                                                      int B, int Cin, int H, int W, int Cout, int Ho, int Wo, int stride)
+{
+    extern __shared__ float sm[];
+    constexpr int NR = G_C * 3, NSPLIT = 10;                       // 24 roles x 10 pixel groups = 240 threads
+    const int PD = (G_T - 1) * stride + 3;
+    float *gs = sm;                                                // [256 px][G_C co]
+    float *xs = sm + 256 * G_C;                                    // [G_C ci][PD][PD]
+    const int ci_tiles = (Cin + G_C - 1) / G_C;
+    const int co0 = (blockIdx.x / ci_tiles) * G_C, ci0 = (blockIdx.x % ci_tiles) * G_C;
+    const int tiles_x = (Wo + G_T - 1) / G_T, tiles_y = (Ho + G_T - 1) / G_T;
+    const int items = B * tiles_x * tiles_y;
+    const int tid = threadIdx.x;
+    const int role = tid % NR, split = tid / NR;
+    const int pci = role / 3, ky = role % 3;
+    const bool active = split < NSPLIT;
+    float acc[3][G_C];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < G_C; ++c) acc[k][c] = 0.0f;
+    for (int it = blockIdx.y; it < items; it += gridDim.y) {
+        const int n = it / (tiles_x * tiles_y), tr = it % (tiles_x * tiles_y);
+        const int ty0 = (tr / tiles_x) * G_T, tx0 = (tr % tiles_x) * G_T;
+        for (int i = tid; i < 256 * G_C; i += 256) {
+            const int co = i / 256, p = i % 256;
+            const int oy = ty0 + p / G_T, ox = tx0 + p % G_T;
+            float v = 0.0f;
+            if (co0 + co < Cout && oy < Ho && ox < Wo) v = g[(((size_t)n * Cout + co0 + co) * Ho + oy) * Wo + ox];
+            gs[p * G_C + co] = v;
+        }
+        for (int i = tid; i < G_C * PD * PD; i += 256) {
+            const int ci = i / (PD * PD), r = i - ci * PD * PD;
+            const int iy = ty0 * stride - 1 + r / PD, ix = tx0 * stride - 1 + r % PD;
+            float v = 0.0f;
+            if (ci0 + ci < Cin && iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)n * Cin + ci0 + ci) * H + iy) * W + ix];
+            xs[i] = v;
+        }
+        __syncthreads();
+        if (active) {
+            for (int p = split; p < 256; p += NSPLIT) {
+                const float *xr = xs + (pci * PD + (p / G_T) * stride + ky) * PD + (p % G_T) * stride;
+                const float x0 = xr[0], x1 = xr[1], x2 = xr[2];
+                const float4 g0 = *reinterpret_cast<const float4 *>(gs + p * G_C), g1 = *reinterpret_cast<const float4 *>(gs + p * G_C + 4);
+                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int c = 0; c < G_C; ++c) {
+                    acc[0][c] = fmaf(x0, gv[c], acc[0][c]);
+                    acc[1][c] = fmaf(x1, gv[c], acc[1][c]);
+                    acc[2][c] = fmaf(x2, gv[c], acc[2][c]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (active && ci0 + pci < Cin) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < G_C; ++c)
+                if (co0 + c < Cout) atomicAdd(dw + ((size_t)(co0 + c) * Cin + ci0 + pci) * 9 + ky * 3 + k, acc[k][c]);
+    }
+}
+
 __device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
 // dx[n, ci, y, x] = sum over co, taps of g[n, co, (y + pad - ky) / s, (x + pad - kx) / s] * w[co, ci, ky, kx]  (when divisible)
@@ -366,6 +509,7 @@ static size_t conv2d_ws(int B, int Cin, int H, int W, int Cout, int ksz, int str
         f.take((size_t)B * tc_npad(Cout) * H * W * 4);
     }
     b.take((size_t)B * Cout * Ho * Wo * 4);
+    b.take((size_t)Cout * Cin * ksz * ksz * 4);                          // rotated weights of the CUDA-core dx path
     if (tc_dgrad_ok(Cin, Cout, ksz, stride)) {
         b.take((size_t)B * pad64(Cout) * Ho * Wo * 4); b.take((size_t)B * Cin * H * W * 4);      // g split, x split (dw on tensor cores)
         b.take((size_t)pad64(Cout) * Cin * ksz * ksz * 4);
@@ -403,7 +547,22 @@ static int launch_generic(int which, const float *x, const float *w, const float
 {
     constexpr int KK = KS * KS;
     const dim3 blk(G_T, G_T);
-    if (which == 0) {
+    if (which == 0 && KS == 3 && stride == 1) {
+        const size_t smem = (size_t)(G_C * R_PH * R_PW + G_C * 9 * G_C) * 4;
+        const dim3 grid(((Wo + R_TW - 1) / R_TW) * ((Ho + R_TH - 1) / R_TH), (Cout + G_C - 1) / G_C, B);
+        k_conv_fwd_r<<<grid, 256, smem, st>>>(x, w, bias, out, Cin, H, W, Cout, act);
+    } else if (which == 2 && KS == 3) {
+        const int PD = (G_T - 1) * stride + 3;
+        const size_t smem = (size_t)(256 * G_C + G_C * PD * PD) * 4;
+        const int pairs = ((Cout + G_C - 1) / G_C) * ((Cin + G_C - 1) / G_C);
+        const int items = B * ((Wo + G_T - 1) / G_T) * ((Ho + G_T - 1) / G_T);
+        int slices = (dev_info().sm_count * 8 + pairs - 1) / pairs;
+        if (slices > items) slices = items;
+        if (slices < 1) slices = 1;
+        static bool attr = false;
+        if (!attr) { ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_wgrad_r, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+        k_conv_wgrad_r<<<dim3(pairs, slices), 256, smem, st>>>(x, g, out, B, Cin, H, W, Cout, Ho, Wo, stride);
+    } else if (which == 0) {
         const int PD = (G_T - 1) * stride + KS;
         const size_t smem = (size_t)(G_C * PD * PD + G_C * G_C * KK) * 4;
         const dim3 grid(((Wo + G_T - 1) / G_T) * ((Ho + G_T - 1) / G_T), (Cout + G_C - 1) / G_C, B);
@@ -540,6 +699,13 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
             if ((rc = conv_tc_prepare(d, &a))) return rc;
             if ((rc = conv_tc_launch(a, st))) return rc;
             if ((rc = nhwc_to_nchw(dt, B, Cin, H * W, dx, st))) return rc;
+        } else if (ksz == 3 && stride == 1) {
+            // dx = conv(g, rot180(w)^T): the register-tiled forward kernel with the roles of Cin and Cout swapped
+            float *wt = (float *)ws.take((size_t)Cout * Cin * 9 * 4);
+            ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small (%zu > %zu)", ws.off, ws.cap);
+            k_weight_rot_t<<<(Cout * Cin * 9 + 255) / 256, 256, 0, st>>>(w, Cout, Cout, Cin, 9, wt);
+            ESR_LAUNCH_CHECK();
+            if ((rc = generic(0, 3, g, wt, nullptr, nullptr, dx, B, Cout, H, W, Cin, H, W, 1, ACT_NONE, st))) return rc;
         } else {
             if ((rc = generic(1, ksz, nullptr, w, nullptr, g, dx, B, Cin, H, W, Cout, Ho, Wo, stride, 0, st))) return rc;
         }

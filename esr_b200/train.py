@@ -150,13 +150,13 @@ def forward_sequence(model, frames, states=None):
         pyramid.append(x)
     pyramid.reverse()
     C, h, w = pyramid[0].shape[1:]
-    f = pyramid[0].view(L, B, C, h, w)
-
+    f = pyramid[0].view(L, B, C, h, w).unbind(0)                          # unbind / split: one stack / cat in backward
+    #                                                                       (indexing would zero-fill a full tensor per use)
     # ---- TimePropagation.local_time_corre (models/model.py:77-89, 133-146) for every (window, slot)
     tp = model.time_propagate
     pairs = sorted({(j, j) for j in range(Wn)} | {(j + 2, j + 2) for j in range(Wn)} | {(j, j + 1) for j in range(L - 1)})
     pm_in = torch.cat([torch.cat([f[a], f[b]], 1) for a, b in pairs], 0)
-    pm = _cl(tp.pred_map[1], _cl(tp.pred_map[0], pm_in, act="relu"), act="sigmoid").view(len(pairs), B, 1, h, w)
+    pm = _cl(tp.pred_map[1], _cl(tp.pred_map[0], pm_in, act="relu"), act="sigmoid").view(len(pairs), B, 1, h, w).unbind(0)
     gate = {p: pm[k] for k, p in enumerate(pairs)}
     cat_in = []
     for wi in range(Wn):
@@ -170,7 +170,7 @@ def forward_sequence(model, frames, states=None):
     mid_feat = torch.cat([f[wi + i] for wi in range(Wn) for i in range(N)], 0)
     ltc = _cl(tp.local_fusion[1], r) + mid_feat
     # ---- TimePropagation.global_time_corre: RecurrentConvLayer + ConvGRU (models/submodules.py:340-344, 496-514)
-    gx = _cl(tp.lstm.conv, ltc, act="relu").view(Wn, N, B, C, h, w)       # the x-side conv of every step at once
+    gx = _cl(tp.lstm.conv, ltc, act="relu").view(Wn * N, B, C, h, w).unbind(0)   # the x-side conv of every step at once
     gru = tp.lstm.recurrent_block
     w_zr = torch.cat([gru.update_gate.weight, gru.reset_gate.weight], 0)   # both gates in one 128 -> 128 convolution
     b_zr = torch.cat([gru.update_gate.bias, gru.reset_gate.bias], 0)
@@ -182,26 +182,27 @@ def forward_sequence(model, frames, states=None):
         for i in range(N):
             if cfg["gtc_frozen"]:
                 hs = None
-            xi = torch.cat([gx[wi, i], gx[wi, N - 1 - i]], 0)
+            xi = torch.cat([gx[wi * N + i], gx[wi * N + N - 1 - i]], 0)
             if hs is None:
                 hs = torch.zeros_like(xi)
             zr = conv2d(torch.cat([xi, hs], 1), w_zr, b_zr, 1, "sigmoid")
-            z, rg = zr[:, :C], zr[:, C:]
+            z, rg = zr.split(C, 1)
             o = conv2d(torch.cat([xi, hs * rg], 1), gru.out_gate.weight, gru.out_gate.bias, 1, "tanh")
             hs = hs * (1 - z) + o * z
-            fwd.append(hs[:B])
-            rev_w[N - 1 - i] = hs[B:]
+            hf, hr = hs.split(B, 0)
+            fwd.append(hf)
+            rev_w[N - 1 - i] = hr
         rev.extend(rev_w)
-    new_states = [None, None] if cfg["gtc_frozen"] else [hs[:B], hs[B:]]
+    new_states = [None, None] if cfg["gtc_frozen"] else list(hs.split(B, 0))
     both = torch.cat([torch.cat(fwd, 0), torch.cat(rev, 0)], 1)           # [(Wn*3*B), 128, h, w]
-    prop = (_cl(tp.global_fusion, both, act="relu") + mid_feat).view(Wn, N, B, C, h, w)
+    prop = (_cl(tp.global_fusion, both, act="relu") + mid_feat).view(Wn, N, B, C, h, w).unbind(1)
 
     # ---- STFusion (models/model.py:208-291): both neighbours of all windows at once
     sf = model.spacetime_fuse
     mid = (N - 1) // 2
-    center = prop[:, mid].reshape(Wn * B, C, h, w)
+    center = prop[mid].reshape(Wn * B, C, h, w)
     others = [i for i in range(N) if i != mid]
-    nb = torch.cat([prop[:, i].reshape(Wn * B, C, h, w) for i in others], 0)
+    nb = torch.cat([prop[i].reshape(Wn * B, C, h, w) for i in others], 0)
     ctr = torch.cat([center] * len(others), 0)
     off_feat = _cl(sf.offset[1], _cl(sf.offset[0], torch.cat([nb, ctr], 1), act="relu"))
     om = conv2d(off_feat, sf.dcn.conv_offset_mask.weight, sf.dcn.conv_offset_mask.bias, 1, None)
@@ -212,13 +213,15 @@ def forward_sequence(model, frames, states=None):
     mlp = sf.fc[0].layers
     ck = torch.relu(F.linear(ft.flatten(2).max(dim=2)[0], mlp[0].weight, mlp[0].bias))
     ck = torch.sigmoid(F.linear(ck, mlp[1].weight, mlp[1].bias))
-    y = torch.cat([aligned * sk[:, 0:1] * ck[:, :C, None, None], ctr * sk[:, 1:2] * ck[:, C:, None, None]], 1)
-    fz = _cl(sf.dcn_fusion[1], _cl(sf.dcn_fusion[0], y, act="relu")).view(len(others), Wn * B, C, h, w)
-    x = torch.cat([fz[k] for k in range(len(others))] + [center], 1)
+    sk0, sk1 = sk.split(1, 1)
+    ck0, ck1 = ck.split(C, 1)
+    y = torch.cat([aligned * sk0 * ck0[:, :, None, None], ctr * sk1 * ck1[:, :, None, None]], 1)
+    fz = _cl(sf.dcn_fusion[1], _cl(sf.dcn_fusion[0], y, act="relu")).view(len(others), Wn * B, C, h, w).unbind(0)
+    x = torch.cat(list(fz) + [center], 1)
     x = _cl(sf.dense_fusion[1], _cl(sf.dense_fusion[0], x, act="relu"))
     for lvl, ft in enumerate(pyramid):                                    # scale_aggre + recons (models/model.py:253-291)
-        prod = (ft * _cl(sf.attens[lvl], ft, act="sigmoid")).view(L, B, *ft.shape[1:])
-        agg = torch.stack([prod[wi:wi + N].mean(0) for wi in range(Wn)], 0).flatten(0, 1)
+        prod = (ft * _cl(sf.attens[lvl], ft, act="sigmoid")).view(L, B, *ft.shape[1:]).unbind(0)
+        agg = torch.cat([(prod[wi] + prod[wi + 1] + prod[wi + 2]) / N for wi in range(Wn)], 0)
         x = F.interpolate(x + agg, scale_factor=2, mode="bilinear", align_corners=False)
         x = _cl(sf.recons[lvl], x, act="relu")
     x = _cl(model.tail, x, act="relu")

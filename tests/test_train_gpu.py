@@ -48,6 +48,10 @@ CONV_CASES = [
     (2, 16, 8, 3, 1, "relu", 40, 40),
     (3, 8, 2, 3, 1, "relu", 31, 17),            # tail
     (1, 32, 1, 3, 1, "sigmoid", 24, 24),        # attens[1]
+    (2, 16, 8, 3, 1, "relu", 40, 150),          # wider than one 64-pixel register tile (halo columns between tiles)
+    (1, 32, 16, 3, 1, None, 70, 130),
+    (1, 8, 2, 3, 1, "relu", 20, 64),            # exactly one tile wide
+    (1, 64, 32, 3, 1, "relu", 20, 70),          # Cout 32: g padded to 64 channels for the tensor-core dx / dw
 ]
 
 
