@@ -156,6 +156,85 @@ def cpu_oracle_step(wl, B_sample, sd, seed):
     return dt, int((ev[:, :, 3] != 0).sum())
 
 
+def cpu_oracle_train_step(wl, sd, seed):
+    """One training iteration (windows with carried state, summed MSE, backward, torch Adam amsgrad) of the CPU oracle on
+    ONE sequence.  Returns seconds."""
+    import torch.nn.functional as F
+    from oracle import model_ref
+    scale, L, lr = wl["scale"], wl["L"], wl["lr"]
+    H, W = lr[0] * scale, lr[1] * scale
+    g = torch.Generator().manual_seed(seed)
+    frames = torch.poisson(torch.full((1, L, 2, H, W), 0.1), generator=g)
+    gt = torch.poisson(torch.full((1, L, 2, H, W), 0.1), generator=g)
+    params = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    t0 = time.perf_counter()
+    opt.zero_grad()
+    states, loss = None, 0
+    for w in range(L - 2):
+        pred, states = model_ref.forward(params, frames[:, w:w + 3], states)
+        loss = loss + F.mse_loss(pred, gt[:, w + 1])
+    loss.backward()
+    opt.step()
+    return time.perf_counter() - t0
+
+
+def measure_training(args, wl, net_sd, dev, rank, world, dist):
+    """the training iteration (forward of all windows, backward through time, gradient all-reduce
+    when N > 1, Adam amsgrad) on the same workload; N = 1 replays one CUDA graph, N > 1 runs eagerly with an NCCL all-reduce
+    of the flat 1.8 M-element gradient.  Device-resident synthetic count tensors (the trainer's input after the dataloader)."""
+    from esr_b200 import train
+    from esr_b200.model import DeepRecurrNet
+    scale, L, lr, B = wl["scale"], wl["L"], wl["lr"], wl["B"]
+    H, W = lr[0] * scale, lr[1] * scale
+    net = DeepRecurrNet(inch=2, basech=8, num_frame=3)
+    net.load_state_dict(net_sd)
+    net = net.to(dev)
+    opt = train.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    g = torch.Generator().manual_seed(200 + rank)
+    frames = torch.poisson(torch.full((B, L, 2, H, W), 0.1), generator=g).to(dev)
+    gt = torch.poisson(torch.full((B, L, 2, H, W), 0.1), generator=g).to(dev)
+    if world > 1:
+        def allred(flat):
+            dist.all_reduce(flat)
+            flat /= world
+        step = lambda: train.train_step(net, opt, frames, gt, all_reduce=allred)
+    else:
+        gstep = train.GraphedTrainStep(net, opt, tuple(frames.shape), dev)
+        step = lambda: gstep(frames, gt)
+    steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    first = last = None
+    for i in range(steps):
+        l = step()
+        if i == 0:
+            first = l.clone()
+        last = l
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    out = {"metric": "training LR event-frames/sec (forward + backward + Adam)", "value": world * B * L / (ms * 1e-3), "unit": "frames/s",
+           "ms_per_step": ms, "steps": steps, "mode": "one CUDA graph per iteration" if world == 1 else "eager + NCCL all-reduce of the flat gradient",
+           "batch_per_gpu": B, "loss_first": float(first), "loss_last": float(last),
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = usable_cores()
+        torch.set_num_threads(cores)
+        tcpu = cpu_oracle_train_step(wl, net_sd, 3)
+        out["cpu_baseline"] = {"value": L / tcpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                               "sample": f"1 sequence x {L} LR frames, one iteration, torch CPU autograd through the oracle + torch Adam"}
+    return out
+
+
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
@@ -190,6 +269,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     ap.add_argument("--profile-out", default=None, help="write the per-launch timing table of one step here")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-iteration measurement (the `train` key)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -388,6 +468,11 @@ def main():
         cpu_baseline = {"value": 1 * L / tcpu, "unit": "frames/s", "cores": cores, "kind": "port",
                         "sample": f"1 sequence x {L} LR frames (same per-sequence work as the GPU arm's B={B}), mean of 3, fp32"}
 
+    # ---- training iteration: reported next to the inference headline, never mixed into `value`
+    train_res = None
+    if not args.no_train:
+        train_res = measure_training(args, wl, sd, dev, rank, world, dist)
+
     if rank == 0:
         n_ev = EVENTS_PER_FRAME * B * L
         ev_out = pipe.run_device(d_xs, d_ys, d_ps, d_off, EVENTS_PER_FRAME)[1]
@@ -413,6 +498,7 @@ def main():
                 "tensor_roofline_whole_path": {"algorithmic_tflops": FLOP_PER_HR_PIXEL * hr[0] * hr[1] * B * (L - 2) * world /
                                                (ms_dev / args.steps / 1e3) / 1e12},
                 "stages_ms_per_step": stages,
+                "train": train_res,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
