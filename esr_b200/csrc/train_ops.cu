@@ -125,6 +125,45 @@ static int split_from_nchw_pad(const float *src, int B, int C, int Cpad, int HW,
     return ESR_OK;
 }
 
+// Backward prologue of a tensor-core layer in ONE pass over dy: g = dy * act'(y) -> split bf16 NHWC (channels padded to
+// Cpad), db[c] += sum g (warp reduction + one atomic per channel and block), and optionally g in fp32 NCHW.
+__global__ void __launch_bounds__(256) k_gprep(const float *__restrict__ dy, const float *__restrict__ y, int act, int C, int Cpad,
+                                               int HW, __nv_bfloat16 *__restrict__ dst, size_t plane, float *__restrict__ db,
+                                               float *__restrict__ g_out)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, p = p0 + tx;
+        float v = 0.0f;
+        if (c < C && p < HW) {
+            const size_t i = ((size_t)n * C + c) * HW + p;
+            v = dy[i];
+            if (act != ACT_NONE) {
+                const float o = y[i];
+                v *= act == ACT_RELU ? (o > 0.0f ? 1.0f : 0.0f) : (act == ACT_SIGMOID ? o * (1.0f - o) : 1.0f - o * o);
+            }
+            if (g_out) g_out[i] = v;
+        }
+        tile[r][tx] = v;
+        float sum = v;
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (tx == 0 && c < C) atomicAdd(db + c, sum);
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int p = p0 + r, c = c0 + tx;
+        if (p < HW && c < Cpad) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(tile[tx][r], hi, lo);
+            const size_t o = ((size_t)n * HW + p) * Cpad + c;
+            dst[o] = hi;
+            dst[plane + o] = lo;
+        }
+    }
+}
+
 static int nhwc_to_nchw(const float *src, int B, int C, int HW, float *dst, cudaStream_t st)
 {
     k_nhwc_to_nchw<<<dim3((HW + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(src, C, HW, dst);
@@ -641,41 +680,42 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
     Bump ws{(uint8_t *)workspace, 0, workspace_bytes};
     int rc;
     const size_t ng = (size_t)B * Cout * Ho * Wo;
-    float *g = (float *)ws.take(ng * 4);
-    ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
-    if (act == ACT_NONE) {
-        ESR_CUDA_CHECK(cudaMemcpyAsync(g, dy, ng * 4, cudaMemcpyDeviceToDevice, st));
-    } else {
-        k_act_bwd<<<(unsigned)min((size_t)4096, (ng + 255) / 256), 256, 0, st>>>(dy, y, g, ng, act);
-        ESR_LAUNCH_CHECK();
-    }
+    const bool tcd = tc_dgrad_ok(Cin, Cout, ksz, stride);
+    const int gC = pad64(Cout);
+    const bool tc_dw = tcd && Cin % 64 == 0 && getenv("ESR_WGRAD_GENERIC") == nullptr;
+    float *g = (float *)ws.take(ng * 4);                           // fp32 g: only the CUDA-core kernels read it
+    __nv_bfloat16 *gsplit = nullptr;
     ESR_CUDA_CHECK(cudaMemsetAsync(db, 0, (size_t)Cout * 4, st));
-    {
+    ESR_CUDA_CHECK(cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * ksz * ksz * 4, st));
+    if (tcd) {
+        // one pass: activation derivative, bias gradient, fp32 -> split bf16 NHWC (padded to a 64-multiple of channels)
+        gsplit = (__nv_bfloat16 *)ws.take((size_t)B * gC * Ho * Wo * 4);
+        ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
+        k_gprep<<<dim3((Ho * Wo + 31) / 32, (gC + 31) / 32, B), 256, 0, st>>>(dy, y, act, Cout, gC, Ho * Wo, gsplit, (size_t)B * Ho * Wo * gC, db,
+                                                                             tc_dw ? nullptr : g);
+        ESR_LAUNCH_CHECK();
+    } else {
+        ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
+        if (act == ACT_NONE) {
+            ESR_CUDA_CHECK(cudaMemcpyAsync(g, dy, ng * 4, cudaMemcpyDeviceToDevice, st));
+        } else {
+            k_act_bwd<<<(unsigned)min((size_t)4096, (ng + 255) / 256), 256, 0, st>>>(dy, y, g, ng, act);
+            ESR_LAUNCH_CHECK();
+        }
         const size_t total = (size_t)B * Ho * Wo;
         int chunks = (int)min((size_t)64, (total + 4095) / 4096);
         k_bias_grad<<<dim3(Cout, chunks < 1 ? 1 : chunks), 256, 0, st>>>(g, B, Cout, Ho * Wo, db);
         ESR_LAUNCH_CHECK();
     }
-    ESR_CUDA_CHECK(cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * ksz * ksz * 4, st));
-    const bool tcd = tc_dgrad_ok(Cin, Cout, ksz, stride);
-    const int gC = pad64(Cout);
-    __nv_bfloat16 *gsplit = nullptr;
-    if (tcd) {
-        gsplit = (__nv_bfloat16 *)ws.take((size_t)B * gC * Ho * Wo * 4);
-        ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
-        if ((rc = split_from_nchw_pad(g, B, Cout, gC, Ho * Wo, gsplit, st))) return rc;
-    }
     // ---- dw
-    static const bool no_tc_wgrad = getenv("ESR_WGRAD_GENERIC") != nullptr;
     bool dw_done = false;
-    if (tcd && !no_tc_wgrad && Cin % 64 == 0) {
+    if (tc_dw) {
         Bump ws2 = ws;                                               // x split is dead after the kernel: dx reuses the space
         __nv_bfloat16 *xsplit = (__nv_bfloat16 *)ws2.take((size_t)B * Cin * H * W * 4);
         ESR_REQUIRE(ws2.off <= ws2.cap, "conv2d_backward: workspace too small");
         if ((rc = split_from_nchw_pad(x, B, Cin, Cin, H * W, xsplit, st))) return rc;
-        rc = wgrad_tc(xsplit, gsplit, B, Cin, H, W, Cout, gC, ksz, dw, st);
-        if (rc == ESR_OK) dw_done = true;
-        else if (rc != ESR_EINVAL) return rc;
+        if ((rc = wgrad_tc(xsplit, gsplit, B, Cin, H, W, Cout, gC, ksz, dw, st))) return rc;   // (fp32 g was not written)
+        dw_done = true;
     }
     if (!dw_done && (rc = generic(2, ksz, x, nullptr, nullptr, g, dw, B, Cin, H, W, Cout, Ho, Wo, stride, 0, st))) return rc;
     // ---- dx
