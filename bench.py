@@ -290,6 +290,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner / debug lines must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     scale, L, lr, B = wl["scale"], wl["L"], wl["lr"], wl["B"]

@@ -12,6 +12,7 @@
 //   stage 3: 16-byte split-bf16 stores.
 // fp32 math throughout.
 #include "net.cuh"
+#include "direct_common.cuh"
 
 namespace esr {
 
@@ -29,51 +30,6 @@ template <int COUT, int TPW> struct DcGeom {
     static constexpr int TW = TILED ? GW * TPW : 16;            // output tile width
     static constexpr int TH = TILED ? GH * 2 : 16;              // output tile height
 };
-
-__device__ __forceinline__ void dc_unpack8(const uint4 h, const uint4 l, float (&o)[8])
-{
-    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        o[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-        o[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
-    }
-}
-__device__ __forceinline__ void dc_ld8(const __nv_bfloat16 *p, size_t plane, float (&o)[8])
-{
-    dc_unpack8(*reinterpret_cast<const uint4 *>(p), *reinterpret_cast<const uint4 *>(p + plane), o);
-}
-// NV values (2, 4 or 8) -> split-bf16, vector stores
-template <int NV>
-__device__ __forceinline__ void dc_store(__nv_bfloat16 *p, size_t plane, const float *x)
-{
-    uint32_t hw[NV / 2], lw[NV / 2];
-#pragma unroll
-    for (int e = 0; e < NV / 2; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(x[2 * e], h0, l0);
-        split_bf16(x[2 * e + 1], h1, l1);
-        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-    if constexpr (NV == 8) {
-        *reinterpret_cast<uint4 *>(p) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4 *>(p + plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-    } else if constexpr (NV == 4) {
-        *reinterpret_cast<uint2 *>(p) = make_uint2(hw[0], hw[1]);
-        *reinterpret_cast<uint2 *>(p + plane) = make_uint2(lw[0], lw[1]);
-    } else {
-        *reinterpret_cast<uint32_t *>(p) = hw[0];
-        *reinterpret_cast<uint32_t *>(p + plane) = lw[0];
-    }
-}
-
-__device__ __forceinline__ float dc_act(float v, int act)
-{
-    if (act == ACT_RELU) return fmaxf(v, 0.0f);
-    if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
-    return v;
-}
 
 template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF, int TPW>
 __global__ void __launch_bounds__(256) k_conv_direct(const DirectArgs a)
@@ -313,6 +269,12 @@ static int launch_direct(const DirectArgs &a, cudaStream_t st)
 
 int conv_direct(DirectKind kind, const DirectArgs &a, cudaStream_t st)
 {
+    // default: warp-level tensor-core variant (mma_conv.cu) where one exists; ESR_DIRECT_FFMA=1 keeps the fp32 FFMA kernels
+    static const bool ffma = getenv("ESR_DIRECT_FFMA") != nullptr;
+    if (!ffma) {
+        const int rc = conv_mma(kind, a, st);
+        if (rc != ESR_EINVAL) return rc;
+    }
     switch (kind) {
     case DK_HEAD:    return launch_direct<2, 8, 1, false, FMT_NCHW_F32, FMT_SPLIT>(a, st);
     case DK_HEAD_ENC0: return launch_direct<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT>(a, st);

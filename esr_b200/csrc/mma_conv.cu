@@ -1,0 +1,309 @@
+// mma_conv.cu -- the small-channel 3x3 convolutions (Cin 8..32, full / half resolution) on the warp-level tensor-core
+// path (mma.sync m16n8k16 / m16n8k8, bf16 operands, fp32 accumulate) instead of FFMA loops.
+//
+// These layers (head+encoder 8->16->32->64 stride 2, decoder bilinear x2 + conv 32->16->8, tail 8->2;
+// models/model.py:20-45, 264-291, 309) have too few channels for a 128 x N tcgen05 tile and their inputs are produced on
+// the fly (fused head, fused bilinear upsampling), which TMA cannot do -- so the operand tile is built by the CTA itself:
+//   stage 1  the input patch of the output tile (+1 halo) is written to shared memory as split bf16 (hi and lo planes),
+//            pixel-major [py][px][CIN] with a 16-byte pad per pixel (conflict-free ldmatrix rows); the split source is
+//            copied as is, the decoder's bilinear x2 and the fused head conv are evaluated in fp32 and split here;
+//   stage 2  implicit GEMM per warp: A fragments (16 consecutive output pixels x 16 channels of one tap) by ldmatrix
+//            straight from the patch (lane addresses carry the stride and the tap shift), B fragments (weights, split,
+//            [tap][co][ci]) by 32-bit shared loads, three MMAs per K step (lo*hi + hi*lo + hi*hi) like the tcgen05 path;
+//   stage 3  accumulators -> shared memory (fp32) -> bias/activation already applied -> 16-byte split-bf16 stores (or the
+//            cropped fp32 NCHW output of the tail).
+// Same DirectArgs interface and results within the split-bf16 operand error (2^-17) of the fp32 kernels in direct_conv.cu,
+// which remain available with ESR_DIRECT_FFMA=1.
+#include "direct_common.cuh"
+
+namespace esr {
+
+template <int CIN, int COUT, int STRIDE, int TW, int TH> struct MmGeom {
+    static constexpr int NP = COUT < 8 ? 8 : COUT;             // N padded to the MMA's 8
+    static constexpr int NT = NP / 8;
+    static constexpr int MTILES = TW * TH / 16;                // 16-pixel row segments per block
+    static constexpr int MT = MTILES / 8;                      // per warp
+    static constexpr int PW = (TW - 1) * STRIDE + 3, PH = (TH - 1) * STRIDE + 3;
+    static constexpr int PITCH = CIN * 2 + 16;                 // bytes per pixel per plane
+    static constexpr int WP = CIN + 8;                         // weight row pitch (elements): conflict-free B loads
+    static constexpr int KS = CIN >= 16 ? CIN / 16 : 1;
+    static constexpr size_t PATCH_BYTES = (size_t)PH * PW * PITCH;
+    static constexpr size_t W_BYTES = (size_t)9 * NP * WP * 2;
+    static_assert(TW % 16 == 0 && MTILES % 8 == 0, "tile must hold a multiple of 8 16-pixel segments");
+};
+
+__device__ __forceinline__ uint32_t smem_u32_generic(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4])
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t (&r)[4])
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_k8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+// 8 fp32 -> split bf16, one 16-byte store per plane (shared memory)
+__device__ __forceinline__ void st_split8(uint8_t *hi, uint8_t *lo, const float (&v)[8])
+{
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * e], h0, l0);
+        split_bf16(v[2 * e + 1], h1, l1);
+        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4 *>(hi) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4 *>(lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF, int TW, int TH>
+__global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
+{
+    using G = MmGeom<CIN, COUT, STRIDE, TW, TH>;
+    constexpr int NP = G::NP, NT = G::NT, MT = G::MT, PW = G::PW, PH = G::PH, PITCH = G::PITCH, WP = G::WP, KS = G::KS;
+    extern __shared__ __align__(16) uint8_t msm[];
+    uint8_t *p_hi = msm, *p_lo = msm + G::PATCH_BYTES;
+    __nv_bfloat16 *w_hi = reinterpret_cast<__nv_bfloat16 *>(msm + 2 * G::PATCH_BYTES);
+    __nv_bfloat16 *w_lo = w_hi + 9 * NP * WP;
+    float *bsm = reinterpret_cast<float *>(w_lo + 9 * NP * WP);            // [NP]
+    constexpr int IPP = (PW + 2 + 3) / 4 * 4;
+    float *inp = bsm + NP;                                                 // fused head: [2][PH+2][IPP], then [9][2][8] + [8]
+    float *w0s = inp + 2 * (PH + 2) * IPP;
+
+    const int img = blockIdx.z;
+    const int oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- weights: fp32 [tap][ci][co] -> split bf16 [tap][co][ci] (+pad), zero rows for co >= COUT
+    for (int i = tid; i < 9 * CIN * NP; i += 256) {
+        const int co = i % NP, ci = (i / NP) % CIN, tap = i / (NP * CIN);
+        const float v = co < COUT ? a.w[(tap * CIN + ci) * COUT + co] : 0.0f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        w_hi[(tap * NP + co) * WP + ci] = h;
+        w_lo[(tap * NP + co) * WP + ci] = l;
+    }
+    if (tid < NP) bsm[tid] = tid < COUT ? a.bias[tid] : 0.0f;
+
+    // ---- stage 1: the input patch as split bf16, pixel-major
+    const int Hc = UPS ? 2 * a.Hin : a.Hin + a.pad_top + a.pad_bottom;
+    const int Wc = UPS ? 2 * a.Win : a.Win + a.pad_left + a.pad_right;
+    const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
+    const int simg = a.in_img ? a.in_img[img] : img;
+    if constexpr (INF == FMT_HEAD_FUSED) {
+        static_assert(INF != FMT_HEAD_FUSED || CIN == 8, "fused head feeds the 8-channel encoder layer");
+        for (int i = tid; i < 9 * 2 * 8 + 8; i += 256) w0s[i] = i < 144 ? a.w0[i] : a.b0[i - 144];
+        for (int i = tid; i < 2 * (PH + 2) * (PW + 2); i += 256) {
+            const int px = i % (PW + 2), py = (i / (PW + 2)) % (PH + 2), ci = i / ((PW + 2) * (PH + 2));
+            const int y = iy0 - 1 + py, x = ix0 - 1 + px;
+            float v = 0.0f;
+            const int sy = y - a.pad_top, sx = x - a.pad_left;           // CropSize zero padding (model_util.py:148-152)
+            if (sy >= 0 && sy < a.Hin && sx >= 0 && sx < a.Win) v = a.in_f32[(((size_t)simg * 2 + ci) * a.Hin + sy) * a.Win + sx];
+            inp[(ci * (PH + 2) + py) * IPP + px] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < PH * PW; i += 256) {
+            const int px = i % PW, py = i / PW;
+            const int y = iy0 + py, x = ix0 + px;
+            float o[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = w0s[144 + c];
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const float xv = inp[(ci * (PH + 2) + py + t / 3) * IPP + px + t % 3];
+                    const float *wp = w0s + (t * 2 + ci) * 8;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) o[c] = fmaf(xv, wp[c], o[c]);
+                }
+            const bool inside = (y >= 0 && y < Hc && x >= 0 && x < Wc);   // outside = the encoder conv's zero padding
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[c] = inside ? fmaxf(o[c], 0.0f) : 0.0f;
+            st_split8(p_hi + (size_t)i * PITCH, p_lo + (size_t)i * PITCH, o);
+        }
+    } else {
+        static_assert(INF == FMT_HEAD_FUSED || INF == FMT_SPLIT, "mma conv reads split tensors");
+        const __nv_bfloat16 *hi = a.in_split;
+        const size_t plane = a.in_plane;
+        constexpr int Q = CIN / 8;
+        for (int i = tid; i < Q * PW * PH; i += 256) {
+            const int q = i % Q, pp = i / Q;                              // consecutive lanes: the 16-byte groups of a pixel
+            const int px = pp % PW, py = pp / PW;
+            const int y = iy0 + py, x = ix0 + px;
+            uint8_t *dh = p_hi + (size_t)pp * PITCH + q * 16, *dl = p_lo + (size_t)pp * PITCH + q * 16;
+            if (!(y >= 0 && y < Hc && x >= 0 && x < Wc)) {
+                *reinterpret_cast<uint4 *>(dh) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4 *>(dl) = make_uint4(0, 0, 0, 0);
+            } else if constexpr (!UPS) {
+                const __nv_bfloat16 *s = hi + (((size_t)simg * a.Hin + y) * a.Win + x) * CIN + q * 8;
+                *reinterpret_cast<uint4 *>(dh) = *reinterpret_cast<const uint4 *>(s);          // already split: copy
+                *reinterpret_cast<uint4 *>(dl) = *reinterpret_cast<const uint4 *>(s + plane);
+            } else {
+                // F.interpolate(scale_factor=2, bilinear, align_corners=False) (submodules.py:290), as in direct_conv.cu
+                const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f);
+                const float fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
+                const int y_0 = (int)fy, x_0 = (int)fx;
+                const int y_1 = min(y_0 + 1, a.Hin - 1), x_1 = min(x_0 + 1, a.Win - 1);
+                const float ly = fy - (float)y_0, lx = fx - (float)x_0;
+                const size_t b0 = ((size_t)simg * a.Hin + y_0) * a.Win, b1 = ((size_t)simg * a.Hin + y_1) * a.Win;
+                float v00[8], v01[8], v10[8], v11[8], v[8];
+                dc_ld8(hi + (b0 + x_0) * CIN + q * 8, plane, v00);
+                dc_ld8(hi + (b0 + x_1) * CIN + q * 8, plane, v01);
+                dc_ld8(hi + (b1 + x_0) * CIN + q * 8, plane, v10);
+                dc_ld8(hi + (b1 + x_1) * CIN + q * 8, plane, v11);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    v[e] = (1.0f - ly) * ((1.0f - lx) * v00[e] + lx * v01[e]) + ly * ((1.0f - lx) * v10[e] + lx * v11[e]);
+                st_split8(dh, dl, v);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: implicit GEMM on the warp-level tensor cores
+    const int g = lane >> 2, t4 = lane & 3;
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            acc[m][n][0] = acc[m][n][2] = bsm[n * 8 + 2 * t4];
+            acc[m][n][1] = acc[m][n][3] = bsm[n * 8 + 2 * t4 + 1];
+        }
+    // ldmatrix lane roles: matrix = lane / 8 -> pixel half (mat & 1) and channel half (mat >> 1); row = lane % 8
+    const int lm_px = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int lm_koff = CIN >= 16 ? (lane >> 4) * 16 : 0;                    // bytes
+    const uint32_t hi_base = smem_u32_generic(p_hi), lo_base = smem_u32_generic(p_lo);
+    uint32_t a_off[MT];                                                      // byte offset of this lane's row for tap (0,0)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int mt = warp * MT + m;
+        const int ty = mt / (TW / 16), cx = mt % (TW / 16);
+        a_off[m] = (uint32_t)(((ty * STRIDE) * PW + (cx * 16 + lm_px) * STRIDE) * PITCH + lm_koff);
+    }
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t tap_off = (uint32_t)(((tap / 3) * PW + tap % 3) * PITCH);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const uint32_t o = a_off[m] + tap_off + ks * 32;
+                if constexpr (CIN >= 16) { ldsm_x4(hi_base + o, ah[m]); ldsm_x4(lo_base + o, al[m]); }
+                else { ldsm_x2(hi_base + o, ah[m]); ldsm_x2(lo_base + o, al[m]); }
+            }
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const int wrow = ((tap * NP + n * 8 + g) * WP + ks * 16 + 2 * t4);
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t *>(w_hi + wrow), bl0 = *reinterpret_cast<const uint32_t *>(w_lo + wrow);
+                if constexpr (CIN >= 16) {
+                    const uint32_t bh1 = *reinterpret_cast<const uint32_t *>(w_hi + wrow + 8), bl1 = *reinterpret_cast<const uint32_t *>(w_lo + wrow + 8);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        mma_k16(acc[m][n], al[m], bh0, bh1);
+                        mma_k16(acc[m][n], ah[m], bl0, bl1);
+                        mma_k16(acc[m][n], ah[m], bh0, bh1);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        mma_k8(acc[m][n], al[m], bh0);
+                        mma_k8(acc[m][n], ah[m], bl0);
+                        mma_k8(acc[m][n], ah[m], bh0);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();                                                         // the patch is dead: reuse it as the output stage
+
+    // ---- stage 3: accumulators (+activation) -> shared fp32 [pixel][NP] -> global
+    float *stage = reinterpret_cast<float *>(msm);
+    static_assert((size_t)TW * TH * NP * 4 <= 2 * G::PATCH_BYTES, "output stage must fit in the patch area");
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int mt = warp * MT + m;
+        const int ty = mt / (TW / 16), cx = mt % (TW / 16);
+        const int p0 = ty * TW + cx * 16 + g;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            *reinterpret_cast<float2 *>(stage + (size_t)p0 * NP + n * 8 + 2 * t4) = make_float2(dc_act(acc[m][n][0], a.act), dc_act(acc[m][n][1], a.act));
+            *reinterpret_cast<float2 *>(stage + (size_t)(p0 + 8) * NP + n * 8 + 2 * t4) = make_float2(dc_act(acc[m][n][2], a.act), dc_act(acc[m][n][3], a.act));
+        }
+    }
+    __syncthreads();
+    if constexpr (OUTF == FMT_SPLIT) {
+        constexpr int QO = COUT / 8;
+        for (int i = tid; i < TW * TH * QO; i += 256) {
+            const int q = i % QO, p = i / QO;
+            const int oy = oy0 + p / TW, ox = ox0 + p % TW;
+            if (oy >= a.Hout || ox >= a.Wout) continue;
+            const float4 v0 = *reinterpret_cast<const float4 *>(stage + (size_t)p * NP + q * 8), v1 = *reinterpret_cast<const float4 *>(stage + (size_t)p * NP + q * 8 + 4);
+            const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            dc_store<8>(a.out_split + (((size_t)img * a.Hout + oy) * a.Wout + ox) * COUT + q * 8, a.out_plane, v);
+        }
+    } else {
+        // fp32 NCHW with the CropSize crop (model_util.py:154-164): only pixels inside the crop window are stored
+        static_assert(OUTF == FMT_SPLIT || OUTF == FMT_NCHW_F32, "unsupported output format");
+        for (int i = tid; i < TW * TH * COUT; i += 256) {
+            const int p = i % (TW * TH), co = i / (TW * TH);
+            const int oy = oy0 + p / TW, ox = ox0 + p % TW;
+            const int cy = oy - a.crop_top, cx = ox - a.crop_left;
+            if (oy < a.Hout && ox < a.Wout && cy >= 0 && cy < a.out_H && cx >= 0 && cx < a.out_W)
+                a.out_f32[(((size_t)img * COUT + co) * a.out_H + cy) * a.out_W + cx] = stage[(size_t)p * NP + co];
+        }
+    }
+}
+
+template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF, int TW, int TH>
+static int launch_mma(const DirectArgs &a, cudaStream_t st)
+{
+    using G = MmGeom<CIN, COUT, STRIDE, TW, TH>;
+    constexpr int IPP = (G::PW + 2 + 3) / 4 * 4;
+    constexpr size_t extra = INF == FMT_HEAD_FUSED ? sizeof(float) * (size_t)(2 * (G::PH + 2) * IPP + 9 * 2 * 8 + 8) : 0;
+    constexpr size_t smem = 2 * G::PATCH_BYTES + 2 * G::W_BYTES + sizeof(float) * G::NP + extra + 16;
+    static_assert(smem <= 227 * 1024, "mma conv tile does not fit in shared memory");
+    static_assert((2 * G::PATCH_BYTES) % 16 == 0 && G::W_BYTES % 16 == 0, "alignment");
+    static bool attr_set = false;
+    if (!attr_set) {
+        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_mma<CIN, COUT, STRIDE, UPS, INF, OUTF, TW, TH>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((a.Wout + TW - 1) / TW, (a.Hout + TH - 1) / TH, a.n_img);
+    k_conv_mma<CIN, COUT, STRIDE, UPS, INF, OUTF, TW, TH><<<grid, 256, smem, st>>>(a);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+// returns ESR_EINVAL for kinds that stay on the FFMA kernels
+int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st)
+{
+    switch (kind) {
+    case DK_HEAD_ENC0: return launch_mma<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT, 16, 16>(a, st);
+    case DK_ENC0:      return launch_mma<8, 16, 2, false, FMT_SPLIT, FMT_SPLIT, 16, 16>(a, st);
+    case DK_ENC1:      return launch_mma<16, 32, 2, false, FMT_SPLIT, FMT_SPLIT, 16, 8>(a, st);
+    case DK_ENC2:      return launch_mma<32, 64, 2, false, FMT_SPLIT, FMT_SPLIT, 16, 8>(a, st);
+    case DK_RECON1:    return launch_mma<32, 16, 1, true, FMT_SPLIT, FMT_SPLIT, 32, 8>(a, st);
+    case DK_RECON2:    return launch_mma<16, 8, 1, true, FMT_SPLIT, FMT_SPLIT, 32, 16>(a, st);
+    case DK_TAIL:      return launch_mma<8, 2, 1, false, FMT_SPLIT, FMT_NCHW_F32, 32, 16>(a, st);
+    default: break;
+    }
+    return ESR_EINVAL;
+}
+
+} // namespace esr
