@@ -256,9 +256,15 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
             const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             dc_store<8>(a.out_split + (((size_t)img * a.Hout + oy) * a.Wout + ox) * COUT + q * 8, a.out_plane, v);
         }
+    } else if constexpr (OUTF == FMT_NHWC_F32) {
+        for (int i = tid; i < TW * TH * COUT; i += 256) {                  // attention maps: [img][y][x][COUT] fp32
+            const int co = i % COUT, p = i / COUT;
+            const int oy = oy0 + p / TW, ox = ox0 + p % TW;
+            if (oy < a.Hout && ox < a.Wout) a.out_f32[(((size_t)img * a.Hout + oy) * a.Wout + ox) * COUT + co] = stage[(size_t)p * NP + co];
+        }
     } else {
         // fp32 NCHW with the CropSize crop (model_util.py:154-164): only pixels inside the crop window are stored
-        static_assert(OUTF == FMT_SPLIT || OUTF == FMT_NCHW_F32, "unsupported output format");
+        static_assert(OUTF == FMT_SPLIT || OUTF == FMT_NCHW_F32 || OUTF == FMT_NHWC_F32, "unsupported output format");
         for (int i = tid; i < TW * TH * COUT; i += 256) {
             const int p = i % (TW * TH), co = i / (TW * TH);
             const int oy = oy0 + p / TW, ox = ox0 + p % TW;
@@ -290,9 +296,13 @@ static int launch_mma(const DirectArgs &a, cudaStream_t st)
     return ESR_OK;
 }
 
-// returns ESR_EINVAL for kinds that stay on the FFMA kernels
+// returns ESR_EINVAL for kinds that stay on the FFMA kernels.  Measured on B200 (cfg2, profiles/r1_notes.md): enc1 88 -> 82,
+// enc2 97 -> 74, recons[1] 203 -> 138, recons[2] 230 -> 172 us; the fused head+enc0 (177 -> 193, dominated by the FFMA head
+// evaluated per patch pixel) and the tail (100 -> 111, N padded 2 -> 8) are slower and only run here with ESR_MMA_ALL=1.
 int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st)
 {
+    static const bool all = getenv("ESR_MMA_ALL") != nullptr;
+    if (!all && (kind == DK_HEAD_ENC0 || kind == DK_TAIL || kind == DK_ATT32 || kind == DK_ATT16)) return ESR_EINVAL;
     switch (kind) {
     case DK_HEAD_ENC0: return launch_mma<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT, 16, 16>(a, st);
     case DK_ENC0:      return launch_mma<8, 16, 2, false, FMT_SPLIT, FMT_SPLIT, 16, 16>(a, st);
@@ -301,6 +311,8 @@ int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st)
     case DK_RECON1:    return launch_mma<32, 16, 1, true, FMT_SPLIT, FMT_SPLIT, 32, 8>(a, st);
     case DK_RECON2:    return launch_mma<16, 8, 1, true, FMT_SPLIT, FMT_SPLIT, 32, 16>(a, st);
     case DK_TAIL:      return launch_mma<8, 2, 1, false, FMT_SPLIT, FMT_NCHW_F32, 32, 16>(a, st);
+    case DK_ATT32:     return launch_mma<32, 1, 1, false, FMT_SPLIT, FMT_NHWC_F32, 32, 8>(a, st);
+    case DK_ATT16:     return launch_mma<16, 1, 1, false, FMT_SPLIT, FMT_NHWC_F32, 32, 16>(a, st);
     default: break;
     }
     return ESR_EINVAL;
