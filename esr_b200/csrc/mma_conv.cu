@@ -86,14 +86,13 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
     const int oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- weights: fp32 [tap][ci][co] -> split bf16 [tap][co][ci] (+pad), zero rows for co >= COUT
-    for (int i = tid; i < 9 * CIN * NP; i += 256) {
-        const int co = i % NP, ci = (i / NP) % CIN, tap = i / (NP * CIN);
-        const float v = co < COUT ? a.w[(tap * CIN + ci) * COUT + co] : 0.0f;
-        __nv_bfloat16 h, l;
-        split_bf16(v, h, l);
-        w_hi[(tap * NP + co) * WP + ci] = h;
-        w_lo[(tap * NP + co) * WP + ci] = l;
+    // ---- weights: the pre-packed split-bf16 image ([plane][tap][co][ci + pad], pack_mma_weight) by asynchronous 16-byte copies
+    {
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.w_mma);
+        const uint32_t dst = smem_u32_generic(w_hi);
+        for (int i = tid; i < (int)(2 * G::W_BYTES / 16); i += 256)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     if (tid < NP) bsm[tid] = tid < COUT ? a.bias[tid] : 0.0f;
 
@@ -139,38 +138,77 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
         const __nv_bfloat16 *hi = a.in_split;
         const size_t plane = a.in_plane;
         constexpr int Q = CIN / 8;
-        for (int i = tid; i < Q * PW * PH; i += 256) {
-            const int q = i % Q, pp = i / Q;                              // consecutive lanes: the 16-byte groups of a pixel
-            const int px = pp % PW, py = pp / PW;
-            const int y = iy0 + py, x = ix0 + px;
-            uint8_t *dh = p_hi + (size_t)pp * PITCH + q * 16, *dl = p_lo + (size_t)pp * PITCH + q * 16;
-            if (!(y >= 0 && y < Hc && x >= 0 && x < Wc)) {
-                *reinterpret_cast<uint4 *>(dh) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4 *>(dl) = make_uint4(0, 0, 0, 0);
-            } else if constexpr (!UPS) {
-                const __nv_bfloat16 *s = hi + (((size_t)simg * a.Hin + y) * a.Win + x) * CIN + q * 8;
-                *reinterpret_cast<uint4 *>(dh) = *reinterpret_cast<const uint4 *>(s);          // already split: copy
-                *reinterpret_cast<uint4 *>(dl) = *reinterpret_cast<const uint4 *>(s + plane);
-            } else {
-                // F.interpolate(scale_factor=2, bilinear, align_corners=False) (submodules.py:290), as in direct_conv.cu
-                const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f);
-                const float fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
-                const int y_0 = (int)fy, x_0 = (int)fx;
-                const int y_1 = min(y_0 + 1, a.Hin - 1), x_1 = min(x_0 + 1, a.Win - 1);
-                const float ly = fy - (float)y_0, lx = fx - (float)x_0;
-                const size_t b0 = ((size_t)simg * a.Hin + y_0) * a.Win, b1 = ((size_t)simg * a.Hin + y_1) * a.Win;
-                float v00[8], v01[8], v10[8], v11[8], v[8];
-                dc_ld8(hi + (b0 + x_0) * CIN + q * 8, plane, v00);
-                dc_ld8(hi + (b0 + x_1) * CIN + q * 8, plane, v01);
-                dc_ld8(hi + (b1 + x_0) * CIN + q * 8, plane, v10);
-                dc_ld8(hi + (b1 + x_1) * CIN + q * 8, plane, v11);
+        constexpr int NI = Q * PW * PH;
+        if constexpr (!UPS) {
+            // already split: asynchronous 16-byte copies global -> shared (all in flight at once), zeros outside the image
+            for (int i = tid; i < NI; i += 256) {
+                const int q = i % Q, pp = i / Q;                          // consecutive lanes: the 16-byte groups of a pixel
+                const int px = pp % PW, py = pp / PW;
+                const int y = iy0 + py, x = ix0 + px;
+                uint8_t *dh = p_hi + (size_t)pp * PITCH + q * 16, *dl = p_lo + (size_t)pp * PITCH + q * 16;
+                if (y >= 0 && y < Hc && x >= 0 && x < Wc) {
+                    const __nv_bfloat16 *s = hi + (((size_t)simg * a.Hin + y) * a.Win + x) * CIN + q * 8;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32_generic(dh)), "l"(s) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32_generic(dl)), "l"(s + plane) : "memory");
+                } else {
+                    *reinterpret_cast<uint4 *>(dh) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(dl) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            // F.interpolate(scale_factor=2, bilinear, align_corners=False) (submodules.py:290), as in direct_conv.cu.
+            // Two items per iteration: all 16 corner loads are issued before the first interpolation (latency-bound otherwise).
+            for (int i0 = tid; i0 < NI; i0 += 512) {
+                uint4 ch[2][4], cl[2][4];
+                float lyv[2], lxv[2];
+                bool ok[2];
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    v[e] = (1.0f - ly) * ((1.0f - lx) * v00[e] + lx * v01[e]) + ly * ((1.0f - lx) * v10[e] + lx * v11[e]);
-                st_split8(dh, dl, v);
+                for (int u = 0; u < 2; ++u) {
+                    const int i = i0 + u * 256;
+                    const int q = i % Q, pp = i / Q;
+                    const int y = iy0 + pp / PW, x = ix0 + pp % PW;
+                    ok[u] = i < NI && y >= 0 && y < Hc && x >= 0 && x < Wc;
+                    const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f);
+                    const float fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
+                    const int y_0 = min((int)fy, a.Hin - 1), x_0 = min((int)fx, a.Win - 1);    // (clamps only matter when !ok)
+                    const int y_1 = min(y_0 + 1, a.Hin - 1), x_1 = min(x_0 + 1, a.Win - 1);
+                    lyv[u] = fy - (float)y_0; lxv[u] = fx - (float)x_0;
+                    const size_t b0 = ((size_t)simg * a.Hin + y_0) * a.Win, b1 = ((size_t)simg * a.Hin + y_1) * a.Win;
+                    const __nv_bfloat16 *s00 = hi + (b0 + x_0) * CIN + q * 8, *s01 = hi + (b0 + x_1) * CIN + q * 8;
+                    const __nv_bfloat16 *s10 = hi + (b1 + x_0) * CIN + q * 8, *s11 = hi + (b1 + x_1) * CIN + q * 8;
+                    if (ok[u]) {
+                        ch[u][0] = __ldg(reinterpret_cast<const uint4 *>(s00)); cl[u][0] = __ldg(reinterpret_cast<const uint4 *>(s00 + plane));
+                        ch[u][1] = __ldg(reinterpret_cast<const uint4 *>(s01)); cl[u][1] = __ldg(reinterpret_cast<const uint4 *>(s01 + plane));
+                        ch[u][2] = __ldg(reinterpret_cast<const uint4 *>(s10)); cl[u][2] = __ldg(reinterpret_cast<const uint4 *>(s10 + plane));
+                        ch[u][3] = __ldg(reinterpret_cast<const uint4 *>(s11)); cl[u][3] = __ldg(reinterpret_cast<const uint4 *>(s11 + plane));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = i0 + u * 256;
+                    if (i >= NI) continue;
+                    const int q = i % Q, pp = i / Q;
+                    uint8_t *dh = p_hi + (size_t)pp * PITCH + q * 16, *dl = p_lo + (size_t)pp * PITCH + q * 16;
+                    if (!ok[u]) {
+                        *reinterpret_cast<uint4 *>(dh) = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4 *>(dl) = make_uint4(0, 0, 0, 0);
+                        continue;
+                    }
+                    float v00[8], v01[8], v10[8], v11[8], v[8];
+                    dc_unpack8(ch[u][0], cl[u][0], v00); dc_unpack8(ch[u][1], cl[u][1], v01);
+                    dc_unpack8(ch[u][2], cl[u][2], v10); dc_unpack8(ch[u][3], cl[u][3], v11);
+                    const float ly = lyv[u], lx = lxv[u];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        v[e] = (1.0f - ly) * ((1.0f - lx) * v00[e] + lx * v01[e]) + ly * ((1.0f - lx) * v10[e] + lx * v11[e]);
+                    st_split8(dh, dl, v);
+                }
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");                   // weights (and the copied patch) have landed
     __syncthreads();
 
     // ---- stage 2: implicit GEMM on the warp-level tensor cores
@@ -296,6 +334,27 @@ static int launch_mma(const DirectArgs &a, cudaStream_t st)
     return ESR_OK;
 }
 
+__global__ void k_pack_mma_weight(const float *__restrict__ w, int cout, int cin, __nv_bfloat16 *__restrict__ dst)
+{
+    const int np = cout < 8 ? 8 : cout, wp = cin + 8;
+    const int total = 9 * np * wp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % wp, co = (i / wp) % np, tap = i / (wp * np);
+        const float v = (ci < cin && co < cout) ? w[((size_t)co * cin + ci) * 9 + tap] : 0.0f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        dst[i] = h;
+        dst[total + i] = l;
+    }
+}
+size_t mma_weight_bytes(int cout, int cin) { return (size_t)2 * 9 * (cout < 8 ? 8 : cout) * (cin + 8) * sizeof(__nv_bfloat16); }
+int pack_mma_weight(const float *w, int cout, int cin, void *dst, cudaStream_t st)
+{
+    k_pack_mma_weight<<<(9 * (cout < 8 ? 8 : cout) * (cin + 8) + 255) / 256, 256, 0, st>>>(w, cout, cin, (__nv_bfloat16 *)dst);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
 // returns ESR_EINVAL for kinds that stay on the FFMA kernels.  Measured on B200 (cfg2, profiles/r1_notes.md): enc1 88 -> 82,
 // enc2 97 -> 74, recons[1] 203 -> 138, recons[2] 230 -> 172 us; the fused head+enc0 (177 -> 193, dominated by the FFMA head
 // evaluated per patch pixel) and the tail (100 -> 111, N padded 2 -> 8) are slower and only run here with ESR_MMA_ALL=1.
@@ -303,6 +362,7 @@ int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st)
 {
     static const bool all = getenv("ESR_MMA_ALL") != nullptr;
     if (!all && (kind == DK_HEAD_ENC0 || kind == DK_TAIL || kind == DK_ATT32 || kind == DK_ATT16)) return ESR_EINVAL;
+    if (!a.w_mma) return ESR_EINVAL;
     switch (kind) {
     case DK_HEAD_ENC0: return launch_mma<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT, 16, 16>(a, st);
     case DK_ENC0:      return launch_mma<8, 16, 2, false, FMT_SPLIT, FMT_SPLIT, 16, 16>(a, st);

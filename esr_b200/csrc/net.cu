@@ -55,6 +55,7 @@ static const DLInfo DLS[D_COUNT] = {
 struct ParamLayout {
     size_t tw[T_COUNT], tb[T_COUNT];     // packed weights / padded bias of TC layers
     size_t dw[D_COUNT], db[D_COUNT];     // direct layers
+    size_t dm[D_COUNT];                  // the same weights as the split-bf16 image of the mma.sync kernels
     size_t fc0w, fc0b, fc1w, fc1b;
     size_t total;
 };
@@ -71,6 +72,7 @@ static const ParamLayout &param_layout()
         for (int i = 0; i < D_COUNT; ++i) {
             l.dw[i] = take(sizeof(float) * 9 * DLS[i].cin * DLS[i].cout);
             l.db[i] = take(sizeof(float) * DLS[i].cout);
+            l.dm[i] = take(mma_weight_bytes(DLS[i].cout, DLS[i].cin));
         }
         l.fc0w = take(sizeof(float) * 32 * 64); l.fc0b = take(sizeof(float) * 32);
         l.fc1w = take(sizeof(float) * 128 * 32); l.fc1b = take(sizeof(float) * 128);
@@ -349,6 +351,7 @@ static int build(Net &n, cudaStream_t st)
     const ParamLayout &Lp = param_layout();
     auto base = [&](int i, int act) {
         DirectArgs a; a.w = (const float *)(n.params + Lp.dw[i]); a.bias = (const float *)(n.params + Lp.db[i]); a.act = act;
+        a.w_mma = n.params + Lp.dm[i];
         return a;
     };
     auto in_split = [&](DirectArgs &a, const SplitTensor &t) { a.in_split = t.base; a.in_plane = t.plane(); a.Hin = t.H; a.Win = t.W; };
@@ -515,6 +518,7 @@ extern "C" int esr_net_pack_params(const float *const *p, void *blob, esr_stream
     for (int i = 0; i < D_COUNT; ++i) {
         const DLInfo &d = DLS[i];
         if ((rc = pack_direct_weight(p[d.w], d.cout, d.cin, (float *)(out + L.dw[i]), st))) return rc;
+        if ((rc = pack_mma_weight(p[d.w], d.cout, d.cin, out + L.dm[i], st))) return rc;
         ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.db[i], p[d.b], sizeof(float) * d.cout, cudaMemcpyDeviceToDevice, st));
     }
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.fc0w, p[P_FC0_W], sizeof(float) * 32 * 64, cudaMemcpyDeviceToDevice, st));

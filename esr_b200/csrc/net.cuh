@@ -18,6 +18,7 @@ struct DirectArgs {
     int pad_top = 0, pad_bottom = 0, pad_left = 0, pad_right = 0;   // CropSize zero padding of the network input
     // weights
     const float *w = nullptr;                   // [9][CIN][COUT]
+    const void *w_mma = nullptr;                // mma_conv.cu: split bf16 image [2 planes][9][max(COUT,8)][CIN+8] (pack_mma_weight)
     const float *bias = nullptr;                // [COUT]
     const float *w0 = nullptr, *b0 = nullptr;   // fused head (2->8): [9][2][8], [8]
     int act = ACT_NONE;
@@ -33,6 +34,9 @@ int conv_direct(DirectKind kind, const DirectArgs &a, cudaStream_t st);
 // mma_conv.cu: the same layers on mma.sync tensor cores; ESR_EINVAL = this kind has no mma variant (use the FFMA kernel)
 int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st);
 int pack_direct_weight(const float *w, int cout, int cin, float *dst, cudaStream_t st);
+// fp32 [Cout,Cin,3,3] -> the shared-memory image the mma kernels copy: split bf16 [plane][tap][co (padded to >= 8)][ci + 8 pad]
+size_t mma_weight_bytes(int cout, int cin);
+int pack_mma_weight(const float *w, int cout, int cin, void *dst, cudaStream_t st);
 
 // ---- element-wise / reduction kernels (elementwise.cu)
 // local_fusion input: out[img=(b,i)] = cat(f[i0]*map[p0], f[i1], f[i2]*map[p1])  (models/model.py:82-86)
