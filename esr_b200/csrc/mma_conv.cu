@@ -159,13 +159,16 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else {
             // F.interpolate(scale_factor=2, bilinear, align_corners=False) (submodules.py:290), as in direct_conv.cu.
-            // Two items per iteration: all 16 corner loads are issued before the first interpolation (latency-bound otherwise).
-            for (int i0 = tid; i0 < NI; i0 += 512) {
-                uint4 ch[2][4], cl[2][4];
-                float lyv[2], lxv[2];
-                bool ok[2];
+            // U items per iteration: all corner loads are issued before the first interpolation (the fill is latency-bound).
+            // U = 2 only where the registers allow it without losing a resident block (measured: recons[1] 138 -> 119 us
+            // with U = 2, recons[2] 172 -> 205 us because 98 registers drop it from 3 to 2 blocks per SM).
+            constexpr int U = CIN >= 32 ? 2 : 1;
+            for (int i0 = tid; i0 < NI; i0 += 256 * U) {
+                uint4 ch[U][4], cl[U][4];
+                float lyv[U], lxv[U];
+                bool ok[U];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int i = i0 + u * 256;
                     const int q = i % Q, pp = i / Q;
                     const int y = iy0 + pp / PW, x = ix0 + pp % PW;
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int i = i0 + u * 256;
                     if (i >= NI) continue;
                     const int q = i % Q, pp = i / Q;

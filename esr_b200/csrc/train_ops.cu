@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) k_gprep(const float *__restrict__ dy, con
         tile[r][tx] = v;
         float sum = v;
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (tx == 0 && c < C) atomicAdd(db + c, sum);
+        if (db && tx == 0 && c < C) atomicAdd(db + c, sum);
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
@@ -672,7 +672,8 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
                         esr_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    ESR_REQUIRE(x && w && dy && dw && db && workspace, "conv2d_backward: null pointer");
+    ESR_REQUIRE(x && w && dy && workspace && ((dw && db) || (!dw && !db && dx)), "conv2d_backward: null pointer");
+    const bool want_dw = dw != nullptr;                               // dw == db == NULL: input gradient only (deferred dw)
     ESR_REQUIRE(act == ACT_NONE || y, "conv2d_backward: the forward output is needed for the activation derivative");
     ESR_REQUIRE((ksz == 3 || ksz == 1) && (stride == 1 || stride == 2) && act >= 0 && act <= 3, "conv2d_backward: ksz=%d stride=%d act=%d", ksz,
                 stride, act);
@@ -685,8 +686,10 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
     const bool tc_dw = tcd && Cin % 64 == 0 && getenv("ESR_WGRAD_GENERIC") == nullptr;
     float *g = (float *)ws.take(ng * 4);                           // fp32 g: only the CUDA-core kernels read it
     __nv_bfloat16 *gsplit = nullptr;
-    ESR_CUDA_CHECK(cudaMemsetAsync(db, 0, (size_t)Cout * 4, st));
-    ESR_CUDA_CHECK(cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * ksz * ksz * 4, st));
+    if (want_dw) {
+        ESR_CUDA_CHECK(cudaMemsetAsync(db, 0, (size_t)Cout * 4, st));
+        ESR_CUDA_CHECK(cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * ksz * ksz * 4, st));
+    }
     if (tcd) {
         // one pass: activation derivative, bias gradient, fp32 -> split bf16 NHWC (padded to a 64-multiple of channels)
         gsplit = (__nv_bfloat16 *)ws.take((size_t)B * gC * Ho * Wo * 4);
@@ -702,14 +705,16 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
             k_act_bwd<<<(unsigned)min((size_t)4096, (ng + 255) / 256), 256, 0, st>>>(dy, y, g, ng, act);
             ESR_LAUNCH_CHECK();
         }
-        const size_t total = (size_t)B * Ho * Wo;
-        int chunks = (int)min((size_t)64, (total + 4095) / 4096);
-        k_bias_grad<<<dim3(Cout, chunks < 1 ? 1 : chunks), 256, 0, st>>>(g, B, Cout, Ho * Wo, db);
-        ESR_LAUNCH_CHECK();
+        if (want_dw) {
+            const size_t total = (size_t)B * Ho * Wo;
+            int chunks = (int)min((size_t)64, (total + 4095) / 4096);
+            k_bias_grad<<<dim3(Cout, chunks < 1 ? 1 : chunks), 256, 0, st>>>(g, B, Cout, Ho * Wo, db);
+            ESR_LAUNCH_CHECK();
+        }
     }
     // ---- dw
-    bool dw_done = false;
-    if (tc_dw) {
+    bool dw_done = !want_dw;
+    if (want_dw && tc_dw) {
         Bump ws2 = ws;                                               // x split is dead after the kernel: dx reuses the space
         __nv_bfloat16 *xsplit = (__nv_bfloat16 *)ws2.take((size_t)B * Cin * H * W * 4);
         ESR_REQUIRE(ws2.off <= ws2.cap, "conv2d_backward: workspace too small");

@@ -15,6 +15,7 @@ Adam(lr, weight_decay, amsgrad).  Here
 `forward_window` is the differentiable counterpart of esr_b200.DeepRecurrNet.forward (which runs the fused inference
 plan and cannot be differentiated); DeepRecurrNet.forward dispatches here when gradients are enabled.
 """
+import contextlib
 import math
 
 import torch
@@ -29,9 +30,57 @@ def _ws(nbytes, device):
     return torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
 
 
+_DEFERRED = None        # None: off.  dict key -> [sink, [(x, y, dy), ...]] while a train_step collects weight-shared layers
+
+
+class _defer_weight_grads:
+    """Inside this context, convolutions called with `defer=(key, sink)` return only dx from backward and stash (x, y, dy);
+    flush() then computes dw / db of each key ONCE over the concatenated batch (the ConvGRU applies the same weights at
+    every step of every window: 18 small weight-gradient launches + 18 x 6 M atomics become one) and hands them to sink."""
+
+    def __enter__(self):
+        global _DEFERRED
+        self.prev, _DEFERRED = _DEFERRED, {}
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFERRED
+        _DEFERRED = self.prev
+
+    @staticmethod
+    def flush():
+        for key, (sink, items, cfg) in list(_DEFERRED.items()):
+            if not items:
+                continue
+            x = torch.cat([t[0] for t in items], 0)
+            y = torch.cat([t[1] for t in items], 0)
+            dy = torch.cat([t[2] for t in items], 0)
+            w, stride, act = cfg
+            dw, db = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=False, need_dw=True)[1:]
+            sink(dw, db)
+            items.clear()
+
+
+def _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=True, need_dw=True):
+    B, Cin, H, W = x.shape
+    Cout, _, k, _ = w.shape
+    L = _lib.lib()
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.empty_like(w) if need_dw else None
+    db = torch.empty((Cout,), dtype=torch.float32, device=x.device) if need_dw else None
+    with torch.cuda.device(x.device):
+        nbytes = L.esr_conv2d_workspace_bytes(B, Cin, H, W, Cout, k, stride)
+        ws = _ws(nbytes, x.device)
+        _lib.check(L.esr_conv2d_backward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), _lib.ptr(dy), B, Cin, H, W, Cout, k, stride,
+                                         act, _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), nbytes,
+                                         _lib.stream_ptr()), "esr_conv2d_backward")
+    return dx, dw, db
+
+
 class _Conv2dFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, stride, act):
+    def forward(ctx, x, w, b, stride, act, defer=None):
+        ctx.defer = defer if (_DEFERRED is not None and defer is not None) else None
         if not x.is_cuda:
             raise _lib.ESRError("esr_b200.train.conv2d needs CUDA tensors (there is no CPU path)")
         x, w, b = x.contiguous().float(), w.contiguous().float(), b.contiguous().float()
@@ -54,24 +103,20 @@ class _Conv2dFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
         stride, act = ctx.cfg
-        B, Cin, H, W = x.shape
-        Cout, _, k, _ = w.shape
         dy = dy.contiguous().float()
-        L = _lib.lib()
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw, db = torch.empty_like(w), torch.empty((Cout,), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            nbytes = L.esr_conv2d_workspace_bytes(B, Cin, H, W, Cout, k, stride)
-            ws = _ws(nbytes, x.device)
-            _lib.check(L.esr_conv2d_backward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), _lib.ptr(dy), B, Cin, H, W, Cout, k, stride,
-                                             act, _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), nbytes,
-                                             _lib.stream_ptr()), "esr_conv2d_backward")
-        return dx, dw, db, None, None
+        if ctx.defer is not None and _DEFERRED is not None and ctx.needs_input_grad[0]:
+            key, sink = ctx.defer
+            _DEFERRED.setdefault(key, [sink, [], (w, stride, act)])[1].append((x, y, dy))
+            dx = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=True, need_dw=False)[0]
+            return dx, None, None, None, None, None
+        dx, dw, db = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=ctx.needs_input_grad[0])
+        return dx, dw, db, None, None, None
 
 
-def conv2d(x, w, b, stride=1, act=None):
-    """act(conv2d(x, w, b, stride, padding=k//2)), differentiable; k = 3 or 1 (ConvLayer, models/submodules.py:159-200)."""
-    return _Conv2dFn.apply(x, w, b, int(stride), _ACT[act])
+def conv2d(x, w, b, stride=1, act=None, defer=None):
+    """act(conv2d(x, w, b, stride, padding=k//2)), differentiable; k = 3 or 1 (ConvLayer, models/submodules.py:159-200).
+    defer=(key, sink): see _defer_weight_grads."""
+    return _Conv2dFn.apply(x, w, b, int(stride), _ACT[act], defer)
 
 
 class _DCNFn(torch.autograd.Function):
@@ -125,6 +170,13 @@ def _cl(m, x, stride=1, act=None):
     return conv2d(x, m.conv2d.weight, m.conv2d.bias, stride, act)
 
 
+def _accumulate(param, grad):
+    if param.grad is None:
+        param.grad = grad.detach().clone().view_as(param)
+    else:
+        param.grad.add_(grad.view_as(param))
+
+
 def forward_sequence(model, frames, states=None):
     """frames BxLx2xHxW (L >= num_frame) -> ((L-2)*B x 2 x H x W window-major, [h_fwd, h_rev]).
 
@@ -174,6 +226,16 @@ def forward_sequence(model, frames, states=None):
     gru = tp.lstm.recurrent_block
     w_zr = torch.cat([gru.update_gate.weight, gru.reset_gate.weight], 0)   # both gates in one 128 -> 128 convolution
     b_zr = torch.cat([gru.update_gate.bias, gru.reset_gate.bias], 0)
+
+    def sink_zr(dw, db):                                                   # batched weight gradient of all steps (train_step)
+        for p, gpart in ((gru.update_gate.weight, dw[:C]), (gru.reset_gate.weight, dw[C:]), (gru.update_gate.bias, db[:C]),
+                         (gru.reset_gate.bias, db[C:])):
+            _accumulate(p, gpart)
+
+    def sink_o(dw, db):
+        _accumulate(gru.out_gate.weight, dw)
+        _accumulate(gru.out_gate.bias, db)
+
     h_f, h_r = states if states is not None else (None, None)
     hs = None if h_f is None else torch.cat([h_f, h_r], 0)                # forward and reverse chains batched as 2B
     fwd, rev = [], []
@@ -185,9 +247,9 @@ def forward_sequence(model, frames, states=None):
             xi = torch.cat([gx[wi * N + i], gx[wi * N + N - 1 - i]], 0)
             if hs is None:
                 hs = torch.zeros_like(xi)
-            zr = conv2d(torch.cat([xi, hs], 1), w_zr, b_zr, 1, "sigmoid")
+            zr = conv2d(torch.cat([xi, hs], 1), w_zr, b_zr, 1, "sigmoid", defer=("gru_zr", sink_zr))
             z, rg = zr.split(C, 1)
-            o = conv2d(torch.cat([xi, hs * rg], 1), gru.out_gate.weight, gru.out_gate.bias, 1, "tanh")
+            o = conv2d(torch.cat([xi, hs * rg], 1), gru.out_gate.weight, gru.out_gate.bias, 1, "tanh", defer=("gru_o", sink_o))
             hs = hs * (1 - z) + o * z
             hf, hr = hs.split(B, 0)
             fwd.append(hf)
@@ -293,10 +355,14 @@ def _step_body(model, optimizer, frames, gt, num_frame, all_reduce):
     optimizer.zero_grad()
     net = model.module if hasattr(model, "module") else model
     net.reset_states()
-    pred = model(frames)                                          # all windows, window-major [(Wn*B), 2, H, W]
-    target = gt[:, mid:mid + Wn].transpose(0, 1).reshape(pred.shape)
-    loss = Wn * mse_loss(pred, target)                            # = sum over windows of MSELoss(pred_w, gt[:, w + mid])
-    loss.backward()
+    ddp = hasattr(model, "module")                                # DDP's reducer must see every gradient in backward: no deferral
+    with contextlib.nullcontext() if ddp else _defer_weight_grads() as deferred:
+        pred = model(frames)                                      # all windows, window-major [(Wn*B), 2, H, W]
+        target = gt[:, mid:mid + Wn].transpose(0, 1).reshape(pred.shape)
+        loss = Wn * mse_loss(pred, target)                        # = sum over windows of MSELoss(pred_w, gt[:, w + mid])
+        loss.backward()
+        if deferred is not None:
+            deferred.flush()                                      # ConvGRU weight gradients: one launch per gate over all steps
     if all_reduce is not None:
         all_reduce(optimizer.flat_grad)
     optimizer.step()

@@ -208,7 +208,8 @@ int esr_dcn_v2_forward(const float *input, const float *weight, const float *bia
  * nn.MSELoss (:774) and torch.optim.Adam(lr, weight_decay, amsgrad) (:781, config/train_ours_enfssyn.yml optimizer).
  * Tensors are fp32 NCHW (x [B,Cin,H,W], w [Cout,Cin,k,k], y/dy [B,Cout,Ho,Wo]); k = 3 (pad 1) or 1 (pad 0); stride 1|2;
  * act: 0 none, 1 relu, 2 sigmoid, 3 tanh (fused into the forward; backward multiplies dy by act'(y)).
- * backward: dx may be NULL (first layer); dw [Cout,Cin,k,k] and db [Cout] are overwritten (not accumulated).
+ * backward: dx may be NULL (first layer); dw [Cout,Cin,k,k] and db [Cout] are overwritten (not accumulated); dw == db ==
+ * NULL computes dx only (a caller that batches the weight gradient of a weight-shared layer, e.g. the ConvGRU steps).
  * workspace: esr_conv2d_workspace_bytes() bytes of device memory owned by the caller.
  * --------------------------------------------------------------------------------------------- */
 size_t esr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ksz, int stride);

@@ -247,3 +247,22 @@ def test_graphed_train_step_equals_eager(dev):
     assert int(ob.step_dev.item()) == 3
     for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         assert torch.allclose(pa.detach(), pb.detach(), rtol=0, atol=3e-3), n     # Adam normalises: +-lr per step at most
+
+
+def test_deferred_gru_weight_gradients_equal_per_step(dev):
+    """train_step batches the ConvGRU weight gradients of all steps into one launch per gate; same gradients as the
+    per-step path."""
+    from esr_b200 import train
+    sd = model_ref.seeded_state_dict(71)
+    frames, gt = _frames(2, 5, 24, 24, 13)
+    fd, gd = frames.to(dev), gt.to(dev)
+    a, b = _net(sd, dev), _net(sd, dev)
+    target = gd[:, 1:4].transpose(0, 1).reshape(6, 2, 24, 24)
+    (3 * train.mse_loss(a(fd), target)).backward()
+    with train._defer_weight_grads() as d:
+        (3 * train.mse_loss(b(fd), target)).backward()
+        assert b.time_propagate.lstm.recurrent_block.out_gate.weight.grad is None     # not produced by backward itself
+        d.flush()
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert pb.grad is not None, n
+        assert _rel(pb.grad, pa.grad.cpu()) <= 1e-4, n
