@@ -245,7 +245,15 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTCArgs &a, const uint32
         for (int j = 0; j < 32; ++j) v[j] += r[j];
     }
     if (a.out && n0 + 32 <= a.cout) store_split32(a.out + pix * a.out_C + a.out_coff + n0, a.out_plane, v);
-    if (a.out_f32) {
+    if (a.out_f32 && a.out_f32_nchw) {
+        // the autograd layout of the training operators: consecutive lanes = consecutive pixels of a tile row -> each of the
+        // 32 per-channel stores of a warp is one or two contiguous segments
+        float *op = a.out_f32 + (((size_t)img * a.out_f32_C + n0) * a.H + y) * a.W + x;
+        const size_t cs = (size_t)a.H * a.W;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (n0 + j < a.cout) op[j * cs] = v[j];
+    } else if (a.out_f32) {
         float *op = a.out_f32 + pix * a.out_f32_C + n0;
         if ((a.out_f32_C & 3) == 0) {                 // 16-byte stores (conv_offset_mask: 216 channels)
 #pragma unroll

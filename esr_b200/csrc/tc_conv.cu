@@ -263,7 +263,7 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
                     "conv_tc: bad split output");
         a.out = d.out.base; a.out_plane = d.out.plane(); a.out_C = d.out.C; a.out_coff = d.out_coff;
     }
-    a.out_f32 = d.out_f32; a.out_f32_C = d.out_f32_C;
+    a.out_f32 = d.out_f32; a.out_f32_C = d.out_f32_C; a.out_f32_nchw = d.out_f32_nchw;
     if (d.epi_mode != EPI_STD) {
         ESR_REQUIRE(d.h_prev.base && d.h_prev.C == 64 && d.z_buf && d.out.base, "conv_tc: GRU epilogue needs h_prev, z_buf, out");
         ESR_REQUIRE((d.epi_mode == EPI_GRU_ZR && a.npad == 128) || (d.epi_mode == EPI_GRU_OUT && a.npad == 64), "conv_tc: GRU epilogue width");

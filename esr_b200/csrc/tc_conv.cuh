@@ -38,6 +38,7 @@ struct ConvTCArgs {
     const __nv_bfloat16 *res; size_t res_plane; int res_C; const int *res_img;
     __nv_bfloat16 *out; size_t out_plane; int out_C, out_coff;   // split output (may be null)
     float *out_f32; int out_f32_C;                                // fp32 NHWC output (may be null)
+    int out_f32_nchw;                                             // 1: out_f32 is NCHW [n_img][out_f32_C][H][W] instead
     // GRU extras
     const __nv_bfloat16 *h_prev; size_t h_plane;                  // [*,H,W,64] split
     float *z_buf;                                                 // [n_img,H,W,64] fp32 (ZR writes, OUT reads)
@@ -56,7 +57,7 @@ struct ConvTCDesc {
     int act = ACT_NONE, act_from = 0, res_mode = RES_NONE, epi_mode = EPI_STD;
     SplitTensor res; const int *res_img = nullptr;
     SplitTensor out; int out_coff = 0;
-    float *out_f32 = nullptr; int out_f32_C = 0;
+    float *out_f32 = nullptr; int out_f32_C = 0; int out_f32_nchw = 0;
     SplitTensor h_prev; float *z_buf = nullptr;
 };
 

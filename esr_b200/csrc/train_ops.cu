@@ -76,23 +76,6 @@ __global__ void k_weight_rot_t(const float *__restrict__ w, int Cout, int CoutPa
     }
 }
 
-// fp32 NHWC [n][HW][C] -> NCHW [n][C][HW] (the tensor-core kernel's fp32 output -> the layout autograd expects)
-__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float *__restrict__ src, int C, int HW, float *__restrict__ dst)
-{
-    __shared__ float tile[32][33];
-    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8
-    for (int r = ty; r < 32; r += 8) {
-        const int p = p0 + r, c = c0 + tx;
-        tile[r][tx] = (p < HW && c < C) ? src[((size_t)n * HW + p) * C + c] : 0.0f;
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int c = c0 + r, p = p0 + tx;
-        if (c < C && p < HW) dst[((size_t)n * C + c) * HW + p] = tile[tx][r];
-    }
-}
-
 // fp32 NCHW -> split bf16 NHWC with the channel count padded to Cpad (extra channels zero): smem-tiled transpose, coalesced
 // on both sides.  Padding lets Cout = 216 (conv_offset_mask) use the 64-channel tensor-core tiles in dx and dw.
 __global__ void __launch_bounds__(256) k_split_from_nchw_t(const float *__restrict__ src, int C, int Cpad, int HW,
@@ -162,13 +145,6 @@ __global__ void __launch_bounds__(256) k_gprep(const float *__restrict__ dy, con
             dst[plane + o] = lo;
         }
     }
-}
-
-static int nhwc_to_nchw(const float *src, int B, int C, int HW, float *dst, cudaStream_t st)
-{
-    k_nhwc_to_nchw<<<dim3((HW + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(src, C, HW, dst);
-    ESR_LAUNCH_CHECK();
-    return ESR_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -299,6 +275,67 @@ __global__ void __launch_bounds__(256) k_conv_fwd_r(const float *__restrict__ x,
             for (int p = 0; p < 4; ++p)
                 if (tx0 + 4 * lx + p < W) dst[p] = act_fwd(acc[p][c], act);
         }
+    }
+}
+
+// dx of a stride-2 3x3 pad-1 convolution by output parity: the four pixels of a 2x2 quad (y = 2m + a, x = 2n + b) receive
+//   (0,0): g[m][n] w11        (0,1): g[m][n+1] w10 + g[m][n] w12        (1,0): g[m+1][n] w01 + g[m][n] w21
+//   (1,1): g[m+1][n+1] w00 + g[m+1][n] w02 + g[m][n+1] w20 + g[m][n] w22
+// i.e. exactly 9 useful FMAs per (co, ci) and quad -- no divisibility tests, no wasted taps.  Block = 16 x 16 quads
+// (32 x 32 dx pixels) x 8 input channels; g patch 17 x 17 per output channel chunk of 8.
+__global__ void __launch_bounds__(256) k_conv_dgrad_s2(const float *__restrict__ g, const float *__restrict__ w, float *__restrict__ dx,
+                                                       int Cin, int H, int W, int Cout, int Ho, int Wo)
+{
+    __shared__ float patch[G_C][17][18];                           // [co][m][n]
+    __shared__ __align__(16) float wsm[G_C][9][G_C];               // [co][tap][ci]
+    const int tiles_x = (W + 31) / 32;
+    const int m0 = (blockIdx.x / tiles_x) * 16, n0 = (blockIdx.x % tiles_x) * 16;     // quad coordinates of the tile
+    const int ci0 = blockIdx.y * G_C, n = blockIdx.z;
+    const int tid = threadIdx.x, qx = tid & 15, qy = tid >> 4;
+    float acc[4][G_C];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < G_C; ++c) acc[p][c] = 0.0f;
+    for (int co0 = 0; co0 < Cout; co0 += G_C) {
+        for (int i = tid; i < G_C * 17 * 17; i += 256) {
+            const int co = i / 289, r = i % 289;
+            const int gy = m0 + r / 17, gx = n0 + r % 17;
+            float v = 0.0f;
+            if (co0 + co < Cout && gy < Ho && gx < Wo) v = g[(((size_t)n * Cout + co0 + co) * Ho + gy) * Wo + gx];
+            patch[co][r / 17][r % 17] = v;
+        }
+        for (int i = tid; i < G_C * 9 * G_C; i += 256) {
+            const int ci = i % G_C, t = (i / G_C) % 9, co = i / (G_C * 9);
+            wsm[co][t][ci] = (co0 + co < Cout && ci0 + ci < Cin) ? w[((size_t)(co0 + co) * Cin + ci0 + ci) * 9 + t] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int co = 0; co < G_C; ++co) {
+            const float g00 = patch[co][qy][qx], g01 = patch[co][qy][qx + 1], g10 = patch[co][qy + 1][qx], g11 = patch[co][qy + 1][qx + 1];
+            float wv[9][G_C];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 a = *reinterpret_cast<const float4 *>(&wsm[co][t][0]), b = *reinterpret_cast<const float4 *>(&wsm[co][t][4]);
+                wv[t][0] = a.x; wv[t][1] = a.y; wv[t][2] = a.z; wv[t][3] = a.w; wv[t][4] = b.x; wv[t][5] = b.y; wv[t][6] = b.z; wv[t][7] = b.w;
+            }
+#pragma unroll
+            for (int c = 0; c < G_C; ++c) {
+                acc[0][c] = fmaf(g00, wv[4][c], acc[0][c]);
+                acc[1][c] = fmaf(g01, wv[3][c], fmaf(g00, wv[5][c], acc[1][c]));
+                acc[2][c] = fmaf(g10, wv[1][c], fmaf(g00, wv[7][c], acc[2][c]));
+                acc[3][c] = fmaf(g11, wv[0][c], fmaf(g10, wv[2][c], fmaf(g01, wv[6][c], fmaf(g00, wv[8][c], acc[3][c]))));
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int y = 2 * (m0 + qy) + (p >> 1), x = 2 * (n0 + qx) + (p & 1);
+        if (y >= H || x >= W) continue;
+#pragma unroll
+        for (int c = 0; c < G_C; ++c)
+            if (ci0 + c < Cin) dx[(((size_t)n * Cin + ci0 + c) * H + y) * W + x] = acc[p][c];
     }
 }
 
@@ -565,7 +602,6 @@ static int conv_tc_nchw(const float *x, const float *w, const float *bias, int B
     SplitTensor xs; xs.base = (__nv_bfloat16 *)ws.take((size_t)B * Cin * H * W * 4); xs.n_img = B; xs.H = H; xs.W = W; xs.C = Cin;
     void *wp = ws.take(tc_packed_weight_bytes(Cout, Cin, ksz * ksz));
     float *bp = (float *)ws.take(256 * 4);
-    float *yt = (float *)ws.take((size_t)B * Cout * H * W * 4);           // fp32 NHWC
     ESR_REQUIRE(ws.off <= ws.cap, "conv2d: workspace too small (%zu > %zu)", ws.off, ws.cap);
     if ((rc = split_from_nchw_pad(x, B, Cin, Cin, H * W, xs.base, st))) return rc;
     if ((rc = pack_conv_weight(w, Cout, Cin, ksz, wp, st))) return rc;
@@ -573,11 +609,10 @@ static int conv_tc_nchw(const float *x, const float *w, const float *bias, int B
     if (bias) ESR_CUDA_CHECK(cudaMemcpyAsync(bp, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, st));
     ConvTCDesc d;
     d.src[0] = xs; d.n_src = 1; d.ntaps = ksz * ksz; d.cout = Cout; d.wpacked = wp; d.bias = bp; d.n_img = B; d.act = act;
-    d.out_f32 = yt; d.out_f32_C = Cout;
+    d.out_f32 = y; d.out_f32_C = Cout; d.out_f32_nchw = 1;              // the epilogue writes fp32 NCHW directly
     ConvTCArgs a;
     if ((rc = conv_tc_prepare(d, &a))) return rc;
-    if ((rc = conv_tc_launch(a, st))) return rc;
-    return nhwc_to_nchw(yt, B, Cout, H * W, y, st);
+    return conv_tc_launch(a, st);
 }
 
 template <int KS>
@@ -608,6 +643,9 @@ static int launch_generic(int which, const float *x, const float *w, const float
         static bool attr = false;
         if (!attr) { ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_fwd_g<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
         k_conv_fwd_g<KS><<<grid, blk, smem, st>>>(x, w, bias, out, Cin, H, W, Cout, Ho, Wo, stride, act);
+    } else if (which == 1 && KS == 3 && stride == 2) {
+        const dim3 grid(((W + 31) / 32) * ((H + 31) / 32), (Cin + G_C - 1) / G_C, B);
+        k_conv_dgrad_s2<<<grid, 256, 0, st>>>(g, w, out, Cin, H, W, Cout, Ho, Wo);
     } else if (which == 1) {
         const int GP = (G_T - 1 + KS - 1) / stride + 2;
         const size_t smem = (size_t)(G_C * GP * GP + G_C * G_C * KK) * 4;
@@ -729,7 +767,6 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
             float *wt = (float *)ws.take((size_t)gC * Cin * ksz * ksz * 4);
             void *wp = ws.take(tc_packed_weight_bytes(Cin, gC, ksz * ksz));
             float *bp = (float *)ws.take(256 * 4);
-            float *dt = (float *)ws.take((size_t)B * Cin * H * W * 4);       // fp32 NHWC
             ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small (%zu > %zu)", ws.off, ws.cap);
             if (gC != Cout) ESR_CUDA_CHECK(cudaMemsetAsync(wt, 0, (size_t)gC * Cin * ksz * ksz * 4, st));
             k_weight_rot_t<<<(Cout * Cin * ksz * ksz + 255) / 256, 256, 0, st>>>(w, Cout, gC, Cin, ksz * ksz, wt);
@@ -739,11 +776,10 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
             SplitTensor gsrc; gsrc.base = gsplit; gsrc.n_img = B; gsrc.H = Ho; gsrc.W = Wo; gsrc.C = gC;
             ConvTCDesc d;
             d.src[0] = gsrc; d.n_src = 1; d.ntaps = ksz * ksz; d.cout = Cin; d.wpacked = wp; d.bias = bp; d.n_img = B; d.act = ACT_NONE;
-            d.out_f32 = dt; d.out_f32_C = Cin;
+            d.out_f32 = dx; d.out_f32_C = Cin; d.out_f32_nchw = 1;
             ConvTCArgs a;
             if ((rc = conv_tc_prepare(d, &a))) return rc;
             if ((rc = conv_tc_launch(a, st))) return rc;
-            if ((rc = nhwc_to_nchw(dt, B, Cin, H * W, dx, st))) return rc;
         } else if (ksz == 3 && stride == 1) {
             // dx = conv(g, rot180(w)^T): the register-tiled forward kernel with the roles of Cin and Cout swapped
             float *wt = (float *)ws.take((size_t)Cout * Cin * 9 * 4);

@@ -214,8 +214,11 @@ int wgrad_tc(const __nv_bfloat16 *x_split, const __nv_bfloat16 *g_split, int B, 
     a.n_img = B; a.H = H; a.W = W;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
     const int n_tiles = B * a.tiles_x * a.tiles_y, base = a.m_blocks * a.n_chunks * a.groups;
+    // one CTA per SM when there is enough work; every CTA ends with 128 x 64 x taps fp32 atomics, so small problems (a single
+    // ConvGRU step: 128 pixel tiles) get fewer, longer CTAs (>= 6 pixel tiles each) instead of 148 atomics-dominated ones
     int slices = (dev_info().sm_count + base - 1) / base;
-    if (slices > n_tiles) slices = n_tiles;
+    static const int min_tiles = getenv("ESR_WGRAD_MIN_TILES") ? atoi(getenv("ESR_WGRAD_MIN_TILES")) : 6;
+    if (slices > n_tiles / min_tiles) slices = n_tiles / min_tiles;
     if (slices < 1) slices = 1;
     a.slices = slices;
     const size_t smem = 1024 + 2 * (size_t)(4 * WG_TILE) + 2 * (size_t)(2 * WG_TILE) + 128;

@@ -17,6 +17,7 @@ plan and cannot be differentiated); DeepRecurrNet.forward dispatches here when g
 """
 import contextlib
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -355,8 +356,10 @@ def _step_body(model, optimizer, frames, gt, num_frame, all_reduce):
     optimizer.zero_grad()
     net = model.module if hasattr(model, "module") else model
     net.reset_states()
-    ddp = hasattr(model, "module")                                # DDP's reducer must see every gradient in backward: no deferral
-    with contextlib.nullcontext() if ddp else _defer_weight_grads() as deferred:
+    # batching the ConvGRU weight gradients over all steps (one launch per gate) is opt-in: measured on B200 it is a wash at
+    # cfg2 (the concatenations cost what the 36 small launches did).  DDP's reducer must see every gradient in backward.
+    defer = os.environ.get("ESR_TRAIN_DEFER", "0") == "1" and not hasattr(model, "module")
+    with _defer_weight_grads() if defer else contextlib.nullcontext() as deferred:
         pred = model(frames)                                      # all windows, window-major [(Wn*B), 2, H, W]
         target = gt[:, mid:mid + Wn].transpose(0, 1).reshape(pred.shape)
         loss = Wn * mse_loss(pred, target)                        # = sum over windows of MSELoss(pred_w, gt[:, w + mid])
