@@ -79,6 +79,8 @@ SIGNATURES.update({
     "esr_conv2d_workspace_bytes": (c_size_t, [c_int] * 7),
     "esr_conv2d_forward": (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "esr_conv2d_backward": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "esr_upsample2x_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "esr_upsample2x_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "esr_mse_loss": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_float, c_void_p]),
     "esr_adam_step": (c_int, [c_void_p] * 5 + [c_size_t, c_void_p] + [c_float] * 5 + [c_void_p]),
 })

@@ -519,6 +519,61 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_g(const float *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// bilinear x2 (F.interpolate(scale_factor=2, mode='bilinear', align_corners=False), models/submodules.py:290) on fp32 NCHW
+// planes, forward and backward.  For scale 2 the source coordinate is oy/2 - 0.25, so output row 2k reads rows (k-1, k)
+// with weights (0.25, 0.75) and row 2k+1 reads (k, k+1) with (0.75, 0.25), clamped at the borders; the backward is the
+// transposed 4-tap gather per input pixel (no atomics, deterministic).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_upsample2x_fwd(const float *__restrict__ x, int H, int W, size_t planes, float *__restrict__ y)
+{
+    const int Ho = 2 * H, Wo = 2 * W;
+    const size_t total = planes * Ho * Wo;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+        const size_t pl = i / ((size_t)Wo * Ho);
+        const float fy = fmaxf(0.0f, ((float)oy + 0.5f) * 0.5f - 0.5f), fx = fmaxf(0.0f, ((float)ox + 0.5f) * 0.5f - 0.5f);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const float *p = x + pl * H * W;
+        const float v00 = p[(size_t)y0 * W + x0], v01 = p[(size_t)y0 * W + x1], v10 = p[(size_t)y1 * W + x0], v11 = p[(size_t)y1 * W + x1];
+        y[i] = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
+    }
+}
+
+// weight of output index o (row or column) on input index k, per dimension: (o, weight) pairs, at most 4
+__device__ __forceinline__ int up2_taps(int k, int n_in, int (&o)[4], float (&wt)[4])
+{
+    int c = 0;
+    if (k >= 1) { o[c] = 2 * k - 1; wt[c++] = 0.25f; }
+    o[c] = 2 * k; wt[c++] = k >= 1 ? 0.75f : 1.0f;
+    o[c] = 2 * k + 1; wt[c++] = k < n_in - 1 ? 0.75f : 1.0f;
+    if (k < n_in - 1) { o[c] = 2 * k + 2; wt[c++] = 0.25f; }
+    return c;
+}
+
+__global__ void __launch_bounds__(256) k_upsample2x_bwd(const float *__restrict__ dy, int H, int W, size_t planes, float *__restrict__ dx)
+{
+    const int Wo = 2 * W;
+    const size_t total = planes * H * W;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int ix = (int)(i % W), iy = (int)((i / W) % H);
+        const size_t pl = i / ((size_t)W * H);
+        int oy[4], ox[4];
+        float wy[4], wx[4];
+        const int ny = up2_taps(iy, H, oy, wy), nx = up2_taps(ix, W, ox, wx);
+        const float *p = dy + pl * (size_t)(2 * H) * Wo;
+        float s = 0.0f;
+        for (int a = 0; a < ny; ++a) {
+            float r = 0.0f;
+            for (int b = 0; b < nx; ++b) r = fmaf(wx[b], p[(size_t)oy[a] * Wo + ox[b]], r);
+            s = fmaf(wy[a], r, s);
+        }
+        dx[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // loss and optimizer
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_mse(const float *__restrict__ p, const float *__restrict__ t, size_t n, float inv_n,
@@ -791,6 +846,26 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
             if ((rc = generic(1, ksz, nullptr, w, nullptr, g, dx, B, Cin, H, W, Cout, Ho, Wo, stride, 0, st))) return rc;
         }
     }
+    return ESR_OK;
+}
+
+int esr_upsample2x_forward(const float *x, int planes, int H, int W, float *y, esr_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_REQUIRE(x && y && planes > 0 && H > 0 && W > 0, "upsample2x_forward: bad arguments");
+    const size_t total = (size_t)planes * 4 * H * W;
+    k_upsample2x_fwd<<<(unsigned)min((size_t)1 << 20, (total + 255) / 256), 256, 0, st>>>(x, H, W, (size_t)planes, y);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+int esr_upsample2x_backward(const float *dy, int planes, int H, int W, float *dx, esr_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_REQUIRE(dy && dx && planes > 0 && H > 0 && W > 0, "upsample2x_backward: bad arguments");
+    const size_t total = (size_t)planes * H * W;
+    k_upsample2x_bwd<<<(unsigned)min((size_t)1 << 20, (total + 255) / 256), 256, 0, st>>>(dy, H, W, (size_t)planes, dx);
+    ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
 

@@ -214,10 +214,10 @@ int wgrad_tc(const __nv_bfloat16 *x_split, const __nv_bfloat16 *g_split, int B, 
     a.n_img = B; a.H = H; a.W = W;
     a.tiles_x = (W + a.TW - 1) / a.TW; a.tiles_y = (H + a.TH - 1) / a.TH;
     const int n_tiles = B * a.tiles_x * a.tiles_y, base = a.m_blocks * a.n_chunks * a.groups;
-    // one CTA per SM when there is enough work; every CTA ends with 128 x 64 x taps fp32 atomics, so small problems (a single
-    // ConvGRU step: 128 pixel tiles) get fewer, longer CTAs (>= 6 pixel tiles each) instead of 148 atomics-dominated ones
+    // one CTA per SM.  (Every CTA ends with 128 x 64 x taps fp32 atomics; giving small problems fewer, longer CTAs was measured
+    // slower on B200: min 6 tiles per CTA +0.3 ms, min 16 +2 ms per cfg2 training iteration -- ESR_WGRAD_MIN_TILES to retest.)
     int slices = (dev_info().sm_count + base - 1) / base;
-    static const int min_tiles = getenv("ESR_WGRAD_MIN_TILES") ? atoi(getenv("ESR_WGRAD_MIN_TILES")) : 6;
+    static const int min_tiles = getenv("ESR_WGRAD_MIN_TILES") ? atoi(getenv("ESR_WGRAD_MIN_TILES")) : 1;
     if (slices > n_tiles / min_tiles) slices = n_tiles / min_tiles;
     if (slices < 1) slices = 1;
     a.slices = slices;

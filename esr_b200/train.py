@@ -141,6 +141,32 @@ def dcn_v2(inp, offset, mask, weight, bias, dg=8):
     return _DCNFn.apply(inp.contiguous(), offset.contiguous(), mask.contiguous(), weight, bias, dg)
 
 
+class _Up2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().float()
+        B, C, H, W = x.shape
+        y = torch.empty((B, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().esr_upsample2x_forward(_lib.ptr(x), B * C, H, W, _lib.ptr(y), _lib.stream_ptr()), "esr_upsample2x_forward")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous().float()
+        B, C, H2, W2 = dy.shape
+        dx = torch.empty((B, C, H2 // 2, W2 // 2), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            _lib.check(_lib.lib().esr_upsample2x_backward(_lib.ptr(dy), B * C, H2 // 2, W2 // 2, _lib.ptr(dx), _lib.stream_ptr()),
+                       "esr_upsample2x_backward")
+        return dx
+
+
+def upsample2x(x):
+    """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) (UpsampleConvLayer, models/submodules.py:290)."""
+    return _Up2Fn.apply(x)
+
+
 class _MSEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
@@ -285,7 +311,7 @@ def forward_sequence(model, frames, states=None):
     for lvl, ft in enumerate(pyramid):                                    # scale_aggre + recons (models/model.py:253-291)
         prod = (ft * _cl(sf.attens[lvl], ft, act="sigmoid")).view(L, B, *ft.shape[1:]).unbind(0)
         agg = torch.cat([(prod[wi] + prod[wi + 1] + prod[wi + 2]) / N for wi in range(Wn)], 0)
-        x = F.interpolate(x + agg, scale_factor=2, mode="bilinear", align_corners=False)
+        x = upsample2x(x + agg)
         x = _cl(sf.recons[lvl], x, act="relu")
     x = _cl(model.tail, x, act="relu")
     if (Hc, Wc) != (H, W):                                               # CropSize.crop (models/model_util.py:154-164)
@@ -356,9 +382,9 @@ def _step_body(model, optimizer, frames, gt, num_frame, all_reduce):
     optimizer.zero_grad()
     net = model.module if hasattr(model, "module") else model
     net.reset_states()
-    # batching the ConvGRU weight gradients over all steps (one launch per gate) is opt-in: measured on B200 it is a wash at
-    # cfg2 (the concatenations cost what the 36 small launches did).  DDP's reducer must see every gradient in backward.
-    defer = os.environ.get("ESR_TRAIN_DEFER", "0") == "1" and not hasattr(model, "module")
+    # the ConvGRU weight gradients are batched over all steps (one launch per gate; measured -1.5 ms per cfg2 iteration,
+    # ESR_TRAIN_DEFER=0 disables).  Not under DDP: its reducer must see every gradient inside backward.
+    defer = os.environ.get("ESR_TRAIN_DEFER", "1") == "1" and not hasattr(model, "module")
     with _defer_weight_grads() if defer else contextlib.nullcontext() as deferred:
         pred = model(frames)                                      # all windows, window-major [(Wn*B), 2, H, W]
         target = gt[:, mid:mid + Wn].transpose(0, 1).reshape(pred.shape)

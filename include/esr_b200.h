@@ -218,6 +218,10 @@ int esr_conv2d_forward(const float *x, const float *w, const float *bias, int B,
 int esr_conv2d_backward(const float *x, const float *w, const float *y, const float *dy, int B, int Cin, int H, int W, int Cout,
                         int ksz, int stride, int act, float *dx, float *dw, float *db, void *workspace, size_t workspace_bytes,
                         esr_stream_t stream);
+/* Bilinear x2 upsampling of `planes` = B*C fp32 planes [H,W] -> [2H,2W] and its backward (dy [2H,2W] -> dx [H,W]):
+ * F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) of UpsampleConvLayer (models/submodules.py:290). */
+int esr_upsample2x_forward(const float *x, int planes, int H, int W, float *y, esr_stream_t stream);
+int esr_upsample2x_backward(const float *dy, int planes, int H, int W, float *dx, esr_stream_t stream);
 /* loss[0] = mean((pred - target)^2); grad (optional) = grad_scale * 2 (pred - target) / n */
 int esr_mse_loss(const float *pred, const float *target, size_t n, float *loss, float *grad, float grad_scale,
                  esr_stream_t stream);

@@ -84,6 +84,21 @@ def test_conv2d_first_layer_needs_no_dx(dev):
     assert w.grad is not None and b.grad is not None
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 8, 8), (1, 5, 7, 13), (3, 2, 1, 9), (2, 16, 33, 20)])
+def test_upsample2x_forward_backward_vs_torch(dev, shape):
+    from esr_b200 import train
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g, requires_grad=True)
+    want = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    dy = torch.randn(want.shape, generator=g)
+    want.backward(dy)
+    xg = x.detach().to(dev).requires_grad_()
+    got = train.upsample2x(xg)
+    assert _rel(got.detach(), want.detach()) <= 1e-6
+    got.backward(dy.to(dev))
+    assert _rel(xg.grad, x.grad) <= 1e-6
+
+
 def test_mse_loss_and_adam_vs_torch(dev):
     from esr_b200 import train
     g = torch.Generator().manual_seed(5)
