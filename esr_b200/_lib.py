@@ -77,10 +77,15 @@ SIGNATURES.update({
     "esr_dcn_v2_backward": (c_int, [c_void_p] * 6 + [c_int] * 10 + [c_void_p] * 6 + [c_size_t, c_void_p]),
     "esr_dcn_v2_forward": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "esr_conv2d_workspace_bytes": (c_size_t, [c_int] * 7),
-    "esr_conv2d_forward": (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_void_p, c_void_p, c_size_t, c_void_p]),
-    "esr_conv2d_backward": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "esr_conv2d_split_bytes": (c_size_t, [c_int] * 7),
+    "esr_conv2d_forward": (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "esr_conv2d_backward": (c_int, [c_void_p] * 5 + [c_int] * 8 + [c_void_p] * 4 + [c_size_t, c_void_p]),
     "esr_upsample2x_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "esr_upsample2x_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "esr_gru_hr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "esr_gru_hr_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "esr_gru_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "esr_gru_blend_backward": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 4),
     "esr_mse_loss": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_float, c_void_p]),
     "esr_adam_step": (c_int, [c_void_p] * 5 + [c_size_t, c_void_p] + [c_float] * 5 + [c_void_p]),
 })

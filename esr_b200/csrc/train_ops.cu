@@ -574,6 +574,53 @@ __global__ void __launch_bounds__(256) k_upsample2x_bwd(const float *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// ConvGRU gate arithmetic (models/submodules.py:507-512) as two fused element-wise operators, forward and backward.
+// zr = sigmoid(conv(cat(x, h))) holds the update gate z in channels [0, C) and the reset gate r in [C, 2C) of each image.
+//   hr    = h * r                                   (input of the candidate convolution)
+//   h_new = h * (1 - z) + o * z
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gru_hr(const float *__restrict__ h, const float *__restrict__ zr, size_t n, int chw, float *__restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const size_t b = i / chw, r = i - b * chw;
+        out[i] = h[i] * zr[b * 2 * chw + chw + r];
+    }
+}
+__global__ void __launch_bounds__(256) k_gru_hr_bwd(const float *__restrict__ h, const float *__restrict__ zr, const float *__restrict__ g, size_t n,
+                                                    int chw, float *__restrict__ dh, float *__restrict__ dzr)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const size_t b = i / chw, r = i - b * chw;
+        const float gi = g[i];
+        dh[i] = gi * zr[b * 2 * chw + chw + r];
+        dzr[b * 2 * chw + r] = 0.0f;
+        dzr[b * 2 * chw + chw + r] = gi * h[i];
+    }
+}
+__global__ void __launch_bounds__(256) k_gru_blend(const float *__restrict__ h, const float *__restrict__ zr, const float *__restrict__ o, size_t n,
+                                                   int chw, float *__restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const size_t b = i / chw, r = i - b * chw;
+        const float z = zr[b * 2 * chw + r];
+        out[i] = h[i] * (1.0f - z) + o[i] * z;
+    }
+}
+__global__ void __launch_bounds__(256) k_gru_blend_bwd(const float *__restrict__ h, const float *__restrict__ zr, const float *__restrict__ o,
+                                                       const float *__restrict__ g, size_t n, int chw, float *__restrict__ dh,
+                                                       float *__restrict__ dzr, float *__restrict__ d_o)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const size_t b = i / chw, r = i - b * chw;
+        const float z = zr[b * 2 * chw + r], gi = g[i];
+        dh[i] = gi * (1.0f - z);
+        d_o[i] = gi * z;
+        dzr[b * 2 * chw + r] = gi * (o[i] - h[i]);
+        dzr[b * 2 * chw + chw + r] = 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // loss and optimizer
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_mse(const float *__restrict__ p, const float *__restrict__ t, size_t n, float inv_n,
@@ -651,10 +698,11 @@ static size_t conv2d_ws(int B, int Cin, int H, int W, int Cout, int ksz, int str
 
 // y = act(conv(x)) on the tensor cores: fp32 NCHW -> split NHWC -> k_conv_tc -> fp32 NCHW
 static int conv_tc_nchw(const float *x, const float *w, const float *bias, int B, int Cin, int H, int W, int Cout, int ksz, int act,
-                        float *y, Bump &ws, cudaStream_t st)
+                        float *y, void *x_split_out, Bump &ws, cudaStream_t st)
 {
     int rc;
-    SplitTensor xs; xs.base = (__nv_bfloat16 *)ws.take((size_t)B * Cin * H * W * 4); xs.n_img = B; xs.H = H; xs.W = W; xs.C = Cin;
+    SplitTensor xs; xs.n_img = B; xs.H = H; xs.W = W; xs.C = Cin;
+    xs.base = (__nv_bfloat16 *)(x_split_out ? x_split_out : ws.take((size_t)B * Cin * H * W * 4));   // kept by the caller for dw
     void *wp = ws.take(tc_packed_weight_bytes(Cout, Cin, ksz * ksz));
     float *bp = (float *)ws.take(256 * 4);
     ESR_REQUIRE(ws.off <= ws.cap, "conv2d: workspace too small (%zu > %zu)", ws.off, ws.cap);
@@ -743,8 +791,14 @@ size_t esr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ks
     return conv2d_ws(B, Cin, H, W, Cout, ksz, stride);
 }
 
+size_t esr_conv2d_split_bytes(int B, int Cin, int H, int W, int Cout, int ksz, int stride)
+{
+    const bool both = tc_fwd_ok(Cin, Cout, ksz, stride) && tc_dgrad_ok(Cin, Cout, ksz, stride) && Cin % 64 == 0;
+    return both ? (size_t)B * Cin * H * W * 4 : 0;
+}
+
 int esr_conv2d_forward(const float *x, const float *w, const float *bias, int B, int Cin, int H, int W, int Cout, int ksz, int stride,
-                       int act, float *y, void *workspace, size_t workspace_bytes, esr_stream_t stream)
+                       int act, float *y, void *x_split_out, void *workspace, size_t workspace_bytes, esr_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     ESR_REQUIRE(x && w && bias && y, "conv2d_forward: null pointer");
@@ -755,17 +809,19 @@ int esr_conv2d_forward(const float *x, const float *w, const float *bias, int B,
     if (tc_fwd_ok(Cin, Cout, ksz, stride)) {
         ESR_REQUIRE(workspace, "conv2d_forward: workspace required");
         Bump ws{(uint8_t *)workspace, 0, workspace_bytes};
-        return conv_tc_nchw(x, w, bias, B, Cin, H, W, Cout, ksz, act, y, ws, st);
+        return conv_tc_nchw(x, w, bias, B, Cin, H, W, Cout, ksz, act, y, x_split_out, ws, st);
     }
     return generic(0, ksz, x, w, bias, nullptr, y, B, Cin, H, W, Cout, Ho, Wo, stride, act, st);
 }
 
-int esr_conv2d_backward(const float *x, const float *w, const float *y, const float *dy, int B, int Cin, int H, int W, int Cout, int ksz,
-                        int stride, int act, float *dx, float *dw, float *db, void *workspace, size_t workspace_bytes,
-                        esr_stream_t stream)
+int esr_conv2d_backward(const float *x, const void *x_split, const float *w, const float *y, const float *dy, int B, int Cin, int H,
+                        int W, int Cout, int ksz, int stride, int act, float *dx, float *dw, float *db, void *workspace,
+                        size_t workspace_bytes, esr_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    ESR_REQUIRE(x && w && dy && workspace && ((dw && db) || (!dw && !db && dx)), "conv2d_backward: null pointer");
+    ESR_REQUIRE((x || x_split) && w && dy && workspace && ((dw && db) || (!dw && !db && dx)), "conv2d_backward: null pointer");
+    ESR_REQUIRE(!x_split || esr_conv2d_split_bytes(B, Cin, H, W, Cout, ksz, stride) > 0, "conv2d_backward: x_split given for a layer without a tensor-core dw");
+    ESR_REQUIRE(x || getenv("ESR_WGRAD_GENERIC") == nullptr, "conv2d_backward: the CUDA-core dw needs x");
     const bool want_dw = dw != nullptr;                               // dw == db == NULL: input gradient only (deferred dw)
     ESR_REQUIRE(act == ACT_NONE || y, "conv2d_backward: the forward output is needed for the activation derivative");
     ESR_REQUIRE((ksz == 3 || ksz == 1) && (stride == 1 || stride == 2) && act >= 0 && act <= 3, "conv2d_backward: ksz=%d stride=%d act=%d", ksz,
@@ -808,10 +864,14 @@ int esr_conv2d_backward(const float *x, const float *w, const float *y, const fl
     // ---- dw
     bool dw_done = !want_dw;
     if (want_dw && tc_dw) {
-        Bump ws2 = ws;                                               // x split is dead after the kernel: dx reuses the space
-        __nv_bfloat16 *xsplit = (__nv_bfloat16 *)ws2.take((size_t)B * Cin * H * W * 4);
-        ESR_REQUIRE(ws2.off <= ws2.cap, "conv2d_backward: workspace too small");
-        if ((rc = split_from_nchw_pad(x, B, Cin, Cin, H * W, xsplit, st))) return rc;
+        const __nv_bfloat16 *xsplit = (const __nv_bfloat16 *)x_split;       // saved by the forward, or converted here
+        if (!xsplit) {
+            Bump ws2 = ws;                                           // dead after the kernel: dx reuses the space
+            __nv_bfloat16 *xs_ = (__nv_bfloat16 *)ws2.take((size_t)B * Cin * H * W * 4);
+            ESR_REQUIRE(ws2.off <= ws2.cap, "conv2d_backward: workspace too small");
+            if ((rc = split_from_nchw_pad(x, B, Cin, Cin, H * W, xs_, st))) return rc;
+            xsplit = xs_;
+        }
         if ((rc = wgrad_tc(xsplit, gsplit, B, Cin, H, W, Cout, gC, ksz, dw, st))) return rc;   // (fp32 g was not written)
         dw_done = true;
     }
@@ -865,6 +925,42 @@ int esr_upsample2x_backward(const float *dy, int planes, int H, int W, float *dx
     ESR_REQUIRE(dy && dx && planes > 0 && H > 0 && W > 0, "upsample2x_backward: bad arguments");
     const size_t total = (size_t)planes * H * W;
     k_upsample2x_bwd<<<(unsigned)min((size_t)1 << 20, (total + 255) / 256), 256, 0, st>>>(dy, H, W, (size_t)planes, dx);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+static inline unsigned ew_grid(size_t n) { return (unsigned)min((size_t)1 << 16, (n + 255) / 256); }
+
+int esr_gru_hr(const float *h, const float *zr, int B, int chw, float *out, esr_stream_t stream)
+{
+    ESR_REQUIRE(h && zr && out && B > 0 && chw > 0, "gru_hr: bad arguments");
+    const size_t n = (size_t)B * chw;
+    k_gru_hr<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, zr, n, chw, out);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+int esr_gru_hr_backward(const float *h, const float *zr, const float *grad, int B, int chw, float *dh, float *dzr, esr_stream_t stream)
+{
+    ESR_REQUIRE(h && zr && grad && dh && dzr && B > 0 && chw > 0, "gru_hr_backward: bad arguments");
+    const size_t n = (size_t)B * chw;
+    k_gru_hr_bwd<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, zr, grad, n, chw, dh, dzr);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+int esr_gru_blend(const float *h, const float *zr, const float *o, int B, int chw, float *out, esr_stream_t stream)
+{
+    ESR_REQUIRE(h && zr && o && out && B > 0 && chw > 0, "gru_blend: bad arguments");
+    const size_t n = (size_t)B * chw;
+    k_gru_blend<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, zr, o, n, chw, out);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+int esr_gru_blend_backward(const float *h, const float *zr, const float *o, const float *grad, int B, int chw, float *dh, float *dzr,
+                           float *d_o, esr_stream_t stream)
+{
+    ESR_REQUIRE(h && zr && o && grad && dh && dzr && d_o && B > 0 && chw > 0, "gru_blend_backward: bad arguments");
+    const size_t n = (size_t)B * chw;
+    k_gru_blend_bwd<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, zr, o, grad, n, chw, dh, dzr, d_o);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

@@ -53,26 +53,31 @@ class _defer_weight_grads:
         for key, (sink, items, cfg) in list(_DEFERRED.items()):
             if not items:
                 continue
-            x = torch.cat([t[0] for t in items], 0)
-            y = torch.cat([t[1] for t in items], 0)
-            dy = torch.cat([t[2] for t in items], 0)
+            y = torch.cat([t[3] for t in items], 0)
+            dy = torch.cat([t[4] for t in items], 0)
+            shp = items[0][2]
+            shape = (sum(t[2][0] for t in items),) + tuple(shp[1:])
+            if items[0][1] is not None:                           # split operands [2 planes][B][...]: concatenate per plane
+                x, xs = None, torch.cat([t[1].view(2, t[2][0], -1) for t in items], 1).reshape(-1)
+            else:
+                x, xs = torch.cat([t[0] for t in items], 0), None
             w, stride, act = cfg
-            dw, db = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=False, need_dw=True)[1:]
+            dw, db = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=False, need_dw=True, x_split=xs, x_shape=shape)[1:]
             sink(dw, db)
             items.clear()
 
 
-def _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=True, need_dw=True):
-    B, Cin, H, W = x.shape
+def _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=True, need_dw=True, x_split=None, x_shape=None):
+    B, Cin, H, W = x_shape if x is None else x.shape
     Cout, _, k, _ = w.shape
     L = _lib.lib()
-    dx = torch.empty_like(x) if need_dx else None
+    dx = torch.empty((B, Cin, H, W), dtype=torch.float32, device=w.device) if need_dx else None
     dw = torch.empty_like(w) if need_dw else None
-    db = torch.empty((Cout,), dtype=torch.float32, device=x.device) if need_dw else None
-    with torch.cuda.device(x.device):
+    db = torch.empty((Cout,), dtype=torch.float32, device=w.device) if need_dw else None
+    with torch.cuda.device(w.device):
         nbytes = L.esr_conv2d_workspace_bytes(B, Cin, H, W, Cout, k, stride)
-        ws = _ws(nbytes, x.device)
-        _lib.check(L.esr_conv2d_backward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), _lib.ptr(dy), B, Cin, H, W, Cout, k, stride,
+        ws = _ws(nbytes, w.device)
+        _lib.check(L.esr_conv2d_backward(_lib.ptr(x), _lib.ptr(x_split), _lib.ptr(w), _lib.ptr(y), _lib.ptr(dy), B, Cin, H, W, Cout, k, stride,
                                          act, _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), nbytes,
                                          _lib.stream_ptr()), "esr_conv2d_backward")
     return dx, dw, db
@@ -94,9 +99,15 @@ class _Conv2dFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             nbytes = L.esr_conv2d_workspace_bytes(B, Cin, H, W, Cout, k, stride)
             ws = _ws(nbytes, x.device)
+            # layers whose dw also runs on the tensor cores keep x in the split-bf16 operand format for the backward
+            # (same bytes as fp32; the backward then needs neither x nor a second conversion)
+            nsplit = L.esr_conv2d_split_bytes(B, Cin, H, W, Cout, k, stride) if ctx.needs_input_grad[1] else 0
+            xs = torch.empty((nsplit,), dtype=torch.uint8, device=x.device) if nsplit else None
             _lib.check(L.esr_conv2d_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), B, Cin, H, W, Cout, k, stride, act,
-                                            _lib.ptr(y), _lib.ptr(ws), nbytes, _lib.stream_ptr()), "esr_conv2d_forward")
-        ctx.save_for_backward(x, w, y)
+                                            _lib.ptr(y), _lib.ptr(xs), _lib.ptr(ws), nbytes, _lib.stream_ptr()), "esr_conv2d_forward")
+        ctx.has_split = xs is not None
+        ctx.save_for_backward(xs if xs is not None else x, w, y)
+        ctx.x_shape = tuple(x.shape)
         ctx.cfg = (stride, act)
         return y
 
@@ -105,12 +116,14 @@ class _Conv2dFn(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         stride, act = ctx.cfg
         dy = dy.contiguous().float()
+        xs = x if ctx.has_split else None                              # saved split operand instead of x itself
+        x = None if ctx.has_split else x
         if ctx.defer is not None and _DEFERRED is not None and ctx.needs_input_grad[0]:
             key, sink = ctx.defer
-            _DEFERRED.setdefault(key, [sink, [], (w, stride, act)])[1].append((x, y, dy))
-            dx = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=True, need_dw=False)[0]
+            _DEFERRED.setdefault(key, [sink, [], (w, stride, act)])[1].append((x, xs, ctx.x_shape, y, dy))
+            dx = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=True, need_dw=False, x_split=xs, x_shape=ctx.x_shape)[0]
             return dx, None, None, None, None, None
-        dx, dw, db = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=ctx.needs_input_grad[0])
+        dx, dw, db = _conv2d_backward_raw(x, w, y, dy, stride, act, need_dx=ctx.needs_input_grad[0], x_split=xs, x_shape=ctx.x_shape)
         return dx, dw, db, None, None, None
 
 
@@ -165,6 +178,51 @@ class _Up2Fn(torch.autograd.Function):
 def upsample2x(x):
     """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) (UpsampleConvLayer, models/submodules.py:290)."""
     return _Up2Fn.apply(x)
+
+
+class _GruHRFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, zr):
+        h, zr = h.contiguous(), zr.contiguous()
+        out = torch.empty_like(h)
+        B, chw = h.shape[0], h[0].numel()
+        with torch.cuda.device(h.device):
+            _lib.check(_lib.lib().esr_gru_hr(_lib.ptr(h), _lib.ptr(zr), B, chw, _lib.ptr(out), _lib.stream_ptr()), "esr_gru_hr")
+        ctx.save_for_backward(h, zr)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, zr = ctx.saved_tensors
+        g = g.contiguous()
+        dh, dzr = torch.empty_like(h), torch.empty_like(zr)
+        with torch.cuda.device(h.device):
+            _lib.check(_lib.lib().esr_gru_hr_backward(_lib.ptr(h), _lib.ptr(zr), _lib.ptr(g), h.shape[0], h[0].numel(), _lib.ptr(dh),
+                                                      _lib.ptr(dzr), _lib.stream_ptr()), "esr_gru_hr_backward")
+        return dh, dzr
+
+
+class _GruBlendFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, zr, o):
+        h, zr, o = h.contiguous(), zr.contiguous(), o.contiguous()
+        out = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            _lib.check(_lib.lib().esr_gru_blend(_lib.ptr(h), _lib.ptr(zr), _lib.ptr(o), h.shape[0], h[0].numel(), _lib.ptr(out),
+                                                _lib.stream_ptr()), "esr_gru_blend")
+        ctx.save_for_backward(h, zr, o)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, zr, o = ctx.saved_tensors
+        g = g.contiguous()
+        dh, dzr, do = torch.empty_like(h), torch.empty_like(zr), torch.empty_like(o)
+        with torch.cuda.device(h.device):
+            _lib.check(_lib.lib().esr_gru_blend_backward(_lib.ptr(h), _lib.ptr(zr), _lib.ptr(o), _lib.ptr(g), h.shape[0], h[0].numel(),
+                                                         _lib.ptr(dh), _lib.ptr(dzr), _lib.ptr(do), _lib.stream_ptr()),
+                       "esr_gru_blend_backward")
+        return dh, dzr, do
 
 
 class _MSEFn(torch.autograd.Function):
@@ -275,9 +333,9 @@ def forward_sequence(model, frames, states=None):
             if hs is None:
                 hs = torch.zeros_like(xi)
             zr = conv2d(torch.cat([xi, hs], 1), w_zr, b_zr, 1, "sigmoid", defer=("gru_zr", sink_zr))
-            z, rg = zr.split(C, 1)
-            o = conv2d(torch.cat([xi, hs * rg], 1), gru.out_gate.weight, gru.out_gate.bias, 1, "tanh", defer=("gru_o", sink_o))
-            hs = hs * (1 - z) + o * z
+            o = conv2d(torch.cat([xi, _GruHRFn.apply(hs, zr)], 1), gru.out_gate.weight, gru.out_gate.bias, 1, "tanh",
+                       defer=("gru_o", sink_o))
+            hs = _GruBlendFn.apply(hs, zr, o)                          # h (1 - z) + o z   (models/submodules.py:511-512)
             hf, hr = hs.split(B, 0)
             fwd.append(hf)
             rev_w[N - 1 - i] = hr

@@ -213,15 +213,29 @@ int esr_dcn_v2_forward(const float *input, const float *weight, const float *bia
  * workspace: esr_conv2d_workspace_bytes() bytes of device memory owned by the caller.
  * --------------------------------------------------------------------------------------------- */
 size_t esr_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int ksz, int stride);
+/* x_split (optional): layers whose forward, dx and dw all run on the tensor cores convert x to the split-bf16 NHWC operand
+ * format once; esr_conv2d_split_bytes() > 0 says so and gives the size of the buffer the forward fills (x_split_out) and the
+ * backward reads (x_split) instead of converting x again -- the backward then does not need x itself (x may be NULL). */
+size_t esr_conv2d_split_bytes(int B, int Cin, int H, int W, int Cout, int ksz, int stride);
 int esr_conv2d_forward(const float *x, const float *w, const float *bias, int B, int Cin, int H, int W, int Cout, int ksz,
-                       int stride, int act, float *y, void *workspace, size_t workspace_bytes, esr_stream_t stream);
-int esr_conv2d_backward(const float *x, const float *w, const float *y, const float *dy, int B, int Cin, int H, int W, int Cout,
-                        int ksz, int stride, int act, float *dx, float *dw, float *db, void *workspace, size_t workspace_bytes,
-                        esr_stream_t stream);
+                       int stride, int act, float *y, void *x_split_out, void *workspace, size_t workspace_bytes,
+                       esr_stream_t stream);
+int esr_conv2d_backward(const float *x, const void *x_split, const float *w, const float *y, const float *dy, int B, int Cin,
+                        int H, int W, int Cout, int ksz, int stride, int act, float *dx, float *dw, float *db, void *workspace,
+                        size_t workspace_bytes, esr_stream_t stream);
 /* Bilinear x2 upsampling of `planes` = B*C fp32 planes [H,W] -> [2H,2W] and its backward (dy [2H,2W] -> dx [H,W]):
  * F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) of UpsampleConvLayer (models/submodules.py:290). */
 int esr_upsample2x_forward(const float *x, int planes, int H, int W, float *y, esr_stream_t stream);
 int esr_upsample2x_backward(const float *dy, int planes, int H, int W, float *dx, esr_stream_t stream);
+/* ConvGRU gate arithmetic (models/submodules.py:507-512), fp32, B images of chw = C*H*W elements; zr [B, 2C, H, W] holds
+ * the update gate z in channels [0,C) and the reset gate r in [C,2C).  hr = h*r;  blend = h*(1-z) + o*z.  The backward
+ * entry points write full-size dzr (the half they do not touch is zero-filled). */
+int esr_gru_hr(const float *h, const float *zr, int B, int chw, float *out, esr_stream_t stream);
+int esr_gru_hr_backward(const float *h, const float *zr, const float *grad, int B, int chw, float *dh, float *dzr,
+                        esr_stream_t stream);
+int esr_gru_blend(const float *h, const float *zr, const float *o, int B, int chw, float *out, esr_stream_t stream);
+int esr_gru_blend_backward(const float *h, const float *zr, const float *o, const float *grad, int B, int chw, float *dh,
+                           float *dzr, float *d_o, esr_stream_t stream);
 /* loss[0] = mean((pred - target)^2); grad (optional) = grad_scale * 2 (pred - target) / n */
 int esr_mse_loss(const float *pred, const float *target, size_t n, float *loss, float *grad, float grad_scale,
                  esr_stream_t stream);
