@@ -524,21 +524,19 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_g(const float *__restrict__ 
 // with weights (0.25, 0.75) and row 2k+1 reads (k, k+1) with (0.75, 0.25), clamped at the borders; the backward is the
 // transposed 4-tap gather per input pixel (no atomics, deterministic).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_upsample2x_fwd(const float *__restrict__ x, int H, int W, size_t planes, float *__restrict__ y)
+// grid (ceil(2W / 256), 2H, planes): no integer divisions in the index math
+__global__ void __launch_bounds__(256) k_upsample2x_fwd(const float *__restrict__ x, int H, int W, float *__restrict__ y)
 {
-    const int Ho = 2 * H, Wo = 2 * W;
-    const size_t total = planes * Ho * Wo;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
-        const size_t pl = i / ((size_t)Wo * Ho);
-        const float fy = fmaxf(0.0f, ((float)oy + 0.5f) * 0.5f - 0.5f), fx = fmaxf(0.0f, ((float)ox + 0.5f) * 0.5f - 0.5f);
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-        const float ly = fy - (float)y0, lx = fx - (float)x0;
-        const float *p = x + pl * H * W;
-        const float v00 = p[(size_t)y0 * W + x0], v01 = p[(size_t)y0 * W + x1], v10 = p[(size_t)y1 * W + x0], v11 = p[(size_t)y1 * W + x1];
-        y[i] = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
-    }
+    const int Wo = 2 * W, ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y;
+    if (ox >= Wo) return;
+    const size_t pl = blockIdx.z;
+    const float fy = fmaxf(0.0f, ((float)oy + 0.5f) * 0.5f - 0.5f), fx = fmaxf(0.0f, ((float)ox + 0.5f) * 0.5f - 0.5f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float *p = x + pl * H * W;
+    const float v00 = p[(size_t)y0 * W + x0], v01 = p[(size_t)y0 * W + x1], v10 = p[(size_t)y1 * W + x0], v11 = p[(size_t)y1 * W + x1];
+    y[(pl * 2 * H + oy) * Wo + ox] = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
 }
 
 // weight of output index o (row or column) on input index k, per dimension: (o, weight) pairs, at most 4
@@ -552,25 +550,22 @@ __device__ __forceinline__ int up2_taps(int k, int n_in, int (&o)[4], float (&wt
     return c;
 }
 
-__global__ void __launch_bounds__(256) k_upsample2x_bwd(const float *__restrict__ dy, int H, int W, size_t planes, float *__restrict__ dx)
+__global__ void __launch_bounds__(256) k_upsample2x_bwd(const float *__restrict__ dy, int H, int W, float *__restrict__ dx)
 {
-    const int Wo = 2 * W;
-    const size_t total = planes * H * W;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-        const int ix = (int)(i % W), iy = (int)((i / W) % H);
-        const size_t pl = i / ((size_t)W * H);
-        int oy[4], ox[4];
-        float wy[4], wx[4];
-        const int ny = up2_taps(iy, H, oy, wy), nx = up2_taps(ix, W, ox, wx);
-        const float *p = dy + pl * (size_t)(2 * H) * Wo;
-        float s = 0.0f;
-        for (int a = 0; a < ny; ++a) {
-            float r = 0.0f;
-            for (int b = 0; b < nx; ++b) r = fmaf(wx[b], p[(size_t)oy[a] * Wo + ox[b]], r);
-            s = fmaf(wy[a], r, s);
-        }
-        dx[i] = s;
+    const int Wo = 2 * W, ix = blockIdx.x * 256 + threadIdx.x, iy = blockIdx.y;
+    if (ix >= W) return;
+    const size_t pl = blockIdx.z;
+    int oy[4], ox[4];
+    float wy[4], wx[4];
+    const int ny = up2_taps(iy, H, oy, wy), nx = up2_taps(ix, W, ox, wx);
+    const float *p = dy + pl * (size_t)(2 * H) * Wo;
+    float s = 0.0f;
+    for (int a = 0; a < ny; ++a) {
+        float r = 0.0f;
+        for (int b = 0; b < nx; ++b) r = fmaf(wx[b], p[(size_t)oy[a] * Wo + ox[b]], r);
+        s = fmaf(wy[a], r, s);
     }
+    dx[(pl * H + iy) * W + ix] = s;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -581,16 +576,18 @@ __global__ void __launch_bounds__(256) k_upsample2x_bwd(const float *__restrict_
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gru_hr(const float *__restrict__ h, const float *__restrict__ zr, size_t n, int chw, float *__restrict__ out)
 {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const size_t b = i / chw, r = i - b * chw;
+    const size_t b = blockIdx.y;                                   // grid (chunks, images): no 64-bit divisions
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < chw; r += gridDim.x * 256) {
+        const size_t i = b * chw + r;
         out[i] = h[i] * zr[b * 2 * chw + chw + r];
     }
 }
 __global__ void __launch_bounds__(256) k_gru_hr_bwd(const float *__restrict__ h, const float *__restrict__ zr, const float *__restrict__ g, size_t n,
                                                     int chw, float *__restrict__ dh, float *__restrict__ dzr)
 {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const size_t b = i / chw, r = i - b * chw;
+    const size_t b = blockIdx.y;
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < chw; r += gridDim.x * 256) {
+        const size_t i = b * chw + r;
         const float gi = g[i];
         dh[i] = gi * zr[b * 2 * chw + chw + r];
         dzr[b * 2 * chw + r] = 0.0f;
@@ -600,8 +597,9 @@ __global__ void __launch_bounds__(256) k_gru_hr_bwd(const float *__restrict__ h,
 __global__ void __launch_bounds__(256) k_gru_blend(const float *__restrict__ h, const float *__restrict__ zr, const float *__restrict__ o, size_t n,
                                                    int chw, float *__restrict__ out)
 {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const size_t b = i / chw, r = i - b * chw;
+    const size_t b = blockIdx.y;
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < chw; r += gridDim.x * 256) {
+        const size_t i = b * chw + r;
         const float z = zr[b * 2 * chw + r];
         out[i] = h[i] * (1.0f - z) + o[i] * z;
     }
@@ -610,8 +608,9 @@ __global__ void __launch_bounds__(256) k_gru_blend_bwd(const float *__restrict__
                                                        const float *__restrict__ g, size_t n, int chw, float *__restrict__ dh,
                                                        float *__restrict__ dzr, float *__restrict__ d_o)
 {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const size_t b = i / chw, r = i - b * chw;
+    const size_t b = blockIdx.y;
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < chw; r += gridDim.x * 256) {
+        const size_t i = b * chw + r;
         const float z = zr[b * 2 * chw + r], gi = g[i];
         dh[i] = gi * (1.0f - z);
         d_o[i] = gi * z;
@@ -913,8 +912,8 @@ int esr_upsample2x_forward(const float *x, int planes, int H, int W, float *y, e
 {
     cudaStream_t st = (cudaStream_t)stream;
     ESR_REQUIRE(x && y && planes > 0 && H > 0 && W > 0, "upsample2x_forward: bad arguments");
-    const size_t total = (size_t)planes * 4 * H * W;
-    k_upsample2x_fwd<<<(unsigned)min((size_t)1 << 20, (total + 255) / 256), 256, 0, st>>>(x, H, W, (size_t)planes, y);
+    ESR_REQUIRE(2 * H <= 65535 && planes <= 65535, "upsample2x_forward: grid limits");
+    k_upsample2x_fwd<<<dim3((2 * W + 255) / 256, 2 * H, planes), 256, 0, st>>>(x, H, W, y);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
@@ -923,19 +922,19 @@ int esr_upsample2x_backward(const float *dy, int planes, int H, int W, float *dx
 {
     cudaStream_t st = (cudaStream_t)stream;
     ESR_REQUIRE(dy && dx && planes > 0 && H > 0 && W > 0, "upsample2x_backward: bad arguments");
-    const size_t total = (size_t)planes * H * W;
-    k_upsample2x_bwd<<<(unsigned)min((size_t)1 << 20, (total + 255) / 256), 256, 0, st>>>(dy, H, W, (size_t)planes, dx);
+    ESR_REQUIRE(H <= 65535 && planes <= 65535, "upsample2x_backward: grid limits");
+    k_upsample2x_bwd<<<dim3((W + 255) / 256, H, planes), 256, 0, st>>>(dy, H, W, dx);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
 
-static inline unsigned ew_grid(size_t n) { return (unsigned)min((size_t)1 << 16, (n + 255) / 256); }
+static inline dim3 ew_grid(int B, int chw) { return dim3((unsigned)min(256, (chw + 255) / 256), (unsigned)B); }
 
 int esr_gru_hr(const float *h, const float *zr, int B, int chw, float *out, esr_stream_t stream)
 {
     ESR_REQUIRE(h && zr && out && B > 0 && chw > 0, "gru_hr: bad arguments");
     const size_t n = (size_t)B * chw;
-    k_gru_hr<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, zr, n, chw, out);
+    k_gru_hr<<<ew_grid(B, chw), 256, 0, (cudaStream_t)stream>>>(h, zr, n, chw, out);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
@@ -943,7 +942,7 @@ int esr_gru_hr_backward(const float *h, const float *zr, const float *grad, int 
 {
     ESR_REQUIRE(h && zr && grad && dh && dzr && B > 0 && chw > 0, "gru_hr_backward: bad arguments");
     const size_t n = (size_t)B * chw;
-    k_gru_hr_bwd<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, zr, grad, n, chw, dh, dzr);
+    k_gru_hr_bwd<<<ew_grid(B, chw), 256, 0, (cudaStream_t)stream>>>(h, zr, grad, n, chw, dh, dzr);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
@@ -951,7 +950,7 @@ int esr_gru_blend(const float *h, const float *zr, const float *o, int B, int ch
 {
     ESR_REQUIRE(h && zr && o && out && B > 0 && chw > 0, "gru_blend: bad arguments");
     const size_t n = (size_t)B * chw;
-    k_gru_blend<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, zr, o, n, chw, out);
+    k_gru_blend<<<ew_grid(B, chw), 256, 0, (cudaStream_t)stream>>>(h, zr, o, n, chw, out);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
@@ -960,7 +959,7 @@ int esr_gru_blend_backward(const float *h, const float *zr, const float *o, cons
 {
     ESR_REQUIRE(h && zr && o && grad && dh && dzr && d_o && B > 0 && chw > 0, "gru_blend_backward: bad arguments");
     const size_t n = (size_t)B * chw;
-    k_gru_blend_bwd<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, zr, o, grad, n, chw, dh, dzr, d_o);
+    k_gru_blend_bwd<<<ew_grid(B, chw), 256, 0, (cudaStream_t)stream>>>(h, zr, o, grad, n, chw, dh, dzr, d_o);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

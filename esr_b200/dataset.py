@@ -7,6 +7,11 @@ tensors live on the GPU and the encodings are the sm_100a kernels of esr_b200.en
   create_scaled_encoding(norm_events, sensor_resolution, mode, time_bins)   dataloader/h5dataset.py:520-536
   create_cnt_encoding(events, sensor_resolution)             dataloader/h5dataset.py:611-619
   sliding_windows(frames, num_frame)                         dataloader/h5dataloader.py:210-246 (custom_collate / concat_dict)
+  collate_sequence(inp_events, gt_events, ...)               the three item tensors the shipped scripts read -- inp_cnt,
+                                                             inp_scaled_cnt, gt_cnt (dataloader/h5dataset.py:339-349,
+                                                             train_ours_cnt_seq.py:219-220, infer_ours_cnt.py:58-60) --
+                                                             for a whole batch of sequences in three scatter launches,
+                                                             windowed as custom_collate does
 """
 import numpy as np
 import torch
@@ -63,3 +68,36 @@ def sliding_windows(frames, num_frame=3):
     never materialises these copies.)"""
     L = frames.shape[1]
     return [frames[:, w:w + num_frame].contiguous() for w in range(L - num_frame + 1)]
+
+
+def collate_sequence(inp_events, gt_events, inp_resolution, gt_resolution, num_frame=3, device=None):
+    """Post-collate GPU replacement of H5Dataset.__getitem__ + custom_collate for the tensors the trainer / inference
+    script read.
+
+    inp_events[b][l], gt_events[b][l]: arrays [4, n] = (x, y, t, p) of frame l of sequence b (LR resp. HR sensor
+    coordinates), as H5Dataset.get_events returns them.  Returns the L - num_frame + 1 window dicts of
+    HDF5DataLoaderSequence.custom_collate with
+        'inp_cnt'        [B, N, 2, H, W]      create_cnt_encoding(inp events)               (h5dataset.py:340, 611-619)
+        'inp_scaled_cnt' [B, N, 2, kH, kW]    x / W * kW lift + count scatter                (h5dataset.py:348, 508-528)
+        'gt_cnt'         [B, N, 2, kH, kW]    create_cnt_encoding(gt events)                 (h5dataset.py:354)
+    Each tensor is a strided view of a [B, L, 2, ., .] frame bank filled by ONE kernel launch (no per-frame Python, no
+    copies per window); the bank itself is returned under 'bank' in every dict for forward_sequence / train_step."""
+    device = device or _dev()
+    B, L = len(inp_events), len(inp_events[0])
+
+    def flat(ev):
+        cols = [np.concatenate([np.asarray(ev[b][l][c], dtype=np.float32) for b in range(B) for l in range(L)]) for c in (0, 1, 3)]
+        off = np.zeros(B * L + 1, dtype=np.int64)
+        off[1:] = np.cumsum([np.asarray(ev[b][l]).shape[1] for b in range(B) for l in range(L)])
+        return [torch.from_numpy(c).to(device, non_blocking=True) for c in cols] + [torch.from_numpy(off).to(device)], int(np.diff(off).max(initial=1))
+
+    (ix, iy, ip, ioff), imax = flat(inp_events)
+    (gx, gy, gp, goff), gmax = flat(gt_events)
+    H, W = int(inp_resolution[0]), int(inp_resolution[1])
+    kH, kW = int(gt_resolution[0]), int(gt_resolution[1])
+    inp_cnt = encodings.encode_frames(ix, iy, ip, ioff, None, (H, W), imax).view(B, L, 2, H, W)
+    inp_scaled = encodings.encode_frames(ix, iy, ip, ioff, (H, W), (kH, kW), imax).view(B, L, 2, kH, kW)
+    gt_cnt = encodings.encode_frames(gx, gy, gp, goff, None, (kH, kW), gmax).view(B, L, 2, kH, kW)
+    bank = {'inp_cnt': inp_cnt, 'inp_scaled_cnt': inp_scaled, 'gt_cnt': gt_cnt}
+    return [{'inp_cnt': inp_cnt[:, w:w + num_frame], 'inp_scaled_cnt': inp_scaled[:, w:w + num_frame],
+             'gt_cnt': gt_cnt[:, w:w + num_frame], 'bank': bank} for w in range(L - num_frame + 1)]

@@ -245,3 +245,32 @@ def test_dataset_glue_matches_reference_semantics(dev, golden_events):
     fr = torch.arange(2 * 5 * 3, device=dev).view(2, 5, 3)
     wins = ds.sliding_windows(fr)
     assert len(wins) == 3 and torch.equal(wins[1], fr[:, 1:4])
+
+
+def test_collate_sequence_matches_per_frame_reference_semantics(dev):
+    """The batched GPU collate = per frame create_cnt_encoding / create_normalized_events + create_scaled_encoding('cnt')
+    (oracle restatement of dataloader/h5dataset.py:508-528, 611-619), windowed like custom_collate."""
+    from esr_b200 import dataset as ds
+    from oracle import events as oe
+    rng = np.random.default_rng(4)
+    B, L, H, W, k = 2, 5, 45, 80, 4
+
+    def frame(n, h, w):
+        ev = np.stack([rng.integers(-1, w + 1, n), rng.integers(-1, h + 1, n), np.sort(rng.random(n)), rng.choice([-1.0, 1.0], n)])
+        return ev.astype(np.float64)
+
+    inp = [[frame(int(rng.integers(0, 700)), H, W) for _ in range(L)] for _ in range(B)]
+    gt = [[frame(int(rng.integers(1, 3000)), H * k, W * k) for _ in range(L)] for _ in range(B)]
+    wins = ds.collate_sequence(inp, gt, (H, W), (H * k, W * k), device=dev)
+    assert len(wins) == L - 2 and wins[0]['inp_scaled_cnt'].shape == (B, 3, 2, H * k, W * k)
+    for b in range(B):
+        for l in range(L):
+            x, y, p = (inp[b][l][c].astype(np.float32) for c in (0, 1, 3))
+            want_cnt = oe.events_to_channels(x.copy(), y.copy(), p, (H, W))
+            want_scaled = oe.events_to_channels(oe.lift_coords(x, W, W * k), oe.lift_coords(y, H, H * k), p, (H * k, W * k))
+            gx, gy, gp = (gt[b][l][c].astype(np.float32) for c in (0, 1, 3))
+            want_gt = oe.events_to_channels(gx.copy(), gy.copy(), gp, (H * k, W * k))
+            w0 = min(l, L - 3)
+            assert np.array_equal(wins[w0]['inp_cnt'][b, l - w0].cpu().numpy(), want_cnt), (b, l)
+            assert np.array_equal(wins[w0]['inp_scaled_cnt'][b, l - w0].cpu().numpy(), want_scaled), (b, l)
+            assert np.array_equal(wins[w0]['gt_cnt'][b, l - w0].cpu().numpy(), want_gt), (b, l)
