@@ -24,9 +24,10 @@ template <int CIN, int COUT, int STRIDE, int TW, int TH> struct MmGeom {
     static constexpr int MTILES = TW * TH / 16;                // 16-pixel row segments per block
     static constexpr int MT = MTILES / 8;                      // per warp
     static constexpr int PW = (TW - 1) * STRIDE + 3, PH = (TH - 1) * STRIDE + 3;
-    static constexpr int PITCH = CIN * 2 + 16;                 // bytes per pixel per plane
-    static constexpr int WP = CIN + 8;                         // weight row pitch (elements): conflict-free B loads
-    static constexpr int KS = CIN >= 16 ? CIN / 16 : 1;
+    static constexpr int CINP = CIN < 8 ? 8 : CIN;             // K per tap padded to the MMA's 8 (1- and 2-channel inputs)
+    static constexpr int PITCH = CINP * 2 + 16;                // bytes per pixel per plane
+    static constexpr int WP = CINP + 8;                        // weight row pitch (elements): conflict-free B loads
+    static constexpr int KS = CINP >= 16 ? CINP / 16 : 1;
     static constexpr size_t PATCH_BYTES = (size_t)PH * PW * PITCH;
     static constexpr size_t W_BYTES = (size_t)9 * NP * WP * 2;
     static_assert(TW % 16 == 0 && MTILES % 8 == 0, "tile must hold a multiple of 8 16-pixel segments");
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
 {
     using G = MmGeom<CIN, COUT, STRIDE, TW, TH>;
     constexpr int NP = G::NP, NT = G::NT, MT = G::MT, PW = G::PW, PH = G::PH, PITCH = G::PITCH, WP = G::WP, KS = G::KS;
+    constexpr int CINP = G::CINP;
     extern __shared__ __align__(16) uint8_t msm[];
     uint8_t *p_hi = msm, *p_lo = msm + G::PATCH_BYTES;
     __nv_bfloat16 *w_hi = reinterpret_cast<__nv_bfloat16 *>(msm + 2 * G::PATCH_BYTES);
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * (size_t)i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (tid < NP) bsm[tid] = tid < COUT ? a.bias[tid] : 0.0f;
+    if (tid < NP) bsm[tid] = (a.bias && tid < COUT) ? a.bias[tid] : 0.0f;
 
     // ---- stage 1: the input patch as split bf16, pixel-major
     const int Hc = UPS ? 2 * a.Hin : a.Hin + a.pad_top + a.pad_bottom;
@@ -133,8 +135,27 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
             for (int c = 0; c < 8; ++c) o[c] = inside ? fmaxf(o[c], 0.0f) : 0.0f;
             st_split8(p_hi + (size_t)i * PITCH, p_lo + (size_t)i * PITCH, o);
         }
+    } else if constexpr (INF == FMT_NCHW_F32) {
+        // training operators: fp32 NCHW planes.  A thread gathers the 8 channels of one pixel (each of the 8 loads is
+        // coalesced across the warp: consecutive lanes = consecutive pixels of a row), splits and stores 16 bytes per plane.
+        constexpr int Q = CINP / 8;
+        const size_t cs = (size_t)a.Hin * a.Win;
+        for (int i = tid; i < Q * PW * PH; i += 256) {
+            const int pp = i % (PW * PH), q = i / (PW * PH);
+            const int y = iy0 + pp / PW, x = ix0 + pp % PW;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+            if (y >= 0 && y < Hc && x >= 0 && x < Wc) {
+                const float *src = a.in_f32 + ((size_t)simg * CIN + q * 8) * cs + (size_t)y * a.Win + x;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (q * 8 + e < CIN) v[e] = __ldg(src + e * cs);
+            }
+            st_split8(p_hi + (size_t)pp * PITCH + q * 16, p_lo + (size_t)pp * PITCH + q * 16, v);
+        }
     } else {
-        static_assert(INF == FMT_HEAD_FUSED || INF == FMT_SPLIT, "mma conv reads split tensors");
+        static_assert(INF == FMT_HEAD_FUSED || INF == FMT_SPLIT || INF == FMT_NCHW_F32, "unsupported input format");
         const __nv_bfloat16 *hi = a.in_split;
         const size_t plane = a.in_plane;
         constexpr int Q = CIN / 8;
@@ -226,7 +247,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
         }
     // ldmatrix lane roles: matrix = lane / 8 -> pixel half (mat & 1) and channel half (mat >> 1); row = lane % 8
     const int lm_px = (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int lm_koff = CIN >= 16 ? (lane >> 4) * 16 : 0;                    // bytes
+    const int lm_koff = CINP >= 16 ? (lane >> 4) * 16 : 0;                   // bytes
     const uint32_t hi_base = smem_u32_generic(p_hi), lo_base = smem_u32_generic(p_lo);
     uint32_t a_off[MT];                                                      // byte offset of this lane's row for tap (0,0)
 #pragma unroll
@@ -244,14 +265,14 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 const uint32_t o = a_off[m] + tap_off + ks * 32;
-                if constexpr (CIN >= 16) { ldsm_x4(hi_base + o, ah[m]); ldsm_x4(lo_base + o, al[m]); }
+                if constexpr (CINP >= 16) { ldsm_x4(hi_base + o, ah[m]); ldsm_x4(lo_base + o, al[m]); }
                 else { ldsm_x2(hi_base + o, ah[m]); ldsm_x2(lo_base + o, al[m]); }
             }
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
                 const int wrow = ((tap * NP + n * 8 + g) * WP + ks * 16 + 2 * t4);
                 const uint32_t bh0 = *reinterpret_cast<const uint32_t *>(w_hi + wrow), bl0 = *reinterpret_cast<const uint32_t *>(w_lo + wrow);
-                if constexpr (CIN >= 16) {
+                if constexpr (CINP >= 16) {
                     const uint32_t bh1 = *reinterpret_cast<const uint32_t *>(w_hi + wrow + 8), bl1 = *reinterpret_cast<const uint32_t *>(w_lo + wrow + 8);
 #pragma unroll
                     for (int m = 0; m < MT; ++m) {
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
 
     // ---- stage 3: accumulators (+activation) -> shared fp32 [pixel][NP] -> global
     float *stage = reinterpret_cast<float *>(msm);
-    static_assert((size_t)TW * TH * NP * 4 <= 2 * G::PATCH_BYTES, "output stage must fit in the patch area");
+    // (the launcher sizes the dynamic shared memory as max(patch + weights + ..., this stage); patch and weights are dead here)
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
         const int mt = warp * MT + m;
@@ -322,7 +343,9 @@ static int launch_mma(const DirectArgs &a, cudaStream_t st)
     using G = MmGeom<CIN, COUT, STRIDE, TW, TH>;
     constexpr int IPP = (G::PW + 2 + 3) / 4 * 4;
     constexpr size_t extra = INF == FMT_HEAD_FUSED ? sizeof(float) * (size_t)(2 * (G::PH + 2) * IPP + 9 * 2 * 8 + 8) : 0;
-    constexpr size_t smem = 2 * G::PATCH_BYTES + 2 * G::W_BYTES + sizeof(float) * G::NP + extra + 16;
+    constexpr size_t smem_in = 2 * G::PATCH_BYTES + 2 * G::W_BYTES + sizeof(float) * G::NP + extra + 16;
+    constexpr size_t smem_stage = (size_t)TW * TH * G::NP * sizeof(float);
+    constexpr size_t smem = smem_in > smem_stage ? smem_in : smem_stage;
     static_assert(smem <= 227 * 1024, "mma conv tile does not fit in shared memory");
     static_assert((2 * G::PATCH_BYTES) % 16 == 0 && G::W_BYTES % 16 == 0, "alignment");
     static bool attr_set = false;
@@ -337,23 +360,34 @@ static int launch_mma(const DirectArgs &a, cudaStream_t st)
     return ESR_OK;
 }
 
-__global__ void k_pack_mma_weight(const float *__restrict__ w, int cout, int cin, __nv_bfloat16 *__restrict__ dst)
+// rot = 0: v(co, ci, tap) = w[co][ci][tap], w = [cout][cin][3][3].  rot = 1 (the convolution that maps g to dx; cout / cin are
+// those of THAT convolution, w is the forward layer's [cin][cout][3][3]): v(co, ci, tap) = w[ci][co][8 - tap].
+__global__ void k_pack_mma_weight(const float *__restrict__ w, int cout, int cin, int rot, __nv_bfloat16 *__restrict__ dst)
 {
-    const int np = cout < 8 ? 8 : cout, wp = cin + 8;
+    const int np = cout < 8 ? 8 : cout, wp = (cin < 8 ? 8 : cin) + 8;
     const int total = 9 * np * wp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ci = i % wp, co = (i / wp) % np, tap = i / (wp * np);
-        const float v = (ci < cin && co < cout) ? w[((size_t)co * cin + ci) * 9 + tap] : 0.0f;
+        float v = 0.0f;
+        if (ci < cin && co < cout) v = rot ? w[((size_t)ci * cout + co) * 9 + (8 - tap)] : w[((size_t)co * cin + ci) * 9 + tap];
         __nv_bfloat16 h, l;
         split_bf16(v, h, l);
         dst[i] = h;
         dst[total + i] = l;
     }
 }
-size_t mma_weight_bytes(int cout, int cin) { return (size_t)2 * 9 * (cout < 8 ? 8 : cout) * (cin + 8) * sizeof(__nv_bfloat16); }
+size_t mma_weight_bytes(int cout, int cin) { return (size_t)2 * 9 * (cout < 8 ? 8 : cout) * ((cin < 8 ? 8 : cin) + 8) * sizeof(__nv_bfloat16); }
 int pack_mma_weight(const float *w, int cout, int cin, void *dst, cudaStream_t st)
 {
-    k_pack_mma_weight<<<(9 * (cout < 8 ? 8 : cout) * (cin + 8) + 255) / 256, 256, 0, st>>>(w, cout, cin, (__nv_bfloat16 *)dst);
+    k_pack_mma_weight<<<(int)(mma_weight_bytes(cout, cin) / 4 + 255) / 256, 256, 0, st>>>(w, cout, cin, 0, (__nv_bfloat16 *)dst);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+// image of the dx convolution (cin_dx = the layer's Cout -> cout_dx = the layer's Cin) from the layer's w [Cout][Cin][3][3]:
+// rotated by 180 degrees and transposed
+int pack_mma_weight_dx(const float *w, int layer_cout, int layer_cin, void *dst, cudaStream_t st)
+{
+    k_pack_mma_weight<<<(int)(mma_weight_bytes(layer_cin, layer_cout) / 4 + 255) / 256, 256, 0, st>>>(w, layer_cin, layer_cout, 1, (__nv_bfloat16 *)dst);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
@@ -378,6 +412,26 @@ int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st)
     case DK_ATT16:     return launch_mma<16, 1, 1, false, FMT_SPLIT, FMT_NHWC_F32, 32, 16>(a, st);
     default: break;
     }
+    return ESR_EINVAL;
+}
+
+// fp32 NCHW in / out (the training operators): y = act(conv3x3(x) + bias), stride 1 or 2, weights as a pack_mma_weight image.
+// ESR_EINVAL = no instantiation for this (Cin, Cout, stride).
+int conv_mma_nchw(const float *x, const void *w_img, const float *bias, int B, int Cin, int H, int W, int Cout, int stride, int act,
+                  float *y, cudaStream_t st)
+{
+    DirectArgs a;
+    a.in_f32 = x; a.Hin = H; a.Win = W; a.w_mma = w_img; a.bias = bias; a.act = act;
+    a.n_img = B; a.Hout = (H + 2 - 3) / stride + 1; a.Wout = (W + 2 - 3) / stride + 1;
+    a.out_f32 = y; a.out_H = a.Hout; a.out_W = a.Wout;
+    if (act != ACT_NONE && act != ACT_RELU && act != ACT_SIGMOID) return ESR_EINVAL;
+#define MMA_CASE(ci, co, s, tw, th) \
+    if (Cin == ci && Cout == co && stride == s) return launch_mma<ci, co, s, false, FMT_NCHW_F32, FMT_NCHW_F32, tw, th>(a, st);
+    MMA_CASE(2, 8, 1, 32, 16) MMA_CASE(32, 16, 1, 32, 8) MMA_CASE(16, 8, 1, 32, 16) MMA_CASE(8, 2, 1, 32, 16)
+    MMA_CASE(32, 1, 1, 32, 8) MMA_CASE(16, 1, 1, 32, 16)
+    MMA_CASE(16, 32, 1, 32, 16) MMA_CASE(8, 16, 1, 32, 16) MMA_CASE(1, 32, 1, 32, 16) MMA_CASE(1, 16, 1, 32, 16) MMA_CASE(1, 64, 1, 32, 8)
+    MMA_CASE(8, 16, 2, 16, 16) MMA_CASE(16, 32, 2, 16, 8) MMA_CASE(32, 64, 2, 16, 8)
+#undef MMA_CASE
     return ESR_EINVAL;
 }
 

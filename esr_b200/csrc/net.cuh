@@ -37,6 +37,9 @@ int pack_direct_weight(const float *w, int cout, int cin, float *dst, cudaStream
 // fp32 [Cout,Cin,3,3] -> the shared-memory image the mma kernels copy: split bf16 [plane][tap][co (padded to >= 8)][ci + 8 pad]
 size_t mma_weight_bytes(int cout, int cin);
 int pack_mma_weight(const float *w, int cout, int cin, void *dst, cudaStream_t st);
+int pack_mma_weight_dx(const float *w, int layer_cout, int layer_cin, void *dst, cudaStream_t st);
+int conv_mma_nchw(const float *x, const void *w_img, const float *bias, int B, int Cin, int H, int W, int Cout, int stride, int act,
+                  float *y, cudaStream_t st);
 
 // ---- element-wise / reduction kernels (elementwise.cu)
 // local_fusion input: out[img=(b,i)] = cat(f[i0]*map[p0], f[i1], f[i2]*map[p1])  (models/model.py:82-86)

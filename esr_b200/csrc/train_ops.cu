@@ -687,6 +687,7 @@ static size_t conv2d_ws(int B, int Cin, int H, int W, int Cout, int ksz, int str
     }
     b.take((size_t)B * Cout * Ho * Wo * 4);
     b.take((size_t)Cout * Cin * ksz * ksz * 4);                          // rotated weights of the CUDA-core dx path
+    b.take(mma_weight_bytes(Cin, Cout)); f.take(mma_weight_bytes(Cout, Cin));   // weight images of the mma.sync kernels
     if (tc_dgrad_ok(Cin, Cout, ksz, stride)) {
         b.take((size_t)B * pad64(Cout) * Ho * Wo * 4); b.take((size_t)B * Cin * H * W * 4);      // g split, x split (dw on tensor cores)
         b.take((size_t)pad64(Cout) * Cin * ksz * ksz * 4);
@@ -810,6 +811,14 @@ int esr_conv2d_forward(const float *x, const float *w, const float *bias, int B,
         Bump ws{(uint8_t *)workspace, 0, workspace_bytes};
         return conv_tc_nchw(x, w, bias, B, Cin, H, W, Cout, ksz, act, y, x_split_out, ws, st);
     }
+    static const bool no_mma = getenv("ESR_TRAIN_NO_MMA") != nullptr;
+    if (ksz == 3 && !no_mma && workspace && workspace_bytes >= mma_weight_bytes(Cout, Cin)) {
+        // narrow layers: warp-level tensor cores (mma_conv.cu) on fp32 NCHW; weights packed to the split-bf16 image first
+        int rc = pack_mma_weight(w, Cout, Cin, workspace, st);
+        if (rc) return rc;
+        rc = conv_mma_nchw(x, workspace, bias, B, Cin, H, W, Cout, stride, act, y, st);
+        if (rc != ESR_EINVAL) return rc;
+    }
     return generic(0, ksz, x, w, bias, nullptr, y, B, Cin, H, W, Cout, Ho, Wo, stride, act, st);
 }
 
@@ -894,6 +903,14 @@ int esr_conv2d_backward(const float *x, const void *x_split, const float *w, con
             ConvTCArgs a;
             if ((rc = conv_tc_prepare(d, &a))) return rc;
             if ((rc = conv_tc_launch(a, st))) return rc;
+        } else if (ksz == 3 && stride == 1 && getenv("ESR_TRAIN_NO_MMA") == nullptr &&
+                   [&] {   // dx = conv(g, rot180(w)^T) on the warp-level tensor cores when the shape is instantiated
+                       Bump w2 = ws;
+                       void *img = w2.take(mma_weight_bytes(Cin, Cout));
+                       if (w2.off > w2.cap) return false;
+                       if (pack_mma_weight_dx(w, Cout, Cin, img, st)) return false;
+                       return conv_mma_nchw(g, img, nullptr, B, Cout, H, W, Cin, 1, ACT_NONE, dx, st) == ESR_OK;
+                   }()) {
         } else if (ksz == 3 && stride == 1) {
             // dx = conv(g, rot180(w)^T): the register-tiled forward kernel with the roles of Cin and Cout swapped
             float *wt = (float *)ws.take((size_t)Cout * Cin * 9 * 4);
