@@ -211,7 +211,8 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     static const bool use_v3 = getenv("ESR_TC_V3") != nullptr;
     const int npad_ = tc_npad(d.cout);
     int a_st = 0, b_st = 0;
-    const bool v3 = d.ntaps == 9 && use_v3 && conv_tc3_plan(npad_, &a_st, &b_st);
+    static const int v3_min_n = getenv("ESR_TC_V3_MIN_N") ? atoi(getenv("ESR_TC_V3_MIN_N")) : 0;   // restrict the experiment to wide layers
+    const bool v3 = d.ntaps == 9 && use_v3 && npad_ >= v3_min_n && conv_tc3_plan(npad_, &a_st, &b_st);
     int BW = TW, BH = TH;
     if (v3) { TW = 8; TH = 16; BW = 16; BH = 18; }
     for (int s = 0; s < d.n_src; ++s) {
