@@ -76,75 +76,66 @@ __global__ void k_weight_rot_t(const float *__restrict__ w, int Cout, int CoutPa
     }
 }
 
-// fp32 NCHW -> split bf16 NHWC with the channel count padded to Cpad (extra channels zero): smem-tiled transpose, coalesced
-// on both sides.  Padding lets Cout = 216 (conv_offset_mask) use the 64-channel tensor-core tiles in dx and dw.
-__global__ void __launch_bounds__(256) k_split_from_nchw_t(const float *__restrict__ src, int C, int Cpad, int HW,
-                                                           __nv_bfloat16 *__restrict__ dst, size_t plane)
+// fp32 NCHW -> split bf16 NHWC with the channel count padded to Cpad (a multiple of 64; extra channels zero): 64-channel x
+// 32-pixel tiles transposed through shared memory -- 128-byte coalesced reads per channel row, one 16-byte store per plane and
+// thread (a pixel's 64 channels = one 128-byte line).  Padding lets Cout = 32 / 216 use the 64-channel tensor-core tiles.
+// With dy/y/act/db it is the backward prologue of a tensor-core layer in ONE pass: g = dy * act'(y) -> split bf16, db[c] += sum g
+// (warp reduction + one atomic per channel and block), optionally g in fp32 NCHW for the CUDA-core dw.
+template <bool PROLOGUE>
+__global__ void __launch_bounds__(256) k_to_split(const float *__restrict__ src, const float *__restrict__ y, int act, int C, int Cpad, int HW,
+                                                  __nv_bfloat16 *__restrict__ dst, size_t plane, float *__restrict__ db, float *__restrict__ g_out)
 {
-    __shared__ float tile[32][33];
-    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    __shared__ float tile[64][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {
+#pragma unroll
+    for (int r = ty; r < 64; r += 8) {
         const int c = c0 + r, p = p0 + tx;
-        tile[r][tx] = (c < C && p < HW) ? src[((size_t)n * C + c) * HW + p] : 0.0f;
+        float v = 0.0f;
+        if (c < C && p < HW) {
+            const size_t i = ((size_t)n * C + c) * HW + p;
+            v = src[i];
+            if (PROLOGUE) {
+                if (act != ACT_NONE) {
+                    const float o = y[i];
+                    v *= act == ACT_RELU ? (o > 0.0f ? 1.0f : 0.0f) : (act == ACT_SIGMOID ? o * (1.0f - o) : 1.0f - o * o);
+                }
+                if (g_out) g_out[i] = v;
+            }
+        }
+        tile[r][tx] = v;
+        if (PROLOGUE) {
+            float sum = v;
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (db && tx == 0 && c < C) atomicAdd(db + c, sum);
+        }
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int p = p0 + r, c = c0 + tx;
-        if (p < HW && c < Cpad) {
-            __nv_bfloat16 hi, lo;
-            split_bf16(tile[tx][r], hi, lo);
-            const size_t o = ((size_t)n * HW + p) * Cpad + c;
-            dst[o] = hi;
-            dst[plane + o] = lo;
+    const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;
+    const int p = p0 + px;
+    if (p < HW) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(tile[cg * 8 + 2 * e][px], h0, l0);
+            split_bf16(tile[cg * 8 + 2 * e + 1][px], h1, l1);
+            hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
         }
+        __nv_bfloat16 *o = dst + ((size_t)n * HW + p) * Cpad + c0 + cg * 8;
+        *reinterpret_cast<uint4 *>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4 *>(o + plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
 }
 
 static int split_from_nchw_pad(const float *src, int B, int C, int Cpad, int HW, __nv_bfloat16 *dst, cudaStream_t st)
 {
-    k_split_from_nchw_t<<<dim3((HW + 31) / 32, (Cpad + 31) / 32, B), 256, 0, st>>>(src, C, Cpad, HW, dst, (size_t)B * HW * Cpad);
+    ESR_REQUIRE(Cpad % 64 == 0 && Cpad >= C, "split_from_nchw_pad: Cpad=%d", Cpad);
+    k_to_split<false><<<dim3((HW + 31) / 32, Cpad / 64, B), 256, 0, st>>>(src, nullptr, ACT_NONE, C, Cpad, HW, dst, (size_t)B * HW * Cpad, nullptr,
+                                                                          nullptr);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
-}
-
-// Backward prologue of a tensor-core layer in ONE pass over dy: g = dy * act'(y) -> split bf16 NHWC (channels padded to
-// Cpad), db[c] += sum g (warp reduction + one atomic per channel and block), and optionally g in fp32 NCHW.
-__global__ void __launch_bounds__(256) k_gprep(const float *__restrict__ dy, const float *__restrict__ y, int act, int C, int Cpad,
-                                               int HW, __nv_bfloat16 *__restrict__ dst, size_t plane, float *__restrict__ db,
-                                               float *__restrict__ g_out)
-{
-    __shared__ float tile[32][33];
-    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {
-        const int c = c0 + r, p = p0 + tx;
-        float v = 0.0f;
-        if (c < C && p < HW) {
-            const size_t i = ((size_t)n * C + c) * HW + p;
-            v = dy[i];
-            if (act != ACT_NONE) {
-                const float o = y[i];
-                v *= act == ACT_RELU ? (o > 0.0f ? 1.0f : 0.0f) : (act == ACT_SIGMOID ? o * (1.0f - o) : 1.0f - o * o);
-            }
-            if (g_out) g_out[i] = v;
-        }
-        tile[r][tx] = v;
-        float sum = v;
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (db && tx == 0 && c < C) atomicAdd(db + c, sum);
-    }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int p = p0 + r, c = c0 + tx;
-        if (p < HW && c < Cpad) {
-            __nv_bfloat16 hi, lo;
-            split_bf16(tile[tx][r], hi, lo);
-            const size_t o = ((size_t)n * HW + p) * Cpad + c;
-            dst[o] = hi;
-            dst[plane + o] = lo;
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -851,8 +842,8 @@ int esr_conv2d_backward(const float *x, const void *x_split, const float *w, con
         // one pass: activation derivative, bias gradient, fp32 -> split bf16 NHWC (padded to a 64-multiple of channels)
         gsplit = (__nv_bfloat16 *)ws.take((size_t)B * gC * Ho * Wo * 4);
         ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
-        k_gprep<<<dim3((Ho * Wo + 31) / 32, (gC + 31) / 32, B), 256, 0, st>>>(dy, y, act, Cout, gC, Ho * Wo, gsplit, (size_t)B * Ho * Wo * gC, db,
-                                                                             tc_dw ? nullptr : g);
+        k_to_split<true><<<dim3((Ho * Wo + 31) / 32, gC / 64, B), 256, 0, st>>>(dy, y, act, Cout, gC, Ho * Wo, gsplit, (size_t)B * Ho * Wo * gC,
+                                                                               want_dw ? db : nullptr, tc_dw ? nullptr : g);
         ESR_LAUNCH_CHECK();
     } else {
         ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
