@@ -83,57 +83,83 @@ __global__ void k_weight_rot_t(const float *__restrict__ w, int Cout, int CoutPa
 // (warp reduction + one atomic per channel and block), optionally g in fp32 NCHW for the CUDA-core dw.
 template <bool PROLOGUE>
 __global__ void __launch_bounds__(256) k_to_split(const float *__restrict__ src, const float *__restrict__ y, int act, int C, int Cpad, int HW,
-                                                  __nv_bfloat16 *__restrict__ dst, size_t plane, float *__restrict__ db, float *__restrict__ g_out)
+                                                  int tiles_per_block, __nv_bfloat16 *__restrict__ dst, size_t plane, float *__restrict__ db,
+                                                  float *__restrict__ g_out)
 {
     __shared__ float tile[64][33];
-    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+    const int n = blockIdx.z, c0 = blockIdx.y * 64;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-#pragma unroll
-    for (int r = ty; r < 64; r += 8) {
-        const int c = c0 + r, p = p0 + tx;
-        float v = 0.0f;
-        if (c < C && p < HW) {
-            const size_t i = ((size_t)n * C + c) * HW + p;
-            v = src[i];
-            if (PROLOGUE) {
-                if (act != ACT_NONE) {
-                    const float o = y[i];
-                    v *= act == ACT_RELU ? (o > 0.0f ? 1.0f : 0.0f) : (act == ACT_SIGMOID ? o * (1.0f - o) : 1.0f - o * o);
-                }
-                if (g_out) g_out[i] = v;
-            }
-        }
-        tile[r][tx] = v;
-        if (PROLOGUE) {
-            float sum = v;
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (db && tx == 0 && c < C) atomicAdd(db + c, sum);
-        }
-    }
-    __syncthreads();
     const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;
-    const int p = p0 + px;
-    if (p < HW) {
-        uint32_t hw[4], lw[4];
+    float bsum[8];                                                 // bias-gradient partial sums of this warp's 8 channel rows
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(tile[cg * 8 + 2 * e][px], h0, l0);
-            split_bf16(tile[cg * 8 + 2 * e + 1][px], h1, l1);
-            hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    for (int j = 0; j < 8; ++j) bsum[j] = 0.0f;
+    // several pixel tiles per block: the per-channel db atomics (all blocks hit the same <= 256 addresses) are issued once per
+    // block, not once per tile -- same-address contention was the cost of the first version of this kernel
+    for (int t = 0; t < tiles_per_block; ++t) {
+        const int p0 = (blockIdx.x * tiles_per_block + t) * 32;
+        if (p0 >= HW) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = ty + 8 * j;
+            const int c = c0 + r, p = p0 + tx;
+            float v = 0.0f;
+            if (c < C && p < HW) {
+                const size_t i = ((size_t)n * C + c) * HW + p;
+                v = src[i];
+                if (PROLOGUE) {
+                    if (act != ACT_NONE) {
+                        const float o = y[i];
+                        v *= act == ACT_RELU ? (o > 0.0f ? 1.0f : 0.0f) : (act == ACT_SIGMOID ? o * (1.0f - o) : 1.0f - o * o);
+                    }
+                    if (g_out) g_out[i] = v;
+                }
+            }
+            tile[r][tx] = v;
+            if (PROLOGUE) bsum[j] += v;
         }
-        __nv_bfloat16 *o = dst + ((size_t)n * HW + p) * Cpad + c0 + cg * 8;
-        *reinterpret_cast<uint4 *>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4 *>(o + plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        __syncthreads();
+        const int p = p0 + px;
+        if (p < HW) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(tile[cg * 8 + 2 * e][px], h0, l0);
+                split_bf16(tile[cg * 8 + 2 * e + 1][px], h1, l1);
+                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            __nv_bfloat16 *o = dst + ((size_t)n * HW + p) * Cpad + c0 + cg * 8;
+            *reinterpret_cast<uint4 *>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4 *>(o + plane) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        __syncthreads();
     }
+    if (PROLOGUE && db) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float sum = bsum[j];
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const int c = c0 + ty + 8 * j;
+            if (tx == 0 && c < C) atomicAdd(db + c, sum);
+        }
+    }
+}
+
+static inline int split_tiles_per_block(int HW, int cblocks, int B)
+{
+    const int tiles = (HW + 31) / 32;
+    int t = 1;                                                     // grow while at least ~4 blocks per SM remain
+    while (t < 16 && (int64_t)((tiles + 2 * t - 1) / (2 * t)) * cblocks * B >= 4 * dev_info().sm_count) t *= 2;
+    return t;
 }
 
 static int split_from_nchw_pad(const float *src, int B, int C, int Cpad, int HW, __nv_bfloat16 *dst, cudaStream_t st)
 {
     ESR_REQUIRE(Cpad % 64 == 0 && Cpad >= C, "split_from_nchw_pad: Cpad=%d", Cpad);
-    k_to_split<false><<<dim3((HW + 31) / 32, Cpad / 64, B), 256, 0, st>>>(src, nullptr, ACT_NONE, C, Cpad, HW, dst, (size_t)B * HW * Cpad, nullptr,
-                                                                          nullptr);
+    const int tpb = split_tiles_per_block(HW, Cpad / 64, B), tiles = (HW + 31) / 32;
+    k_to_split<false><<<dim3((tiles + tpb - 1) / tpb, Cpad / 64, B), 256, 0, st>>>(src, nullptr, ACT_NONE, C, Cpad, HW, tpb, dst,
+                                                                                   (size_t)B * HW * Cpad, nullptr, nullptr);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
@@ -842,8 +868,10 @@ int esr_conv2d_backward(const float *x, const void *x_split, const float *w, con
         // one pass: activation derivative, bias gradient, fp32 -> split bf16 NHWC (padded to a 64-multiple of channels)
         gsplit = (__nv_bfloat16 *)ws.take((size_t)B * gC * Ho * Wo * 4);
         ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
-        k_to_split<true><<<dim3((Ho * Wo + 31) / 32, gC / 64, B), 256, 0, st>>>(dy, y, act, Cout, gC, Ho * Wo, gsplit, (size_t)B * Ho * Wo * gC,
-                                                                               want_dw ? db : nullptr, tc_dw ? nullptr : g);
+        const int tpb = split_tiles_per_block(Ho * Wo, gC / 64, B), tiles = (Ho * Wo + 31) / 32;
+        k_to_split<true><<<dim3((tiles + tpb - 1) / tpb, gC / 64, B), 256, 0, st>>>(dy, y, act, Cout, gC, Ho * Wo, tpb, gsplit,
+                                                                                   (size_t)B * Ho * Wo * gC, want_dw ? db : nullptr,
+                                                                                   tc_dw ? nullptr : g);
         ESR_LAUNCH_CHECK();
     } else {
         ESR_REQUIRE(ws.off <= ws.cap, "conv2d_backward: workspace too small");
