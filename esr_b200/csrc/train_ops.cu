@@ -861,7 +861,9 @@ static int launch_generic(int which, const float *x, const float *w, const float
         const size_t smem = (size_t)(G_C * R_PH * R_PW + G_C * 9 * G_C) * 4;
         const dim3 grid(((Wo + R_TW - 1) / R_TW) * ((Ho + R_TH - 1) / R_TH), (Cout + G_C - 1) / G_C, B);
         k_conv_fwd_r<<<grid, 256, smem, st>>>(x, w, bias, out, Cin, H, W, Cout, act);
-    } else if (which == 2 && KS == 3 && getenv("ESR_TRAIN_NO_MMA") == nullptr) {
+    } else if (which == 2 && KS == 3 && getenv("ESR_WGRAD_MMA") != nullptr) {
+        // opt-in experiment: parity-green but staging-bound (the three packed copies of the x patch cost more global loads than
+        // the FFMA kernel's single patch): 3.29 ms vs 3.35 ms for the narrow layers of a cfg2 iteration, +0.7 ms on the whole step
         const int PD = 15 * stride + 3;
         const size_t smem = (size_t)2 * 16 * WM_GP * 2 + (size_t)2 * 3 * 8 * PD * 8 * 4 + 16 * 72 * 4;
         const int pairs = ((Cout + 15) / 16) * ((Cin + 7) / 8);
