@@ -78,23 +78,55 @@ def synth_sr_bias(B, L, hr, seed):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of ONE GPU during the timed region.  NVML in-process (nvidia_ml_py): a query costs
+    microseconds; spawning `nvidia-smi` per sample from every rank (the first version) took the driver lock for ~0.5 s each
+    and visibly slowed the timed steps at N >= 4.  Falls back to one nvidia-smi call per second if NVML is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.nvml, self.handle = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda m: "Active" if bits & m else "Not Active"
+        # bit masks (nvml.h): SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        self.rows.append([str(self.gpu), str(sm), str(mx), "", hex(bits), flag(0x8), flag(0x40), flag(0x20), flag(0x4)])
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05 if self.nvml is not None else 1.0)
 
     def summary(self):
         sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
@@ -106,7 +138,7 @@ class ClockSampler(threading.Thread):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def usable_cores(cap=32):
@@ -120,6 +152,9 @@ def usable_cores(cap=32):
     except Exception:
         pass
     return max(1, min(n, cap))
+
+
+_JSON_OUT = sys.stdout
 
 
 def measured_peaks():
@@ -255,7 +290,8 @@ def run_reference(args, wl, rank, world):
                        "the reference's own Python cannot travel to the GPU box"},
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -271,6 +307,12 @@ def main():
     ap.add_argument("--profile-out", default=None, help="write the per-launch timing table of one step here")
     ap.add_argument("--no-train", action="store_true", help="skip the training-iteration measurement (the `train` key)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version banner at N > 1) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(json_fd, "w")
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -501,7 +543,8 @@ def main():
                 "stages_ms_per_step": stages,
                 "train": train_res,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        _JSON_OUT.write(json.dumps(line) + "\n")
+        _JSON_OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
