@@ -19,6 +19,8 @@ constexpr uint32_t DF_A_STAGE = 2u * TC_A_BYTES, DF_B_STAGE = 2u * DF_B_BYTES;
 
 struct DcnFusedArgs {
     CUtensorMap bmap;                          // packed DCN weight: (64, 64, 2*9), box (64, 64, 1)
+    CUtensorMap wmap;                          // window variant: features (64 ch, W, H, img, plane), box (64, WW, WH, 1, 1)
+    int R, WW, WH;                             // window = tile grown by R pixels (+1 for the bilinear upper corners)
     const __nv_bfloat16 *feat; size_t f_plane; // features to sample (split, 64 ch), indexed through feat_img
     const int *feat_img;
     const float *om;                           // [n_img, H, W, 216]: 144 offsets, 72 masks (sigmoid applied)
@@ -201,7 +203,211 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
 }
 
-struct DcnFusedPlan { DcnFusedArgs args; unsigned grid; size_t smem; };
+// ------------------------------------------------------------------------------------------------------------------
+// Window variant (default): the features a tile can sample -- the tile grown by R pixels on every side -- are staged ONCE in
+// shared memory by two TMA boxes (hi and lo plane, 128B-swizzled, out-of-image pixels zero-filled = DCN's zero padding), and
+// the samplers read the bilinear corners from there with 16-byte shared loads instead of four dependent L2 gathers per item.
+// A corner outside the window (offset larger than R) falls back to the global load, so any offset is still exact; the
+// offsets / masks of the NEXT tap are prefetched into registers while the current tap is sampled.  One CTA per SM.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void df_unpack(const uint4 h, const uint4 l, float (&o)[8])
+{
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        o[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+        o[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+    }
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_constant__ DcnFusedArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t win_plane = ((uint32_t)(a.WW * a.WH) * 128u + 1023u) & ~1023u;
+    const uint32_t win_base = smem_base, a_ring = win_base + 2u * win_plane, b_ring = a_ring + 2u * DF_A_STAGE;
+    const uint32_t bar_base = b_ring + 2u * DF_B_STAGE;
+    const uint32_t bar_afull = bar_base, bar_aempty = bar_base + 16u, bar_bfull = bar_base + 32u, bar_bempty = bar_base + 48u;
+    const uint32_t bar_accum = bar_base + 64u, bar_win = bar_base + 72u, tmem_slot = bar_base + 80u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+    const int fimg = a.feat_img ? a.feat_img[img] : img;
+    const int wy0 = y0 - a.R, wx0 = x0 - a.R;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_afull + 8u * s, 256); mbar_init(bar_aempty + 8u * s, 1);
+            mbar_init(bar_bfull + 8u * s, 1); mbar_init(bar_bempty + 8u * s, 1);
+        }
+        mbar_init(bar_accum, 1); mbar_init(bar_win, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_win, 2u * (uint32_t)(a.WW * a.WH) * 128u);
+            tma_load_5d(&a.wmap, bar_win, win_base, 0, wx0, wy0, fimg, 0);
+            tma_load_5d(&a.wmap, bar_win, win_base + win_plane, 0, wx0, wy0, fimg, 1);
+            for (int t = 0; t < 9; ++t) {
+                const uint32_t s = t & 1, ph = (t >> 1) & 1;
+                mbar_wait(bar_bempty + 8u * s, ph ^ 1u);
+                mbar_expect_tx(bar_bfull + 8u * s, DF_B_STAGE);
+                tma_load_3d(&a.bmap, bar_bfull + 8u * s, b_ring + s * DF_B_STAGE, 0, 0, t);
+                tma_load_3d(&a.bmap, bar_bfull + 8u * s, b_ring + s * DF_B_STAGE + DF_B_BYTES, 0, 0, 9 + t);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64);
+            for (int t = 0; t < 9; ++t) {
+                const uint32_t s = t & 1, ph = (t >> 1) & 1;
+                mbar_wait(bar_afull + 8u * s, ph);
+                mbar_wait(bar_bfull + 8u * s, ph);
+                tc_fence_after();
+                const uint32_t a_hi = a_ring + s * DF_A_STAGE, a_lo = a_hi + TC_A_BYTES;
+                const uint32_t b_hi = b_ring + s * DF_B_STAGE, b_lo = b_hi + DF_B_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                    umma_bf16(tmem_base, dal, dbh, idesc, (t | k) != 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+                    umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+                }
+                umma_commit(bar_aempty + 8u * s);
+                umma_commit(bar_bempty + 8u * s);
+            }
+            umma_commit(bar_accum);
+        }
+    } else {
+        // ===================== samplers: 256 threads, 4 (pixel, group) items each per tap =====================
+        const int st = threadIdx.x - 64;
+        const int g = st & 7;                                   // deformable group of all of this thread's items
+        const uint8_t *win_hi = smem_gen, *win_lo = smem_gen + win_plane;
+        const __nv_bfloat16 *f0 = a.feat + ((size_t)fimg * a.H * a.W * 64) + g * 8;
+        int py[4], pxx[4];
+        bool inb[4];
+        const float *omp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = (j * 256 + st) >> 3;
+            py[j] = y0 + m / a.TW; pxx[j] = x0 + m % a.TW;
+            inb[j] = py[j] < a.H && pxx[j] < a.W;
+            omp[j] = a.om + (((size_t)img * a.H + (inb[j] ? py[j] : 0)) * a.W + (inb[j] ? pxx[j] : 0)) * 216;
+        }
+        float oh[4], ow[4], omk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                            // tap 0
+            oh[j] = __ldg(omp[j] + g * 18); ow[j] = __ldg(omp[j] + g * 18 + 1); omk[j] = __ldg(omp[j] + 144 + g * 9);
+        }
+        mbar_wait(bar_win, 0);
+        for (int t = 0; t < 9; ++t) {
+            const uint32_t s = t & 1, ph = (t >> 1) & 1;
+            float noh[4], now_[4], nomk[4];                      // next tap's offsets / masks: in flight while this tap is sampled
+            const int tn = t < 8 ? t + 1 : 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                noh[j] = __ldg(omp[j] + g * 18 + 2 * tn); now_[j] = __ldg(omp[j] + g * 18 + 2 * tn + 1); nomk[j] = __ldg(omp[j] + 144 + g * 9 + tn);
+            }
+            mbar_wait(bar_aempty + 8u * s, ph ^ 1u);
+            uint8_t *stage = smem_gen + (a_ring - smem_base) + (size_t)s * DF_A_STAGE;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = (j * 256 + st) >> 3;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+                if (inb[j]) {
+                    const float h_im = (float)(py[j] - 1 + t / 3) + oh[j];
+                    const float w_im = (float)(pxx[j] - 1 + t % 3) + ow[j];
+                    if (h_im > -1.0f && w_im > -1.0f && h_im < (float)a.H && w_im < (float)a.W) {
+                        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                        const int h_high = h_low + 1, w_high = w_low + 1;
+                        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+                        const float hh = 1.0f - lh, hw = 1.0f - lw;
+                        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+                        float c[4][8];
+                        const int ch[4] = {h_low, h_low, h_high, h_high}, cw[4] = {w_low, w_high, w_low, w_high};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const bool in_img = ch[q] >= 0 && ch[q] <= a.H - 1 && cw[q] >= 0 && cw[q] <= a.W - 1;
+                            const int wy = ch[q] - wy0, wx = cw[q] - wx0;
+                            if (!in_img) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) c[q][e] = 0.0f;
+                            } else if ((unsigned)wy < (unsigned)a.WH && (unsigned)wx < (unsigned)a.WW) {
+                                const uint32_t p = (uint32_t)(wy * a.WW + wx);
+                                const uint32_t off = p * 128u + (uint32_t)((g ^ (int)(p & 7u)) << 4);     // 128B swizzle of the TMA box
+                                df_unpack(*reinterpret_cast<const uint4 *>(win_hi + off), *reinterpret_cast<const uint4 *>(win_lo + off), c[q]);
+                            } else {
+                                df_ld8(f0 + ((size_t)ch[q] * a.W + cw[q]) * 64, a.f_plane, c[q]);                // offset beyond the window
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = (w1 * c[0][e] + w2 * c[1][e] + w3 * c[2][e] + w4 * c[3][e]) * omk[j];
+                    }
+                }
+                uint32_t hw_[4], lw_[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(v[2 * e], h0, l0);
+                    split_bf16(v[2 * e + 1], h1, l1);
+                    hw_[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lw_[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                const uint32_t off = (uint32_t)m * 128u + (uint32_t)((g ^ (m & 7)) << 4);
+                *reinterpret_cast<uint4 *>(stage + off) = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);
+                *reinterpret_cast<uint4 *>(stage + TC_A_BYTES + off) = make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_afull + 8u * s) : "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { oh[j] = noh[j]; ow[j] = now_[j]; omk[j] = nomk[j]; }
+        }
+        // ===================== epilogue: two warps per TMEM lane quadrant, 32 columns each =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int m = quad * 32 + lane;
+        const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+        const bool valid = (y < a.H) && (x < a.W);
+        mbar_wait(bar_accum, 0);
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), raw);
+        if (valid) {
+            float v[32];
+            const float4 *bp = reinterpret_cast<const float4 *>(a.bias + half * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b = bp[q];
+                v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+                v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+                v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+                v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+            }
+            act32(v, a.act);
+            const size_t pix = ((size_t)img * a.H + y) * a.W + x;
+            store_split32(a.out + pix * 64 + half * 32, a.out_plane, v);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+struct DcnFusedPlan { DcnFusedArgs args; unsigned grid; size_t smem; bool window; };
 
 int dcn_fused_prepare(const SplitTensor &feat, const int *feat_img, const float *om, const void *wpacked, const float *bias,
                       int n_img, int act, const SplitTensor &out, void **plan_out)
@@ -221,6 +427,20 @@ int dcn_fused_prepare(const SplitTensor &feat, const int *feat_img, const float 
     p->smem = 1024 + 2 * DF_A_STAGE + 2 * DF_B_STAGE + 128;
     cudaError_t e = cudaFuncSetAttribute(k_dcn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     if (e != cudaSuccess) { set_error("dcn_fused: %s", cudaGetErrorString(e)); delete p; return ESR_ECUDA; }
+    // window variant (default; ESR_DCN_NO_WINDOW=1 keeps the gather-from-L2 samplers)
+    p->window = getenv("ESR_DCN_NO_WINDOW") == nullptr;
+    if (p->window) {
+        a.R = 4; a.WW = a.TW + 2 * a.R + 1; a.WH = a.TH + 2 * a.R + 1;
+        const size_t win_plane = align_up((size_t)a.WW * a.WH * 128, 1024);
+        const size_t smem_w = 1024 + 2 * win_plane + 2 * DF_A_STAGE + 2 * DF_B_STAGE + 128;
+        if (a.WW > 256 || a.WH > 256 || smem_w > (size_t)dev_info().max_smem_optin) p->window = false;
+        else {
+            if ((rc = tc_make_amap(feat, a.WW, a.WH, &a.wmap))) { delete p; return rc; }
+            e = cudaFuncSetAttribute(k_dcn_fused_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+            if (e != cudaSuccess) { set_error("dcn_fused: %s", cudaGetErrorString(e)); delete p; return ESR_ECUDA; }
+            p->smem = smem_w;
+        }
+    }
     *plan_out = p;
     return ESR_OK;
 }
@@ -228,7 +448,8 @@ int dcn_fused_prepare(const SplitTensor &feat, const int *feat_img, const float 
 int dcn_fused_launch(void *plan, cudaStream_t st)
 {
     DcnFusedPlan *p = (DcnFusedPlan *)plan;
-    k_dcn_fused<<<p->grid, DF_THREADS, p->smem, st>>>(p->args);
+    if (p->window) k_dcn_fused_win<<<p->grid, DF_THREADS, p->smem, st>>>(p->args);
+    else k_dcn_fused<<<p->grid, DF_THREADS, p->smem, st>>>(p->args);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

@@ -123,6 +123,30 @@ def test_fused_dcn_equals_columns_path(dev, B, L, H, W, monkeypatch):
     assert torch.equal(fused, cols), (fused - cols).abs().max().item()
 
 
+@pytest.mark.parametrize("scale", [1.0, 60.0])
+def test_dcn_window_sampler_equals_gather_and_columns(dev, monkeypatch, scale):
+    """The TMA-staged sampling window (default) vs the L2-gather samplers vs the columns path: same bits, also when the
+    learned offsets are far larger than the window margin (scale 60 -> offsets of many pixels: every corner takes the
+    global-load fallback) and at ragged sizes."""
+    sd = model_ref.seeded_state_dict(12)
+    sd["spacetime_fuse.dcn.conv_offset_mask.weight"] = sd["spacetime_fuse.dcn.conv_offset_mask.weight"] * scale
+    sd["spacetime_fuse.dcn.conv_offset_mask.bias"] = sd["spacetime_fuse.dcn.conv_offset_mask.bias"] + (0.0 if scale == 1.0 else 2.5)
+    g = torch.Generator().manual_seed(3)
+    frames = torch.poisson(torch.full((2, 4, 2, 72, 104), 0.4), generator=g).to(dev)
+    outs = []
+    for env in (None, "ESR_DCN_NO_WINDOW", "ESR_DCN_COLUMNS"):
+        if env:
+            monkeypatch.setenv(env, "1")
+        with torch.no_grad():
+            outs.append(_net(sd, dev).forward_sequence(frames))
+        if env:
+            monkeypatch.delenv(env)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ora = model_ref.OracleNet(sd)
+    want = torch.cat([ora(frames[:, w:w + 3].cpu()) for w in range(2)], 0)
+    assert _rel(outs[0].cpu(), want) <= REL
+
+
 @pytest.mark.parametrize("B,L,H,W", [(1, 3, 8, 8), (1, 4, 16, 24), (2, 3, 20, 300), (1, 5, 130, 70), (5, 3, 24, 24)])
 def test_edge_shapes_vs_oracle(dev, B, L, H, W):
     """Tiny feature maps (1x1 at 8x8 input), very flat / odd sizes that need the CropSize pad, odd batch sizes: the TMA
