@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Window variant (default): the features a tile can sample -- the tile grown by R pixels on every side -- are staged ONCE in
+// Window variant (opt-in, ESR_DCN_WINDOW=1): the features a tile can sample -- the tile grown by R pixels on every side -- are staged ONCE in
 // shared memory by two TMA boxes (hi and lo plane, 128B-swizzled, out-of-image pixels zero-filled = DCN's zero padding), and
 // the samplers read the bilinear corners from there with 16-byte shared loads instead of four dependent L2 gathers per item.
 // A corner outside the window (offset larger than R) falls back to the global load, so any offset is still exact; the
@@ -427,8 +427,10 @@ int dcn_fused_prepare(const SplitTensor &feat, const int *feat_img, const float 
     p->smem = 1024 + 2 * DF_A_STAGE + 2 * DF_B_STAGE + 128;
     cudaError_t e = cudaFuncSetAttribute(k_dcn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
     if (e != cudaSuccess) { set_error("dcn_fused: %s", cudaGetErrorString(e)); delete p; return ESR_ECUDA; }
-    // window variant (default; ESR_DCN_NO_WINDOW=1 keeps the gather-from-L2 samplers)
-    p->window = getenv("ESR_DCN_NO_WINDOW") == nullptr;
+    // window variant: opt-in (ESR_DCN_WINDOW=1).  Bit-identical, but measured SLOWER on B200 (cfg2: 248 vs 208 us): it needs
+    // ~110 KB for the window -> one CTA per SM, and the samplers are not L2-latency bound but issue/latency bound on their own
+    // ~370 instructions per (pixel, tap, group) item (ncu: 36 % issue slots, 64 % no-eligible at 10 warps per SM).
+    p->window = getenv("ESR_DCN_WINDOW") != nullptr;
     if (p->window) {
         a.R = 4; a.WW = a.TW + 2 * a.R + 1; a.WH = a.TH + 2 * a.R + 1;
         const size_t win_plane = align_up((size_t)a.WW * a.WH * 128, 1024);

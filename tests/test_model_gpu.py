@@ -125,8 +125,8 @@ def test_fused_dcn_equals_columns_path(dev, B, L, H, W, monkeypatch):
 
 @pytest.mark.parametrize("scale", [1.0, 60.0])
 def test_dcn_window_sampler_equals_gather_and_columns(dev, monkeypatch, scale):
-    """The TMA-staged sampling window (default) vs the L2-gather samplers vs the columns path: same bits, also when the
-    learned offsets are far larger than the window margin (scale 60 -> offsets of many pixels: every corner takes the
+    """The L2-gather samplers (default) vs the opt-in TMA-staged sampling window vs the columns path: same bits, also when
+    the learned offsets are far larger than the window margin (scale 60 -> offsets of many pixels: every corner takes the
     global-load fallback) and at ragged sizes."""
     sd = model_ref.seeded_state_dict(12)
     sd["spacetime_fuse.dcn.conv_offset_mask.weight"] = sd["spacetime_fuse.dcn.conv_offset_mask.weight"] * scale
@@ -134,7 +134,7 @@ def test_dcn_window_sampler_equals_gather_and_columns(dev, monkeypatch, scale):
     g = torch.Generator().manual_seed(3)
     frames = torch.poisson(torch.full((2, 4, 2, 72, 104), 0.4), generator=g).to(dev)
     outs = []
-    for env in (None, "ESR_DCN_NO_WINDOW", "ESR_DCN_COLUMNS"):
+    for env in (None, "ESR_DCN_WINDOW", "ESR_DCN_COLUMNS"):
         if env:
             monkeypatch.setenv(env, "1")
         with torch.no_grad():
