@@ -66,6 +66,14 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bflo
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
+// two values at once: one packed cvt.rn.bf16x2.f32 per plane (same roundings as split_bf16; a in the low half)
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t &hi, uint32_t &lo)
+{
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 __device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo)
 {
     return __bfloat162float(hi) + __bfloat162float(lo);

@@ -71,11 +71,7 @@ k_dcn_columns(const __nv_bfloat16 *__restrict__ feat, size_t f_plane, const int 
         uint32_t hw_[4], lw_[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[2 * e], h0, l0);
-            split_bf16(v[2 * e + 1], h1, l1);
-            hw_[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lw_[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            split_pack2(v[2 * e], v[2 * e + 1], hw_[e], lw_[e]);
         }
         __nv_bfloat16 *dst = cols + p * 576 + k * 64 + g * 8;
         *reinterpret_cast<uint4 *>(dst) = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);

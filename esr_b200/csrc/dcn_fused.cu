@@ -108,35 +108,40 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
     } else {
         // ===================== samplers: 256 threads, 4 (pixel, group) items each per tap =====================
         const int st = threadIdx.x - 64;                       // 0..255
-        const size_t fbase = (size_t)(a.feat_img ? a.feat_img[img] : img) * a.H * a.W;
+        const int g = st & 7;                                   // deformable group: the same for this thread's 4 items
+        // everything that does not depend on the tap is computed once per item (integer divisions, 64-bit addressing)
+        const __nv_bfloat16 *f0 = a.feat + (size_t)(a.feat_img ? a.feat_img[img] : img) * a.H * a.W * 64 + g * 8;
+        int iy[4], ix[4];
+        const float *omp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = (j * 256 + st) >> 3;
+            iy[j] = y0 + m / a.TW; ix[j] = x0 + m % a.TW;
+            const bool inb = iy[j] < a.H && ix[j] < a.W;
+            if (!inb) iy[j] = -1000000;                         // far outside: every tap fails the range test below
+            omp[j] = a.om + (((size_t)img * a.H + (inb ? iy[j] : 0)) * a.W + (inb ? ix[j] : 0)) * 216 + g * 18;
+        }
         for (int t = 0; t < 9; ++t) {
             const uint32_t s = t & 1, ph = (t >> 1) & 1;
             mbar_wait(bar_aempty + 8u * s, ph ^ 1u);
             uint8_t *stage = smem_gen + (size_t)s * DF_A_STAGE;
+            const int ty_ = t / 3 - 1, tx_ = t % 3 - 1;
             // the offsets / masks of this thread's 4 items first: one L2 round trip instead of one per item
             float oh[4], ow[4], omk[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int m = (j * 256 + st) >> 3, g = st & 7;
-                const int y = y0 + m / a.TW, x = x0 + m % a.TW;
-                oh[j] = ow[j] = omk[j] = 0.0f;
-                if (y < a.H && x < a.W) {
-                    const float *o = a.om + (((size_t)img * a.H + y) * a.W + x) * 216;
-                    oh[j] = __ldg(o + g * 18 + 2 * t); ow[j] = __ldg(o + g * 18 + 2 * t + 1); omk[j] = __ldg(o + 144 + g * 9 + t);
-                }
+                oh[j] = __ldg(omp[j] + 2 * t); ow[j] = __ldg(omp[j] + 2 * t + 1); omk[j] = __ldg(omp[j] + 144 - g * 9 + t);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int item = j * 256 + st;
-                const int m = item >> 3, g = item & 7;         // tile row (pixel) and deformable group
-                const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+                const int m = (j * 256 + st) >> 3;              // tile row (pixel)
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = 0.0f;
-                if (y < a.H && x < a.W) {
-                    const float off_h = oh[j], off_w = ow[j], mk = omk[j];
-                    const float h_im = (float)(y - 1 + t / 3) + off_h;
-                    const float w_im = (float)(x - 1 + t % 3) + off_w;
+                {
+                    const float mk = omk[j];
+                    const float h_im = (float)(iy[j] + ty_) + oh[j];
+                    const float w_im = (float)(ix[j] + tx_) + ow[j];
                     if (h_im > -1.0f && w_im > -1.0f && h_im < (float)a.H && w_im < (float)a.W) {
                         const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
                         const int h_high = h_low + 1, w_high = w_low + 1;
@@ -146,11 +151,11 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
                         float c1[8], c2[8], c3[8], c4[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) c1[e] = c2[e] = c3[e] = c4[e] = 0.0f;
-                        const __nv_bfloat16 *f0 = a.feat + (fbase * 64) + g * 8;
-                        if (h_low >= 0 && w_low >= 0) df_ld8(f0 + ((size_t)h_low * a.W + w_low) * 64, a.f_plane, c1);
-                        if (h_low >= 0 && w_high <= a.W - 1) df_ld8(f0 + ((size_t)h_low * a.W + w_high) * 64, a.f_plane, c2);
-                        if (h_high <= a.H - 1 && w_low >= 0) df_ld8(f0 + ((size_t)h_high * a.W + w_low) * 64, a.f_plane, c3);
-                        if (h_high <= a.H - 1 && w_high <= a.W - 1) df_ld8(f0 + ((size_t)h_high * a.W + w_high) * 64, a.f_plane, c4);
+                        const int o00 = (h_low * a.W + w_low) * 64;    // 32-bit element offsets within the image (H*W*64 < 2^31)
+                        if (h_low >= 0 && w_low >= 0) df_ld8(f0 + o00, a.f_plane, c1);
+                        if (h_low >= 0 && w_high <= a.W - 1) df_ld8(f0 + o00 + 64, a.f_plane, c2);
+                        if (h_high <= a.H - 1 && w_low >= 0) df_ld8(f0 + o00 + a.W * 64, a.f_plane, c3);
+                        if (h_high <= a.H - 1 && w_high <= a.W - 1) df_ld8(f0 + o00 + a.W * 64 + 64, a.f_plane, c4);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = (w1 * c1[e] + w2 * c2[e] + w3 * c3[e] + w4 * c4[e]) * mk;
                     }
@@ -158,11 +163,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
                 uint32_t hw_[4], lw_[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(v[2 * e], h0, l0);
-                    split_bf16(v[2 * e + 1], h1, l1);
-                    hw_[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lw_[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    split_pack2(v[2 * e], v[2 * e + 1], hw_[e], lw_[e]);
                 }
                 // K-major SWIZZLE_128B: row m at m*128, 16-byte chunk g stored at chunk (g ^ (m & 7))
                 const uint32_t off = (uint32_t)m * 128u + (uint32_t)((g ^ (m & 7)) << 4);
@@ -361,11 +362,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_co
                 uint32_t hw_[4], lw_[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(v[2 * e], h0, l0);
-                    split_bf16(v[2 * e + 1], h1, l1);
-                    hw_[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lw_[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    split_pack2(v[2 * e], v[2 * e + 1], hw_[e], lw_[e]);
                 }
                 const uint32_t off = (uint32_t)m * 128u + (uint32_t)((g ^ (m & 7)) << 4);
                 *reinterpret_cast<uint4 *>(stage + off) = make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]);

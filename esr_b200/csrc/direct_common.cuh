@@ -24,11 +24,7 @@ __device__ __forceinline__ void dc_store(__nv_bfloat16 *p, size_t plane, const f
     uint32_t hw[NV / 2], lw[NV / 2];
 #pragma unroll
     for (int e = 0; e < NV / 2; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(x[2 * e], h0, l0);
-        split_bf16(x[2 * e + 1], h1, l1);
-        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        split_pack2(x[2 * e], x[2 * e + 1], hw[e], lw[e]);
     }
     if constexpr (NV == 8) {
         *reinterpret_cast<uint4 *>(p) = make_uint4(hw[0], hw[1], hw[2], hw[3]);

@@ -59,11 +59,7 @@ __device__ __forceinline__ void st_split8(uint8_t *hi, uint8_t *lo, const float 
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * e], h0, l0);
-        split_bf16(v[2 * e + 1], h1, l1);
-        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        split_pack2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
     }
     *reinterpret_cast<uint4 *>(hi) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     *reinterpret_cast<uint4 *>(lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);

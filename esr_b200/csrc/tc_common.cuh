@@ -133,11 +133,7 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16 *hi_ptr, size_t plan
     uint32_t hw[16], lw[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(x[2 * e], h0, l0);
-        split_bf16(x[2 * e + 1], h1, l1);
-        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        split_pack2(x[2 * e], x[2 * e + 1], hw[e], lw[e]);
     }
     uint4 *ph = reinterpret_cast<uint4 *>(hi_ptr);
     uint4 *pl = reinterpret_cast<uint4 *>(hi_ptr + plane);

@@ -123,11 +123,7 @@ __global__ void __launch_bounds__(256) k_to_split(const float *__restrict__ src,
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(tile[cg * 8 + 2 * e][px], h0, l0);
-                split_bf16(tile[cg * 8 + 2 * e + 1][px], h1, l1);
-                hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                split_pack2(tile[cg * 8 + 2 * e][px], tile[cg * 8 + 2 * e + 1][px], hw[e], lw[e]);
             }
             __nv_bfloat16 *o = dst + ((size_t)n * HW + p) * Cpad + c0 + cg * 8;
             *reinterpret_cast<uint4 *>(o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
