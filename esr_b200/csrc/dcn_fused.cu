@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
         if (lane == 0) {
             for (int t = 0; t < 9; ++t) {
                 const uint32_t s = t & 1, ph = (t >> 1) & 1;
-                mbar_wait(bar_bempty + 8u * s, ph ^ 1u);
+                mbar_wait_backoff(bar_bempty + 8u * s, ph ^ 1u);
                 mbar_expect_tx(bar_bfull + 8u * s, DF_B_STAGE);
                 tma_load_3d(&a.bmap, bar_bfull + 8u * s, b_ring + s * DF_B_STAGE, 0, 0, t);
                 tma_load_3d(&a.bmap, bar_bfull + 8u * s, b_ring + s * DF_B_STAGE + DF_B_BYTES, 0, 0, 9 + t);
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
             const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64);
             for (int t = 0; t < 9; ++t) {
                 const uint32_t s = t & 1, ph = (t >> 1) & 1;
-                mbar_wait(bar_afull + 8u * s, ph);
+                mbar_wait_backoff(bar_afull + 8u * s, ph);          // the samplers take microseconds per tap
                 mbar_wait(bar_bfull + 8u * s, ph);
                 tc_fence_after();
                 const uint32_t a_hi = a_ring + s * DF_A_STAGE, a_lo = a_hi + TC_A_BYTES;
@@ -142,23 +142,25 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
                     const float mk = omk[j];
                     const float h_im = (float)(iy[j] + ty_) + oh[j];
                     const float w_im = (float)(ix[j] + tx_) + ow[j];
-                    if (h_im > -1.0f && w_im > -1.0f && h_im < (float)a.H && w_im < (float)a.W) {
-                        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                        const int h_high = h_low + 1, w_high = w_low + 1;
-                        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
-                        const float hh = 1.0f - lh, hw = 1.0f - lw;
-                        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-                        float c1[8], c2[8], c3[8], c4[8];
+                    // branch-free: corners are clamped into the image and always loaded (8 independent 16-byte loads in flight);
+                    // a corner outside the image, or a sample outside (-1, H) x (-1, W), gets weight 0 instead
+                    const bool ok = h_im > -1.0f && w_im > -1.0f && h_im < (float)a.H && w_im < (float)a.W;
+                    const float hf = floorf(h_im), wf = floorf(w_im);
+                    const int h_low = ok ? (int)hf : 0, w_low = ok ? (int)wf : 0;
+                    const float lh = h_im - hf, lw = w_im - wf;
+                    const float hh = 1.0f - lh, hw = 1.0f - lw;
+                    const bool t_ok = ok && h_low >= 0, b_ok = ok && h_low + 1 <= a.H - 1, l_ok = w_low >= 0, r_ok = w_low + 1 <= a.W - 1;
+                    const float w1 = (t_ok && l_ok) ? hh * hw : 0.0f, w2 = (t_ok && r_ok) ? hh * lw : 0.0f;
+                    const float w3 = (b_ok && l_ok) ? lh * hw : 0.0f, w4 = (b_ok && r_ok) ? lh * lw : 0.0f;
+                    const int r0 = max(h_low, 0) * a.W, r1 = min(h_low + 1, a.H - 1) * a.W;
+                    const int q0 = max(w_low, 0), q1 = min(w_low + 1, a.W - 1);
+                    float c1[8], c2[8], c3[8], c4[8];
+                    df_ld8(f0 + (r0 + q0) * 64, a.f_plane, c1);
+                    df_ld8(f0 + (r0 + q1) * 64, a.f_plane, c2);
+                    df_ld8(f0 + (r1 + q0) * 64, a.f_plane, c3);
+                    df_ld8(f0 + (r1 + q1) * 64, a.f_plane, c4);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) c1[e] = c2[e] = c3[e] = c4[e] = 0.0f;
-                        const int o00 = (h_low * a.W + w_low) * 64;    // 32-bit element offsets within the image (H*W*64 < 2^31)
-                        if (h_low >= 0 && w_low >= 0) df_ld8(f0 + o00, a.f_plane, c1);
-                        if (h_low >= 0 && w_high <= a.W - 1) df_ld8(f0 + o00 + 64, a.f_plane, c2);
-                        if (h_high <= a.H - 1 && w_low >= 0) df_ld8(f0 + o00 + a.W * 64, a.f_plane, c3);
-                        if (h_high <= a.H - 1 && w_high <= a.W - 1) df_ld8(f0 + o00 + a.W * 64 + 64, a.f_plane, c4);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = (w1 * c1[e] + w2 * c2[e] + w3 * c3[e] + w4 * c4[e]) * mk;
-                    }
+                    for (int e = 0; e < 8; ++e) v[e] = (w1 * c1[e] + w2 * c2[e] + w3 * c3[e] + w4 * c4[e]) * mk;
                 }
                 uint32_t hw_[4], lw_[4];
 #pragma unroll

@@ -34,6 +34,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "DONE:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// same, for waits that last microseconds (an MMA / producer thread idling while other warps of the CTA do the real work): back
+// off between polls so the spin does not eat the issue slots of the warps it is waiting for
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done) __nanosleep(40);
+    } while (!done);
+}
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
                                             int c3, int c4)
 {
