@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
         // accumulator p&1 is overwritten by phase p+2, whose MMAs only start after phase p+1's state-side loads, i.e.
         // after the grid barrier that this CTA's epilogue of phase p has already arrived on: no extra hand-shake needed
         for (int p = 0; p < n_phases; ++p) {
-            mbar_wait(bar_accum + 8u * (uint32_t)(p & 1), (uint32_t)((p >> 1) & 1));
+            mbar_wait_backoff(bar_accum + 8u * (uint32_t)(p & 1), (uint32_t)((p >> 1) & 1));
             tc_fence_after();
             gc_epilogue(a, p & 1, p >> 1, img, y0, x0, warp, lane, tmem_base + (uint32_t)(p & 1) * 128u);
             tc_fence_before();

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const __grid_constant
         const int y = y0 + m / a.TW, x = x0 + m % a.TW;
         const bool valid = (y < a.H) && (x < a.W);
         const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);
-        mbar_wait(bar_accum, 0);
+        mbar_wait_backoff(bar_accum, 0);   // four warps idle for the whole main loop: poll with back-off
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         for (int n0 = 0; n0 < a.npad; n0 += 32) {

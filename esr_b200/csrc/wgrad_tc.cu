@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
         const int quad = warp & 3;
         const int m = quad * 32 + lane;                                  // accumulator row = M-side channel
         const bool row_ok = (m < 64 || !m_dup) && (m0 + m < m_real);
-        mbar_wait(bar_accum, 0);
+        mbar_wait_backoff(bar_accum, 0);
         tc_fence_after();
         for (int j = 0; j < ntap; ++j) {
             const int tap = tap0 + j;
