@@ -512,17 +512,6 @@ static void net_dims(Net &n, int B, int N, int L, int H, int W)
 
 extern "C" size_t esr_net_param_bytes(void) { return param_layout().total; }
 
-// x-halves (input channels [0, 64) of cat(x, h)) of the three ConvGRU gate weights [64][128][3][3] -> [192][64][3][3]
-__global__ void k_gather_gru_xhalf(const float *__restrict__ wz, const float *__restrict__ wr, const float *__restrict__ wo,
-                                   float *__restrict__ dst)
-{
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 192 * 64 * 9; i += gridDim.x * blockDim.x) {
-        const int t = i % 9, ci = (i / 9) % 64, co = i / (9 * 64);
-        const float *w = co < 64 ? wz : (co < 128 ? wr : wo);
-        dst[i] = w[((size_t)(co & 63) * 128 + ci) * 9 + t];
-    }
-}
-
 extern "C" int esr_net_pack_params(const float *const *p, void *blob, esr_stream_t stream)
 {
     ESR_REQUIRE(p && blob, "esr_net_pack_params: null pointer");
@@ -558,6 +547,17 @@ extern "C" int esr_net_pack_params(const float *const *p, void *blob, esr_stream
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.gxp_b + sizeof(float) * 64, p[P_GR_B], sizeof(float) * 64, cudaMemcpyDeviceToDevice, st));
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.gxp_b + sizeof(float) * 128, p[P_GO_B], sizeof(float) * 64, cudaMemcpyDeviceToDevice, st));
     return ESR_OK;
+}
+
+// x-halves (input channels [0, 64) of cat(x, h)) of the three ConvGRU gate weights [64][128][3][3] -> [192][64][3][3]
+__global__ void k_gather_gru_xhalf(const float *__restrict__ wz, const float *__restrict__ wr, const float *__restrict__ wo,
+                                   float *__restrict__ dst)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 192 * 64 * 9; i += gridDim.x * blockDim.x) {
+        const int t = i % 9, ci = (i / 9) % 64, co = i / (9 * 64);
+        const float *w = co < 64 ? wz : (co < 128 ? wr : wo);
+        dst[i] = w[((size_t)(co & 63) * 128 + ci) * 9 + t];
+    }
 }
 
 extern "C" size_t esr_net_workspace_bytes(int B, int N, int L, int H, int W)
