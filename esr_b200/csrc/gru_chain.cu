@@ -10,11 +10,6 @@
 // maps are set up once, every phase (2 per step) is a tcgen05 implicit GEMM over the CTA's tile(s) followed by the
 // fused gate epilogue, and phases are separated by a grid barrier (co-residency guaranteed by the cooperative launch).
 //
-// The x-side half of both convolutions (the taps over the step's input features: 9 of the 18 K-blocks) does not depend on the
-// recurrent state, so it is NOT part of the chain: one batched tensor-core launch (net.cu, `xpart`: conv 64 -> 192 over all
-// window slots, bias included) produces it in fp32 beforehand and the gate epilogue adds it.  The serial phases then stream
-// only the 9 state-side K-blocks -- the chain was L2->SM bandwidth bound (7.7 TB/s aggregate), and this halves its traffic.
-//
 // Memory ordering across a phase boundary: the epilogue writes h*r / h' with generic-proxy stores; the next phase reads
 // them through TMA (async proxy) from OTHER CTAs.  Writers: stores -> fence.proxy.async -> __threadfence -> barrier
 // arrive (release); readers: barrier wait (acquire) -> fence.proxy.async -> TMA.  z and h are re-read only by the thread
@@ -30,8 +25,7 @@ constexpr int GC_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogu
 struct GruChainArgs {
     CUtensorMap amap_xc, amap_hs, amap_rh;      // 5-D maps (64 ch, W, H, img, plane), box (64, TW, TH, 1, 1)
     CUtensorMap bmap_zr, bmap_go;               // packed weights: update|reset (N=128), out gate (N=64); 18 K-blocks each
-    const float *bias_zr, *bias_go;             // [128], [64] (unused when xpart carries them)
-    const float *xpart;                         // fp32 [n_xc_img, H, W, 192]: x-side partial sums + bias: [0,128) gates, [128,192) candidate
+    const float *bias_zr, *bias_go;             // [128], [64]
     __nv_bfloat16 *hs; size_t hs_plane;         // state slots: image = slot * 2B + j
     __nv_bfloat16 *rh; size_t rh_plane;         // h * r, [2B, H, W, 64]
     float *zbuf;                                // update gate, fp32 [2B, H, W, 64]
@@ -58,8 +52,8 @@ __device__ __forceinline__ void gc_grid_barrier(unsigned int *counter, unsigned 
 
 // Fused gate epilogue of one tile: TMEM -> registers -> sigmoid / tanh / blend -> z (fp32), h*r or h' (split bf16).
 // Eight warps: two per TMEM lane quadrant, each taking half of the columns.
-__device__ __forceinline__ void gc_epilogue(const GruChainArgs &a, int which, int g, int img, int xc_img, int y0, int x0, int warp,
-                                            int lane, uint32_t tmem_acc)
+__device__ __forceinline__ void gc_epilogue(const GruChainArgs &a, int which, int g, int img, int y0, int x0, int warp, int lane,
+                                            uint32_t tmem_acc)
 {
     const int B2 = 2 * a.B;
     const int npad = which == 0 ? 128 : 64;
@@ -75,8 +69,7 @@ __device__ __forceinline__ void gc_epilogue(const GruChainArgs &a, int which, in
         tmem_ld32(taddr + (uint32_t)n0, raw);
         if (valid) {
             float v[32];
-            // x-side partial sum (+ bias) of this pixel, computed by the batched launch before the chain
-            const float4 *bp = reinterpret_cast<const float4 *>(a.xpart + (((size_t)xc_img * a.H + y) * a.W + x) * 192 + (which == 0 ? 0 : 128) + n0);
+            const float4 *bp = reinterpret_cast<const float4 *>((which == 0 ? a.bias_zr : a.bias_go) + n0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 b = bp[q];
@@ -170,14 +163,14 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
             const int hs_img = g * B2 + img;
             if (warp == 0) {
                 if (lane == 0) {
-                    for (int kb = 9; kb < 18; ++kb) {                    // state-side K-blocks only (x side: xpart)
-                        const int tap = kb - 9;
+                    for (int kb = 0; kb < 18; ++kb) {
+                        const int src = kb / 9, tap = kb - src * 9;
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                         mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
                         mbar_expect_tx(bar_full + 8u * ps, stage_bytes);
                         const uint32_t st = smem_base + ps * STAGE;
-                        const CUtensorMap *am = which == 0 ? &a.amap_hs : &a.amap_rh;
-                        const int simg = which == 0 ? hs_img : img;
+                        const CUtensorMap *am = src == 0 ? &a.amap_xc : (which == 0 ? &a.amap_hs : &a.amap_rh);
+                        const int simg = src == 0 ? xc_img : (which == 0 ? hs_img : img);
                         tma_load_5d(am, bar_full + 8u * ps, st, 0, x0 + dx, y0 + dy, simg, 0);
                         tma_load_5d(am, bar_full + 8u * ps, st + TC_A_BYTES, 0, x0 + dx, y0 + dy, simg, 1);
                         tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, 0, kb);
@@ -188,7 +181,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
             } else if (warp == 1) {
                 if (lane == 0) {
                     const uint32_t idesc = umma_idesc(TC_BLOCK_M, npad);
-                    for (int kb = 9; kb < 18; ++kb) {
+                    for (int kb = 0; kb < 18; ++kb) {
                         mbar_wait(bar_full + 8u * ms, mph);
                         tc_fence_after();
                         const uint32_t st = smem_base + ms * STAGE;
@@ -197,7 +190,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
                             const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
-                            umma_bf16(tmem_base, dal, dbh, idesc, (kb != 9 || k != 0) ? 1u : 0u);
+                            umma_bf16(tmem_base, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
                             umma_bf16(tmem_base, dah, dbl, idesc, 1u);
                             umma_bf16(tmem_base, dah, dbh, idesc, 1u);
                         }
@@ -209,7 +202,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
             } else {
                 mbar_wait(bar_accum, acc_ph);
                 tc_fence_after();
-                gc_epilogue(a, which, g, img, xc_img, y0, x0, warp, lane, tmem_base);
+                gc_epilogue(a, which, g, img, y0, x0, warp, lane, tmem_base);
                 tc_fence_before();
             }
             acc_ph ^= 1u;
@@ -269,45 +262,32 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
             uint32_t ps = 0, pph = 0;
             for (int p = 0; p < n_phases; ++p) {
                 const int g = p >> 1, which = p & 1;
+                const int w_idx = g / a.N, s_idx = g - w_idx * a.N;
                 const uint32_t b_bytes = (which == 0 ? 128u : 64u) * 128u;
                 const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
                 const CUtensorMap *bmap = which == 0 ? &a.bmap_zr : &a.bmap_go;
-                const CUtensorMap *am = which == 0 ? &a.amap_hs : &a.amap_rh;
-                const int simg = which == 0 ? g * B2 + img : img;
-                // The weight tiles do not depend on the previous phase: the first `stages` K-blocks get their B loads BEFORE the
-                // grid barrier (they land while the epilogue warps are still finishing phase p-1); only the A tiles (h, or h*r,
-                // written by every CTA's epilogue of phase p-1) wait for it.  Both halves complete on the same full barrier.
-                const int npre = a.stages < 9 ? a.stages : 9;
-                uint32_t qs = ps, qph = pph;
-                for (int i = 0; i < npre; ++i) {
-                    const int kb = 9 + i;
-                    mbar_wait(bar_empty + 8u * qs, qph ^ 1u);
-                    mbar_expect_tx(bar_full + 8u * qs, stage_bytes);
-                    const uint32_t st = smem_base + qs * STAGE;
-                    tma_load_3d(bmap, bar_full + 8u * qs, st + 2u * TC_A_BYTES, 0, 0, kb);
-                    tma_load_3d(bmap, bar_full + 8u * qs, st + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + kb);
-                    if (++qs == (uint32_t)a.stages) { qs = 0; qph ^= 1u; }
-                }
-                if (p > 0) {
-                    const unsigned int target = (unsigned int)p * gridDim.x;
-                    unsigned int v;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barrier) : "memory");
-                    } while (v < target);
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                }
-                for (int i = 0; i < 9; ++i) {
-                    const int kb = 9 + i, tap = i;
+                const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
+                for (int kb = 0; kb < 18; ++kb) {
+                    const int src = kb / 9, tap = kb - src * 9;
                     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    const uint32_t st = smem_base + ps * STAGE;
-                    if (i >= npre) {
-                        mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
-                        mbar_expect_tx(bar_full + 8u * ps, stage_bytes);
-                        tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, 0, kb);
-                        tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + kb);
+                    if (kb == 9 && p > 0) {
+                        // state-side operands are written by every CTA's epilogue of phase p-1: wait for all of them
+                        const unsigned int target = (unsigned int)p * gridDim.x;
+                        unsigned int v;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barrier) : "memory");
+                        } while (v < target);
+                        asm volatile("fence.proxy.async;" ::: "memory");
                     }
+                    mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
+                    mbar_expect_tx(bar_full + 8u * ps, stage_bytes);
+                    const uint32_t st = smem_base + ps * STAGE;
+                    const CUtensorMap *am = src == 0 ? &a.amap_xc : (which == 0 ? &a.amap_hs : &a.amap_rh);
+                    const int simg = src == 0 ? xc_img : (which == 0 ? g * B2 + img : img);
                     tma_load_5d(am, bar_full + 8u * ps, st, 0, x0 + dx, y0 + dy, simg, 0);
                     tma_load_5d(am, bar_full + 8u * ps, st + TC_A_BYTES, 0, x0 + dx, y0 + dy, simg, 1);
+                    tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, 0, kb);
+                    tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + kb);
                     if (++ps == (uint32_t)a.stages) { ps = 0; pph ^= 1u; }
                 }
             }
@@ -319,8 +299,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                 const int npad = (p & 1) == 0 ? 128 : 64;
                 const uint32_t b_bytes = (uint32_t)npad * 128u;
                 const uint32_t idesc = umma_idesc(TC_BLOCK_M, npad);
-                const uint32_t acc = tmem_base + (uint32_t)(p & 1) * 128u;
-                for (int kb = 9; kb < 18; ++kb) {
+                const uint32_t acc = tmem_base + (uint32_t)(p & 1) * 128u;   // phase p's epilogue reads this one while p+1 fills the other
+                for (int kb = 0; kb < 18; ++kb) {
                     mbar_wait(bar_full + 8u * ms, mph);
                     tc_fence_after();
                     const uint32_t st = smem_base + ms * STAGE;
@@ -329,7 +309,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
                         const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
-                        umma_bf16(acc, dal, dbh, idesc, (kb != 9 || k != 0) ? 1u : 0u);
+                        umma_bf16(acc, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
                         umma_bf16(acc, dah, dbl, idesc, 1u);
                         umma_bf16(acc, dah, dbh, idesc, 1u);
                     }
@@ -345,9 +325,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
         for (int p = 0; p < n_phases; ++p) {
             mbar_wait_backoff(bar_accum + 8u * (uint32_t)(p & 1), (uint32_t)((p >> 1) & 1));
             tc_fence_after();
-            const int g_ = p >> 1, w_idx = g_ / a.N, s_idx = g_ - w_idx * a.N;
-            const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);   // frame read at this step (reverse: N-1-s)
-            gc_epilogue(a, p & 1, g_, img, xc_img, y0, x0, warp, lane, tmem_base + (uint32_t)(p & 1) * 128u);
+            gc_epilogue(a, p & 1, p >> 1, img, y0, x0, warp, lane, tmem_base + (uint32_t)(p & 1) * 128u);
             tc_fence_before();
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
@@ -369,9 +347,9 @@ struct GruChainPlan {
     bool pipelined;
 };
 
-int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const float *xpart,
-                      const void *w_zr, const float *b_zr, const void *w_go, const float *b_go, unsigned int *barrier, int B,
-                      int N, int nsteps, void **plan_out)
+int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const void *w_zr,
+                      const float *b_zr, const void *w_go, const float *b_go, unsigned int *barrier, int B, int N,
+                      int nsteps, void **plan_out)
 {
     GruChainPlan *p = new GruChainPlan();
     GruChainArgs &a = p->args;
@@ -383,7 +361,7 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
     if ((rc = tc_make_amap(xc, TW, TH, &a.amap_xc)) || (rc = tc_make_amap(hs, TW, TH, &a.amap_hs)) ||
         (rc = tc_make_amap(rh, TW, TH, &a.amap_rh)) || (rc = tc_make_bmap(w_zr, 128, 18, 128, &a.bmap_zr)) ||
         (rc = tc_make_bmap(w_go, 64, 18, 64, &a.bmap_go))) { delete p; return rc; }
-    a.bias_zr = b_zr; a.bias_go = b_go; a.xpart = xpart;
+    a.bias_zr = b_zr; a.bias_go = b_go;
     a.hs = hs.base; a.hs_plane = hs.plane(); a.rh = rh.base; a.rh_plane = rh.plane(); a.zbuf = zbuf; a.barrier = barrier;
     a.B = B; a.N = N; a.nsteps = nsteps; a.H = H; a.W = W; a.TW = TW; a.TH = TH;
     a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH;

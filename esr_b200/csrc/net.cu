@@ -57,7 +57,6 @@ struct ParamLayout {
     size_t dw[D_COUNT], db[D_COUNT];     // direct layers
     size_t dm[D_COUNT];                  // the same weights as the split-bf16 image of the mma.sync kernels
     size_t fc0w, fc0b, fc1w, fc1b;
-    size_t gxp_tmp, gxp_w, gxp_b;        // ConvGRU x-side conv 64 -> 192 (update | reset | candidate x-halves): fp32 gather, packed, bias
     size_t total;
 };
 static const ParamLayout &param_layout()
@@ -77,9 +76,6 @@ static const ParamLayout &param_layout()
         }
         l.fc0w = take(sizeof(float) * 32 * 64); l.fc0b = take(sizeof(float) * 32);
         l.fc1w = take(sizeof(float) * 128 * 32); l.fc1b = take(sizeof(float) * 128);
-        l.gxp_tmp = take(sizeof(float) * 192 * 64 * 9);
-        l.gxp_w = take(tc_packed_weight_bytes(192, 64, 9));
-        l.gxp_b = take(sizeof(float) * tc_npad(192));
         l.total = off;
         return l;
     }();
@@ -101,8 +97,6 @@ struct Net {
     SplitTensor t_e0, t_e1, F, t_pm0, t_cat, t_lf1, t_lf2, ltc, xc, hs, rh, tp;
     SplitTensor t_of0, t_off, cols, aligned, t_cb0, feat, ycat, t_df0, fused, t_dn0, x0, pre0, up0, x1, pre1, x2, pre2, x3;
     float *maps, *zbuf, *om, *sk, *mx, *ck, *att0, *att1, *att2;
-    float *xpart = nullptr;            // ConvGRU x-side partial sums [VN, h, w, 192] fp32 (gru_chain.cu)
-    ConvTCArgs c_gxp;
     // index maps (device)
     int *m_fr, *m_pairA, *m_pairB, *m_ltc5, *m_lf3res, *m_f0, *m_fm, *m_dn[3], *m_gf_f, *m_gf_r, *m_gfres;
     std::vector<int *> m_gx, m_gh;     // per GRU step (Wn * N of them)
@@ -153,7 +147,6 @@ static size_t layout(Net &n)
     n.xc = A.split(VN, h, w, 64);
     n.rh = A.split(2 * B, h, w, 64);
     n.zbuf = (float *)A.take(sizeof(float) * 2 * B * h * w * 64);
-    n.xpart = (float *)A.take(sizeof(float) * (size_t)VN * h * w * 192);
     n.tp = A.split(VN, h, w, 64);
     n.t_of0 = A.split(nf, h, w, 64);
     n.t_off = A.split(nf, h, w, 64);
@@ -310,12 +303,7 @@ static int build(Net &n, cudaStream_t st)
     // the same chain as ONE cooperative kernel (default); ESR_GRU_PER_STEP=1 keeps the two-launches-per-step path
     static const bool per_step = getenv("ESR_GRU_PER_STEP") != nullptr;
     if (!per_step) {
-        ConvTCDesc dx_;
-        dx_.src[0] = n.xc; dx_.n_src = 1; dx_.ntaps = 9; dx_.cout = 192; dx_.n_img = VN; dx_.act = ACT_NONE;
-        dx_.wpacked = n.params + param_layout().gxp_w; dx_.bias = (const float *)(n.params + param_layout().gxp_b);
-        dx_.out_f32 = n.xpart; dx_.out_f32_C = 192;
-        if ((rc = conv_tc_prepare(dx_, &n.c_gxp))) return rc;
-        if ((rc = gru_chain_prepare(n.xc, n.hs, n.rh, n.zbuf, n.xpart, pw(n, T_GZR), pb(n, T_GZR), pw(n, T_GO), pb(n, T_GO), n.gru_barrier,
+        if ((rc = gru_chain_prepare(n.xc, n.hs, n.rh, n.zbuf, pw(n, T_GZR), pb(n, T_GZR), pw(n, T_GO), pb(n, T_GO), n.gru_barrier,
                                     B, N, nsteps, &n.gru_plan)))
             return rc;
     }
@@ -443,9 +431,7 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     if (n.gru_plan) {
         double fl = 0.0;
         for (int g = 0; g < nsteps; ++g) fl += tc_flops(n.c_gzr[g]) + tc_flops(n.c_go[g]);
-        const double fl_x = tc_flops(n.c_gxp);              // the x-side half of those FLOPs runs as one batched launch
-        RUNT(n.c_gxp);
-        RUNC(PC_GRU, fl - fl_x, gru_chain_launch(n.gru_plan, st));
+        RUNC(PC_GRU, fl, gru_chain_launch(n.gru_plan, st));
     } else {
         for (int g = 0; g < nsteps; ++g) {
             RUNT(n.c_gzr[g]);
@@ -539,25 +525,7 @@ extern "C" int esr_net_pack_params(const float *const *p, void *blob, esr_stream
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.fc0b, p[P_FC0_B], sizeof(float) * 32, cudaMemcpyDeviceToDevice, st));
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.fc1w, p[P_FC1_W], sizeof(float) * 128 * 32, cudaMemcpyDeviceToDevice, st));
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.fc1b, p[P_FC1_B], sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
-    // ConvGRU x-side convolution of the chain kernel (gru_chain.cu): gates z | r | candidate, bias folded in
-    k_gather_gru_xhalf<<<(192 * 64 * 9 + 255) / 256, 256, 0, st>>>(p[P_GU_W], p[P_GR_W], p[P_GO_W], (float *)(out + L.gxp_tmp));
-    ESR_LAUNCH_CHECK();
-    if ((rc = pack_conv_weight((const float *)(out + L.gxp_tmp), 192, 64, 3, out + L.gxp_w, st))) return rc;
-    ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.gxp_b, p[P_GU_B], sizeof(float) * 64, cudaMemcpyDeviceToDevice, st));
-    ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.gxp_b + sizeof(float) * 64, p[P_GR_B], sizeof(float) * 64, cudaMemcpyDeviceToDevice, st));
-    ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.gxp_b + sizeof(float) * 128, p[P_GO_B], sizeof(float) * 64, cudaMemcpyDeviceToDevice, st));
     return ESR_OK;
-}
-
-// x-halves (input channels [0, 64) of cat(x, h)) of the three ConvGRU gate weights [64][128][3][3] -> [192][64][3][3]
-__global__ void k_gather_gru_xhalf(const float *__restrict__ wz, const float *__restrict__ wr, const float *__restrict__ wo,
-                                   float *__restrict__ dst)
-{
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 192 * 64 * 9; i += gridDim.x * blockDim.x) {
-        const int t = i % 9, ci = (i / 9) % 64, co = i / (9 * 64);
-        const float *w = co < 64 ? wz : (co < 128 ? wr : wo);
-        dst[i] = w[((size_t)(co & 63) * 128 + ci) * 9 + t];
-    }
 }
 
 extern "C" size_t esr_net_workspace_bytes(int B, int N, int L, int H, int W)

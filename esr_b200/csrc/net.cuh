@@ -72,10 +72,9 @@ int dcn_fused_launch(void *plan, cudaStream_t st);
 void dcn_fused_destroy(void *plan);
 
 // ---- the ConvGRU recurrence of a whole sequence batch in one cooperative kernel (gru_chain.cu)
-// xpart: fp32 [n_xc_img, H, W, 192] = conv3x3 of xc with the x-halves of the gate weights (+ bias): [0,128) update|reset, [128,192) candidate
-int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const float *xpart,
-                      const void *w_zr, const float *b_zr, const void *w_go, const float *b_go, unsigned int *barrier, int B,
-                      int N, int nsteps, void **plan_out);
+int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const void *w_zr,
+                      const float *b_zr, const void *w_go, const float *b_go, unsigned int *barrier, int B, int N,
+                      int nsteps, void **plan_out);
 int gru_chain_launch(void *plan, cudaStream_t st);
 void gru_chain_destroy(void *plan);
 
