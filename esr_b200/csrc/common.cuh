@@ -66,6 +66,12 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bflo
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
+// Gate activations of the epilogues: MUFU-based (ex2 + rcp), ~1e-6 relative error -- three orders below the 1e-3 parity
+// budget; the IEEE expf / division / tanhf versions cost ~40-60 instructions per element and made the ConvGRU gate epilogue
+// (128 sigmoids or 64 tanh per pixel) the longest part of every serial phase (clock64 trace, profiles/r1_notes.md).
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
 // two values at once: one packed cvt.rn.bf16x2.f32 per plane (same roundings as split_bf16; a in the low half)
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t &hi, uint32_t &lo)
 {

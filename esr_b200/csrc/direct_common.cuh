@@ -41,7 +41,7 @@ __device__ __forceinline__ void dc_store(__nv_bfloat16 *p, size_t plane, const f
 __device__ __forceinline__ float dc_act(float v, int act)
 {
     if (act == ACT_RELU) return fmaxf(v, 0.0f);
-    if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+    if (act == ACT_SIGMOID) return fast_sigmoid(v);
     return v;
 }
 

@@ -122,8 +122,8 @@ __device__ __forceinline__ uint32_t umma_idesc(int M, int N)
 __device__ __forceinline__ float apply_act(float x, int act)
 {
     if (act == ACT_RELU) return fmaxf(x, 0.0f);
-    if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
-    if (act == ACT_TANH) return tanhf(x);
+    if (act == ACT_SIGMOID) return fast_sigmoid(x);
+    if (act == ACT_TANH) return fast_tanh(x);
     return x;
 }
 
@@ -167,10 +167,10 @@ __device__ __forceinline__ void act32(float (&v)[32], int act)
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
     } else if (act == ACT_SIGMOID) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+        for (int j = 0; j < 32; ++j) v[j] = fast_sigmoid(v[j]);
     } else if (act == ACT_TANH) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
     }
 }
 
