@@ -328,9 +328,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
             gc_epilogue(a, p & 1, p >> 1, img, y0, x0, warp, lane, tmem_base + (uint32_t)(p & 1) * 128u);
             tc_fence_before();
             asm volatile("fence.proxy.async;" ::: "memory");
-            __threadfence();
             asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps
-            if (warp == 2 && lane == 0) atomicAdd(a.barrier, 1u);
+            // one release for the CTA: the named barrier orders the other threads' stores before this thread's gpu-scope fence
+            // (cumulativity -- the pattern of cooperative-groups grid.sync), so 255 threads skip their own membar.gl
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(a.barrier, 1u); }
         }
     }
 
