@@ -116,6 +116,113 @@ __device__ __forceinline__ void gc_epilogue(const GruChainArgs &a, int which, in
     }
 }
 
+// The same epilogue for the pipelined kernel, split in two: the h / z operands of this warp's columns do not depend on the
+// phase's MMAs (h is the previous step's state, z was written by this very thread one phase earlier), so they are loaded into
+// registers BEFORE the accumulator barrier is awaited -- their L2 latency (queued behind the next phase's operand prefetch)
+// overlaps the main loop instead of extending the serial epilogue.
+struct GcPre { uint4 hh[2][4], hl[2][4]; float4 zq[8]; };
+
+__device__ __forceinline__ void gc_prefetch(const GruChainArgs &a, int which, int g, int img, int y0, int x0, int warp, int lane, GcPre &pre)
+{
+    const int B2 = 2 * a.B;
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;
+    const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+    if (!(y < a.H && x < a.W)) return;
+    const size_t pix = ((size_t)img * a.H + y) * a.W + x;
+    const __nv_bfloat16 *h_prev = a.hs + ((size_t)g * B2 * a.H * a.W + pix) * 64;
+    if (which == 0) {
+        if (half == 1) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const uint4 *ph = reinterpret_cast<const uint4 *>(h_prev + c * 32), *pl = reinterpret_cast<const uint4 *>(h_prev + c * 32 + a.hs_plane);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { pre.hh[c][q] = ph[q]; pre.hl[c][q] = pl[q]; }
+            }
+        }
+    } else {
+        const uint4 *ph = reinterpret_cast<const uint4 *>(h_prev + half * 32), *pl = reinterpret_cast<const uint4 *>(h_prev + half * 32 + a.hs_plane);
+        const float4 *zp = reinterpret_cast<const float4 *>(a.zbuf + pix * 64 + half * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { pre.hh[0][q] = ph[q]; pre.hl[0][q] = pl[q]; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pre.zq[q] = zp[q];
+    }
+}
+
+__device__ __forceinline__ void gc_unpack32(const uint4 (&hh)[4], const uint4 (&hl)[4], float (&o)[32])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t hw[4] = {hh[q].x, hh[q].y, hh[q].z, hh[q].w}, lw[4] = {hl[q].x, hl[q].y, hl[q].z, hl[q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            o[q * 8 + e * 2 + 0] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            o[q * 8 + e * 2 + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+        }
+    }
+}
+
+__device__ __forceinline__ void gc_epilogue_pre(const GruChainArgs &a, int which, int g, int img, int y0, int x0, int warp, int lane,
+                                                uint32_t tmem_acc, const GcPre &pre)
+{
+    const int B2 = 2 * a.B;
+    const int npad = which == 0 ? 128 : 64;
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int m = quad * 32 + lane;
+    const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+    const bool valid = (y < a.H) && (x < a.W);
+    const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16);
+    int c = 0;
+    for (int n0 = half * (npad / 2); n0 < (half + 1) * (npad / 2); n0 += 32, ++c) {
+        uint32_t raw[32];
+        tmem_ld32(taddr + (uint32_t)n0, raw);
+        if (valid) {
+            float v[32];
+            const float4 *bp = reinterpret_cast<const float4 *>((which == 0 ? a.bias_zr : a.bias_go) + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b = bp[q];
+                v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+                v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+                v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+                v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+            }
+            if (which == 0) {
+                act32(v, ACT_SIGMOID);
+                if (n0 < 64) {
+                    float4 *zp = reinterpret_cast<float4 *>(a.zbuf + pix * 64 + n0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) zp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else {
+                    float h[32];
+                    if (c == 0) gc_unpack32(pre.hh[0], pre.hl[0], h); else gc_unpack32(pre.hh[1], pre.hl[1], h);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= h[j];
+                    store_split32(a.rh + pix * 64 + (n0 - 64), a.rh_plane, v);
+                }
+            } else {
+                float h[32];
+                gc_unpack32(pre.hh[0], pre.hl[0], h);
+                act32(v, ACT_TANH);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float zz[4] = {pre.zq[q].x, pre.zq[q].y, pre.zq[q].z, pre.zq[q].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * q + e;
+                        v[j] = h[j] * (1.0f - zz[e]) + v[j] * zz[e];
+                    }
+                }
+                __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64;
+                store_split32(h_new + n0, a.hs_plane, v);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_constant__ GruChainArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -323,9 +430,11 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
         // accumulator p&1 is overwritten by phase p+2, whose MMAs only start after phase p+1's state-side loads, i.e.
         // after the grid barrier that this CTA's epilogue of phase p has already arrived on: no extra hand-shake needed
         for (int p = 0; p < n_phases; ++p) {
+            GcPre pre;
+            gc_prefetch(a, p & 1, p >> 1, img, y0, x0, warp, lane, pre);     // h / z operands: in flight during the main loop
             mbar_wait_backoff(bar_accum + 8u * (uint32_t)(p & 1), (uint32_t)((p >> 1) & 1));
             tc_fence_after();
-            gc_epilogue(a, p & 1, p >> 1, img, y0, x0, warp, lane, tmem_base + (uint32_t)(p & 1) * 128u);
+            gc_epilogue_pre(a, p & 1, p >> 1, img, y0, x0, warp, lane, tmem_base + (uint32_t)(p & 1) * 128u, pre);
             tc_fence_before();
             asm volatile("fence.proxy.async;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps
