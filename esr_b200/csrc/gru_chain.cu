@@ -381,10 +381,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                         // state-side operands are written by every CTA's epilogue of phase p-1: wait for all of them
                         const unsigned int target = (unsigned int)p * gridDim.x;
                         unsigned int v;
-                        do {                                        // relaxed polls (an acquire load invalidates L1 on every try) ...
-                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barrier) : "memory");
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barrier) : "memory");
                         } while (v < target);
-                        asm volatile("fence.acq_rel.gpu;" ::: "memory");   // ... one acquire once the count is reached
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
                     mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
