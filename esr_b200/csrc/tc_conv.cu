@@ -137,6 +137,134 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent variant for the wide layers (N > 128: one stage ring fills most of the shared memory, so only ONE CTA fits per
+// SM and k_conv_tc's epilogue -- 6-7 chunks of tcgen05.ld + bias/residual/activation + stores -- runs with the tensor core
+// idle).  Here a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with TWO accumulators in TMEM (2 x 256 columns):
+// the MMA thread starts tile i+1 in the other accumulator while the epilogue warps drain tile i; the TMA producer simply
+// streams K-blocks across tile boundaries.  Same operand order, same epilogue code: results are bit-identical to k_conv_tc.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_constant__ ConvTCArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)a.npad * 128u;
+    const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages;
+    const uint32_t bar_afull = bar_base + 16u * a.stages, bar_aempty = bar_afull + 16u;      // per accumulator
+    const uint32_t tmem_slot = bar_aempty + 16u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = a.tiles_x * a.tiles_y, n_tiles = a.n_img * tiles_per_img;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_afull + 8u * i, 1); mbar_init(bar_aempty + 8u * i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int img = tile / tiles_per_img, trem = tile - img * tiles_per_img;
+                const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+                int src = 0, chunk_base = 0;
+                for (int kb = 0; kb < a.nkb; ++kb) {
+                    const int gchunk = kb / a.ntaps, tap = kb - gchunk * a.ntaps;
+                    while (gchunk >= a.chunk_end[src]) { chunk_base = a.chunk_end[src]; ++src; }
+                    const int dy = a.ntaps == 9 ? tap / 3 - 1 : 0, dx = a.ntaps == 9 ? tap % 3 - 1 : 0;
+                    const int simg = a.src_img[src] ? a.src_img[src][img] : img;
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    mbar_expect_tx(bar_full + 8u * s, stage_bytes);
+                    const uint32_t st = smem_base + s * stage_bytes;
+                    const int c0 = (gchunk - chunk_base) * 64;
+                    tma_load_5d(&a.amap[src], bar_full + 8u * s, st, c0, x0 + dx, y0 + dy, simg, 0);
+                    tma_load_5d(&a.amap[src], bar_full + 8u * s, st + TC_A_BYTES, c0, x0 + dx, y0 + dy, simg, 1);
+                    tma_load_3d(&a.bmap, bar_full + 8u * s, st + 2u * TC_A_BYTES, 0, 0, kb);
+                    tma_load_3d(&a.bmap, bar_full + 8u * s, st + 2u * TC_A_BYTES + b_bytes, 0, 0, a.nkb + kb);
+                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(TC_BLOCK_M, a.npad);
+            uint32_t s = 0, ph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t ai = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
+                mbar_wait(bar_aempty + 8u * ai, aph ^ 1u);          // the epilogue of tile it-2 has drained this accumulator
+                tc_fence_after();
+                const uint32_t acc = tmem_base + ai * 256u;
+                for (int kb = 0; kb < a.nkb; ++kb) {
+                    mbar_wait(bar_full + 8u * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_base + s * stage_bytes;
+                    const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                        const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                        umma_bf16(acc, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(acc, dah, dbl, idesc, 1u);
+                        umma_bf16(acc, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(bar_empty + 8u * s);
+                    if (++s == (uint32_t)a.stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(bar_afull + 8u * ai);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t ai = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
+            const int img = tile / tiles_per_img, trem = tile - img * tiles_per_img;
+            const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+            const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+            const bool valid = (y < a.H) && (x < a.W);
+            const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);
+            mbar_wait_backoff(bar_afull + 8u * ai, aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ai * 256u + ((uint32_t)(quad * 32) << 16);
+            for (int n0 = 0; n0 < a.npad; n0 += 32) {
+                uint32_t raw[32];
+                if (a.npad - n0 >= 32) {
+                    tmem_ld32(taddr + (uint32_t)n0, raw);
+                } else {
+                    uint32_t r16[16];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                 : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]),
+                                   "=r"(r16[6]), "=r"(r16[7]), "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]),
+                                   "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
+                                 : "r"(taddr + (uint32_t)n0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { raw[j] = r16[j]; raw[16 + j] = 0u; }
+                }
+                if (valid) epilogue_chunk(a, raw, n0, pix, img, y, x);
+                __syncwarp();
+            }
+            tc_fence_before();                                       // this thread's TMEM reads are done: release the accumulator
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_aempty + 8u * ai) : "memory");
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: tensor maps and launch
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -285,6 +413,19 @@ int conv_tc_launch(const ConvTCArgs &a, cudaStream_t st)
         max_set = (int)smem;
     }
     const unsigned grid = (unsigned)(a.n_img * a.tiles_x * a.tiles_y);
+    // wide layers (one CTA per SM) on multi-wave grids: persistent CTAs with two TMEM accumulators (ESR_TC_NO_PERSIST=1: off)
+    static const bool no_persist = getenv("ESR_TC_NO_PERSIST") != nullptr;
+    if (!no_persist && a.npad > 128 && (int)grid > dev_info().sm_count) {
+        static int max_set_p = 0;
+        const size_t smem_p = smem + 64;
+        if ((int)smem_p > max_set_p) {
+            ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            max_set_p = (int)smem_p;
+        }
+        k_conv_tc_persist<<<(unsigned)dev_info().sm_count, TC_THREADS, smem_p, st>>>(a);
+        ESR_LAUNCH_CHECK();
+        return ESR_OK;
+    }
     k_conv_tc<<<grid, TC_THREADS, smem, st>>>(a);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
