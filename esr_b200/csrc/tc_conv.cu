@@ -368,7 +368,10 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     const int n_tiles = d.n_img * a.tiles_x * a.tiles_y;
     int stages = 6;
     while (stages > 2 && tc_smem_bytes(a.npad, stages) > smem_cap) --stages;
-    if (n_tiles > dev_info().sm_count) {
+    // multi-wave grids of layers with N >= 64: persistent CTAs (one per SM, all the stages that fit) with two TMEM accumulators
+    static const int persist_min_n = getenv("ESR_TC_NO_PERSIST") ? 1 << 30 : (getenv("ESR_TC_PERSIST_MIN_N") ? atoi(getenv("ESR_TC_PERSIST_MIN_N")) : 64);   // measured: 129 -> 3.196 ms, 64 -> 3.159 ms, 16 -> 3.165 ms per cfg2 step
+    a.persist = (!v3 && a.npad >= persist_min_n && n_tiles > dev_info().sm_count) ? 1 : 0;
+    if (n_tiles > dev_info().sm_count && !a.persist) {
         int s2 = stages;
         while (s2 > 2 && 2 * (tc_smem_bytes(a.npad, s2) + 1024) > smem_cap) --s2;
         if (2 * (tc_smem_bytes(a.npad, s2) + 1024) <= smem_cap) stages = s2;
@@ -414,8 +417,7 @@ int conv_tc_launch(const ConvTCArgs &a, cudaStream_t st)
     }
     const unsigned grid = (unsigned)(a.n_img * a.tiles_x * a.tiles_y);
     // wide layers (one CTA per SM) on multi-wave grids: persistent CTAs with two TMEM accumulators (ESR_TC_NO_PERSIST=1: off)
-    static const bool no_persist = getenv("ESR_TC_NO_PERSIST") != nullptr;
-    if (!no_persist && a.npad > 128 && (int)grid > dev_info().sm_count) {
+    if (a.persist) {
         static int max_set_p = 0;
         const size_t smem_p = smem + 64;
         if ((int)smem_p > max_set_p) {

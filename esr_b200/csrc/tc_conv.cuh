@@ -26,6 +26,7 @@ struct ConvTCArgs {
     CUtensorMap bmap;               // 3-D map over packed weights (64, npad, 2*nkb), box (64, npad, 1)
     CUtensorMap bmap_half;          // same tensor, box (64, npad/2, 1): the half a CTA multicasts in a 2-CTA cluster
     int kernel_ver;                 // 1: tc_conv.cu (tap-shifted tiles), 3: tc_conv3.cu (halo reuse + weight multicast)
+    int persist;                    // 1: k_conv_tc_persist (one CTA per SM walks the tiles, two TMEM accumulators)
     int a_stages, cluster;          // v3 only: halo ring depth, cluster size (1 or 2)
     const int *src_img[TC_MAX_SRC]; // output image -> source image (nullptr = identity)
     int chunk_end[TC_MAX_SRC];      // cumulative number of 64-channel chunks after source s
