@@ -451,14 +451,15 @@ def main():
         top = max((v for v in per_launch.values() if v[2] == 0), key=lambda v: v[1], default=None)
         top_ms = top[0] / reps if top else 0.0
         top_tf = top[1] / (top_ms * 1e-3) / 1e12 if top_ms > 0 else 0.0
-        roofline = {"kernel": "k_conv_tc (tcgen05 implicit-GEMM conv): largest launch = local_fusion 192->192 3x3 over all window slots",
+        roofline = {"kernel": "k_conv_tc_persist (tcgen05 implicit-GEMM conv, persistent, two TMEM accumulators): largest launch = "
+                              "local_fusion 192->192 3x3 over all window slots",
                     "bound": "tensor", "achieved": top_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": top_tf / peak_tf,
                     "peak_source": peak_src + ", bf16 sustained",
                     "launch_ms": top_ms, "algorithmic_gflop_per_launch": top[1] / 1e9 if top else None,
                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch at cfg2, ncu --set full,
-                    # profiles/r1_ncu_tc.md (114.8 MB + 66.3 MB); algorithmic bytes: 144 x 32 x 32 x 192 x 4 B in + out = 226.5 MB
-                    "traffic": 181.07e6 if args.workload == "cfg2" else None,
-                    "tensor_pipe_active_pct_ncu": 55.4 if args.workload == "cfg2" else None,
+                    # profiles/r1_ncu_tcpersist.md (114.86 MB + 63.87 MB); algorithmic bytes: 144 x 32 x 32 x 192 x 4 B in + out = 226.5 MB
+                    "traffic": 178.73e6 if args.workload == "cfg2" else None,
+                    "tensor_pipe_active_pct_ncu": 75.0 if args.workload == "cfg2" else None,
                     "all_tc_launches": {"achieved": achieved, "frac": achieved / peak_tf},
                     "gru_chain_ms_per_step": acc[3][0] / reps,
                     "launches_per_step": tc_n // reps, "avg_launch_us": tc_ms / max(tc_n, 1) * 1e3,
