@@ -351,6 +351,11 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
     const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
     const int bb = img < a.B ? img : img - a.B;
     const int n_phases = 2 * a.nsteps;
+    // A tile's 3x3 halo only reaches tiles of the SAME image, so the phase barrier is per image (tiles_per_img CTAs, own
+    // counter 32 bytes apart) instead of grid-wide: 16 x fewer arrivals per counter and no waiting for other images' stragglers.
+    const bool per_img = B2 <= 64;
+    unsigned int *bar_ctr = a.barrier + (per_img ? img * 8 : 0);
+    const unsigned int bar_n = per_img ? (unsigned int)tiles_per_img : gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
@@ -379,10 +384,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                     if (kb == 9 && p > 0) {
                         // state-side operands are written by every CTA's epilogue of phase p-1: wait for all of them
-                        const unsigned int target = (unsigned int)p * gridDim.x;
+                        const unsigned int target = (unsigned int)p * bar_n;
                         unsigned int v;
                         do {
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barrier) : "memory");
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
                         } while (v < target);
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
@@ -440,7 +445,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
             asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps
             // one release for the CTA: the named barrier orders the other threads' stores before this thread's gpu-scope fence
             // (cumulativity -- the pattern of cooperative-groups grid.sync), so 255 threads skip their own membar.gl
-            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(a.barrier, 1u); }
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
         }
     }
 
@@ -494,7 +499,7 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
 int gru_chain_launch(void *plan, cudaStream_t st)
 {
     GruChainPlan *p = (GruChainPlan *)plan;
-    ESR_CUDA_CHECK(cudaMemsetAsync(p->args.barrier, 0, sizeof(unsigned int), st));
+    ESR_CUDA_CHECK(cudaMemsetAsync(p->args.barrier, 0, 64 * 8 * sizeof(unsigned int), st));   // per-image counters, 32 bytes apart
     void *kargs[] = {(void *)&p->args};
     ESR_CUDA_CHECK(cudaLaunchCooperativeKernel(p->pipelined ? (void *)k_gru_chain_pipe : (void *)k_gru_chain, dim3(p->grid),
                                                dim3(GC_THREADS), kargs, p->smem, st));

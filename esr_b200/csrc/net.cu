@@ -179,7 +179,7 @@ static size_t layout(Net &n)
     n.m_gf_f = ints(VN); n.m_gf_r = ints(VN); n.m_gfres = ints(VN);
     n.m_gx.resize(nsteps); n.m_gh.resize(nsteps);
     for (int s = 0; s < nsteps; ++s) { n.m_gx[s] = ints(2 * B); n.m_gh[s] = ints(2 * B); }
-    n.gru_barrier = (unsigned int *)A.take(256);
+    n.gru_barrier = (unsigned int *)A.take(64 * 8 * sizeof(unsigned int));   // per-image phase counters of the GRU chain kernel
     return A.off;
 }
 
