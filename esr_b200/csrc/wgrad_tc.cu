@@ -29,6 +29,8 @@ struct WgradArgs {
     float *dw;                        // [Cout][Cin][KK]
     int Cout, CoutPad, Cin, KK;       // g has CoutPad (64-multiple) channels, the first Cout are real
     int a_is_x;                       // 1: M side = x channels (shifted per tap), N side = g; 0: M side = g, N side = x
+    CUtensorMap hmap;                 // halo mode: x as (64 ch, TW + 2, TH + 2, 1, 1) boxes
+    int halo;                         // 1: ONE halo tile of x per pixel tile feeds all taps (shifted MN-major descriptors)
     int m_blocks, n_chunks, groups;   // grid decomposition
     int n_img, H, W, TW, TH, tiles_x, tiles_y, slices;
 };
@@ -52,7 +54,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
     // shared memory: [once buffers x2][per-tap ring x2][barriers]; sizes depend on which tensor is on the M side
     const uint32_t m_bytes = 4u * WG_TILE, n_bytes = 2u * WG_TILE;      // M side: 2 tiles x 2 planes; N side: 1 tile x 2 planes
     const uint32_t once_bytes = a.a_is_x ? n_bytes : m_bytes;           // the unshifted tensor (g)
-    const uint32_t tap_bytes = a.a_is_x ? m_bytes : n_bytes;            // the shifted tensor (x)
+    const uint32_t halo_plane = ((uint32_t)((a.TW + 2) * (a.TH + 2)) * 128u + 1023u) & ~1023u;
+    const uint32_t tap_bytes = a.halo ? 2u * halo_plane : (a.a_is_x ? m_bytes : n_bytes);   // the shifted tensor (x), or its halo box
     const uint32_t once_base = smem_base, ring_base = smem_base + 2u * once_bytes;
     const uint32_t bar_base = ring_base + 2u * tap_bytes;
     const uint32_t bar_gfull = bar_base, bar_gempty = bar_base + 16u, bar_xfull = bar_base + 32u, bar_xempty = bar_base + 48u;
@@ -109,6 +112,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
                     tma_load_5d(&a.gmap, bar_gfull + 8u * gs, gb + WG_TILE, n0, x0, y0, img, 1);
                 }
                 if (++gs == 2) { gs = 0; gph ^= 1u; }
+                if (a.halo) {
+                    // ---- ONE halo box of x for all taps of this pixel tile (hi and lo planes); zero fill outside = padding
+                    mbar_wait(bar_xempty + 8u * xs, xph ^ 1u);
+                    mbar_expect_tx(bar_xfull + 8u * xs, 2u * (uint32_t)((a.TW + 2) * (a.TH + 2)) * 128u);
+                    const uint32_t xb = ring_base + xs * tap_bytes;
+                    tma_load_5d(&a.hmap, bar_xfull + 8u * xs, xb, n0, x0 - 1, y0 - 1, img, 0);
+                    tma_load_5d(&a.hmap, bar_xfull + 8u * xs, xb + halo_plane, n0, x0 - 1, y0 - 1, img, 1);
+                    if (++xs == 2) { xs = 0; xph ^= 1u; }
+                    continue;
+                }
                 // ---- x tile(s), one per tap, shifted; out-of-image pixels are zero-filled = the conv padding
                 for (int j = 0; j < ntap; ++j) {
                     const int tap = tap0 + j;
@@ -139,6 +152,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
             for (int t = slice; t < n_tiles; t += a.slices) {
                 mbar_wait(bar_gfull + 8u * gs, gph);
                 const uint32_t gb = once_base + gs * once_bytes;
+                if (a.halo) {
+                    mbar_wait(bar_xfull + 8u * xs, xph);
+                    tc_fence_after();
+                    const uint32_t xb = ring_base + xs * tap_bytes;
+                    const uint32_t m_hi = gb, m_lo = gb + 2u * WG_TILE;
+                    const uint32_t hw = (uint32_t)(a.TW + 2);
+                    for (int j = 0; j < ntap; ++j) {
+                        const int tap = tap0 + j, ky = tap / 3, kx = tap % 3;
+                        const uint32_t d = tmem_base + (uint32_t)j * 64u;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {                    // K step k = tile row k: 16 pixels = 16 rows of the halo box
+                            const uint32_t sh = (((uint32_t)(k + ky)) * hw + (uint32_t)kx) * 128u;
+                            const uint64_t dah = umma_desc_mn(m_hi + 2048u * k, WG_TILE), dal = umma_desc_mn(m_lo + 2048u * k, WG_TILE);
+                            const uint64_t dbh = umma_desc_mn(xb + sh, WG_TILE), dbl = umma_desc_mn(xb + halo_plane + sh, WG_TILE);
+                            umma_bf16(d, dal, dbh, idesc, (first && k == 0) ? 0u : 1u);
+                            umma_bf16(d, dah, dbl, idesc, 1u);
+                            umma_bf16(d, dah, dbh, idesc, 1u);
+                        }
+                    }
+                    umma_commit(bar_xempty + 8u * xs);
+                    if (++xs == 2) { xs = 0; xph ^= 1u; }
+                    umma_commit(bar_gempty + 8u * gs);
+                    if (++gs == 2) { gs = 0; gph ^= 1u; }
+                    first = false;
+                    continue;
+                }
                 for (int j = 0; j < ntap; ++j) {
                     mbar_wait(bar_xfull + 8u * xs, xph);
                     tc_fence_after();
@@ -203,11 +242,14 @@ int wgrad_tc(const __nv_bfloat16 *x_split, const __nv_bfloat16 *g_split, int B, 
     SplitTensor gs; gs.base = const_cast<__nv_bfloat16 *>(g_split); gs.n_img = B; gs.H = H; gs.W = W; gs.C = CoutPad;
     WgradArgs a;
     memset(&a, 0, sizeof(a));
-    a.TW = W >= 24 ? 32 : (W >= 12 ? 16 : 8); a.TH = TC_BLOCK_M / a.TW;
-    if ((rc = tc_make_amap(gs, a.TW, a.TH, &a.gmap))) return rc;
-    if ((rc = tc_make_amap(xs, a.TW, a.TH, &a.xmap))) return rc;
     a.dw = dw; a.Cout = Cout; a.Cin = Cin; a.KK = ksz * ksz;
     a.a_is_x = (Cout == 64 && Cin >= 128) ? 1 : 0;
+    // halo mode: 16 x 8 tiles (a K step = one 16-pixel tile row, contiguous in the halo box); ESR_WGRAD_NO_HALO=1 turns it off
+    a.halo = (ksz == 3 && !a.a_is_x && W >= 12 && getenv("ESR_WGRAD_NO_HALO") == nullptr) ? 1 : 0;
+    a.TW = a.halo ? 16 : (W >= 24 ? 32 : (W >= 12 ? 16 : 8)); a.TH = TC_BLOCK_M / a.TW;
+    if ((rc = tc_make_amap(gs, a.TW, a.TH, &a.gmap))) return rc;
+    if ((rc = tc_make_amap(xs, a.TW, a.TH, &a.xmap))) return rc;
+    if (a.halo && (rc = tc_make_amap(xs, a.TW + 2, a.TH + 2, &a.hmap))) return rc;
     const int m_ch = a.a_is_x ? Cin : CoutPad, n_ch = a.a_is_x ? CoutPad : Cin;
     a.CoutPad = CoutPad;
     a.m_blocks = (m_ch + 127) / 128; a.n_chunks = n_ch / 64; a.groups = ksz == 3 ? 2 : 1;
@@ -221,11 +263,12 @@ int wgrad_tc(const __nv_bfloat16 *x_split, const __nv_bfloat16 *g_split, int B, 
     if (slices > n_tiles / min_tiles) slices = n_tiles / min_tiles;
     if (slices < 1) slices = 1;
     a.slices = slices;
-    const size_t smem = 1024 + 2 * (size_t)(4 * WG_TILE) + 2 * (size_t)(2 * WG_TILE) + 128;
-    static bool attr_done = false;
-    if (!attr_done) {
+    const size_t halo_plane = align_up((size_t)(a.TW + 2) * (a.TH + 2) * 128, 1024);
+    const size_t smem = 1024 + 2 * (size_t)(4 * WG_TILE) + 2 * (a.halo ? 2 * halo_plane : (size_t)(2 * WG_TILE)) + 128;
+    static size_t attr_done = 0;
+    if (smem > attr_done) {
         ESR_CUDA_CHECK(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_done = smem;
     }
     k_wgrad_tc<<<(unsigned)(base * slices), WG_THREADS, smem, st>>>(a);
     ESR_LAUNCH_CHECK();
