@@ -37,8 +37,14 @@ def _rank_table(m, dev):
     return _RANK_CACHE[key]
 
 
-def expand(vals, kind, mode):
-    """vals: CUDA fp32 tensor [B,2,H,W] (kind 0) or [B,P,C,H,W] / [B,C,H,W] (kind 1) -> CUDA fp32 [B,maxlen,4]."""
+class _ExpandCtx:
+    __slots__ = ("vals", "kind", "dims", "counts", "stats", "stats_host", "event", "parts")
+
+
+def expand_begin(vals, kind):
+    """Phase 1 (asynchronous): round / count every slot, per-sample statistics -> pinned host memory.  Returns a context for
+    expand_finish; nothing here waits for the GPU, so a caller can enqueue more work (the next batch's network) before it
+    pays for the host side of phase 2."""
     if not vals.is_cuda:
         raise _lib.ESRError("esr_b200.expand needs a CUDA tensor (no CPU fallback)")
     vals = vals.contiguous().float()
@@ -53,8 +59,33 @@ def expand(vals, kind, mode):
         P = 1
     else:
         raise Exception("wrong event stack")
+    ctx = _ExpandCtx()
+    ctx.vals, ctx.kind, ctx.dims, ctx.parts = vals, kind, (B, P, C, H, W), None
     if B > 256:   # the radix sort carries the sample index in one 8-bit digit
-        parts = [expand(vals[i:i + 256], kind, mode) for i in range(0, B, 256)]
+        ctx.parts = [expand_begin(vals[i:i + 256], kind) for i in range(0, B, 256)]
+        return ctx
+    L = _lib.lib()
+    dev = vals.device
+    S = P * C * H * W
+    ctx.stats = torch.empty((B, 4), dtype=torch.int64, device=dev)
+    ctx.counts = torch.empty((B * S,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.esr_expand_count(_lib.ptr(vals), B, P, C, H, W, kind, _lib.ptr(ctx.stats), _lib.ptr(ctx.counts), _lib.stream_ptr()),
+                   "esr_expand_count")
+        ctx.stats_host = torch.empty((B, 4), dtype=torch.int64).pin_memory()
+        ctx.stats_host.copy_(ctx.stats, non_blocking=True)
+        ctx.event = torch.cuda.Event()
+        ctx.event.record()
+    return ctx
+
+
+def expand_finish(ctx, mode):
+    """Phase 2: wait for the statistics (the one inherent host synchronisation: the output length is data dependent), size the
+    output, emit and sort.  Returns CUDA fp32 [B, maxlen, 4]."""
+    vals, kind = ctx.vals, ctx.kind
+    B, P, C, H, W = ctx.dims
+    if ctx.parts is not None:
+        parts = [expand_finish(c, mode) for c in ctx.parts]
         maxlen = max(p.shape[1] for p in parts)
         out = vals.new_zeros((B, maxlen, 4))
         for i, p in enumerate(parts):
@@ -63,13 +94,11 @@ def expand(vals, kind, mode):
     L = _lib.lib()
     dev = vals.device
     S = P * C * H * W
-    stats = torch.empty((B, 4), dtype=torch.int64, device=dev)
-    counts = torch.empty((B * S,), dtype=torch.int32, device=dev)
+    counts = ctx.counts
     with torch.cuda.device(dev):
         st = _lib.stream_ptr()
-        _lib.check(L.esr_expand_count(_lib.ptr(vals), B, P, C, H, W, kind, _lib.ptr(stats), _lib.ptr(counts), st),
-                   "esr_expand_count")
-        h = stats.cpu().numpy()                     # the one host sync
+        ctx.event.synchronize()                     # the one host sync
+        h = ctx.stats_host.numpy()
         sums, nev, neg = h[:, 0], h[:, 1], h[:, 2]
         if int(sums.sum()) == 0:                    # `if event_cnt_round.sum() != 0` (cnt2event.pyx:56)
             if mode == 1:
@@ -104,3 +133,8 @@ def expand(vals, kind, mode):
                                      act32.ctypes.data_as(ctypes.c_void_p), start.ctypes.data_as(ctypes.c_void_p),
                                      total, maxlen, _lib.ptr(out), _lib.ptr(ws), nbytes, st), "esr_expand_emit")
     return out
+
+
+def expand(vals, kind, mode):
+    """vals: CUDA fp32 tensor [B,2,H,W] (kind 0) or [B,P,C,H,W] / [B,C,H,W] (kind 1) -> CUDA fp32 [B,maxlen,4]."""
+    return expand_finish(expand_begin(vals, kind), mode)

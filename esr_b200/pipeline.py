@@ -13,7 +13,7 @@ on the GPU and no intermediate host round trip:
 import torch
 
 from . import encodings
-from .expand import expand
+from .expand import expand, expand_begin, expand_finish
 
 
 class EventSRPipeline:
@@ -77,23 +77,45 @@ class EventSRPipeline:
         events = expand(sr, 0, mode)
         return sr, events
 
-    # ---- asynchronous end-to-end API: the D2H of step i overlaps the H2D + compute of step i+1 --------------------
+    # ---- asynchronous end-to-end API, software-pipelined in three stages ------------------------------------------
+    #   submit_host(i) : H2D of the events, encode, network (CUDA graph), count kernel of the redistribution, statistics
+    #                    -> pinned host memory; returns at once
+    #   finish(i)      : the one data-dependent host synchronisation (output length), emit + sort kernels, D2H of the event
+    #                    list on a side stream into one of two pinned buffers
+    #   collect(i)     : wait for that copy
+    # Calling submit_host(i+1) BEFORE finish(i) keeps the GPU busy with batch i+1's network while the host sizes batch i's
+    # output (bench.py's e2e loop); submit / collect alone (finish implied) is the simple two-in-flight form.
     @torch.no_grad()
     def submit_host(self, xs_h, ys_h, ps_h, off_h, n_max_frame, mode=0):
-        """Enqueue one batch (pinned host buffers in) and return a handle; `collect(handle)` yields the host event
-        tensor.  Compute runs on the current stream; the result is copied out on a side stream into one of two pinned
-        buffers, so up to two batches can be in flight."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.dev)
             self._host_pool = [None, None]
+            self._sr_pool = [None, None]
             self._slot = 0
         xs = xs_h.to(self.dev, non_blocking=True)
         ys = ys_h.to(self.dev, non_blocking=True)
         ps = ps_h.to(self.dev, non_blocking=True)
         off = off_h.to(self.dev, non_blocking=True)
-        _, events = self.run_device(xs, ys, ps, off, n_max_frame, mode)
+        encodings.encode_frames(xs, ys, ps, off, lr_size=self.lr_size, hr_size=self.hr_size, n_max_frame=n_max_frame, out=self.bank)
         slot = self._slot
         self._slot ^= 1
+        if self._graph is not None:
+            self._graph.replay()
+            if self._sr_pool[slot] is None:
+                self._sr_pool[slot] = torch.empty_like(self._graph_sr)
+            sr = self._sr_pool[slot]
+            sr.copy_(self._graph_sr)                 # the graph's output buffer is overwritten by the next replay
+        else:
+            sr = self._windows()
+        return {"ctx": expand_begin(sr, 0), "mode": mode, "slot": slot, "host": None, "done": None}
+
+    @torch.no_grad()
+    def finish(self, handle):
+        if handle["done"] is not None:
+            return handle
+        events = expand_finish(handle["ctx"], handle["mode"])
+        handle["ctx"] = None
+        slot = handle["slot"]
         n = events.numel()
         buf = self._host_pool[slot]
         if buf is None or buf.numel() < n:
@@ -108,13 +130,13 @@ class EventSRPipeline:
             done = torch.cuda.Event()
             done.record()
         events.record_stream(self._copy_stream)
-        return (host, done)
+        handle["host"], handle["done"] = host, done
+        return handle
 
-    @staticmethod
-    def collect(handle):
-        host, done = handle
-        done.synchronize()
-        return host
+    def collect(self, handle):
+        self.finish(handle)
+        handle["done"].synchronize()
+        return handle["host"]
 
     @torch.no_grad()
     def run_host(self, xs_h, ys_h, ps_h, off_h, n_max_frame, mode=0):
