@@ -388,13 +388,14 @@ int pack_mma_weight_dx(const float *w, int layer_cout, int layer_cin, void *dst,
     return ESR_OK;
 }
 
-// returns ESR_EINVAL for kinds that stay on the FFMA kernels.  Measured on B200 (cfg2, profiles/r1_notes.md): enc1 88 -> 82,
-// enc2 97 -> 74, recons[1] 203 -> 138, recons[2] 230 -> 172 us; the fused head+enc0 (177 -> 193, dominated by the FFMA head
-// evaluated per patch pixel) and the tail (100 -> 111, N padded 2 -> 8) are slower and only run here with ESR_MMA_ALL=1.
+// returns ESR_EINVAL for kinds that stay on the FFMA kernels.  Measured on B200 (cfg2, profiles/r1_notes.md), FFMA -> mma.sync:
+// enc1 88 -> 52, enc2 97 -> 50, recons[1] 203 -> 111, recons[2] 230 -> 156, tail 103 -> 86, attention maps 37 -> 25 and 62 -> 45 us;
+// the fused head+enc0 is a tie (173 vs 174: dominated by the FFMA head evaluated per patch pixel) and stays on the FFMA kernel
+// unless ESR_MMA_ALL=1.
 int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st)
 {
     static const bool all = getenv("ESR_MMA_ALL") != nullptr;
-    if (!all && (kind == DK_HEAD_ENC0 || kind == DK_TAIL || kind == DK_ATT32 || kind == DK_ATT16)) return ESR_EINVAL;
+    if (!all && kind == DK_HEAD_ENC0) return ESR_EINVAL;
     if (!a.w_mma) return ESR_EINVAL;
     switch (kind) {
     case DK_HEAD_ENC0: return launch_mma<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT, 16, 16>(a, st);
