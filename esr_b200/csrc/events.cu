@@ -362,44 +362,65 @@ constexpr int RS_WARPS = 8;
 constexpr int RS_IPT = 8;                                  // rounds of 32 consecutive items per warp
 constexpr int RS_TILE = RS_WARPS * 32 * RS_IPT;            // 2048 items per block
 
-// key_passes = 4 for raw fp32 timestamp bits, 1 or 2 for compact ranks (low 16 bits of tkey)
-__device__ __forceinline__ uint32_t rs_digit(const Item &it, int pass, int key_passes, uint32_t slots_per_sample)
+// key digits: 4 passes over the raw fp32 timestamp bits, or 1-2 over the compact ranks (low 16 bits of tkey)
+__device__ __forceinline__ uint32_t rs_digit(const Item &it, int pass) { return ((it.tkey & 0x7fffffffu) >> (8 * pass)) & 255u; }
+
+// The sort is SEGMENTED by sample: events are emitted sample-major, so every pass only permutes items inside their own
+// sample's range [start[b], start[b] + n[b]) and no pass over the sample index is needed.  Tiles are aligned to the sample
+// starts: block -> (sample b, local tile lt) through the prefix of per-sample tile counts; the histogram of sample b's tiles
+// lives at hist[256 * tile_prefix[b] + digit * T_b + lt], so ONE exclusive scan over the whole array yields, for each
+// (sample, digit, tile), exactly the output offset of the sample-major, then key, then input-order (stable) arrangement.
+struct SegTile { int b, lt, nt; int64_t base, end; uint32_t hoff; };
+
+__device__ __forceinline__ SegTile rs_tile(const int64_t *__restrict__ seg /*[3][B]: start, n, tile_prefix*/, int B)
 {
-    if (pass < key_passes) return ((it.tkey & 0x7fffffffu) >> (8 * pass)) & 255u;
-    return (it.slot / slots_per_sample) & 255u;
+    const int64_t *start = seg, *nev = seg + B, *tpre = seg + 2 * B;
+    int lo = 0, hi = B - 1;                                     // last b with tile_prefix[b] <= blockIdx.x
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tpre[mid] <= (int64_t)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    SegTile t;
+    t.b = lo; t.lt = (int)((int64_t)blockIdx.x - tpre[lo]);
+    t.nt = (int)((nev[lo] + RS_TILE - 1) / RS_TILE);
+    t.base = start[lo] + (int64_t)t.lt * RS_TILE;
+    t.end = start[lo] + nev[lo];
+    t.hoff = (uint32_t)(256 * tpre[lo]) + (uint32_t)t.lt;
+    return t;
 }
 
 __global__ void __launch_bounds__(RS_WARPS * 32)
-k_radix_hist(const Item *__restrict__ items, int64_t n, int pass, int key_passes, uint32_t slots_per_sample,
-             uint32_t *__restrict__ hist /*[256][nblocks]*/)
+k_radix_hist(const Item *__restrict__ items, const int64_t *__restrict__ seg, int B, int pass, uint32_t *__restrict__ hist)
 {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+    const SegTile t = rs_tile(seg, B);
     for (int k = threadIdx.x; k < RS_TILE; k += RS_WARPS * 32) {
-        const int64_t i = base + k;
-        if (i < n) atomicAdd(&h[rs_digit(items[i], pass, key_passes, slots_per_sample)], 1u);
+        const int64_t i = t.base + k;
+        if (i < t.end) atomicAdd(&h[rs_digit(items[i], pass)], 1u);
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+    hist[t.hoff + (uint32_t)threadIdx.x * (uint32_t)t.nt] = h[threadIdx.x];
 }
 
 // Final pass writes the padded [B, maxlen, 4] rows directly instead of items.
 __global__ void __launch_bounds__(RS_WARPS * 32)
-k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, int64_t n, int pass, int key_passes, uint32_t slots_per_sample,
-                const uint32_t *__restrict__ hist_scanned /*[256][nblocks] exclusive*/,
-                int final_pass, float *__restrict__ rows, const int64_t *__restrict__ sample_start, int64_t maxlen,
+k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, const int64_t *__restrict__ seg, int B, int pass,
+                uint32_t slots_per_sample, const uint32_t *__restrict__ hist_scanned /*segmented layout, exclusive*/,
+                int final_pass, float *__restrict__ rows, int64_t maxlen,
                 int W, int H, const uint32_t *__restrict__ counts /*non-null: compact keys*/)
 {
     __shared__ uint32_t cnt[RS_WARPS][256];     // per-warp digit counters -> then per-warp bases
     __shared__ uint32_t gbase[256];
+    const SegTile t = rs_tile(seg, B);
+    const int64_t n = t.end;
     for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_WARPS * 32) (&cnt[0][0])[k] = 0;
-    gbase[threadIdx.x] = hist_scanned[(size_t)threadIdx.x * gridDim.x + blockIdx.x];
+    gbase[threadIdx.x] = hist_scanned[t.hoff + (uint32_t)threadIdx.x * (uint32_t)t.nt];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_IPT);
+    const int64_t wbase = t.base + (int64_t)warp * (32 * RS_IPT);
     Item it[RS_IPT];
     uint32_t dig[RS_IPT], rank[RS_IPT];
 #pragma unroll
@@ -407,7 +428,7 @@ k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, int64_t n, 
         const int64_t i = wbase + r * 32 + lane;
         const bool valid = i < n;
         if (valid) it[r] = in[i];
-        dig[r] = valid ? rs_digit(it[r], pass, key_passes, slots_per_sample) : 0xffffffffu;
+        dig[r] = valid ? rs_digit(it[r], pass) : 0xffffffffu;
         // rank among the lanes of this round holding the same digit
         const uint32_t peers = __match_any_sync(0xffffffffu, dig[r]);
         const uint32_t before = __popc(peers & ((1u << lane) - 1u));
@@ -444,7 +465,7 @@ k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, int64_t n, 
         row.z = counts ? linspace_f32(0.0, 1.0, counts[slot], (it[r].tkey >> 16) & 255u)
                        : __uint_as_float(it[r].tkey & 0x7fffffffu);
         row.w = (it[r].tkey >> 31) ? -1.0f : 1.0f;
-        const int64_t local = (int64_t)pos - sample_start[b];
+        const int64_t local = (int64_t)pos - seg[b];              // seg[0..B) = sample starts
         reinterpret_cast<float4 *>(rows)[(size_t)b * maxlen + local] = row;
     }
 }
@@ -567,14 +588,14 @@ static size_t expand_ws_layout(int64_t slots, int64_t E, size_t *o_offs, size_t 
 {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t r = off; off = align_up(off + bytes, 256); return r; };
-    const int64_t nblk = ceil_div64(E > 0 ? E : 1, RS_TILE);
+    const int64_t nblk = ceil_div64(E > 0 ? E : 1, RS_TILE) + 256;   // sample-aligned tiles: at most one partial tile per sample more
     *o_offs = take(sizeof(uint32_t) * (size_t)slots);
     *o_scanws = take(sizeof(uint32_t) * scan_ws_elems(slots));
     *o_items0 = take(sizeof(Item) * (size_t)(E > 0 ? E : 1));
     *o_items1 = take(sizeof(Item) * (size_t)(E > 0 ? E : 1));
     *o_hist = take(sizeof(uint32_t) * 256 * (size_t)nblk);
     *o_histws = take(sizeof(uint32_t) * scan_ws_elems(256 * nblk));
-    *o_start = take(sizeof(int64_t) * 256);
+    *o_start = take(sizeof(int64_t) * 3 * 256);                      // [start | n | tile_prefix] per sample
     return off;
 }
 
@@ -611,7 +632,16 @@ extern "C" int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P
     // samples the reference treats as empty (rounded values sum to zero) emit nothing
     for (int b = 0; b < B; ++b)
         if (!active_host[b]) ESR_CUDA_CHECK(cudaMemsetAsync(counts + (size_t)b * S, 0, sizeof(uint32_t) * (size_t)S, st));
-    ESR_CUDA_CHECK(cudaMemcpyAsync(d_start, start_host, sizeof(int64_t) * (size_t)B, cudaMemcpyHostToDevice, st));
+    // per-sample segments of the sort: start, event count, prefix of the per-sample tile counts
+    int64_t seg_host[3 * 256];
+    int64_t n_tiles_total = 0;
+    for (int b = 0; b < B; ++b) {
+        const int64_t nb = (b + 1 < B ? start_host[b + 1] : total_events) - start_host[b];
+        seg_host[b] = start_host[b]; seg_host[B + b] = nb; seg_host[2 * B + b] = n_tiles_total;
+        n_tiles_total += ceil_div64(nb, RS_TILE);
+    }
+    ESR_CUDA_CHECK(cudaMemcpyAsync(d_start, seg_host, sizeof(int64_t) * 3 * (size_t)B, cudaMemcpyHostToDevice, st));
+    // (pageable source: the driver stages the bytes before the call returns, so the stack buffer is safe)
 
     int rc = exclusive_scan_u32(counts, offs, slots, scanws, st);
     if (rc) return rc;
@@ -622,18 +652,17 @@ extern "C" int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P
         k_expand_emit<<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, slots, C, H * W, kind, mode, rnd, rank_table, rank_m, items[0]);
         ESR_LAUNCH_CHECK();
     }
-    const int64_t nblk = ceil_div64(total_events, RS_TILE);
-    const int key_passes = rank_table ? (rank_bits + 7) / 8 : 4;
-    const int npass = key_passes + (B > 1 ? 1 : 0);
+    const int64_t nblk = n_tiles_total;
+    const int npass = rank_table ? (rank_bits + 7) / 8 : 4;          // key passes only: the sort is segmented by sample
     int cur = 0;
     for (int p = 0; p < npass; ++p) {
-        k_radix_hist<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], total_events, p, key_passes, (uint32_t)S, hist);
+        k_radix_hist<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], d_start, B, p, hist);
         ESR_LAUNCH_CHECK();
         rc = exclusive_scan_u32(hist, hist, 256 * nblk, histws, st);
         if (rc) return rc;
         const int fin = p == npass - 1;
-        k_radix_scatter<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], items[cur ^ 1], total_events, p, key_passes, (uint32_t)S,
-                                                                  hist, fin, out, d_start, maxlen, W, H, rank_table ? counts : nullptr);
+        k_radix_scatter<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], items[cur ^ 1], d_start, B, p, (uint32_t)S,
+                                                                  hist, fin, out, maxlen, W, H, rank_table ? counts : nullptr);
         ESR_LAUNCH_CHECK();
         cur ^= 1;
     }
