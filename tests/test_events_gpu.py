@@ -186,6 +186,30 @@ def test_cnt2event_compact_and_raw_sort_keys(dev, peak):
     assert np.array_equal(got, oe.cnt2event(cnt, 0))
 
 
+@pytest.mark.parametrize("peak", [3, 300])
+def test_cnt2event_ragged_segments(dev, peak):
+    """The sort is segmented by sample with tiles aligned to the sample starts: empty samples (leading, in the middle and
+    trailing), a 3-event sample, samples of exactly one tile (2048 events) and one tile + 1, and a many-tile sample, for
+    the 1-pass rank keys (peak 3), the 4-pass raw keys (peak 300) and the random mode."""
+    from esr_b200 import cnt2event as c2e
+    from oracle import events as oe
+    rng = np.random.default_rng(peak)
+    H, W = 48, 64
+    cnt = np.zeros((8, 2, H, W), np.float32)
+    cnt[1, 0, 5, 7] = 3                                                   # 3 events
+    flat = cnt[2].reshape(-1)
+    flat[rng.choice(flat.size, 2048, replace=False)] = 1                  # exactly one tile
+    flat = cnt[4].reshape(-1)
+    flat[rng.choice(flat.size, 2047, replace=False)] = 1
+    flat[np.flatnonzero(flat)[0]] = 2                                     # one tile + 1
+    cnt[5] = rng.integers(0, 4, (2, H, W))                                # ~9k events, several tiles
+    cnt[5, 1, 0, 0] = peak
+    cnt[6, 1, H - 1, W - 1] = 1                                           # single event; samples 0, 3, 7 stay empty
+    for mode in (0, 1):
+        got = c2e.cnt2event_cuda(torch.from_numpy(cnt).to(dev), mode).cpu().numpy()
+        assert np.array_equal(got, oe.cnt2event(cnt, mode)), mode
+
+
 @pytest.mark.parametrize("H,W,n", [(32, 32, 60000), (64, 48, 200000), (128, 128, 400000)])
 def test_dense_frames_scatter_vs_oracle(dev, H, W, n):
     """Dense frames (many events per image cell, heavy atomic contention): unit polarities are integer sums and must be
