@@ -18,6 +18,9 @@
 
 namespace esr {
 
+// weight row pitch in elements ([tap][co][ci + pad]): rows of 8 lanes (g) x 4 lanes (t4) 32-bit loads must cover 32 distinct banks
+__host__ __device__ constexpr int mma_wp(int cinp) { return cinp == 8 ? 8 : cinp + 8; }
+
 template <int CIN, int COUT, int STRIDE, int TW, int TH> struct MmGeom {
     static constexpr int NP = COUT < 8 ? 8 : COUT;             // N padded to the MMA's 8
     static constexpr int NT = NP / 8;
@@ -25,8 +28,15 @@ template <int CIN, int COUT, int STRIDE, int TW, int TH> struct MmGeom {
     static constexpr int MT = MTILES / 8;                      // per warp
     static constexpr int PW = (TW - 1) * STRIDE + 3, PH = (TH - 1) * STRIDE + 3;
     static constexpr int CINP = CIN < 8 ? 8 : CIN;             // K per tap padded to the MMA's 8 (1- and 2-channel inputs)
-    static constexpr int PITCH = CINP * 2 + 16;                // bytes per pixel per plane
-    static constexpr int WP = CINP + 8;                        // weight row pitch (elements): conflict-free B loads
+    // bytes per pixel per plane: + 16 makes the 8 rows of an ldmatrix fall into distinct 16-byte bank groups for 32- and 64-byte
+    // pixels; 16-byte pixels (CINP = 8) are conflict-free unpadded at stride 1 (8 consecutive pixels = 128 contiguous bytes)
+    // 32-byte pixels at stride 1 are stored unpadded with the 16-byte halves of pixels 4..7 (mod 8) swapped (SWZ): any 8
+    // consecutive pixels then cover the 8 distinct 16-byte bank groups, and the patch is a third smaller (one more resident block)
+    static constexpr bool SWZ = CINP == 16 && STRIDE == 1;
+    static constexpr int PITCH = ((CINP == 8 && STRIDE == 1) || SWZ) ? CINP * 2 : CINP * 2 + 16;
+    static constexpr int WP = mma_wp(CINP);                    // weight row pitch (elements): conflict-free B loads
+    // decoder layers: the source (half-resolution) patch of the tile, unpacked once to fp32
+    static constexpr int SW = TW / 2 + 2, SH = TH / 2 + 2, SPITCH = CINP * 4 + 16;
     static constexpr int KS = CINP >= 16 ? CINP / 16 : 1;
     static constexpr size_t PATCH_BYTES = (size_t)PH * PW * PITCH;
     static constexpr size_t W_BYTES = (size_t)9 * NP * WP * 2;
@@ -52,6 +62,12 @@ __device__ __forceinline__ void mma_k8(float (&d)[4], const uint32_t (&a)[4], ui
 {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+// byte offset of 16-byte chunk q of patch pixel pp
+template <typename G> __device__ __forceinline__ uint32_t patch_off(int pp, int q)
+{
+    if constexpr (G::SWZ) return (uint32_t)(pp * 32 + ((q ^ ((pp >> 2) & 1)) << 4));
+    else return (uint32_t)(pp * G::PITCH + q * 16);
 }
 // 8 fp32 -> split bf16, one 16-byte store per plane (shared memory)
 __device__ __forceinline__ void st_split8(uint8_t *hi, uint8_t *lo, const float (&v)[8])
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
             const bool inside = (y >= 0 && y < Hc && x >= 0 && x < Wc);   // outside = the encoder conv's zero padding
 #pragma unroll
             for (int c = 0; c < 8; ++c) o[c] = inside ? fmaxf(o[c], 0.0f) : 0.0f;
-            st_split8(p_hi + (size_t)i * PITCH, p_lo + (size_t)i * PITCH, o);
+            st_split8(p_hi + patch_off<G>(i, 0), p_lo + patch_off<G>(i, 0), o);
         }
     } else if constexpr (INF == FMT_NCHW_F32) {
         // training operators: fp32 NCHW planes.  A thread gathers the 8 channels of one pixel (each of the 8 loads is
@@ -148,7 +164,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
                 for (int e = 0; e < 8; ++e)
                     if (q * 8 + e < CIN) v[e] = __ldg(src + e * cs);
             }
-            st_split8(p_hi + (size_t)pp * PITCH + q * 16, p_lo + (size_t)pp * PITCH + q * 16, v);
+            st_split8(p_hi + patch_off<G>(pp, q), p_lo + patch_off<G>(pp, q), v);
         }
     } else {
         static_assert(INF == FMT_HEAD_FUSED || INF == FMT_SPLIT || INF == FMT_NCHW_F32, "unsupported input format");
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
                 const int q = i % Q, pp = i / Q;                          // consecutive lanes: the 16-byte groups of a pixel
                 const int px = pp % PW, py = pp / PW;
                 const int y = iy0 + py, x = ix0 + px;
-                uint8_t *dh = p_hi + (size_t)pp * PITCH + q * 16, *dl = p_lo + (size_t)pp * PITCH + q * 16;
+                uint8_t *dh = p_hi + patch_off<G>(pp, q), *dl = p_lo + patch_off<G>(pp, q);
                 if (y >= 0 && y < Hc && x >= 0 && x < Wc) {
                     const __nv_bfloat16 *s = hi + (((size_t)simg * a.Hin + y) * a.Win + x) * CIN + q * 8;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32_generic(dh)), "l"(s) : "memory");
@@ -175,56 +191,56 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else {
-            // F.interpolate(scale_factor=2, bilinear, align_corners=False) (submodules.py:290), as in direct_conv.cu.
-            // U items per iteration: all corner loads are issued before the first interpolation (the fill is latency-bound).
-            // U = 2 only where the registers allow it without losing a resident block (measured: recons[1] 138 -> 119 us
-            // with U = 2, recons[2] 172 -> 205 us because 98 registers drop it from 3 to 2 blocks per SM).
-            constexpr int U = CIN >= 32 ? 2 : 1;
-            for (int i0 = tid; i0 < NI; i0 += 256 * U) {
-                uint4 ch[U][4], cl[U][4];
-                float lyv[U], lxv[U];
-                bool ok[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i = i0 + u * 256;
-                    const int q = i % Q, pp = i / Q;
-                    const int y = iy0 + pp / PW, x = ix0 + pp % PW;
-                    ok[u] = i < NI && y >= 0 && y < Hc && x >= 0 && x < Wc;
-                    const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f);
-                    const float fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
-                    const int y_0 = min((int)fy, a.Hin - 1), x_0 = min((int)fx, a.Win - 1);    // (clamps only matter when !ok)
-                    const int y_1 = min(y_0 + 1, a.Hin - 1), x_1 = min(x_0 + 1, a.Win - 1);
-                    lyv[u] = fy - (float)y_0; lxv[u] = fx - (float)x_0;
-                    const size_t b0 = ((size_t)simg * a.Hin + y_0) * a.Win, b1 = ((size_t)simg * a.Hin + y_1) * a.Win;
-                    const __nv_bfloat16 *s00 = hi + (b0 + x_0) * CIN + q * 8, *s01 = hi + (b0 + x_1) * CIN + q * 8;
-                    const __nv_bfloat16 *s10 = hi + (b1 + x_0) * CIN + q * 8, *s11 = hi + (b1 + x_1) * CIN + q * 8;
-                    if (ok[u]) {
-                        ch[u][0] = __ldg(reinterpret_cast<const uint4 *>(s00)); cl[u][0] = __ldg(reinterpret_cast<const uint4 *>(s00 + plane));
-                        ch[u][1] = __ldg(reinterpret_cast<const uint4 *>(s01)); cl[u][1] = __ldg(reinterpret_cast<const uint4 *>(s01 + plane));
-                        ch[u][2] = __ldg(reinterpret_cast<const uint4 *>(s10)); cl[u][2] = __ldg(reinterpret_cast<const uint4 *>(s10 + plane));
-                        ch[u][3] = __ldg(reinterpret_cast<const uint4 *>(s11)); cl[u][3] = __ldg(reinterpret_cast<const uint4 *>(s11 + plane));
-                    }
+            // F.interpolate(scale_factor=2, bilinear, align_corners=False) (submodules.py:290), as in direct_conv.cu, in two
+            // phases so that every source pixel is loaded and unpacked ONCE (the direct form unpacked 4 corners per patch
+            // pixel and was bound by those integer instructions):
+            //  A  the (TH/2+2) x (TW/2+2) source patch, indices clamped to the image, split bf16 -> fp32 in shared memory;
+            //  B  per patch pixel: 4 corner reads, ATen's h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11), split, store.
+            // Output row y of the x2 image reads source rows y_0 = floor(max(0, y/2 - 0.25)) and min(y_0 + 1, Hin - 1); for the
+            // tile rows iy0 .. iy0 + PH - 1 (iy0 = oy0 - 1, oy0 even) that is oy0/2 - 1 .. oy0/2 + TH/2, and because the stored
+            // patch is clamped the same way, "y_0 + 1" is simply the next stored row.
+            constexpr int SW = G::SW, SH = G::SH, SPITCH = G::SPITCH;
+            uint8_t *srcp = reinterpret_cast<uint8_t *>(inp);
+            const int sy0 = oy0 / 2 - 1, sx0 = ox0 / 2 - 1;
+            for (int i = tid; i < Q * SW * SH; i += 256) {
+                const int q = i % Q, sp = i / Q;
+                const int sy = min(max(sy0 + sp / SW, 0), a.Hin - 1), sx = min(max(sx0 + sp % SW, 0), a.Win - 1);
+                const __nv_bfloat16 *s = hi + (((size_t)simg * a.Hin + sy) * a.Win + sx) * CIN + q * 8;
+                float v[8];
+                dc_unpack8(__ldg(reinterpret_cast<const uint4 *>(s)), __ldg(reinterpret_cast<const uint4 *>(s + plane)), v);
+                float4 *d = reinterpret_cast<float4 *>(srcp + (size_t)sp * SPITCH + q * 32);
+                d[0] = make_float4(v[0], v[1], v[2], v[3]);
+                d[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            __syncthreads();
+            for (int i = tid; i < NI; i += 256) {
+                const int q = i % Q, pp = i / Q;
+                const int y = iy0 + pp / PW, x = ix0 + pp % PW;
+                uint8_t *dh = p_hi + patch_off<G>(pp, q), *dl = p_lo + patch_off<G>(pp, q);
+                if (!(y >= 0 && y < Hc && x >= 0 && x < Wc)) {
+                    *reinterpret_cast<uint4 *>(dh) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(dl) = make_uint4(0, 0, 0, 0);
+                    continue;
                 }
+                const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f);
+                const float fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
+                const int y_0 = (int)fy, x_0 = (int)fx;
+                const float ly = fy - (float)y_0, lx = fx - (float)x_0;
+                const int r0 = y_0 - sy0, c0 = x_0 - sx0;                    // in [0, SH - 2] x [0, SW - 2]
+                const uint8_t *b00 = srcp + (size_t)(r0 * SW + c0) * SPITCH + q * 32;
+                const float4 *p00 = reinterpret_cast<const float4 *>(b00), *p01 = reinterpret_cast<const float4 *>(b00 + SPITCH);
+                const float4 *p10 = reinterpret_cast<const float4 *>(b00 + SW * SPITCH), *p11 = reinterpret_cast<const float4 *>(b00 + (SW + 1) * SPITCH);
+                const float w0 = 1.0f - lx, h0 = 1.0f - ly;
+                float v[8];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i = i0 + u * 256;
-                    if (i >= NI) continue;
-                    const int q = i % Q, pp = i / Q;
-                    uint8_t *dh = p_hi + (size_t)pp * PITCH + q * 16, *dl = p_lo + (size_t)pp * PITCH + q * 16;
-                    if (!ok[u]) {
-                        *reinterpret_cast<uint4 *>(dh) = make_uint4(0, 0, 0, 0);
-                        *reinterpret_cast<uint4 *>(dl) = make_uint4(0, 0, 0, 0);
-                        continue;
-                    }
-                    float v00[8], v01[8], v10[8], v11[8], v[8];
-                    dc_unpack8(ch[u][0], cl[u][0], v00); dc_unpack8(ch[u][1], cl[u][1], v01);
-                    dc_unpack8(ch[u][2], cl[u][2], v10); dc_unpack8(ch[u][3], cl[u][3], v11);
-                    const float ly = lyv[u], lx = lxv[u];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        v[e] = (1.0f - ly) * ((1.0f - lx) * v00[e] + lx * v01[e]) + ly * ((1.0f - lx) * v10[e] + lx * v11[e]);
-                    st_split8(dh, dl, v);
+                for (int h = 0; h < 2; ++h) {
+                    const float4 a00 = p00[h], a01 = p01[h], a10 = p10[h], a11 = p11[h];
+                    v[4 * h + 0] = h0 * (w0 * a00.x + lx * a01.x) + ly * (w0 * a10.x + lx * a11.x);
+                    v[4 * h + 1] = h0 * (w0 * a00.y + lx * a01.y) + ly * (w0 * a10.y + lx * a11.y);
+                    v[4 * h + 2] = h0 * (w0 * a00.z + lx * a01.z) + ly * (w0 * a10.z + lx * a11.z);
+                    v[4 * h + 3] = h0 * (w0 * a00.w + lx * a01.w) + ly * (w0 * a10.w + lx * a11.w);
                 }
+                st_split8(dh, dl, v);
             }
         }
     }
@@ -246,21 +262,24 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
     const int lm_koff = CINP >= 16 ? (lane >> 4) * 16 : 0;                   // bytes
     const uint32_t hi_base = smem_u32_generic(p_hi), lo_base = smem_u32_generic(p_lo);
     uint32_t a_off[MT];                                                      // byte offset of this lane's row for tap (0,0)
+    int a_px[MT];                                                            // (SWZ) its patch pixel
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
         const int mt = warp * MT + m;
         const int ty = mt / (TW / 16), cx = mt % (TW / 16);
-        a_off[m] = (uint32_t)(((ty * STRIDE) * PW + (cx * 16 + lm_px) * STRIDE) * PITCH + lm_koff);
+        a_px[m] = (ty * STRIDE) * PW + (cx * 16 + lm_px) * STRIDE;
+        a_off[m] = (uint32_t)(a_px[m] * PITCH + lm_koff);
     }
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
-        const uint32_t tap_off = (uint32_t)(((tap / 3) * PW + tap % 3) * PITCH);
+        const int tap_px = (tap / 3) * PW + tap % 3;
+        const uint32_t tap_off = (uint32_t)(tap_px * PITCH);
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-                const uint32_t o = a_off[m] + tap_off + ks * 32;
+                const uint32_t o = G::SWZ ? patch_off<G>(a_px[m] + tap_px, lane >> 4) : a_off[m] + tap_off + ks * 32;
                 if constexpr (CINP >= 16) { ldsm_x4(hi_base + o, ah[m]); ldsm_x4(lo_base + o, al[m]); }
                 else { ldsm_x2(hi_base + o, ah[m]); ldsm_x2(lo_base + o, al[m]); }
             }
@@ -338,7 +357,8 @@ static int launch_mma(const DirectArgs &a, cudaStream_t st)
 {
     using G = MmGeom<CIN, COUT, STRIDE, TW, TH>;
     constexpr int IPP = (G::PW + 2 + 3) / 4 * 4;
-    constexpr size_t extra = INF == FMT_HEAD_FUSED ? sizeof(float) * (size_t)(2 * (G::PH + 2) * IPP + 9 * 2 * 8 + 8) : 0;
+    constexpr size_t extra = INF == FMT_HEAD_FUSED ? sizeof(float) * (size_t)(2 * (G::PH + 2) * IPP + 9 * 2 * 8 + 8)
+                             : (UPS ? (size_t)G::SW * G::SH * G::SPITCH : 0);
     constexpr size_t smem_in = 2 * G::PATCH_BYTES + 2 * G::W_BYTES + sizeof(float) * G::NP + extra + 16;
     constexpr size_t smem_stage = (size_t)TW * TH * G::NP * sizeof(float);
     constexpr size_t smem = smem_in > smem_stage ? smem_in : smem_stage;
@@ -360,7 +380,7 @@ static int launch_mma(const DirectArgs &a, cudaStream_t st)
 // those of THAT convolution, w is the forward layer's [cin][cout][3][3]): v(co, ci, tap) = w[ci][co][8 - tap].
 __global__ void k_pack_mma_weight(const float *__restrict__ w, int cout, int cin, int rot, __nv_bfloat16 *__restrict__ dst)
 {
-    const int np = cout < 8 ? 8 : cout, wp = (cin < 8 ? 8 : cin) + 8;
+    const int np = cout < 8 ? 8 : cout, wp = mma_wp(cin < 8 ? 8 : cin);
     const int total = 9 * np * wp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ci = i % wp, co = (i / wp) % np, tap = i / (wp * np);
@@ -372,7 +392,7 @@ __global__ void k_pack_mma_weight(const float *__restrict__ w, int cout, int cin
         dst[total + i] = l;
     }
 }
-size_t mma_weight_bytes(int cout, int cin) { return (size_t)2 * 9 * (cout < 8 ? 8 : cout) * ((cin < 8 ? 8 : cin) + 8) * sizeof(__nv_bfloat16); }
+size_t mma_weight_bytes(int cout, int cin) { return (size_t)2 * 9 * (cout < 8 ? 8 : cout) * mma_wp(cin < 8 ? 8 : cin) * sizeof(__nv_bfloat16); }
 int pack_mma_weight(const float *w, int cout, int cin, void *dst, cudaStream_t st)
 {
     k_pack_mma_weight<<<(int)(mma_weight_bytes(cout, cin) / 4 + 255) / 256, 256, 0, st>>>(w, cout, cin, 0, (__nv_bfloat16 *)dst);
@@ -389,7 +409,8 @@ int pack_mma_weight_dx(const float *w, int layer_cout, int layer_cin, void *dst,
 }
 
 // returns ESR_EINVAL for kinds that stay on the FFMA kernels.  Measured on B200 (cfg2, profiles/r1_notes.md), FFMA -> mma.sync:
-// enc1 88 -> 52, enc2 97 -> 50, recons[1] 203 -> 111, recons[2] 230 -> 156, tail 103 -> 86, attention maps 37 -> 25 and 62 -> 45 us;
+// enc1 88 -> 48, enc2 97 -> 43, recons[1] 203 -> 98, recons[2] 230 -> 146, tail 103 -> 64, attention maps 37 -> 23 and 62 -> 37 us
+// (with the unpack-once upsampling fill and the conflict-free unpadded 16- / 32-byte pixel layouts);
 // the fused head+enc0 is a tie (173 vs 174: dominated by the FFMA head evaluated per patch pixel) and stays on the FFMA kernel
 // unless ESR_MMA_ALL=1.
 int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st)
