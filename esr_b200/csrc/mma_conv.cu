@@ -33,12 +33,15 @@ template <int CIN, int COUT, int STRIDE, int TW, int TH> struct MmGeom {
     // 32-byte pixels at stride 1 are stored unpadded with the 16-byte halves of pixels 4..7 (mod 8) swapped (SWZ): any 8
     // consecutive pixels then cover the 8 distinct 16-byte bank groups, and the patch is a third smaller (one more resident block)
     static constexpr bool SWZ = CINP == 16 && STRIDE == 1;
-    static constexpr int PITCH = ((CINP == 8 && STRIDE == 1) || SWZ) ? CINP * 2 : CINP * 2 + 16;
+    // 16-byte pixels read at stride 2: pixels 8..15 (mod 16) swap places pairwise (slot = px ^ 1), so that 8 rows two pixels
+    // apart cover the 8 distinct 16-byte bank groups (padding cannot: any pitch puts them 32 * k bytes apart)
+    static constexpr bool SWZ8 = CINP == 8 && STRIDE == 2;
+    static constexpr int PITCH = (CINP == 8 || SWZ) ? CINP * 2 : CINP * 2 + 16;
     static constexpr int WP = mma_wp(CINP);                    // weight row pitch (elements): conflict-free B loads
     // decoder layers: the source (half-resolution) patch of the tile, unpacked once to fp32
     static constexpr int SW = TW / 2 + 2, SH = TH / 2 + 2, SPITCH = CINP * 4 + 16;
     static constexpr int KS = CINP >= 16 ? CINP / 16 : 1;
-    static constexpr size_t PATCH_BYTES = (size_t)PH * PW * PITCH;
+    static constexpr size_t PATCH_BYTES = (size_t)((PH * PW + 15) / 16 * 16) * PITCH;   // (SWZ8 swaps within pixel pairs)
     static constexpr size_t W_BYTES = (size_t)9 * NP * WP * 2;
     static_assert(TW % 16 == 0 && MTILES % 8 == 0, "tile must hold a multiple of 8 16-pixel segments");
 };
@@ -67,6 +70,7 @@ __device__ __forceinline__ void mma_k8(float (&d)[4], const uint32_t (&a)[4], ui
 template <typename G> __device__ __forceinline__ uint32_t patch_off(int pp, int q)
 {
     if constexpr (G::SWZ) return (uint32_t)(pp * 32 + ((q ^ ((pp >> 2) & 1)) << 4));
+    else if constexpr (G::SWZ8) return (uint32_t)((pp ^ ((pp >> 3) & 1)) << 4);
     else return (uint32_t)(pp * G::PITCH + q * 16);
 }
 // 8 fp32 -> split bf16, one 16-byte store per plane (shared memory)
@@ -94,7 +98,6 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
     float *bsm = reinterpret_cast<float *>(w_lo + 9 * NP * WP);            // [NP]
     constexpr int IPP = (PW + 2 + 3) / 4 * 4;
     float *inp = bsm + NP;                                                 // fused head: [2][PH+2][IPP], then [9][2][8] + [8]
-    float *w0s = inp + 2 * (PH + 2) * IPP;
 
     const int img = blockIdx.z;
     const int oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
@@ -116,36 +119,58 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
     const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
     const int simg = a.in_img ? a.in_img[img] : img;
     if constexpr (INF == FMT_HEAD_FUSED) {
+        // head (2 -> 8, relu; models/model.py:301,330) evaluated for the PH x PW patch this tile needs, on the tensor cores too:
+        // K = 18 = 3 rows of (3 pixels x 2 channels), padded to 3 x 8 with a fourth pixel whose weights are zero, so that the
+        // A fragment of row ky is just the split input words (one 32-bit word = both channels of a pixel) at pixels x .. x + 3.
         static_assert(INF != FMT_HEAD_FUSED || CIN == 8, "fused head feeds the 8-channel encoder layer");
-        for (int i = tid; i < 9 * 2 * 8 + 8; i += 256) w0s[i] = i < 144 ? a.w0[i] : a.b0[i - 144];
-        for (int i = tid; i < 2 * (PH + 2) * (PW + 2); i += 256) {
-            const int px = i % (PW + 2), py = (i / (PW + 2)) % (PH + 2), ci = i / ((PW + 2) * (PH + 2));
-            const int y = iy0 - 1 + py, x = ix0 - 1 + px;
-            float v = 0.0f;
-            const int sy = y - a.pad_top, sx = x - a.pad_left;           // CropSize zero padding (model_util.py:148-152)
-            if (sy >= 0 && sy < a.Hin && sx >= 0 && sx < a.Win) v = a.in_f32[(((size_t)simg * 2 + ci) * a.Hin + sy) * a.Win + sx];
-            inp[(ci * (PH + 2) + py) * IPP + px] = v;
-        }
-        __syncthreads();
-        for (int i = tid; i < PH * PW; i += 256) {
-            const int px = i % PW, py = i / PW;
-            const int y = iy0 + py, x = ix0 + px;
-            float o[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) o[c] = w0s[144 + c];
-#pragma unroll
-            for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const float xv = inp[(ci * (PH + 2) + py + t / 3) * IPP + px + t % 3];
-                    const float *wp = w0s + (t * 2 + ci) * 8;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) o[c] = fmaf(xv, wp[c], o[c]);
+        constexpr int IW = PW + 2, IH = PH + 2, IN_N = IW * IH, NPX = PH * PW;
+        static_assert(INF != FMT_HEAD_FUSED || 2 * (IN_N + 4) <= 2 * IH * IPP, "input patch does not fit its region");
+        uint32_t *in_hi = reinterpret_cast<uint32_t *>(inp), *in_lo = in_hi + IN_N + 4;
+        for (int i = tid; i < IN_N + 4; i += 256) {                        // (+4: the zero-weight fourth pixel of the last rows)
+            float v0 = 0.0f, v1 = 0.0f;
+            if (i < IN_N) {
+                const int y = iy0 - 1 + i / IW, x = ix0 - 1 + i % IW;      // head-input coordinates (padded frame)
+                const int sy = y - a.pad_top, sx = x - a.pad_left;       // CropSize zero padding (model_util.py:148-152)
+                if (sy >= 0 && sy < a.Hin && sx >= 0 && sx < a.Win) {
+                    const float *src = a.in_f32 + ((size_t)simg * 2 * a.Hin + sy) * a.Win + sx;
+                    v0 = __ldg(src); v1 = __ldg(src + (size_t)a.Hin * a.Win);
                 }
-            const bool inside = (y >= 0 && y < Hc && x >= 0 && x < Wc);   // outside = the encoder conv's zero padding
+            }
+            split_pack2(v0, v1, in_hi[i], in_lo[i]);
+        }
+        const int hg = lane >> 2, ht = lane & 3;
+        uint32_t hbh[3], hbl[3];                                           // B fragments: k = (kx = ht, ci), n = hg
 #pragma unroll
-            for (int c = 0; c < 8; ++c) o[c] = inside ? fmaxf(o[c], 0.0f) : 0.0f;
-            st_split8(p_hi + patch_off<G>(i, 0), p_lo + patch_off<G>(i, 0), o);
+        for (int ky = 0; ky < 3; ++ky) {
+            float w_a = 0.0f, w_b = 0.0f;
+            if (ht < 3) { w_a = a.w0[((ky * 3 + ht) * 2 + 0) * 8 + hg]; w_b = a.w0[((ky * 3 + ht) * 2 + 1) * 8 + hg]; }
+            split_pack2(w_a, w_b, hbh[ky], hbl[ky]);
+        }
+        const float hb0 = a.b0[2 * ht], hb1 = a.b0[2 * ht + 1];
+        __syncthreads();
+        for (int mt = warp; mt < (NPX + 15) / 16; mt += 8) {
+            const int pa = mt * 16 + hg, pb = pa + 8;
+            const int qa = min(pa, NPX - 1), qb = min(pb, NPX - 1);
+            const int oa = (qa / PW) * IW + qa % PW + ht, ob = (qb / PW) * IW + qb % PW + ht;
+            float acc[4] = {hb0, hb1, hb0, hb1};
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const uint32_t ah[4] = {in_hi[oa + ky * IW], in_hi[ob + ky * IW], 0, 0}, al[4] = {in_lo[oa + ky * IW], in_lo[ob + ky * IW], 0, 0};
+                mma_k8(acc, al, hbh[ky]);
+                mma_k8(acc, ah, hbl[ky]);
+                mma_k8(acc, ah, hbh[ky]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int pp = h ? pb : pa;
+                if (pp >= NPX) continue;
+                const int y = iy0 + pp / PW, x = ix0 + pp % PW;
+                const bool inside = (y >= 0 && y < Hc && x >= 0 && x < Wc);   // outside = the encoder conv's zero padding
+                uint32_t vh, vl;
+                split_pack2(inside ? fmaxf(acc[2 * h], 0.0f) : 0.0f, inside ? fmaxf(acc[2 * h + 1], 0.0f) : 0.0f, vh, vl);
+                *reinterpret_cast<uint32_t *>(p_hi + patch_off<G>(pp, 0) + 4 * ht) = vh;
+                *reinterpret_cast<uint32_t *>(p_lo + patch_off<G>(pp, 0) + 4 * ht) = vl;
+            }
         }
     } else if constexpr (INF == FMT_NCHW_F32) {
         // training operators: fp32 NCHW planes.  A thread gathers the 8 channels of one pixel (each of the 8 loads is
@@ -279,7 +304,7 @@ __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
             uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-                const uint32_t o = G::SWZ ? patch_off<G>(a_px[m] + tap_px, lane >> 4) : a_off[m] + tap_off + ks * 32;
+                const uint32_t o = (G::SWZ || G::SWZ8) ? patch_off<G>(a_px[m] + tap_px, lane >> 4) : a_off[m] + tap_off + ks * 32;
                 if constexpr (CINP >= 16) { ldsm_x4(hi_base + o, ah[m]); ldsm_x4(lo_base + o, al[m]); }
                 else { ldsm_x2(hi_base + o, ah[m]); ldsm_x2(lo_base + o, al[m]); }
             }
@@ -411,12 +436,10 @@ int pack_mma_weight_dx(const float *w, int layer_cout, int layer_cin, void *dst,
 // returns ESR_EINVAL for kinds that stay on the FFMA kernels.  Measured on B200 (cfg2, profiles/r1_notes.md), FFMA -> mma.sync:
 // enc1 88 -> 48, enc2 97 -> 43, recons[1] 203 -> 98, recons[2] 230 -> 146, tail 103 -> 64, attention maps 37 -> 23 and 62 -> 37 us
 // (with the unpack-once upsampling fill and the conflict-free unpadded 16- / 32-byte pixel layouts);
-// the fused head+enc0 is a tie (173 vs 174: dominated by the FFMA head evaluated per patch pixel) and stays on the FFMA kernel
-// unless ESR_MMA_ALL=1.
+// fused head+enc0 173 (FFMA) -> 174 (FFMA head + mma encoder, 4-way ldmatrix conflicts) -> ~123 (SWZ8 layout) -> see
+// profiles/r1_notes.md for the version with the head itself on mma.sync.
 int conv_mma(DirectKind kind, const DirectArgs &a, cudaStream_t st)
 {
-    static const bool all = getenv("ESR_MMA_ALL") != nullptr;
-    if (!all && kind == DK_HEAD_ENC0) return ESR_EINVAL;
     if (!a.w_mma) return ESR_EINVAL;
     switch (kind) {
     case DK_HEAD_ENC0: return launch_mma<8, 16, 2, false, FMT_HEAD_FUSED, FMT_SPLIT, 16, 16>(a, st);
