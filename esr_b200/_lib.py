@@ -82,6 +82,7 @@ SIGNATURES.update({
     "esr_conv2d_backward": (c_int, [c_void_p] * 5 + [c_int] * 8 + [c_void_p] * 4 + [c_size_t, c_void_p]),
     "esr_upsample2x_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "esr_upsample2x_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "esr_resize_planes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "esr_gru_hr": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "esr_gru_hr_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "esr_gru_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -12,6 +12,9 @@ tensors live on the GPU and the encodings are the sm_100a kernels of esr_b200.en
                                                              train_ours_cnt_seq.py:219-220, infer_ours_cnt.py:58-60) --
                                                              for a whole batch of sequences in three scatter launches,
                                                              windowed as custom_collate does
+  create_unsupervised_data(norm_events, ...)                 dataloader/h5dataset.py:538-550
+  create_item(inp_events, gt_events, ...)                    the whole event-derived item dict of H5Dataset.__getitem__
+                                                             (dataloader/h5dataset.py:276-406) for one frame, on the GPU
 """
 import numpy as np
 import torch
@@ -60,6 +63,60 @@ def create_scaled_encoding(normalized_events, sensor_resolution, mode, time_bins
 def create_cnt_encoding(events, sensor_resolution):
     xs, ys, ts, ps = events[0], events[1], events[2], events[3]
     return encodings.events_to_channels(xs, ys, ps, sensor_size=sensor_resolution)
+
+
+def create_stack_encoding(events, sensor_resolution, time_bins=1):
+    xs, ys, ts, ps = events[0], events[1], events[2], events[3]
+    return encodings.events_to_stack_no_polarity(xs, ys, ts, ps, B=time_bins, sensor_size=sensor_resolution)
+
+
+def create_unsupervised_data(normalized_events, inp_sensor_resolution, inp_down_sensor_resolution, scale):
+    """inp_down_cnt, inp_down_scaled_cnt (dataloader/h5dataset.py:538-550): events re-quantised to the LR/scale grid, counted
+    there and on the LR grid, floor-divided by scale**2."""
+    xs, ys, ts, ps = normalized_events[0], normalized_events[1], normalized_events[2], normalized_events[3]
+    down = inp_down_sensor_resolution
+    inp_down_events = torch.stack([(xs * down[1]).long(), (ys * down[0]).long(), ts, ps], dim=0)   # promotes to fp32
+    inp_down_normalized_events = create_normalized_events(inp_down_events, down)
+    inp_down_cnt = create_scaled_encoding(inp_down_normalized_events, down, mode='cnt') // scale ** 2
+    inp_down_scaled_cnt = create_scaled_encoding(inp_down_normalized_events, inp_sensor_resolution, mode='cnt') // scale ** 2
+    return inp_down_cnt, inp_down_scaled_cnt
+
+
+def create_item(inp_events, gt_events, inp_sensor_resolution, scale, time_bins=1, gt_sensor_resolution=None, device=None):
+    """The item dict of H5Dataset.__getitem__ (dataloader/h5dataset.py:276-406) for one frame, built on the GPU from the raw
+    event arrays get_events / get_gt_events return ([4, n] = x, y, t, p): same keys, shapes and values, every tensor on
+    `device`.  The calls are made in the reference's order because its encodings modify the event tensors in place
+    (out-of-range events are zeroed by events_to_image, encodings.py:251-256, and the next encoding sees that).
+    Image entries (gt_img, gt_inp_size_img, frame) are the zeros the reference returns when need_gt_frame is off -- decoding
+    and cv2-resizing the stored frames is not on this path; the custom_* entries are zeros (custom_resolution None)."""
+    device = device or _dev()
+    inp_res = [int(v) for v in inp_sensor_resolution]
+    gt_res = [int(v) for v in gt_sensor_resolution] if gt_sensor_resolution is not None else [round(i * scale) for i in inp_res]
+    down_res = [round(i / scale) for i in inp_res]
+    inp_events_torch = event_formatting(inp_events, device)
+    gt_events_torch = event_formatting(gt_events, device) if gt_events is not None else torch.zeros([4, 1], device=device)
+
+    inp_event_stack = create_stack_encoding(inp_events_torch, inp_res, time_bins)
+    inp_event_cnt = create_cnt_encoding(inp_events_torch, inp_res)
+    inp_bicubic_cnt = encodings.interpolate_planes(inp_event_cnt, gt_res, 'bicubic')
+    inp_bicubic_stack = encodings.interpolate_planes(inp_event_stack, gt_res, 'bicubic')
+    inp_near_cnt = encodings.interpolate_planes(inp_event_cnt, gt_res, 'nearest')
+    inp_near_stack = encodings.interpolate_planes(inp_event_stack, gt_res, 'nearest')
+    inp_normalized_events = create_normalized_events(inp_events_torch, inp_res)
+    inp_scaled_cnt = create_scaled_encoding(inp_normalized_events, gt_res, 'cnt')
+    inp_scaled_stack = create_scaled_encoding(inp_normalized_events, gt_res, 'stack', time_bins)
+    inp_down_cnt, inp_down_scaled_cnt = create_unsupervised_data(inp_normalized_events, inp_res, down_res, scale)
+    gt_event_stack = create_stack_encoding(gt_events_torch, gt_res, time_bins)
+    gt_event_cnt = create_cnt_encoding(gt_events_torch, gt_res)
+    zeros = [torch.zeros_like(inp_event_cnt) for _ in range(5)]
+    return {'inp_stack': inp_event_stack, 'inp_cnt': inp_event_cnt, 'inp_bicubic_cnt': inp_bicubic_cnt,
+            'inp_bicubic_stack': inp_bicubic_stack, 'inp_near_cnt': inp_near_cnt, 'inp_near_stack': inp_near_stack,
+            'inp_scaled_cnt': inp_scaled_cnt, 'inp_scaled_stack': inp_scaled_stack, 'inp_down_cnt': inp_down_cnt,
+            'inp_down_scaled_cnt': inp_down_scaled_cnt, 'inp_custom_cnt': zeros[0], 'inp_custom_scaled_cnt': zeros[1],
+            'inp_custom_down_cnt': zeros[2], 'inp_custom_down_scaled_cnt': zeros[3], 'gt_custom_cnt': zeros[4],
+            'gt_stack': gt_event_stack, 'gt_cnt': gt_event_cnt,
+            'gt_img': torch.zeros([1] + gt_res, device=device), 'gt_inp_size_img': torch.zeros([1] + inp_res, device=device),
+            'frame': torch.zeros([1] + gt_res, device=device)}
 
 
 def sliding_windows(frames, num_frame=3):

@@ -166,6 +166,25 @@ def encode_frames(xs, ys, ps, frame_off, lr_size=None, hr_size=(180, 240), n_max
     return out
 
 
+def interpolate_planes(x, size, mode):
+    """F.interpolate(x.unsqueeze(0), size=size, mode=mode[, align_corners=False]).squeeze(0) for x [C, H, W] with mode
+    'bicubic' or 'nearest' (dataloader/h5dataset.py:341-344, infer_ours_cnt.py:76-78), on the GPU (esr_resize_planes).
+    CPU tensors are moved to the device and the result returned on the CPU, like the other encodings."""
+    if mode not in ('bicubic', 'nearest'):
+        raise ValueError(f"mode {mode!r} is not supported (bicubic | nearest)")
+    dev = x.device if x.is_cuda else _dev()
+    dx, _ = _to_dev_f32(x, dev)
+    lead = dx.shape[:-2]
+    Hin, Win = int(dx.shape[-2]), int(dx.shape[-1])
+    Hout, Wout = int(size[0]), int(size[1])
+    planes = int(np.prod(lead)) if len(lead) else 1
+    out = torch.empty(tuple(lead) + (Hout, Wout), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().esr_resize_planes(_lib.ptr(dx), planes, Hin, Win, Hout, Wout, 1 if mode == 'bicubic' else 0,
+                                                _lib.ptr(out), _lib.stream_ptr()), "esr_resize_planes")
+    return out if x.is_cuda else out.cpu()
+
+
 def cython_event_redistribute(event_stack, mode='linear'):
     if mode == 'linear':
         cmode = 0

@@ -227,6 +227,12 @@ int esr_conv2d_backward(const float *x, const void *x_split, const float *w, con
  * F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) of UpsampleConvLayer (models/submodules.py:290). */
 int esr_upsample2x_forward(const float *x, int planes, int H, int W, float *y, esr_stream_t stream);
 int esr_upsample2x_backward(const float *dy, int planes, int H, int W, float *dx, esr_stream_t stream);
+/* Resize of `planes` fp32 planes [Hin,Win] -> [Hout,Wout] as torch.nn.functional.interpolate(size=..., align_corners=False)
+ * does on the CPU: mode 1 = 'bicubic' (Keys, A = -0.75, clamped taps), mode 0 = legacy 'nearest'.  Replaces the per-frame
+ * calls of the dataset's tensor factory (dataloader/h5dataset.py:341-344: inp_bicubic_cnt / _stack, inp_near_cnt / _stack)
+ * and the bicubic baseline of infer_ours_cnt.py:76-78. */
+int esr_resize_planes(const float *x, int planes, int Hin, int Win, int Hout, int Wout, int mode, float *out,
+                      esr_stream_t stream);
 /* ConvGRU gate arithmetic (models/submodules.py:507-512), fp32, B images of chw = C*H*W elements; zr [B, 2C, H, W] holds
  * the update gate z in channels [0,C) and the reset gate r in [C,2C).  hr = h*r;  blend = h*(1-z) + o*z.  The backward
  * entry points write full-size dzr (the half they do not touch is zero-filled). */
