@@ -218,8 +218,12 @@ static size_t scan_ws_elems(int64_t n)
 }
 
 // in-place allowed (in == out).  ws needs scan_ws_elems(n) uint32.
-static int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *ws, cudaStream_t st)
+// defer_add: skip the final pass over `out`; out[i] is then exclusive WITHIN its SCAN_TILE and the consumer adds
+// (*tile_prefix)[i / SCAN_TILE] itself (nullptr when there is a single tile).
+static int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *ws, cudaStream_t st,
+                              const uint32_t **tile_prefix = nullptr)
 {
+    if (tile_prefix) *tile_prefix = nullptr;
     if (n <= 0) return ESR_OK;
     const int64_t nt = ceil_div64(n, SCAN_TILE);
     if (nt == 1) {
@@ -231,6 +235,7 @@ static int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint
     ESR_LAUNCH_CHECK();
     int rc = exclusive_scan_u32(ws, ws, nt, ws + align_up((size_t)nt, 64), st);
     if (rc) return rc;
+    if (tile_prefix) { *tile_prefix = ws; return ESR_OK; }
     k_scan_add<<<(unsigned)nt, SCAN_THREADS, 0, st>>>(out, ws, n);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
@@ -241,6 +246,7 @@ static int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint
 // =============================================================================================
 // grid = (tiles per sample, B).  counts[slot] = number of events the slot emits; per-sample stats are
 // reduced in the block and added with one atomic per block.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_expand_count(const float *__restrict__ vals, int64_t S, int kind, uint32_t *__restrict__ counts,
                unsigned long long *__restrict__ stats /*[B,4]: sum(as i64), nev, neg, maxn*/)
@@ -251,8 +257,8 @@ k_expand_count(const float *__restrict__ vals, int64_t S, int kind, uint32_t *__
     long long sum = 0, nev = 0;
     int neg = 0;
     unsigned int mx = 0;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
-        const float r = rintf(v[s]);               // numpy round(): half to even (cnt2event.pyx:31)
+    auto one = [&](float x) -> unsigned int {
+        const float r = rintf(x);                  // numpy round(): half to even (cnt2event.pyx:31)
         const long long ri = (long long)r;
         sum += ri;
         unsigned int n;
@@ -260,7 +266,16 @@ k_expand_count(const float *__restrict__ vals, int64_t S, int kind, uint32_t *__
         else n = (unsigned int)(ri < 0 ? -ri : ri);
         nev += n;
         mx = max(mx, n);
-        c[s] = n;
+        return n;
+    };
+    if constexpr (VEC) {                           // S % 4 == 0 and 16-byte aligned bases: 16-byte loads / stores
+        const int64_t S4 = S >> 2;
+        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < S4; q += (int64_t)gridDim.x * blockDim.x) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(v) + q);
+            reinterpret_cast<uint4 *>(c)[q] = make_uint4(one(x.x), one(x.y), one(x.z), one(x.w));
+        }
+    } else {
+        for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) c[s] = one(v[s]);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -307,14 +322,14 @@ __device__ __forceinline__ float linspace_f32(double t0, double t1, unsigned int
 // rank | j << 16 | negative << 31 and the timestamp is re-derived from (n, j) when the row is written.
 __global__ void __launch_bounds__(256)
 k_expand_emit(const float *__restrict__ vals, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offs,
-              int64_t total_slots, int C, int HW, int kind, int mode, const double *__restrict__ rnd,
+              const uint32_t *__restrict__ offs_tile_prefix /*nullable: offs is exclusive per SCAN_TILE, add this*/, int64_t total_slots, int C, int HW, int kind, int mode, const double *__restrict__ rnd,
               const uint16_t *__restrict__ rank, int rank_m, Item *__restrict__ items)
 {
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total_slots;
          s += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t n = counts[s];
         if (n == 0) continue;
-        const uint32_t off = offs[s];
+        const uint32_t off = offs[s] + (offs_tile_prefix ? offs_tile_prefix[s / SCAN_TILE] : 0u);
         uint32_t negbit;
         double t0 = 0.0, t1 = 1.0;
         float t0f = 0.0f, t1f = 1.0f;
@@ -408,6 +423,7 @@ k_radix_hist(const Item *__restrict__ items, const int64_t *__restrict__ seg, in
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, const int64_t *__restrict__ seg, int B, int pass,
                 uint32_t slots_per_sample, const uint32_t *__restrict__ hist_scanned /*segmented layout, exclusive*/,
+                const uint32_t *__restrict__ hist_tile_prefix /*nullable: hist_scanned is exclusive per SCAN_TILE*/,
                 int final_pass, float *__restrict__ rows, int64_t maxlen,
                 int W, int H, const uint32_t *__restrict__ counts /*non-null: compact keys*/)
 {
@@ -416,7 +432,10 @@ k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, const int64
     const SegTile t = rs_tile(seg, B);
     const int64_t n = t.end;
     for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_WARPS * 32) (&cnt[0][0])[k] = 0;
-    gbase[threadIdx.x] = hist_scanned[t.hoff + (uint32_t)threadIdx.x * (uint32_t)t.nt];
+    {
+        const uint32_t hi = t.hoff + (uint32_t)threadIdx.x * (uint32_t)t.nt;
+        gbase[threadIdx.x] = hist_scanned[hi] + (hist_tile_prefix ? hist_tile_prefix[hi / SCAN_TILE] : 0u);
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -578,7 +597,9 @@ extern "C" int esr_expand_count(const float *vals, int B, int P, int C, int H, i
     const int64_t cap = (int64_t)dev_info().sm_count * 8;
     if (bx > cap) bx = cap;
     dim3 grid((unsigned)bx, (unsigned)B);
-    k_expand_count<<<grid, 256, 0, st>>>(vals, S, kind, counts, reinterpret_cast<unsigned long long *>(stats));
+    const bool vec = S % 4 == 0 && ((uintptr_t)vals & 15) == 0 && ((uintptr_t)counts & 15) == 0;
+    if (vec) k_expand_count<true><<<grid, 256, 0, st>>>(vals, S, kind, counts, reinterpret_cast<unsigned long long *>(stats));
+    else k_expand_count<false><<<grid, 256, 0, st>>>(vals, S, kind, counts, reinterpret_cast<unsigned long long *>(stats));
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }
@@ -643,13 +664,14 @@ extern "C" int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P
     ESR_CUDA_CHECK(cudaMemcpyAsync(d_start, seg_host, sizeof(int64_t) * 3 * (size_t)B, cudaMemcpyHostToDevice, st));
     // (pageable source: the driver stages the bytes before the call returns, so the stack buffer is safe)
 
-    int rc = exclusive_scan_u32(counts, offs, slots, scanws, st);
+    const uint32_t *offs_tp = nullptr;
+    int rc = exclusive_scan_u32(counts, offs, slots, scanws, st, &offs_tp);       // the emit kernel adds the tile prefixes itself
     if (rc) return rc;
     {
         int64_t bx = ceil_div64(slots, 256 * 2);
         const int64_t cap = (int64_t)dev_info().sm_count * 32;
         if (bx > cap) bx = cap;
-        k_expand_emit<<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, slots, C, H * W, kind, mode, rnd, rank_table, rank_m, items[0]);
+        k_expand_emit<<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, offs_tp, slots, C, H * W, kind, mode, rnd, rank_table, rank_m, items[0]);
         ESR_LAUNCH_CHECK();
     }
     const int64_t nblk = n_tiles_total;
@@ -658,11 +680,12 @@ extern "C" int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P
     for (int p = 0; p < npass; ++p) {
         k_radix_hist<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], d_start, B, p, hist);
         ESR_LAUNCH_CHECK();
-        rc = exclusive_scan_u32(hist, hist, 256 * nblk, histws, st);
+        const uint32_t *hist_tp = nullptr;
+        rc = exclusive_scan_u32(hist, hist, 256 * nblk, histws, st, &hist_tp);
         if (rc) return rc;
         const int fin = p == npass - 1;
         k_radix_scatter<<<(unsigned)nblk, RS_WARPS * 32, 0, st>>>(items[cur], items[cur ^ 1], d_start, B, p, (uint32_t)S,
-                                                                  hist, fin, out, maxlen, W, H, rank_table ? counts : nullptr);
+                                                                  hist, hist_tp, fin, out, maxlen, W, H, rank_table ? counts : nullptr);
         ESR_LAUNCH_CHECK();
         cur ^= 1;
     }
