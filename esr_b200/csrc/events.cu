@@ -334,10 +334,10 @@ k_expand_emit(const float *__restrict__ vals, const uint32_t *__restrict__ count
         double t0 = 0.0, t1 = 1.0;
         float t0f = 0.0f, t1f = 1.0f;
         if (kind == 0) {
-            negbit = (uint32_t)((s / HW) & 1);                    // channel 1 = negative (cnt2event.pyx:80-90)
+            negbit = ((uint32_t)s / (uint32_t)HW) & 1u;           // channel 1 = negative (cnt2event.pyx:80-90); slots < 2^32
         } else {
             negbit = vals[s] < 0.0f ? 1u : 0u;                    // p = sign(value); P index ignored
-            const int c = (int)((s / HW) % C);
+            const int c = (int)(((uint32_t)s / (uint32_t)HW) % (uint32_t)C);
             // cdef float t0, t1 <- float64 expressions (event_redistribute.pyx:61-62)
             t0f = (float)__dadd_rn(__ddiv_rn((double)c, (double)C), __ddiv_rn(1.0, (double)(100 * C)));
             t1f = (float)__ddiv_rn((double)(c + 1), (double)C);
