@@ -320,48 +320,73 @@ __device__ __forceinline__ float linspace_f32(double t0, double t1, unsigned int
 // float32(linspace(0,1,n)[j]); `rank[n*rank_m + j]` is its index among the sorted distinct values, so the sort key is
 // ceil(log2(#distinct)) bits instead of 30 and one or two radix passes replace four.  The item then carries
 // rank | j << 16 | negative << 31 and the timestamp is re-derived from (n, j) when the row is written.
-__global__ void __launch_bounds__(256)
-k_expand_emit(const float *__restrict__ vals, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offs,
-              const uint32_t *__restrict__ offs_tile_prefix /*nullable: offs is exclusive per SCAN_TILE, add this*/, int64_t total_slots, int C, int HW, int kind, int mode, const double *__restrict__ rnd,
-              const uint16_t *__restrict__ rank, int rank_m, Item *__restrict__ items)
+// one slot with n > 0 events starting at output offset `off`
+__device__ __forceinline__ void emit_slot(int64_t s, uint32_t n, uint32_t off, const float *__restrict__ vals, int C, int HW, int kind,
+                                          int mode, const double *__restrict__ rnd, const uint16_t *__restrict__ rank, int rank_m,
+                                          Item *__restrict__ items)
 {
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total_slots;
-         s += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t n = counts[s];
-        if (n == 0) continue;
-        const uint32_t off = offs[s] + (offs_tile_prefix ? offs_tile_prefix[s / SCAN_TILE] : 0u);
-        uint32_t negbit;
-        double t0 = 0.0, t1 = 1.0;
-        float t0f = 0.0f, t1f = 1.0f;
-        if (kind == 0) {
-            negbit = ((uint32_t)s / (uint32_t)HW) & 1u;           // channel 1 = negative (cnt2event.pyx:80-90); slots < 2^32
-        } else {
-            negbit = vals[s] < 0.0f ? 1u : 0u;                    // p = sign(value); P index ignored
-            const int c = (int)(((uint32_t)s / (uint32_t)HW) % (uint32_t)C);
-            // cdef float t0, t1 <- float64 expressions (event_redistribute.pyx:61-62)
-            t0f = (float)__dadd_rn(__ddiv_rn((double)c, (double)C), __ddiv_rn(1.0, (double)(100 * C)));
-            t1f = (float)__ddiv_rn((double)(c + 1), (double)C);
-            t0 = (double)t0f; t1 = (double)t1f;
-        }
-        if (rank) {                                                   // compact-key path (kind 0, mode 0, n <= rank_m)
-            const uint16_t *rk = rank + (size_t)n * rank_m;
-            for (uint32_t j = 0; j < n; ++j) {
-                Item it;
-                it.tkey = (uint32_t)rk[j] | (j << 16) | (negbit << 31);
-                it.slot = (uint32_t)s;
-                items[(size_t)off + j] = it;
-            }
-            continue;
-        }
+    uint32_t negbit;
+    double t0 = 0.0, t1 = 1.0;
+    float t0f = 0.0f, t1f = 1.0f;
+    if (kind == 0) {
+        negbit = ((uint32_t)s / (uint32_t)HW) & 1u;           // channel 1 = negative (cnt2event.pyx:80-90); slots < 2^32
+    } else {
+        negbit = vals[s] < 0.0f ? 1u : 0u;                    // p = sign(value); P index ignored
+        const int c = (int)(((uint32_t)s / (uint32_t)HW) % (uint32_t)C);
+        // cdef float t0, t1 <- float64 expressions (event_redistribute.pyx:61-62)
+        t0f = (float)__dadd_rn(__ddiv_rn((double)c, (double)C), __ddiv_rn(1.0, (double)(100 * C)));
+        t1f = (float)__ddiv_rn((double)(c + 1), (double)C);
+        t0 = (double)t0f; t1 = (double)t1f;
+    }
+    if (rank) {                                                   // compact-key path (kind 0, mode 0, n <= rank_m)
+        const uint16_t *rk = rank + (size_t)n * rank_m;
         for (uint32_t j = 0; j < n; ++j) {
-            float t;
-            if (mode == 0) t = linspace_f32(t0, t1, n, j);
-            else if (kind == 0) t = (float)rnd[(size_t)off + j];
-            else t = (float)__dadd_rn(__dmul_rn(rnd[(size_t)off + j], (double)__fsub_rn(t1f, t0f)), t0);
             Item it;
-            it.tkey = __float_as_uint(t) | (negbit << 31);
+            it.tkey = (uint32_t)rk[j] | (j << 16) | (negbit << 31);
             it.slot = (uint32_t)s;
             items[(size_t)off + j] = it;
+        }
+        return;
+    }
+    for (uint32_t j = 0; j < n; ++j) {
+        float t;
+        if (mode == 0) t = linspace_f32(t0, t1, n, j);
+        else if (kind == 0) t = (float)rnd[(size_t)off + j];
+        else t = (float)__dadd_rn(__dmul_rn(rnd[(size_t)off + j], (double)__fsub_rn(t1f, t0f)), t0);
+        Item it;
+        it.tkey = __float_as_uint(t) | (negbit << 31);
+        it.slot = (uint32_t)s;
+        items[(size_t)off + j] = it;
+    }
+}
+
+// VEC (total_slots % 4 == 0, 16-byte aligned counts / offs): a thread takes 4 consecutive slots, so the count and offset
+// loads of a group are two independent 16-byte loads in flight instead of a dependent chain per slot (the kernel is
+// latency-bound: ncu long_scoreboard 15 per issue).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_expand_emit(const float *__restrict__ vals, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ offs,
+              const uint32_t *__restrict__ offs_tile_prefix /*nullable: offs is exclusive per SCAN_TILE, add this*/, int64_t total_slots,
+              int C, int HW, int kind, int mode, const double *__restrict__ rnd,
+              const uint16_t *__restrict__ rank, int rank_m, Item *__restrict__ items)
+{
+    if constexpr (VEC) {
+        const int64_t groups = total_slots >> 2;
+        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += (int64_t)gridDim.x * blockDim.x) {
+            const uint4 c4 = __ldg(reinterpret_cast<const uint4 *>(counts) + q);
+            const uint4 o4 = __ldg(reinterpret_cast<const uint4 *>(offs) + q);
+            if ((c4.x | c4.y | c4.z | c4.w) == 0) continue;
+            const uint32_t tp = offs_tile_prefix ? offs_tile_prefix[(q * 4) / SCAN_TILE] : 0u;   // SCAN_TILE % 4 == 0: one tile per group
+            const uint32_t cn[4] = {c4.x, c4.y, c4.z, c4.w}, co[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (cn[e]) emit_slot(q * 4 + e, cn[e], co[e] + tp, vals, C, HW, kind, mode, rnd, rank, rank_m, items);
+        }
+    } else {
+        for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total_slots; s += (int64_t)gridDim.x * blockDim.x) {
+            const uint32_t n = counts[s];
+            if (n == 0) continue;
+            emit_slot(s, n, offs[s] + (offs_tile_prefix ? offs_tile_prefix[s / SCAN_TILE] : 0u), vals, C, HW, kind, mode, rnd, rank, rank_m, items);
         }
     }
 }
@@ -443,10 +468,14 @@ k_radix_scatter(const Item *__restrict__ in, Item *__restrict__ out, const int64
     Item it[RS_IPT];
     uint32_t dig[RS_IPT], rank[RS_IPT];
 #pragma unroll
+    for (int r = 0; r < RS_IPT; ++r) {                     // all loads first: the ranking rounds below are serial (shared counters)
+        const int64_t i = wbase + r * 32 + lane;
+        if (i < n) it[r] = in[i];
+    }
+#pragma unroll
     for (int r = 0; r < RS_IPT; ++r) {
         const int64_t i = wbase + r * 32 + lane;
         const bool valid = i < n;
-        if (valid) it[r] = in[i];
         dig[r] = valid ? rs_digit(it[r], pass) : 0xffffffffu;
         // rank among the lanes of this round holding the same digit
         const uint32_t peers = __match_any_sync(0xffffffffu, dig[r]);
@@ -668,10 +697,12 @@ extern "C" int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P
     int rc = exclusive_scan_u32(counts, offs, slots, scanws, st, &offs_tp);       // the emit kernel adds the tile prefixes itself
     if (rc) return rc;
     {
-        int64_t bx = ceil_div64(slots, 256 * 2);
+        const bool vec = slots % 4 == 0 && ((uintptr_t)counts & 15) == 0 && ((uintptr_t)offs & 15) == 0;
+        int64_t bx = ceil_div64(slots, 256 * 4);
         const int64_t cap = (int64_t)dev_info().sm_count * 32;
         if (bx > cap) bx = cap;
-        k_expand_emit<<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, offs_tp, slots, C, H * W, kind, mode, rnd, rank_table, rank_m, items[0]);
+        if (vec) k_expand_emit<true><<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, offs_tp, slots, C, H * W, kind, mode, rnd, rank_table, rank_m, items[0]);
+        else k_expand_emit<false><<<(unsigned)bx, 256, 0, st>>>(vals, counts, offs, offs_tp, slots, C, H * W, kind, mode, rnd, rank_table, rank_m, items[0]);
         ESR_LAUNCH_CHECK();
     }
     const int64_t nblk = n_tiles_total;
