@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from . import event_redistribute as c_event_redistribute
+from . import event_redistribute as c_event_redistribute  # noqa: F401  (the reference exposes its Cython module here, encodings.py:5)
 from .expand import expand
 
 

@@ -5,7 +5,6 @@ network: autograd through the oracle restatement of models/model.py).
 Tolerance: max |got - want| <= 1e-3 * max |want| per tensor (BASELINE.json north_star's fp32 bar), a little wider for
 whole-network gradients where it says so.
 """
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
