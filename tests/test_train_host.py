@@ -133,7 +133,7 @@ def _worker(rank, world, port, q):
     loss.backward()
     grads = [p.grad for p in net.parameters()]
     ed.flat_allreduce_(grads, average=True)                                  # the step's single exchange (DDP's role)
-    q.put((rank, torch.cat([g.reshape(-1) for g in grads])))
+    q.put((rank, torch.cat([g.reshape(-1) for g in grads]).numpy()))       # numpy: pickled by value, no fd hand-back to an exited worker
     dist.barrier()
     dist.destroy_process_group()
 
@@ -148,7 +148,7 @@ def test_two_rank_gradient_exchange_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in range(2))
+    res = {r: torch.from_numpy(a) for r, a in (q.get(timeout=300) for _ in range(2))}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
