@@ -65,7 +65,7 @@ SIGNATURES.update({
     "esr_net_reset_states": (c_int, [c_void_p, c_void_p]),
     "esr_net_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "esr_net_forward_profiled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                         c_void_p, c_void_p]),
+                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "esr_net_get_states": (c_int, [c_void_p, c_void_p, c_void_p]),
     "esr_net_set_states": (c_int, [c_void_p, c_void_p, c_void_p]),
 })

@@ -378,7 +378,7 @@ static int build(Net &n, cudaStream_t st)
 
 // Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every kernel.
 struct Prof {
-    struct Entry { cudaEvent_t e0, e1; int cls; double flops; };
+    struct Entry { cudaEvent_t e0, e1; int cls; double flops, bytes; const char *name; };
     std::vector<Entry> entries;
 };
 enum ProfClass : int { PC_TC = 0, PC_DIRECT = 1, PC_OTHER = 2, PC_GRU = 3 };
@@ -388,91 +388,104 @@ static double direct_flops(int dl, const DirectArgs &a)
 {
     return 2.0 * a.n_img * a.Hout * a.Wout * (double)DLS[dl].cout * (double)DLS[dl].cin * 9.0;
 }
+// algorithmic bytes of a launch: every input and output element once at 4 bytes (fp32, or split bf16 = 2 x 2 bytes); weights
+// (<= 1.3 MB per layer, L2-resident) are not counted
+static double tc_bytes(const ConvTCArgs &a)
+{
+    return 4.0 * a.n_img * a.H * a.W * ((double)a.nkb * 64.0 / a.ntaps + (double)a.cout);
+}
+static double direct_bytes(int dl, const DirectArgs &a)
+{
+    const double in_px = a.Hin > 0 ? (double)a.Hin * a.Win : (double)a.Hout * a.Wout;
+    return 4.0 * a.n_img * (in_px * DLS[dl].cin + (double)a.Hout * a.Wout * DLS[dl].cout);
+}
 
 static int forward(Net &n, const float *input, const int *in_img, float *output, cudaStream_t st, Prof *prof = nullptr)
 {
     int rc;
-#define RUNC(cls_, flops_, x)                                                              \
+#define RUNC(name_, cls_, flops_, bytes_, x)                                               \
     do {                                                                                   \
         Prof::Entry pe{};                                                                  \
         if (prof) {                                                                        \
             cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1);                              \
-            pe.cls = (cls_); pe.flops = (flops_);                                          \
+            pe.cls = (cls_); pe.flops = (flops_); pe.bytes = (bytes_); pe.name = (name_);  \
             cudaEventRecord(pe.e0, st);                                                    \
         }                                                                                  \
         rc = (x);                                                                          \
         if (prof) { cudaEventRecord(pe.e1, st); prof->entries.push_back(pe); }             \
         if (rc) return rc;                                                                 \
     } while (0)
-#define RUN(x) RUNC(PC_OTHER, 0.0, x)
-#define RUNT(args) RUNC(PC_TC, tc_flops(args), conv_tc_launch(args, st))
-#define RUND(kind, dl, args) RUNC(PC_DIRECT, direct_flops(dl, args), conv_direct(kind, args, st))
+#define RUN(name_, bytes_, x) RUNC(name_, PC_OTHER, 0.0, bytes_, x)
+#define RUNT(name_, args) RUNC(name_, PC_TC, tc_flops(args), tc_bytes(args), conv_tc_launch(args, st))
+#define RUND(name_, kind, dl, args) RUNC(name_, PC_DIRECT, direct_flops(dl, args), direct_bytes(dl, args), conv_direct(kind, args, st))
     const int B = n.B, N = n.N, VB = n.VB, VN = VB * N, nf = (N - 1) * VB, nsteps = n.Wn * N;
     const ParamLayout &L = param_layout();
     // ---- per-frame work, once per bank frame: head + encoder (models/model.py:329-331) and the three attention maps
     //      of scale_aggre (model.py:259-262), which depend on the encoder features only
+    const double px = (double)n.h * n.w;             // feature-resolution pixels per image
     DirectArgs a = n.d[D_ENC0]; a.in_f32 = input; a.in_img = in_img;
-    RUNC(PC_DIRECT, direct_flops(D_ENC0, a) + 2.0 * a.n_img * n.Hc * n.Wc * 8.0 * 2.0 * 9.0, conv_direct(DK_HEAD_ENC0, a, st));
-    RUND(DK_ENC1, D_ENC1, n.d[D_ENC1]);
-    RUND(DK_ENC2, D_ENC2, n.d[D_ENC2]);
-    RUNT(n.c_at0);
-    RUND(DK_ATT32, D_AT1, n.d[D_AT1]);
-    RUND(DK_ATT16, D_AT2, n.d[D_AT2]);
+    RUNC("head+enc0", PC_DIRECT, direct_flops(D_ENC0, a) + 2.0 * a.n_img * n.Hc * n.Wc * 8.0 * 2.0 * 9.0,
+         4.0 * a.n_img * ((double)n.H * n.W * 2.0 + (double)a.Hout * a.Wout * 16.0), conv_direct(DK_HEAD_ENC0, a, st));
+    RUND("enc1", DK_ENC1, D_ENC1, n.d[D_ENC1]);
+    RUND("enc2", DK_ENC2, D_ENC2, n.d[D_ENC2]);
+    RUNT("atten0", n.c_at0);
+    RUND("atten1", DK_ATT32, D_AT1, n.d[D_AT1]);
+    RUND("atten2", DK_ATT16, D_AT2, n.d[D_AT2]);
     // ---- TimePropagation.local_time_corre for every window (model.py:77-89,133-146)
-    RUNT(n.c_pm0);
-    RUNT(n.c_pm1);
-    RUN(ltc_cat(n.F, n.maps, n.m_ltc5, VN, n.t_cat, st));
-    RUNT(n.c_lf1);
-    RUNT(n.c_lf2);
-    RUNT(n.c_lf3);
+    RUNT("pred_map0", n.c_pm0);
+    RUNT("pred_map1", n.c_pm1);
+    RUN("ltc_cat", 4.0 * VN * px * (192.0 + 192.0 + 2.0), ltc_cat(n.F, n.maps, n.m_ltc5, VN, n.t_cat, st));
+    RUNT("local_fusion.res.conv1", n.c_lf1);
+    RUNT("local_fusion.res.conv2", n.c_lf2);
+    RUNT("local_fusion.conv", n.c_lf3);
     // ---- TimePropagation.global_time_corre: bidirectional ConvGRU (model.py:91-124); the only serial part:
     //      window after window, step after step, both directions batched as 2B images
-    RUNT(n.c_gx);
+    RUNT("gru.xconv", n.c_gx);
     if (n.gru_plan) {
-        double fl = 0.0;
-        for (int g = 0; g < nsteps; ++g) fl += tc_flops(n.c_gzr[g]) + tc_flops(n.c_go[g]);
-        RUNC(PC_GRU, fl, gru_chain_launch(n.gru_plan, st));
+        double fl = 0.0, by = 0.0;
+        for (int g = 0; g < nsteps; ++g) { fl += tc_flops(n.c_gzr[g]) + tc_flops(n.c_go[g]); by += tc_bytes(n.c_gzr[g]) + tc_bytes(n.c_go[g]); }
+        RUNC("gru.chain", PC_GRU, fl, by, gru_chain_launch(n.gru_plan, st));
     } else {
         for (int g = 0; g < nsteps; ++g) {
-            RUNT(n.c_gzr[g]);
-            RUNT(n.c_go[g]);
+            RUNT("gru.zr", n.c_gzr[g]);
+            RUNT("gru.out", n.c_go[g]);
         }
     }
-    RUNT(n.c_gf);
+    RUNT("global_fusion", n.c_gf);
     // carried states: the last slot becomes slot 0 of the next call
-    RUN(copy_split(view_imgs(n.hs, nsteps * 2 * B), nullptr, 2 * B, view_imgs(n.hs, 0), st));
+    RUN("state_carry", 4.0 * 2 * B * px * 128.0, copy_split(view_imgs(n.hs, nsteps * 2 * B), nullptr, 2 * B, view_imgs(n.hs, 0), st));
     // ---- STFusion.fuse for the non-middle frames (model.py:208-231)
-    RUNT(n.c_of0);
-    RUNT(n.c_of1);
-    RUNT(n.c_com);
+    RUNT("offset0", n.c_of0);
+    RUNT("offset1", n.c_of1);
+    RUNT("conv_offset_mask", n.c_com);
     if (n.dcn_plan) {
-        RUNC(PC_TC, 2.0 * 64 * 576 * (double)nf * n.h * n.w, dcn_fused_launch(n.dcn_plan, st));
+        RUNC("dcn_fused", PC_TC, 2.0 * 64 * 576 * (double)nf * px, 4.0 * nf * px * (64.0 + 216.0 + 64.0), dcn_fused_launch(n.dcn_plan, st));
     } else {
-        RUN(dcn_columns(n.tp, n.m_f0, n.om, nf, n.cols, st));
-        RUNT(n.c_dcn);
+        RUN("dcn_columns", 4.0 * nf * px * (64.0 + 216.0 + 576.0), dcn_columns(n.tp, n.m_f0, n.om, nf, n.cols, st));
+        RUNT("dcn_gemm", n.c_dcn);
     }
-    RUNT(n.c_cb0);
-    RUNT(n.c_cb1);
-    RUNT(n.c_ker);
-    RUN(chan_max(n.feat, nf, n.mx, st));
-    RUN(attn_mlp(n.mx, nf, (const float *)(n.params + L.fc0w), (const float *)(n.params + L.fc0b),
+    RUNT("convblock0", n.c_cb0);
+    RUNT("convblock1", n.c_cb1);
+    RUNT("spatial_kernel", n.c_ker);
+    RUN("chan_max", 4.0 * nf * px * 64.0, chan_max(n.feat, nf, n.mx, st));
+    RUN("attn_mlp", 4.0 * nf * 192.0, attn_mlp(n.mx, nf, (const float *)(n.params + L.fc0w), (const float *)(n.params + L.fc0b),
                  (const float *)(n.params + L.fc1w), (const float *)(n.params + L.fc1b), n.ck, st));
-    RUN(attn_apply(n.aligned, n.tp, n.m_fm, n.sk, n.ck, nf, n.ycat, st));
-    RUNT(n.c_df0);
-    RUNT(n.c_df1);
+    RUN("attn_apply", 4.0 * nf * px * (64.0 + 64.0 + 2.0 + 128.0), attn_apply(n.aligned, n.tp, n.m_fm, n.sk, n.ck, nf, n.ycat, st));
+    RUNT("dcn_fusion0", n.c_df0);
+    RUNT("dcn_fusion1", n.c_df1);
     // ---- dense fusion (model.py:233-251)
-    RUNT(n.c_dn0);
-    RUNT(n.c_dn1);
+    RUNT("dense_fusion0", n.c_dn0);
+    RUNT("dense_fusion1", n.c_dn1);
     // ---- scale aggregation + reconstruction x3 (model.py:253-291), tail (model.py:337)
-    RUN(scale_aggregate(n.x0, n.F, n.att0, n.m_fr, VB, N, n.pre0, st));
-    RUN(upsample2x(n.pre0, VB, n.up0, st));
-    RUNT(n.c_rc0);
-    RUN(scale_aggregate(n.x1, n.t_e1, n.att1, n.m_fr, VB, N, n.pre1, st));
-    RUND(DK_RECON1, D_RC1, n.d[D_RC1]);
-    RUN(scale_aggregate(n.x2, n.t_e0, n.att2, n.m_fr, VB, N, n.pre2, st));
-    RUND(DK_RECON2, D_RC2, n.d[D_RC2]);
+    RUN("scale_aggre0", 4.0 * VB * px * (64.0 * (2 + N) + N), scale_aggregate(n.x0, n.F, n.att0, n.m_fr, VB, N, n.pre0, st));
+    RUN("upsample2x", 4.0 * VB * px * 64.0 * 5.0, upsample2x(n.pre0, VB, n.up0, st));
+    RUNT("recons0", n.c_rc0);
+    RUN("scale_aggre1", 4.0 * VB * 4.0 * px * (32.0 * (2 + N) + N), scale_aggregate(n.x1, n.t_e1, n.att1, n.m_fr, VB, N, n.pre1, st));
+    RUND("recons1", DK_RECON1, D_RC1, n.d[D_RC1]);
+    RUN("scale_aggre2", 4.0 * VB * 16.0 * px * (16.0 * (2 + N) + N), scale_aggregate(n.x2, n.t_e0, n.att2, n.m_fr, VB, N, n.pre2, st));
+    RUND("recons2", DK_RECON2, D_RC2, n.d[D_RC2]);
     a = n.d[D_TAIL]; a.out_f32 = output;
-    RUND(DK_TAIL, D_TAIL, a);
+    RUNC("tail", PC_DIRECT, direct_flops(D_TAIL, a), 4.0 * a.n_img * ((double)n.Hc * n.Wc * 8.0 + (double)n.H * n.W * 2.0), conv_direct(DK_TAIL, a, st));
 #undef RUN
 #undef RUNT
 #undef RUND
@@ -586,7 +599,7 @@ extern "C" int esr_net_forward(esr_net_t net, const float *input, const int32_t 
 
 extern "C" int esr_net_forward_profiled(esr_net_t net, const float *input, const int32_t *in_img, float *output,
                                         int max_entries, int *n_entries_host, int *cls_host, float *ms_host,
-                                        double *flops_host, esr_stream_t stream)
+                                        double *flops_host, double *bytes_host, char *names_host, esr_stream_t stream)
 {
     ESR_REQUIRE(net && input && output && n_entries_host && cls_host && ms_host && flops_host, "esr_net_forward_profiled: null pointer");
     Prof prof;
@@ -597,7 +610,12 @@ extern "C" int esr_net_forward_profiled(esr_net_t net, const float *input, const
     for (auto &pe : prof.entries) {
         float ms = 0.0f;
         if (e == cudaSuccess) cudaEventElapsedTime(&ms, pe.e0, pe.e1);
-        if (k < max_entries) { cls_host[k] = pe.cls; ms_host[k] = ms; flops_host[k] = pe.flops; ++k; }
+        if (k < max_entries) {
+            cls_host[k] = pe.cls; ms_host[k] = ms; flops_host[k] = pe.flops;
+            if (bytes_host) bytes_host[k] = pe.bytes;
+            if (names_host) { snprintf(names_host + 32 * k, 32, "%s", pe.name ? pe.name : ""); }
+            ++k;
+        }
         cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1);
     }
     *n_entries_host = k;

@@ -33,6 +33,7 @@ struct ConvTCArgs {
     int n_src, ntaps, nkb, npad, cout;
     int H, W, TW, TH, tiles_x, tiles_y, n_img;
     int stages;
+    int diag;                       // measurement aid (ESR_TC_DIAG): bit 0 = do not load the lo plane of B, bit 1 = not the lo plane of A (wrong results)
     // epilogue
     const float *bias;              // [npad]
     int act, act_from, res_mode, epi_mode;

@@ -171,10 +171,12 @@ int esr_net_reset_states(esr_net_t net, esr_stream_t stream);
 int esr_net_forward(esr_net_t net, const float *input, const int32_t *in_img, float *output, esr_stream_t stream);
 /* Same as esr_net_forward, but brackets every kernel launch with CUDA events on `stream`, synchronises, and reports
  * per-launch {class (0 tensor-core conv, 1 CUDA-core conv, 2 element-wise/sampling, 3 cooperative ConvGRU chain),
- * milliseconds, algorithmic FLOPs}
- * into host arrays (measurement aid for bench.py's roofline object; not on the production path). */
+ * milliseconds, algorithmic FLOPs, algorithmic bytes (every input / output element once at 4 bytes), layer name (32 chars each)}
+ * into host arrays (measurement aid for bench.py's roofline objects; not on the production path).  bytes_host / names_host
+ * may be null. */
 int esr_net_forward_profiled(esr_net_t net, const float *input, const int32_t *in_img, float *output, int max_entries,
-                             int *n_entries_host, int *cls_host, float *ms_host, double *flops_host, esr_stream_t stream);
+                             int *n_entries_host, int *cls_host, float *ms_host, double *flops_host, double *bytes_host,
+                             char *names_host, esr_stream_t stream);
 /* states: fp32 [2,B,64,H/8,W/8] (forward-direction state, reverse-direction state), the reference's self.states */
 int esr_net_get_states(esr_net_t net, float *states, esr_stream_t stream);
 int esr_net_set_states(esr_net_t net, const float *states, esr_stream_t stream);
