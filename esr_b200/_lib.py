@@ -72,7 +72,16 @@ SIGNATURES.update({
 
 
 SIGNATURES.update({
+    "esr_ts_search": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p]),
+    "esr_gather_events": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_i64, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "esr_metrics_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "esr_metrics_planes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
+})
+
+SIGNATURES.update({
     "esr_dcn_v2_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "esr_dcn_v2_workspace_bytes_ex": (c_size_t, [c_int] * 11),
     "esr_dcn_v2_backward_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "esr_dcn_v2_backward": (c_int, [c_void_p] * 6 + [c_int] * 10 + [c_void_p] * 6 + [c_size_t, c_void_p]),
     "esr_dcn_v2_forward": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -89,6 +98,7 @@ SIGNATURES.update({
     "esr_gru_blend_backward": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 4),
     "esr_mse_loss": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_float, c_void_p]),
     "esr_adam_step": (c_int, [c_void_p] * 5 + [c_size_t, c_void_p] + [c_float] * 5 + [c_void_p]),
+    "esr_adam_step_dev": (c_int, [c_void_p] * 5 + [c_size_t, c_void_p, c_void_p, c_void_p]),
 })
 
 

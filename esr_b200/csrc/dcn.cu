@@ -134,17 +134,23 @@ extern "C" size_t esr_dcn_v2_workspace_bytes(int B, int H, int W)
     return dcn_ws_layout(B, H, W, &a, &b, &c, &d, &e, &f);
 }
 
+extern "C" size_t esr_dcn_v2_workspace_bytes_ex(int B, int C, int H, int W, int Co, int kernel, int stride, int pad, int dilation,
+                                                int deformable_group, int backward)
+{
+    if (dcn_is_tuned(C, Co, kernel, stride, pad, dilation, deformable_group))
+        return backward ? esr_dcn_v2_backward_workspace_bytes(B, H, W) : esr_dcn_v2_workspace_bytes(B, H, W);
+    return dcn_generic_ws_bytes(B, C, H, W, Co, kernel, stride, pad, dilation, deformable_group, backward);
+}
+
 extern "C" int esr_dcn_v2_forward(const float *input, const float *weight, const float *bias, const float *offset,
                                   const float *mask, int B, int C, int H, int W, int Co, int kernel, int stride, int pad,
                                   int dilation, int deformable_group, float *output, void *workspace, size_t ws_bytes,
                                   esr_stream_t stream)
 {
     ESR_REQUIRE(input && weight && bias && offset && mask && output && workspace, "esr_dcn_v2_forward: null pointer");
-    if (!(C == 64 && Co == 64 && kernel == 3 && stride == 1 && pad == 1 && dilation == 1 && deformable_group == 8)) {
-        set_error("esr_dcn_v2_forward: only the configuration ESR uses is implemented (64->64, 3x3, s1 p1 d1, 8 groups; "
-                  "models/model.py:173); got C=%d Co=%d k=%d s=%d p=%d d=%d g=%d", C, Co, kernel, stride, pad, dilation, deformable_group);
-        return ESR_EUNSUPPORTED;
-    }
+    if (!dcn_is_tuned(C, Co, kernel, stride, pad, dilation, deformable_group))      // any other configuration: dcn_generic.cu
+        return dcn_generic_forward(input, weight, bias, offset, mask, B, C, H, W, Co, kernel, stride, pad, dilation, deformable_group,
+                                   output, workspace, ws_bytes, (cudaStream_t)stream);
     size_t o_feat, o_om, o_cols, o_out, o_w, o_b;
     const size_t need = dcn_ws_layout(B, H, W, &o_feat, &o_om, &o_cols, &o_out, &o_w, &o_b);
     if (ws_bytes < need) { set_error("esr_dcn_v2_forward: workspace %zu < %zu", ws_bytes, need); return ESR_EWORKSPACE; }

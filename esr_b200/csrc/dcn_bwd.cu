@@ -197,10 +197,10 @@ extern "C" int esr_dcn_v2_backward(const float *input, const float *weight, cons
     (void)bias;
     ESR_REQUIRE(input && weight && offset && mask && grad_output && grad_input && grad_offset && grad_mask && grad_weight &&
                 grad_bias && workspace, "esr_dcn_v2_backward: null pointer");
-    if (!(C == 64 && Co == 64 && kernel == 3 && stride == 1 && pad == 1 && dilation == 1 && deformable_group == 8)) {
-        set_error("esr_dcn_v2_backward: only the configuration ESR uses is implemented (64->64, 3x3, s1 p1 d1, 8 groups)");
-        return ESR_EUNSUPPORTED;
-    }
+    if (!dcn_is_tuned(C, Co, kernel, stride, pad, dilation, deformable_group))      // any other configuration: dcn_generic.cu
+        return dcn_generic_backward(input, weight, offset, mask, grad_output, B, C, H, W, Co, kernel, stride, pad, dilation,
+                                    deformable_group, grad_input, grad_offset, grad_mask, grad_weight, grad_bias, workspace, ws_bytes,
+                                    (cudaStream_t)stream);
     const DcnBwdWs L = dcn_bwd_layout(B, H, W);
     if (ws_bytes < L.total) { set_error("esr_dcn_v2_backward: workspace %zu < %zu", ws_bytes, L.total); return ESR_EWORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;

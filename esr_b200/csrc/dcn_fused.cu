@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
         mbar_init(bar_accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             for (int t = 0; t < 9; ++t) {
                 const uint32_t s = t & 1, ph = (t >> 1) & 1;
                 mbar_wait_backoff(bar_bempty + 8u * s, ph ^ 1u);
@@ -83,22 +83,22 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64);
+        if (elect_one_sync()) {
+            const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64), idesc2 = umma_idesc(TC_BLOCK_M, 128);
             for (int t = 0; t < 9; ++t) {
                 const uint32_t s = t & 1, ph = (t >> 1) & 1;
                 mbar_wait_backoff(bar_afull + 8u * s, ph);          // the samplers take microseconds per tap
                 mbar_wait(bar_bfull + 8u * s, ph);
                 tc_fence_after();
                 const uint32_t a_hi = a_ring + s * DF_A_STAGE, a_lo = a_hi + TC_A_BYTES;
-                const uint32_t b_hi = b_ring + s * DF_B_STAGE, b_lo = b_hi + DF_B_BYTES;
+                const uint32_t b_hi = b_ring + s * DF_B_STAGE;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
-                    umma_bf16(tmem_base, dal, dbh, idesc, (t | k) != 0 ? 1u : 0u);
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+                    // stacked weights (tc_conv.cu, ConvTCArgs::stack): [B_hi; B_lo] are adjacent -> one N = 128 operand
+                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k);
+                    umma_bf16(tmem_base, dah, dbh, idesc2, (t | k) != 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, dal, dbh, idesc, 1u);
                 }
                 umma_commit(bar_aempty + 8u * s);
                 umma_commit(bar_bempty + 8u * s);
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
         mbar_wait(bar_accum, 0);
         tc_fence_after();
         uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), raw);
+        tmem_ld_chunk_stacked(tmem_base + ((uint32_t)(quad * 32) << 16), half * 32, 64, raw);
         if (valid) {
             float v[32];
             const float4 *bp = reinterpret_cast<const float4 *>(a.bias + half * 32);
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_co
         mbar_init(bar_accum, 1); mbar_init(bar_win, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_co
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(bar_win, 2u * (uint32_t)(a.WW * a.WH) * 128u);
             tma_load_5d(&a.wmap, bar_win, win_base, 0, wx0, wy0, fimg, 0);
             tma_load_5d(&a.wmap, bar_win, win_base + win_plane, 0, wx0, wy0, fimg, 1);
@@ -271,22 +271,22 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_co
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64);
+        if (elect_one_sync()) {
+            const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64), idesc2 = umma_idesc(TC_BLOCK_M, 128);
             for (int t = 0; t < 9; ++t) {
                 const uint32_t s = t & 1, ph = (t >> 1) & 1;
                 mbar_wait(bar_afull + 8u * s, ph);
                 mbar_wait(bar_bfull + 8u * s, ph);
                 tc_fence_after();
                 const uint32_t a_hi = a_ring + s * DF_A_STAGE, a_lo = a_hi + TC_A_BYTES;
-                const uint32_t b_hi = b_ring + s * DF_B_STAGE, b_lo = b_hi + DF_B_BYTES;
+                const uint32_t b_hi = b_ring + s * DF_B_STAGE;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
-                    umma_bf16(tmem_base, dal, dbh, idesc, (t | k) != 0 ? 1u : 0u);
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+                    // stacked weights (tc_conv.cu, ConvTCArgs::stack): [B_hi; B_lo] are adjacent -> one N = 128 operand
+                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k);
+                    umma_bf16(tmem_base, dah, dbh, idesc2, (t | k) != 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, dal, dbh, idesc, 1u);
                 }
                 umma_commit(bar_aempty + 8u * s);
                 umma_commit(bar_bempty + 8u * s);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_co
         mbar_wait(bar_accum, 0);
         tc_fence_after();
         uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32), raw);
+        tmem_ld_chunk_stacked(tmem_base + ((uint32_t)(quad * 32) << 16), half * 32, 64, raw);
         if (valid) {
             float v[32];
             const float4 *bp = reinterpret_cast<const float4 *>(a.bias + half * 32);
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_co
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
 struct DcnFusedPlan { DcnFusedArgs args; unsigned grid; size_t smem; bool window; };

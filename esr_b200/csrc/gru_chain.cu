@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
             const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
             const int hs_img = g * B2 + img;
             if (warp == 0) {
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     for (int kb = 0; kb < 18; ++kb) {
                         const int src = kb / 9, tap = kb - src * 9;
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
                     }
                 }
             } else if (warp == 1) {
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t idesc = umma_idesc(TC_BLOCK_M, npad);
                     for (int kb = 0; kb < 18; ++kb) {
                         mbar_wait(bar_full + 8u * ms, mph);
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t ps = 0, pph = 0;
             for (int p = 0; p < n_phases; ++p) {
                 const int g = p >> 1, which = p & 1;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t ms = 0, mph = 0;
             for (int p = 0; p < n_phases; ++p) {
                 const int npad = (p & 1) == 0 ? 128 : 64;

@@ -78,6 +78,20 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
 int gru_chain_launch(void *plan, cudaStream_t st);
 void gru_chain_destroy(void *plan);
 
+// ---- the operators for any other configuration (dcn_generic.cu): fp32 CUDA-core kernels, reference NCHW layouts
+size_t dcn_generic_ws_bytes(int B, int C, int H, int W, int Co, int kernel, int stride, int pad, int dil, int G, int backward);
+int dcn_generic_forward(const float *input, const float *weight, const float *bias, const float *offset, const float *mask, int B,
+                        int C, int H, int W, int Co, int kernel, int stride, int pad, int dil, int G, float *output,
+                        void *workspace, size_t ws_bytes, cudaStream_t st);
+int dcn_generic_backward(const float *input, const float *weight, const float *offset, const float *mask, const float *grad_output,
+                         int B, int C, int H, int W, int Co, int kernel, int stride, int pad, int dil, int G, float *grad_input,
+                         float *grad_offset, float *grad_mask, float *grad_weight, float *grad_bias, void *workspace,
+                         size_t ws_bytes, cudaStream_t st);
+static inline bool dcn_is_tuned(int C, int Co, int kernel, int stride, int pad, int dil, int G)
+{
+    return C == 64 && Co == 64 && kernel == 3 && stride == 1 && pad == 1 && dil == 1 && G == 8;   // models/model.py:173
+}
+
 // offset [B,144,HW] + mask [B,72,HW] (reference NCHW) -> om [B*HW, 216]
 int om_from_nchw(const float *offset, const float *mask, int B, int HW, float *om, cudaStream_t st);
 

@@ -14,6 +14,22 @@ constexpr int TC_A_BYTES = TC_BLOCK_M * 128;          // one plane of one A tile
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  Unlike `lane == 0`, elect.sync tells ptxas that exactly one thread runs the guarded code, so the
+// uniform-datapath instructions inside (UTCHMMA, UTMALDG, UTCBAR) are emitted directly instead of each being wrapped in an
+// ELECT / BRA.U.ANY loop over the "possibly many" active lanes -- measured on B200: 69-74 cycles per tcgen05.mma issued from an
+// `if (lane == 0)` block, which made the N <= 64 layers issue-bound (profiles/r2_notes.md).
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -99,6 +115,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32])
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(addr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// one epilogue chunk of accumulator columns [n0, n0 + 32) (16 valid columns when fewer remain: npad is a multiple of 16)
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, int n0, int npad, uint32_t (&raw)[32])
+{
+    if (npad - n0 >= 32) {
+        tmem_ld32(taddr + (uint32_t)n0, raw);
+    } else {
+        uint32_t r16[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]),
+                       "=r"(r16[6]), "=r"(r16[7]), "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]),
+                       "=r"(r16[12]), "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
+                     : "r"(taddr + (uint32_t)n0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { raw[j] = r16[j]; raw[16 + j] = 0u; }
+    }
+}
+// "stacked" accumulators (ConvTCArgs::stack): columns [0, npad) hold A_hi.B_hi + A_lo.B_hi, columns [npad, 2 npad) hold A_hi.B_lo
+__device__ __forceinline__ void tmem_ld_chunk_stacked(uint32_t taddr, int n0, int npad, uint32_t (&raw)[32])
+{
+    uint32_t lo[32];
+    tmem_ld_chunk(taddr, n0, npad, raw);
+    tmem_ld_chunk(taddr + (uint32_t)npad, n0, npad, lo);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(lo[j]));
 }
 
 // K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart).

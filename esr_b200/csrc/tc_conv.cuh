@@ -25,7 +25,9 @@ struct ConvTCArgs {
     CUtensorMap amap[TC_MAX_SRC];   // 5-D maps over the source split tensors (C, W, H, img, plane), box (64, TW, TH, 1, 1)
     CUtensorMap bmap;               // 3-D map over packed weights (64, npad, 2*nkb), box (64, npad, 1)
     CUtensorMap bmap_half;          // same tensor, box (64, npad/2, 1): the half a CTA multicasts in a 2-CTA cluster
-    int kernel_ver;                 // 1: tc_conv.cu (tap-shifted tiles), 3: tc_conv3.cu (halo reuse + weight multicast)
+    int kernel_ver;                 // 1: tc_conv.cu (tap-shifted tiles), 3: tc_conv3.cu (halo reuse + weight multicast), 4: tc_conv_halo.cu
+    int stack;                      // 1: [B_hi; B_lo] stacked along N -- two MMAs per K-step (A_hi x [B_hi;B_lo], A_lo x B_hi) instead of three
+    int pair;                       // 1 (with persist): k_conv_tc_pair, two-CTA clusters issuing tcgen05.mma.cta_group::2
     int persist;                    // 1: k_conv_tc_persist (one CTA per SM walks the tiles, two TMEM accumulators)
     int a_stages, cluster;          // v3 only: halo ring depth, cluster size (1 or 2)
     const int *src_img[TC_MAX_SRC]; // output image -> source image (nullptr = identity)
@@ -33,6 +35,7 @@ struct ConvTCArgs {
     int n_src, ntaps, nkb, npad, cout;
     int H, W, TW, TH, tiles_x, tiles_y, n_img;
     int stages;
+    long long *trace;               // measurement aid (ESR_TC_TRACE): clock64 stamps of CTA 0's producer / MMA / epilogue threads
     int diag;                       // measurement aid (ESR_TC_DIAG): bit 0 = do not load the lo plane of B, bit 1 = not the lo plane of A (wrong results)
     // epilogue
     const float *bias;              // [npad]
@@ -76,6 +79,9 @@ int conv_tc_launch(const ConvTCArgs &args, cudaStream_t st);
 // tensor-map builders (shared with gru_chain.cu)
 int tc_make_amap(const SplitTensor &t, int box_w, int box_h, CUtensorMap *out);
 int tc_make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap *out);
+// tc_conv_halo.cu: persistent halo-reuse kernel for multi-wave 3x3 layers (kernel_ver 4)
+bool conv_tc_halo_plan(int npad, int *a_stages, int *b_stages);
+int conv_tc_halo_launch(const ConvTCArgs &args, cudaStream_t st);
 // tc_conv3.cu
 bool conv_tc3_plan(int npad, int *a_stages, int *b_stages);
 int conv_tc3_launch(const ConvTCArgs &args, cudaStream_t st);

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_conv_tc3(const __grid_constan
     const int n_chunks = a.nkb / 9;
     if (warp == 0) {
         // ===================== A producer: one halo box per 64-channel chunk and plane =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t s = 0, ph = 0;
             int src = 0, chunk_base = 0;
             for (int c = 0; c < n_chunks; ++c) {
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_conv_tc3(const __grid_constan
         }
     } else if (warp == 2) {
         // ===================== B producer: weight tiles, multicast across the cluster =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t s = 0, ph = 0;
             const uint32_t half_rows = (uint32_t)a.npad / csize;
             const uint16_t mask = (uint16_t)((1u << csize) - 1u);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_conv_tc3(const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = umma_idesc(TC_BLOCK_M, a.npad);
             const uint16_t mask = (uint16_t)((1u << csize) - 1u);
             uint32_t sa = 0, pha = 0, sb = 0, phb = 0;

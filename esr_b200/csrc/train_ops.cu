@@ -775,8 +775,11 @@ __global__ void k_adam_tick(int *step) { *step += 1; }
 
 __global__ void __launch_bounds__(256) k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                                               float *__restrict__ v, float *__restrict__ vmax, size_t n, float lr, float b1, float b2,
-                                              float eps, float wd, const int *__restrict__ step)
+                                              float eps, float wd, const int *__restrict__ step, const float *__restrict__ hyper)
 {
+    // hyper (optional, device): {lr, beta1, beta2, eps, weight_decay} read at run time, so that a replayed CUDA graph follows a
+    // learning-rate schedule (train_ours_cnt_seq.py:784 esr_lr_scheduler) instead of freezing the values captured with it
+    if (hyper) { lr = hyper[0]; b1 = hyper[1]; b2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; }
     __shared__ float s_bc[2];
     if (threadIdx.x == 0) {                                        // bias corrections from the device-side step counter
         const int t = *step;
@@ -1148,7 +1151,20 @@ int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_av
     k_adam_tick<<<1, 1, 0, st>>>(step_counter);
     ESR_LAUNCH_CHECK();
     k_adam<<<(unsigned)min((size_t)2048, (n + 255) / 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                                        weight_decay, step_counter);
+                                                                        weight_decay, step_counter, nullptr);
+    ESR_LAUNCH_CHECK();
+    return ESR_OK;
+}
+
+int esr_adam_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n,
+                      int32_t *step_counter, const float *hyper, esr_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    ESR_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_counter && hyper && n > 0, "adam_step_dev: bad arguments");
+    k_adam_tick<<<1, 1, 0, st>>>(step_counter);
+    ESR_LAUNCH_CHECK();
+    k_adam<<<(unsigned)min((size_t)2048, (n + 255) / 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, 0.f, 0.f, 0.f, 0.f,
+                                                                        0.f, step_counter, hyper);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             uint32_t gs = 0, gph = 0, xs = 0, xph = 0;
             for (int t = slice; t < n_tiles; t += a.slices) {
                 const int img = t / tiles_per_img, tr = t - img * tiles_per_img;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // MN-major A and B (bits 15, 16), fp32 accumulate, bf16 operands, M = 128, N = 64
             const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64) | (1u << 15) | (1u << 16);
             uint32_t gs = 0, gph = 0, xs = 0, xph = 0;

@@ -29,10 +29,12 @@ def dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride
         raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)." % (C, weight.shape[1]))
     L = _lib.lib()
     args = [t.contiguous() for t in (input, weight, bias, offset, mask)]
-    out = torch.empty((B, Co, H, W), dtype=torch.float32, device=input.device)
+    Ho = (H + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) // stride_h + 1
+    Wo = (W + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) // stride_w + 1
+    out = torch.empty((B, Co, Ho, Wo), dtype=torch.float32, device=input.device)
     with torch.cuda.device(input.device):
-        nbytes = L.esr_dcn_v2_workspace_bytes(B, H, W)
-        ws = torch.empty((nbytes,), dtype=torch.uint8, device=input.device)
+        nbytes = L.esr_dcn_v2_workspace_bytes_ex(B, C, H, W, Co, kernel_h, stride_h, pad_h, dilation_h, deformable_group, 0)
+        ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=input.device)
         rc = L.esr_dcn_v2_forward(*[_lib.ptr(t) for t in args], B, C, H, W, Co, kernel_h, stride_h, pad_h, dilation_h,
                                   deformable_group, _lib.ptr(out), _lib.ptr(ws), nbytes, _lib.stream_ptr())
     if rc != 0:
@@ -55,8 +57,8 @@ def dcn_v2_backward(input, weight, bias, offset, mask, grad_output, kernel_h, ke
     outs = [torch.empty_like(args[0]), torch.empty_like(args[3]), torch.empty_like(args[4]), torch.empty_like(args[1]),
             torch.empty_like(args[2])]
     with torch.cuda.device(input.device):
-        nbytes = L.esr_dcn_v2_backward_workspace_bytes(B, H, W)
-        ws = torch.empty((nbytes,), dtype=torch.uint8, device=input.device)
+        nbytes = L.esr_dcn_v2_workspace_bytes_ex(B, C, H, W, Co, kernel_h, stride_h, pad_h, dilation_h, deformable_group, 1)
+        ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=input.device)
         rc = L.esr_dcn_v2_backward(*[_lib.ptr(t) for t in args], B, C, H, W, Co, kernel_h, stride_h, pad_h, dilation_h,
                                    deformable_group, *[_lib.ptr(t) for t in outs], _lib.ptr(ws), nbytes, _lib.stream_ptr())
     if rc != 0:

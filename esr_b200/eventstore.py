@@ -1,0 +1,272 @@
+"""Columnar event reader feeding the GPU encodings directly.
+
+The reference reads HDF5 event files through h5py, one Python `__getitem__` per frame and per DataLoader worker
+(dataloader/h5dataset.py:32-38, 147-161, 196-270, 451-506; file layout written by
+generate_dataset/tools/event_packagers.py:121-224: groups `{ori,down2,down4,down8,down16}_events/{xs:int16, ys:int16,
+ts:float64, ps:float64}`, `ori_images/image%09d` with a `timestamp` attribute, file attribute `sensor_resolution`).
+At B200 speed (20 k LR frames/s) that loader is the limiter.  Here:
+
+  * `EventStore`  -- the same columns in ONE flat file (4 KiB header with a JSON table, 4 KiB-aligned raw little-endian arrays),
+    opened with numpy.memmap and (optionally) copied once into pinned host memory or HBM.  `convert_hdf5` makes one from a
+    reference HDF5 file where h5py exists (it does not in this image; the converter is import-guarded and says so);
+    `EventStore.write` makes one from arrays (tests, synthetic data).
+  * `WindowIndex` -- H5Dataset's window tables: `compute_k_indices` / `compute_timeblock_indices` / `compute_frame_indices`
+    with the ground-truth alignment of `get_gt_event_indices_num` (h5dataset.py:196-262, 451-475).  Every timestamp lookup of
+    a table is ONE batched launch of esr_ts_search, which reproduces the reference's bisection (exact hit returns the probed
+    index, base_dataset.py:78-91 = binary_search.pyx:17-38) bit for bit.
+  * `SequenceReader` -- SequenceDataset's frame selection (h5dataset.py:729-791, pauses off) for a BATCH of sequences:
+    per-frame slices are gathered from the columns by one kernel launch per event stream (esr_gather_events: int16 / float64
+    -> fp32 SoA + frame offsets) and scattered by esr_b200.encodings.encode_frames into the three frame banks the scripts
+    read, returned in the window layout of HDF5DataLoaderSequence.custom_collate (esr_b200.dataset.collate_sequence's
+    output format) -- no per-frame Python, no per-frame H2D copy.
+There is no CPU fallback for the indexing / gather: they are C-ABI calls on a CUDA device.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, encodings
+
+MAGIC = b"ESRCOL01"
+HEADER_BYTES = 4096
+ALIGN = 4096
+SCALES = ("ori", "down2", "down4", "down8", "down16", "down8_real")
+_DTYPES = {"xs": np.int16, "ys": np.int16, "ts": np.float64, "ps": np.float64}
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class EventStore:
+    """columns[prefix] = {"xs", "ys", "ts", "ps"} numpy (memmap) arrays; image_ts float64 [num_imgs]; sensor_resolution [H, W]."""
+
+    def __init__(self, path):
+        self.path = path
+        with open(path, "rb") as f:
+            head = f.read(HEADER_BYTES)
+        if head[:8] != MAGIC:
+            raise _lib.ESRError(f"{path}: not an ESR columnar event file")
+        n = int.from_bytes(head[8:12], "little")
+        self.meta = json.loads(head[12:12 + n].decode())
+        self.sensor_resolution = list(self.meta["sensor_resolution"])
+        self.columns = {}
+        for prex, cols in self.meta["columns"].items():
+            self.columns[prex] = {c: np.memmap(path, dtype=_DTYPES[c], mode="r", offset=o, shape=(cnt,)) for c, (o, cnt) in cols.items()}
+        o, cnt = self.meta["image_ts"]
+        self.image_ts = np.memmap(path, dtype=np.float64, mode="r", offset=o, shape=(cnt,)) if cnt else np.zeros(0, np.float64)
+        self._resident = {}
+
+    # ---- writing ---------------------------------------------------------------------------------------------------
+    @staticmethod
+    def write(path, columns, sensor_resolution, image_ts=None):
+        """columns: {prefix: {"xs","ys","ts","ps"}} array-likes (cast to the on-disk dtypes of event_packagers.py:129-132)."""
+        image_ts = np.zeros(0, np.float64) if image_ts is None else np.asarray(image_ts, np.float64)
+        table, blobs, off = {}, [], HEADER_BYTES
+        for prex, cols in columns.items():
+            table[prex] = {}
+            n = len(cols["ts"])
+            for c, dt in _DTYPES.items():
+                a = np.ascontiguousarray(np.asarray(cols[c]).astype(dt))
+                assert a.shape == (n,), (prex, c, a.shape)
+                table[prex][c] = (off, int(n))
+                blobs.append((off, a))
+                off = (off + a.nbytes + ALIGN - 1) // ALIGN * ALIGN
+        meta = {"sensor_resolution": [int(v) for v in sensor_resolution], "columns": table, "image_ts": (off, int(len(image_ts)))}
+        blobs.append((off, image_ts))
+        js = json.dumps(meta).encode()
+        assert 12 + len(js) <= HEADER_BYTES, "too many columns for the header"
+        with open(path, "wb") as f:
+            f.write(MAGIC + len(js).to_bytes(4, "little") + js)
+            for o, a in blobs:
+                f.seek(o)
+                f.write(a.tobytes())
+            f.truncate(max(off + image_ts.nbytes, HEADER_BYTES))
+        return path
+
+    # ---- residency -------------------------------------------------------------------------------------------------
+    def resident(self, prex, where="pinned"):
+        """The four columns of `prex` as torch tensors: 'pinned' (page-locked host memory the gather kernel reads through
+        the unified address space, one copy from the page cache), or 'device' (HBM; 20 bytes per event)."""
+        key = (prex, where)
+        if key not in self._resident:
+            out = {}
+            for c, a in self.columns[prex].items():
+                t = torch.from_numpy(np.ascontiguousarray(a))
+                out[c] = t.pin_memory() if where == "pinned" else t.to(_dev())
+            self._resident[key] = out
+        return self._resident[key]
+
+
+def convert_hdf5(h5_path, out_path):
+    """Reference HDF5 event file -> EventStore file.  Needs h5py (absent from the build image: raises ImportError there)."""
+    import h5py  # noqa: F401  (import-guarded on purpose)
+    with h5py.File(h5_path, "r") as f:
+        cols = {}
+        for prex in SCALES:
+            g = f.get(f"{prex}_events")
+            if g is not None:
+                cols[prex] = {c: g[c][:] for c in _DTYPES}
+        img_ts = [f[f"ori_images/{name}"].attrs["timestamp"] for name in f["ori_images"]] if "ori_images" in f else []
+        return EventStore.write(out_path, cols, f.attrs["sensor_resolution"].tolist(), img_ts)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def ts_search(ts_dev, queries):
+    """Batched BaseDataset.binary_search_h5_dset(ts, x) (side='left'): CUDA float64 [n], array-like queries -> numpy int64."""
+    q = torch.as_tensor(np.asarray(queries, dtype=np.float64)).to(ts_dev.device)
+    out = torch.empty((q.numel(),), dtype=torch.int64, device=ts_dev.device)
+    with torch.cuda.device(ts_dev.device):
+        _lib.check(_lib.lib().esr_ts_search(_lib.ptr(ts_dev), ts_dev.numel(), _lib.ptr(q), q.numel(), _lib.ptr(out), _lib.stream_ptr()),
+                   "esr_ts_search")
+    return out.cpu().numpy()
+
+
+def resolutions(sensor_resolution, scale, ori_scale, need_gt_events):
+    """H5Dataset.set_data_scale (h5dataset.py:30-137) for the synthetic-data branches: -> (inp_res, gt_res, inp_prex, gt_prex)."""
+    div = {"ori": 1, "down2": 2, "down4": 4, "down8": 8, "down16": 16}
+    if ori_scale not in div:
+        raise Exception(f"Error scale setting: scale {scale}, ori_scale {ori_scale}")
+    d = div[ori_scale]
+    inp_res = [round(i / d) for i in sensor_resolution]
+    if not need_gt_events:
+        return inp_res, [round(i * scale) for i in inp_res], ori_scale, ori_scale
+    if scale > d or d % scale or (d // scale) not in (1, 2, 4, 8):
+        raise Exception(f"Error scale setting: scale {scale}, ori_scale {ori_scale}")
+    gd = d // scale
+    return inp_res, [round(i / gd) for i in sensor_resolution], ori_scale, {1: "ori", 2: "down2", 4: "down4", 8: "down8"}[gd]
+
+
+class WindowIndex:
+    """The (idx0, idx1) / (gt_idx0, gt_idx1) tables of H5Dataset.set_data_mode (h5dataset.py:163-262)."""
+
+    def __init__(self, store, config):
+        self.store, self.config = store, config
+        self.scale, self.need_gt_events = config["scale"], config.get("need_gt_events", False)
+        self.inp_res, self.gt_res, self.inp_prex, self.gt_prex = resolutions(store.sensor_resolution, self.scale, config["ori_scale"],
+                                                                           self.need_gt_events)
+        inp_ts = store.columns[self.inp_prex]["ts"]
+        self.num_events = len(inp_ts)
+        self.num_gt_events = len(store.columns[self.gt_prex]["ts"]) if self.need_gt_events else None
+        self.t0, self.tk = float(inp_ts[0]), float(inp_ts[-1])
+        self.window, self.sliding_window = config["window"], config["sliding_window"]
+        dev = _dev()
+        self._inp_ts_dev = torch.from_numpy(np.ascontiguousarray(inp_ts)).to(dev)
+        self._gt_ts_dev = torch.from_numpy(np.ascontiguousarray(store.columns[self.gt_prex]["ts"])).to(dev) if self.need_gt_events else None
+        mode, dl = config["mode"], config.get("dataset_length", None)
+        step = self.window - self.sliding_window
+        if mode == "events":
+            max_length = max(int(self.num_events / step), 0)
+        elif mode == "time":
+            max_length = max(int((self.tk - self.t0) / step), 0)
+        elif mode == "frame":
+            max_length = len(store.image_ts) - 1
+        else:
+            raise Exception("Invalid data mode chosen ({})".format(mode))
+        self.length = (dl if dl <= max_length else max_length) if dl is not None else max_length
+        if self.length == 0:
+            raise Exception("Current voxel generation parameters lead to sequence length of zero")
+        i = np.arange(self.length, dtype=np.int64)
+        if mode == "events":                                             # compute_k_indices
+            idx0 = step * i
+            idx1 = np.minimum(idx0 + self.window, self.num_events - 1)
+        else:
+            if mode == "time":                                           # compute_timeblock_indices
+                ends = (step * i.astype(np.float64) + self.t0) + self.window
+            else:                                                        # compute_frame_indices
+                ends = np.asarray(store.image_ts[:self.length], np.float64)
+            idx1 = np.minimum(ts_search(self._inp_ts_dev, ends), self.num_events - 1)       # find_ts_index
+            idx0 = np.concatenate([[0], idx1[:-1]])
+        self.event_indices = np.stack([idx0, idx1], 1).astype(np.int64)
+        self.gt_event_indices = self._gt_num(idx0, idx1) if self.need_gt_events else None
+
+    def _gt_num(self, idx0, idx1):
+        """get_gt_event_indices_num (h5dataset.py:451-475), all windows at once."""
+        n_gt = self.scale ** 2 * (idx1 - idx0)
+        t0 = np.asarray(self.store.columns[self.inp_prex]["ts"])[idx0]
+        g0 = ts_search(self._gt_ts_dev, t0)
+        g1 = g0 + n_gt
+        neg = g0 < 0
+        g0 = np.where(neg, 0, g0)
+        g1 = np.where(neg, g0 + n_gt, g1)
+        over = g1 > self.num_gt_events - 1
+        g1 = np.where(over, self.num_gt_events - 1, g1)
+        g0 = np.where(over, g1 - n_gt, g0)
+        if not (np.all(g0 >= 0) and np.all(g1 < self.num_gt_events)):
+            bad = int(np.argmax(~((g0 >= 0) & (g1 < self.num_gt_events))))
+            raise Exception("WARNING: GT event indices {},{} out of bounds 0,{}".format(int(g0[bad]), int(g1[bad]), self.num_gt_events))
+        return np.stack([g0, g1], 1).astype(np.int64)
+
+    def __len__(self):
+        return self.length
+
+
+class SequenceReader:
+    """Batched SequenceDataset (h5dataset.py:729-791; pause.enabled = False) + custom_collate on the GPU."""
+
+    def __init__(self, store, config, where="pinned"):
+        self.index = WindowIndex(store, config)
+        seq = config["sequence"]
+        self.L = seq["sequence_length"]
+        self.step_size = seq["step_size"] if seq.get("step_size") is not None else self.L
+        assert self.L > 0 and self.step_size > 0
+        if seq.get("pause", {}).get("enabled", False):
+            raise _lib.ESRError("SequenceReader: random pauses are a training augmentation of the CPU loader, not implemented")
+        if self.L >= self.index.length:
+            self.length, self.L = 1, self.index.length
+        else:
+            self.length = (self.index.length - self.L) // self.step_size + 1
+        self.num_frame = seq.get("seqn", 3)
+        self.inp_cols = store.resident(self.index.inp_prex, where)
+        self.gt_cols = store.resident(self.index.gt_prex, where) if self.index.need_gt_events else None
+        self.inp_sensor_resolution, self.gt_sensor_resolution = self.index.inp_res, self.index.gt_res
+
+    def __len__(self):
+        return self.length
+
+    def _gather(self, cols, table, frames, need_ts=False):
+        """table [len, 2]; frames: flat list of dataset indices -> (xs, ys, ts|None, ps, off) CUDA fp32 SoA + int64 offsets."""
+        dev = _dev()
+        start = torch.from_numpy(np.ascontiguousarray(table[frames, 0]))
+        lens = table[frames, 1] - table[frames, 0]
+        off = np.zeros(len(frames) + 1, dtype=np.int64)
+        off[1:] = np.cumsum(lens)
+        total, mx = int(off[-1]), int(lens.max(initial=1))
+        start_d, off_d = start.to(dev), torch.from_numpy(off).to(dev)
+        oxs, oys, ops = (torch.empty((max(total, 1),), dtype=torch.float32, device=dev) for _ in range(3))
+        ots = torch.empty((max(total, 1),), dtype=torch.float32, device=dev) if need_ts else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().esr_gather_events(_lib.ptr(cols["xs"]), _lib.ptr(cols["ys"]), _lib.ptr(cols["ts"]), _lib.ptr(cols["ps"]),
+                                                    _lib.ptr(start_d), _lib.ptr(off_d), len(frames), mx, _lib.ptr(oxs), _lib.ptr(oys),
+                                                    _lib.ptr(ots), _lib.ptr(ops), _lib.stream_ptr()), "esr_gather_events")
+        return oxs[:total], oys[:total], (ots[:total] if need_ts else None), ops[:total], off_d, mx
+
+    def frames_of(self, seq_indices):
+        return np.array([i * self.step_size + k for i in seq_indices for k in range(self.L)], dtype=np.int64)
+
+    def load_batch(self, seq_indices):
+        """-> the L - num_frame + 1 window dicts of custom_collate for sequences `seq_indices` ('inp_cnt', 'inp_scaled_cnt',
+        'gt_cnt' as [B, N, 2, ., .] views of frame banks, 'bank' = the [B, L, 2, ., .] banks for forward_sequence / train_step)."""
+        for i in seq_indices:
+            assert 0 <= i < self.length
+        B, L = len(seq_indices), self.L
+        frames = self.frames_of(seq_indices)
+        ix, iy, _, ip, ioff, imax = self._gather(self.inp_cols, self.index.event_indices, frames)
+        H, W = self.inp_sensor_resolution
+        kH, kW = self.gt_sensor_resolution
+        inp_cnt = encodings.encode_frames(ix, iy, ip, ioff, None, (H, W), imax).view(B, L, 2, H, W)
+        inp_scaled = encodings.encode_frames(ix, iy, ip, ioff, (H, W), (kH, kW), imax).view(B, L, 2, kH, kW)
+        bank = {"inp_cnt": inp_cnt, "inp_scaled_cnt": inp_scaled}
+        if self.gt_cols is not None:
+            gx, gy, _, gp, goff, gmax = self._gather(self.gt_cols, self.index.gt_event_indices, frames)
+            bank["gt_cnt"] = encodings.encode_frames(gx, gy, gp, goff, None, (kH, kW), gmax).view(B, L, 2, kH, kW)
+        N = self.num_frame
+        return [dict({k: v[:, w:w + N] for k, v in bank.items()}, bank=bank) for w in range(L - N + 1)]
+
+    def events_of_frame(self, frame, gt=False):
+        """One frame's formatted events [4, n] fp32 on the GPU = BaseDataset.event_formatting(H5Dataset.get_events(idx0, idx1))."""
+        cols, table = (self.gt_cols, self.index.gt_event_indices) if gt else (self.inp_cols, self.index.event_indices)
+        xs, ys, ts, ps, _, _ = self._gather(cols, table, np.array([frame], dtype=np.int64), need_ts=True)
+        return torch.stack([xs, ys, ts, ps])

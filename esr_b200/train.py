@@ -387,20 +387,29 @@ def forward_window(model, inp, states=None):
 # ------------------------------------------------------------------------------------------------------------------
 # optimizer and the step
 # ------------------------------------------------------------------------------------------------------------------
-class Adam:
+class Adam(torch.optim.Optimizer):
     """torch.optim.Adam(params, lr, betas, eps, weight_decay, amsgrad) semantics (the reference's optimizer,
     train_ours_cnt_seq.py:781 + config optimizer args) with one kernel launch per step: parameters and gradients are
-    re-homed as views of two flat fp32 buffers (so DDP buckets and the update see contiguous memory); the step counter
-    is a device int the kernel increments itself, so a captured CUDA graph of the step stays correct on replay."""
+    re-homed as views of two flat fp32 buffers (so the gradient exchange and the update see contiguous memory); the step
+    counter and the hyper-parameters live on the device (the kernel reads them when it runs), so a captured CUDA graph of the
+    step stays correct on replay AND follows a learning-rate schedule.
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False):
+    `param_groups` is the single group torch schedulers read and write (`torch.optim.lr_scheduler.*` only touch
+    `optimizer.param_groups[i]['lr']`, `initial_lr`): every step() / graph replay uploads lr, betas, eps and weight_decay from
+    it.  `log_slots` extra floats ride at the tail of the gradient buffer (`exchange`): the trainer's logging scalars
+    (train_ours_cnt_seq.py:238-239: last-window MSE, summed loss) take part in the ONE all-reduce of the iteration instead of
+    two extra barrier + all-reduce pairs (myutils/utils.py:43-54) and the per-step dist.barrier (:339)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, log_slots=2):
         self.params = [p for p in params if p.requires_grad]
         if not self.params or not self.params[0].is_cuda:
             raise _lib.ESRError("esr_b200.train.Adam needs CUDA parameters")
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
         self.flat = torch.empty((n,), dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.exchange = torch.zeros((n + int(log_slots),), dtype=torch.float32, device=dev)   # gradients | logging scalars
+        self.flat_grad = self.exchange[:n]
+        self.log = self.exchange[n:]
         off = 0
         for p in self.params:
             k = p.numel()
@@ -410,12 +419,32 @@ class Adam:
             off += k
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
         self.max_exp_avg_sq = torch.zeros_like(self.flat) if amsgrad else None
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)   # step counter lives on the device (graph replays)
-        self.param_groups = [dict(params=self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)]
+        # torch.optim.Optimizer base: param_groups / defaults / hooks, so torch.optim.lr_scheduler.* attach to it
+        # (train_ours_cnt_seq.py:784); the per-parameter `state` of the base class stays empty, the moments are flat buffers
+        super().__init__(self.params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=amsgrad))
+        self.hyper = torch.zeros((5,), dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros((5,), dtype=torch.float32).pin_memory()
+        self._hyper_sig = None
+        self.upload_hyper()
+
+    # the attributes torch's schedulers / older callers read
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    def upload_hyper(self):
+        """param_groups[0] -> device (called before every step / graph replay; 20 bytes, only when something changed)."""
+        g = self.param_groups[0]
+        sig = (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]))
+        if sig != self._hyper_sig:
+            for i, v in enumerate(sig):
+                self._hyper_host[i] = v
+            self.hyper.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_sig = sig
 
     def zero_grad(self, set_to_none=False):
-        self.flat_grad.zero_()
+        self.exchange.zero_()
         off = 0
         for p in self.params:                                    # keep the views if something replaced .grad
             k = p.numel()
@@ -423,15 +452,27 @@ class Adam:
                 p.grad = self.flat_grad[off:off + k].view_as(p.data)
             off += k
 
-    def step(self):
-        lr = self.param_groups[0]["lr"]
+    def step(self, closure=None):
+        if not torch.cuda.is_current_stream_capturing():
+            self.upload_hyper()
         with torch.cuda.device(self.flat.device):
-            _lib.check(_lib.lib().esr_adam_step(_lib.ptr(self.flat), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
-                                                _lib.ptr(self.exp_avg_sq), _lib.ptr(self.max_exp_avg_sq), self.flat.numel(),
-                                                _lib.ptr(self.step_dev), lr, self.betas[0], self.betas[1], self.eps,
-                                                self.weight_decay, _lib.stream_ptr()), "esr_adam_step")
+            _lib.check(_lib.lib().esr_adam_step_dev(_lib.ptr(self.flat), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                                    _lib.ptr(self.exp_avg_sq), _lib.ptr(self.max_exp_avg_sq), self.flat.numel(),
+                                                    _lib.ptr(self.step_dev), _lib.ptr(self.hyper), _lib.stream_ptr()), "esr_adam_step_dev")
         torch._C._increment_version(self.params)                  # the kernel wrote the parameters behind autograd's back:
         #                                                           bump their versions so cached inference blobs repack
+
+    def state_dict(self):
+        return {"step": int(self.step_dev.item()), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "max_exp_avg_sq": self.max_exp_avg_sq, "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+
+    def load_state_dict(self, sd):
+        self.step_dev.fill_(int(sd["step"]))
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        if self.max_exp_avg_sq is not None and sd.get("max_exp_avg_sq") is not None:
+            self.max_exp_avg_sq.copy_(sd["max_exp_avg_sq"])
+        self.param_groups[0].update(sd["param_groups"][0])
+        self.upload_hyper()
 
 
 def _step_body(model, optimizer, frames, gt, num_frame, all_reduce):
@@ -450,8 +491,15 @@ def _step_body(model, optimizer, frames, gt, num_frame, all_reduce):
         loss.backward()
         if deferred is not None:
             deferred.flush()                                      # ConvGRU weight gradients: one launch per gate over all steps
+    if optimizer.log.numel() >= 2:
+        # the trainer's two logging scalars (train_ours_cnt_seq.py:238-239): MSE of the last window and the summed loss; they
+        # travel at the tail of the gradient bucket, so the single exchange below reduces them too
+        B = frames.shape[0]
+        with torch.no_grad():
+            optimizer.log[0:1].copy_(mse_loss(pred.detach()[-B:], target[-B:]).reshape(1))
+            optimizer.log[1:2].copy_(loss.detach().reshape(1))
     if all_reduce is not None:
-        all_reduce(optimizer.flat_grad)
+        all_reduce(optimizer.exchange)
     optimizer.step()
     return loss.detach()
 
@@ -462,7 +510,9 @@ def train_step(model, optimizer, frames, gt, num_frame=3, all_reduce=None):
     frames: BxLx2xHxW input count tensors (inp_scaled_cnt of each frame); gt: BxLx2xHxW target count tensors.
     Windows slide by one frame (dataloader/h5dataloader.py:229-231); the loss is the sum over windows of
     MSE(pred, gt[:, window middle]) with the ConvGRU state carried from window to window; one backward; optional
-    `all_reduce(flat_grad)` (DDP's role when the model is not DDP-wrapped); one Adam step.  Returns the summed loss."""
+    `all_reduce(exchange)` over the flat gradient bucket + the two logging scalars (DDP's role when the model is not
+    DDP-wrapped; after it `optimizer.log` holds the rank-reduced last-window MSE and summed loss, which is everything
+    train_ours_cnt_seq.py:238-239 + :339 need -- no extra barrier or collective); one Adam step.  Returns the local summed loss."""
     return _step_body(model, optimizer, frames, gt, num_frame, all_reduce)
 
 
@@ -495,6 +545,7 @@ class GraphedTrainStep:
     def __call__(self, frames, gt):
         self.frames.copy_(frames)
         self.gt.copy_(gt)
+        self.opt.upload_hyper()                                   # a scheduler may have changed param_groups[0]['lr']
         self.graph.replay()
         torch._C._increment_version(self.opt.params)
         return self.loss

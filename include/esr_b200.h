@@ -189,7 +189,12 @@ int esr_net_set_states(esr_net_t net, const float *states, esr_stream_t stream);
  * Implemented configuration: the one ESR instantiates (C=Co=64, 3x3, stride 1, pad 1, dilation 1, dg=8);
  * anything else returns ESR_EUNSUPPORTED.
  * --------------------------------------------------------------------------------------------- */
-size_t esr_dcn_v2_workspace_bytes(int B, int H, int W);
+size_t esr_dcn_v2_workspace_bytes(int B, int H, int W);   /* the configuration ESR uses (64 -> 64, 3x3, s1 p1 d1, 8 groups) */
+/* workspace for ANY configuration the reference operator accepts (backward = 1: for esr_dcn_v2_backward).  The configuration
+ * of models/model.py:173 runs on the tcgen05 path; every other one (the reference's own tests use 2 -> 2 channels and
+ * deformable_groups 1 / 2, models/DCNv2/testcuda.py:14-17,169-180) on fp32 CUDA-core kernels (csrc/dcn_generic.cu). */
+size_t esr_dcn_v2_workspace_bytes_ex(int B, int C, int H, int W, int Co, int kernel, int stride, int pad, int dilation,
+                                     int deformable_group, int backward);
 /* Replaces: models/DCNv2/src/dcn_v2.h:29-50 dcn_v2_backward -> src/cuda/dcn_v2_cuda.cu:97-216 (+ the col2im / coord kernels
  * src/cuda/dcn_v2_im2col_cuda.cu:197-327), called from models/DCNv2/dcn_v2.py:50.  Same five gradients, reference layouts:
  * grad_input [B,C,H,W], grad_offset [B,dg*18,H,W], grad_mask [B,dg*9,H,W], grad_weight [Co,C,3,3], grad_bias [Co].
@@ -253,6 +258,35 @@ int esr_mse_loss(const float *pred, const float *target, size_t n, float *loss, 
 int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n,
                   int32_t *step_counter, float lr, float beta1, float beta2, float eps, float weight_decay,
                   esr_stream_t stream);
+/* Same step with the hyper-parameters {lr, beta1, beta2, eps, weight_decay} read from DEVICE memory when the kernel runs: a
+ * CUDA graph that contains the call follows a learning-rate schedule (train_ours_cnt_seq.py:784) by rewriting 20 bytes. */
+int esr_adam_step_dev(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float *max_exp_avg_sq, size_t n,
+                      int32_t *step_counter, const float *hyper, esr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation metrics on the GPU.  Replaces the per-channel CPU calls of infer_ours_cnt.py:81-100:
+ * nn.L1Loss / nn.MSELoss, loss/restore.py:42-61 ssim_loss (skimage structural_similarity, 7x7 uniform window, sample
+ * covariance, K1 0.01, K2 0.03) and :64-90 psnr_loss (skimage peak_signal_noise_ratio).
+ * pred, tgt: fp32 [n_planes, H, W] (plane = sample x channel).  stats: fp64 [n_planes][6] =
+ *   {sum |pred - tgt|, sum (pred - tgt)^2, max tgt, min tgt, sum of the SSIM map over the valid region, its pixel count};
+ * the host side (esr_b200/metrics.py) turns them into the reference's scalars. */
+size_t esr_metrics_workspace_bytes(int n_planes, int H, int W, int win);
+int esr_metrics_planes(const float *pred, const float *tgt, int n_planes, int H, int W, int win, double data_range, double *stats,
+                       void *workspace, size_t workspace_bytes, esr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Columnar event reader, device side.  Replaces, for whole batches of frames:
+ *   BaseDataset.binary_search_h5_dset (dataloader/base_dataset.py:78-91; same algorithm as
+ *   dataloader/binary_search/binary_search.pyx:17-38) used by H5Dataset.find_ts_index / get_gt_event_indices_num
+ *   (dataloader/h5dataset.py:264-270, 451-475): out[i] = the index that bisection returns for queries[i] (exact hit -> the probed
+ *   index, else the left insertion point); ts sorted float64 [n], device or host-mapped memory;
+ *   H5Dataset.get_events / get_gt_events + BaseDataset.event_formatting (h5dataset.py:492-506, base_dataset.py:26-33):
+ *   frame f = rows [start[f], start[f] + off[f+1] - off[f]) of the int16 x / y and float64 t / p columns -> fp32 SoA at
+ *   out_*[off[f] ...]; out_ts (optional) = per-frame normalised time (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6) in fp32. */
+int esr_ts_search(const double *ts, int64_t n, const double *queries, int64_t nq, int64_t *out, esr_stream_t stream);
+int esr_gather_events(const int16_t *xs, const int16_t *ys, const double *ts, const double *ps, const int64_t *start,
+                      const int64_t *off, int n_frames, int64_t max_len, float *out_xs, float *out_ys, float *out_ts,
+                      float *out_ps, esr_stream_t stream);
 
 #ifdef __cplusplus
 }

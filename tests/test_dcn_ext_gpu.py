@@ -37,13 +37,21 @@ def test_against_oracle(H, W, scale):
     assert ((got - want).abs().max() / want.abs().max()).item() < 1e-4
 
 
-def test_unsupported_config_raises():
+def test_invalid_config_raises():
+    """every configuration the reference operator accepts is served (tests/test_dropin.py); what it rejects raises RuntimeError:
+    channels not divisible by the groups (dcn_v2_cuda.cu:38-62 AT_ASSERTM), kernel / weight shape mismatch, CPU tensors"""
     from esr_b200 import dcn_v2_ext as ext
     dev = torch.device("cuda:0")
     x = torch.randn(1, 32, 8, 8, device=dev)
     with pytest.raises(RuntimeError):
         ext.dcn_v2_forward(x, torch.randn(32, 32, 3, 3, device=dev), torch.zeros(32, device=dev),
-                           torch.zeros(1, 18, 8, 8, device=dev), torch.zeros(1, 9, 8, 8, device=dev), 3, 3, 1, 1, 1, 1, 1, 1, 1)
+                           torch.zeros(1, 54, 8, 8, device=dev), torch.zeros(1, 27, 8, 8, device=dev), 3, 3, 1, 1, 1, 1, 1, 1, 3)
+    with pytest.raises(RuntimeError):
+        ext.dcn_v2_forward(x, torch.randn(32, 32, 3, 3, device=dev), torch.zeros(32, device=dev),
+                           torch.zeros(1, 18, 8, 8, device=dev), torch.zeros(1, 9, 8, 8, device=dev), 5, 5, 1, 1, 2, 2, 1, 1, 1)
+    with pytest.raises(RuntimeError):
+        ext.dcn_v2_forward(x.cpu(), torch.randn(32, 32, 3, 3), torch.zeros(32), torch.zeros(1, 18, 8, 8), torch.zeros(1, 9, 8, 8),
+                           3, 3, 1, 1, 1, 1, 1, 1, 1)
 
 
 @pytest.mark.parametrize("H,W,scale", [(16, 16, 0.5), (12, 20, 3.0)])

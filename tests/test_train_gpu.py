@@ -297,3 +297,84 @@ def test_opt_in_mma_weight_gradient(dev, monkeypatch, B, Cin, Cout, stride, H, W
     xg, wg, bg = (t.detach().to(dev).requires_grad_() for t in (x, w, b))
     train.conv2d(xg, wg, bg, stride, "relu").backward(dy.to(dev))
     assert _rel(wg.grad, w.grad) <= REL and _rel(xg.grad, x.grad) <= REL
+
+
+def test_adam_follows_a_torch_lr_scheduler_also_inside_the_graph(dev):
+    """train_ours_cnt_seq.py:784 attaches a torch lr_scheduler to the optimizer: esr_b200.train.Adam is a torch.optim.Optimizer
+    whose hyper-parameters are read from device memory by the update kernel, so StepLR changes reach eager steps AND replays of a
+    captured iteration (by-value lr was frozen into the graph)."""
+    from esr_b200 import train
+    g = torch.Generator().manual_seed(11)
+    shapes = [(16, 8, 3, 3), (16,), (7,)]
+    ref = [torch.randn(s, generator=g).requires_grad_() for s in shapes]
+    mine = [r.detach().clone().to(dev).requires_grad_() for r in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-2, weight_decay=1e-4, amsgrad=True)
+    o_mine = train.Adam(mine, lr=1e-2, weight_decay=1e-4, amsgrad=True)
+    s_ref = torch.optim.lr_scheduler.StepLR(o_ref, step_size=2, gamma=0.1)
+    s_mine = torch.optim.lr_scheduler.StepLR(o_mine, step_size=2, gamma=0.1)
+    grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(6)]
+    static = [torch.zeros(s, device=dev) for s in shapes]
+    graph = None
+    for step in range(6):
+        for r, m, gr, st in zip(ref, mine, grads[step], static):
+            r.grad = gr.clone()
+            st.copy_(gr.to(dev))
+        if step < 2:                                   # eager
+            for m, st in zip(mine, static):
+                m.grad.copy_(st)
+            o_mine.step()
+        else:                                          # the same update replayed from a CUDA graph captured at step 2
+            if graph is None:
+                o_mine.upload_hyper()
+                keep = [t.clone() for t in (o_mine.flat, o_mine.exp_avg, o_mine.exp_avg_sq, o_mine.max_exp_avg_sq, o_mine.step_dev)]
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    for m, st in zip(mine, static):
+                        m.grad.copy_(st)
+                    o_mine.step()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                for dst, src in zip((o_mine.flat, o_mine.exp_avg, o_mine.exp_avg_sq, o_mine.max_exp_avg_sq, o_mine.step_dev), keep):
+                    dst.copy_(src)
+                with torch.cuda.graph(graph):
+                    for m, st in zip(mine, static):
+                        m.grad.copy_(st)
+                    o_mine.step()
+                for dst, src in zip((o_mine.flat, o_mine.exp_avg, o_mine.exp_avg_sq, o_mine.max_exp_avg_sq, o_mine.step_dev), keep):
+                    dst.copy_(src)
+            o_mine.upload_hyper()
+            graph.replay()
+        o_ref.step()
+        s_ref.step()
+        s_mine.step()
+        assert o_mine.param_groups[0]["lr"] == pytest.approx(o_ref.param_groups[0]["lr"])
+        for r, m in zip(ref, mine):
+            assert torch.allclose(m.detach().cpu(), r.detach(), rtol=3e-6, atol=3e-7), step
+    assert o_ref.param_groups[0]["lr"] == pytest.approx(1e-5)
+
+
+def test_logging_scalars_ride_in_the_gradient_bucket(dev):
+    """the two scalars the trainer logs (train_ours_cnt_seq.py:238-239: last-window MSE, summed loss) sit at the
+    tail of the flat exchange buffer, so the iteration's single all-reduce covers them (no reduce_tensor barriers)."""
+    from esr_b200 import train
+    sd = model_ref.seeded_state_dict(2)
+    frames, gt = _frames(2, 5, 16, 24, 91)
+    net = _net(sd, dev)
+    opt = train.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    seen = {}
+
+    def fake_allreduce(buf):
+        seen["n"] = buf.numel()
+        seen["log"] = buf[-2:].clone()
+        buf[-2:] *= 0.5                                # what an average with a rank holding zeros would do
+
+    loss = train.train_step(net, opt, frames.to(dev), gt.to(dev), all_reduce=fake_allreduce)
+    assert seen["n"] == 1813120 + 2 and opt.exchange.data_ptr() == opt.flat_grad.data_ptr()
+    assert seen["log"][1].item() == pytest.approx(loss.item(), rel=1e-6)
+    # last-window MSE against the oracle's prediction of that window
+    ora = model_ref.OracleNet(sd)
+    outs = [ora(frames[:, w:w + 3].contiguous()) for w in range(3)]
+    want_last = F.mse_loss(outs[-1], gt[:, 3]).item()
+    assert seen["log"][0].item() == pytest.approx(want_last, rel=2e-3)
+    assert opt.log[1].item() == pytest.approx(0.5 * loss.item(), rel=1e-6)
