@@ -364,31 +364,6 @@ def measure_training(args, wl, net_sd, dev, rank, world, dist, steps=None, cpu=T
     if world > 1:
         def allred(flat):
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-        # gradient-exchange check on hardware (pytest -m gpu has one GPU): after the all-reduce every rank must hold the same
-        # flat gradient, equal to the mean of the per-rank gradients gathered separately
-        opt.zero_grad()
-        net.reset_states()
-        pred = net(frames)
-        Wn = L - 2
-        loss = Wn * train.mse_loss(pred, gt[:, 1:1 + Wn].transpose(0, 1).reshape(pred.shape))
-        loss.backward()
-        opt.log[0] = float(rank + 1)                                  # the logging slots ride in the same bucket
-        opt.log[1] = loss.detach()
-        local = opt.exchange.clone()
-        gathered = [torch.empty_like(local) for _ in range(world)]
-        dist.all_gather(gathered, local)
-        want = torch.stack(gathered).mean(0)
-        allred(opt.exchange)
-        err = ((opt.exchange - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
-        same = torch.tensor([float(opt.exchange.double().sum())], dtype=torch.float64, device=dev)
-        lo, hi = same.clone(), same.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        log_ok = abs(float(opt.log[0]) - (world + 1) / 2.0) < 1e-5
-        grad_check = {"rel_err_vs_mean_of_gathered": err, "identical_on_all_ranks": bool((hi - lo).abs().item() == 0.0),
-                      "logging_scalars_reduced_in_the_same_bucket": bool(log_ok),
-                      "ok": bool(err < 1e-5 and (hi - lo).abs().item() == 0.0 and log_ok)}
-        opt.zero_grad()
     step = None
     if not args.no_graph:
         try:
@@ -426,6 +401,33 @@ def measure_training(args, wl, net_sd, dev, rank, world, dist, steps=None, cpu=T
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item() / steps
+    if world > 1:                                                     # after the timed loop: an eager backward on the default
+        #                                                               stream before the capture invalidated it (measured at N = 2)
+        # gradient-exchange check on hardware (pytest -m gpu has one GPU): after the all-reduce every rank must hold the same
+        # flat gradient, equal to the mean of the per-rank gradients gathered separately
+        opt.zero_grad()
+        net.reset_states()
+        pred = net(frames)
+        Wn = L - 2
+        loss = Wn * train.mse_loss(pred, gt[:, 1:1 + Wn].transpose(0, 1).reshape(pred.shape))
+        loss.backward()
+        opt.log[0] = float(rank + 1)                                  # the logging slots ride in the same bucket
+        opt.log[1] = loss.detach()
+        local = opt.exchange.clone()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        want = torch.stack(gathered).mean(0)
+        allred(opt.exchange)
+        err = ((opt.exchange - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+        same = torch.tensor([float(opt.exchange.double().sum())], dtype=torch.float64, device=dev)
+        lo, hi = same.clone(), same.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        log_ok = abs(float(opt.log[0]) - (world + 1) / 2.0) < 1e-5
+        grad_check = {"rel_err_vs_mean_of_gathered": err, "identical_on_all_ranks": bool((hi - lo).abs().item() == 0.0),
+                      "logging_scalars_reduced_in_the_same_bucket": bool(log_ok),
+                      "ok": bool(err < 1e-5 and (hi - lo).abs().item() == 0.0 and log_ok)}
+        opt.zero_grad()
     out = {"metric": "training LR event-frames/sec (forward + backward + Adam)", "value": world * B * L / (ms * 1e-3), "unit": "frames/s",
            "ms_per_step": ms, "steps": steps, "mode": mode,
            "batch_per_gpu": B, "loss_first": float(first), "loss_last": float(last),

@@ -42,6 +42,32 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
         }                                                                                          \
     } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The network is ~50 dependent kernels of 20-200 us; a normal stream edge drains the GPU
+// between two of them (tail of the last wave, launch latency, the next kernel's prologue: barrier init, TMEM allocation,
+// descriptor fetch).  With the programmatic-serialization attribute the next grid is launched as soon as every CTA of the
+// current one has executed `griddepcontrol.launch_dependents` (first instruction of our kernels): its CTAs take over SMs as
+// they free up and run their prologue, then block in `griddepcontrol.wait` until the predecessor grid has COMPLETED and its
+// memory is visible.  Rules kept by every kernel launched through launch_pdl(): no global-memory access of any kind before
+// PDL_WAIT().  Works inside stream capture (the edge becomes a programmatic graph dependency).  ESR_NO_PDL=1: plain launches.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+#define PDL_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -43,6 +43,7 @@ __device__ __forceinline__ void df_ld8(const __nv_bfloat16 *hi, size_t plane, fl
 
 __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_constant__ DcnFusedArgs a)
 {
+    PDL_LAUNCH_DEPENDENTS();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));        // generic pointer to the aligned base
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    PDL_WAIT();                      // everything above is CTA-local set-up; global memory only from here on
 
     if (warp == 0) {
         if (elect_one_sync()) {
@@ -225,6 +227,7 @@ __device__ __forceinline__ void df_unpack(const uint4 h, const uint4 l, float (&
 
 __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_constant__ DcnFusedArgs a)
 {
+    PDL_LAUNCH_DEPENDENTS();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_co
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    PDL_WAIT();                      // everything above is CTA-local set-up; global memory only from here on
 
     if (warp == 0) {
         if (elect_one_sync()) {
@@ -449,8 +453,8 @@ int dcn_fused_prepare(const SplitTensor &feat, const int *feat_img, const float 
 int dcn_fused_launch(void *plan, cudaStream_t st)
 {
     DcnFusedPlan *p = (DcnFusedPlan *)plan;
-    if (p->window) k_dcn_fused_win<<<p->grid, DF_THREADS, p->smem, st>>>(p->args);
-    else k_dcn_fused<<<p->grid, DF_THREADS, p->smem, st>>>(p->args);
+    if (p->window) ESR_CUDA_CHECK(launch_pdl(k_dcn_fused_win, dim3(p->grid), dim3(DF_THREADS), p->smem, st, p->args));
+    else ESR_CUDA_CHECK(launch_pdl(k_dcn_fused, dim3(p->grid), dim3(DF_THREADS), p->smem, st, p->args));
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

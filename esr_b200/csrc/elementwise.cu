@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(256)
 k_ltc_cat(const __nv_bfloat16 *__restrict__ f, size_t f_plane, const float *__restrict__ maps, const int *__restrict__ idx,
           int n_img, int HW, __nv_bfloat16 *__restrict__ out, size_t out_plane)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     const size_t total = (size_t)n_img * HW * 24;            // 24 groups of 8 channels = 192
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int g = (int)(i % 24);
@@ -53,9 +55,9 @@ int ltc_cat(const SplitTensor &f, const float *maps, const int *idx, int n_img, 
 {
     const int HW = f.H * f.W;
     const size_t total = (size_t)n_img * HW * 24;
-    k_ltc_cat<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(f.base, f.plane(), maps, idx, n_img, HW, out.base,
-                                                                         out.plane());
-    ESR_LAUNCH_CHECK();
+    ESR_CUDA_CHECK(launch_pdl(k_ltc_cat, dim3((unsigned)ceil_div64((int64_t)total, 256)), dim3(256), 0, st, f.base, f.plane(), maps, idx, n_img, HW, out.base,
+                                                                         out.plane()));
+    esr::count_launch();
     return ESR_OK;
 }
 
@@ -68,6 +70,8 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 __global__ void __launch_bounds__(256)
 k_chan_max(const __nv_bfloat16 *__restrict__ t, size_t plane, int HW, int *__restrict__ out_ord)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     const int img = blockIdx.y;
     const int c8 = threadIdx.x & 7;                      // 8 groups of 8 channels
     const int lane_pix = threadIdx.x >> 3;               // 32 pixels per pass
@@ -93,18 +97,20 @@ k_chan_max(const __nv_bfloat16 *__restrict__ t, size_t plane, int HW, int *__res
 static int f2ord_host_neg_inf() { return (int)(0xFF800000u ^ 0x7FFFFFFFu); }
 __global__ void k_fill_int(int *p, int n, int v)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
 int chan_max(const SplitTensor &t, int n_img, float *out, cudaStream_t st)
 {
     const int HW = t.H * t.W;
-    k_fill_int<<<(n_img * 64 + 255) / 256, 256, 0, st>>>((int *)out, n_img * 64, f2ord_host_neg_inf());
-    ESR_LAUNCH_CHECK();
+    ESR_CUDA_CHECK(launch_pdl(k_fill_int, dim3((n_img * 64 + 255) / 256), dim3(256), 0, st, (int *)out, n_img * 64, f2ord_host_neg_inf()));
+    esr::count_launch();
     int slices = (HW + 32 * 8 - 1) / (32 * 8);
     if (slices > 64) slices = 64;
-    k_chan_max<<<dim3(slices, n_img), 256, 0, st>>>(t.base, t.plane(), HW, (int *)out);
-    ESR_LAUNCH_CHECK();
+    ESR_CUDA_CHECK(launch_pdl(k_chan_max, dim3(slices, n_img), dim3(256), 0, st, t.base, t.plane(), HW, (int *)out));
+    esr::count_launch();
     return ESR_OK;
 }
 
@@ -113,6 +119,8 @@ __global__ void __launch_bounds__(128)
 k_attn_mlp(const int *__restrict__ mx_ord, const float *__restrict__ w0, const float *__restrict__ b0,
            const float *__restrict__ w1, const float *__restrict__ b1, float *__restrict__ ck)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     __shared__ float m[64], hdn[32];
     const int img = blockIdx.x, t = threadIdx.x;
     if (t < 64) m[t] = ord2f(mx_ord[img * 64 + t]);
@@ -130,8 +138,8 @@ k_attn_mlp(const int *__restrict__ mx_ord, const float *__restrict__ w0, const f
 int attn_mlp(const float *mx, int n_img, const float *w0, const float *b0, const float *w1, const float *b1, float *ck,
              cudaStream_t st)
 {
-    k_attn_mlp<<<n_img, 128, 0, st>>>((const int *)mx, w0, b0, w1, b1, ck);
-    ESR_LAUNCH_CHECK();
+    ESR_CUDA_CHECK(launch_pdl(k_attn_mlp, dim3(n_img), dim3(128), 0, st, (const int *)mx, w0, b0, w1, b1, ck));
+    esr::count_launch();
     return ESR_OK;
 }
 
@@ -141,6 +149,8 @@ k_attn_apply(const __nv_bfloat16 *__restrict__ al, size_t al_plane, const __nv_b
              const int *__restrict__ mid_img, const float *__restrict__ sk, const float *__restrict__ ck, int n_img, int HW,
              __nv_bfloat16 *__restrict__ out, size_t out_plane)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     const size_t total = (size_t)n_img * HW * 16;            // 16 groups of 8 channels = 128
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int g = (int)(i % 16);
@@ -162,10 +172,10 @@ int attn_apply(const SplitTensor &aligned, const SplitTensor &mid_src, const int
 {
     const int HW = aligned.H * aligned.W;
     const size_t total = (size_t)n_img * HW * 16;
-    k_attn_apply<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(aligned.base, aligned.plane(), mid_src.base,
+    ESR_CUDA_CHECK(launch_pdl(k_attn_apply, dim3((unsigned)ceil_div64((int64_t)total, 256)), dim3(256), 0, st, aligned.base, aligned.plane(), mid_src.base,
                                                                             mid_src.plane(), mid_img, sk, ck, n_img, HW,
-                                                                            out.base, out.plane());
-    ESR_LAUNCH_CHECK();
+                                                                            out.base, out.plane()));
+    esr::count_launch();
     return ESR_OK;
 }
 
@@ -175,6 +185,8 @@ k_scale_aggregate(const __nv_bfloat16 *__restrict__ x, size_t x_plane, const __n
                   const float *__restrict__ att, const int *__restrict__ fidx, int B, int N, int HW, int C,
                   __nv_bfloat16 *__restrict__ out, size_t out_plane)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     const int G = C / 8;
     const size_t total = (size_t)B * HW * G;
     const float inv = 1.0f / (float)N;
@@ -205,9 +217,9 @@ int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float 
 {
     const int HW = x.H * x.W, C = x.C;
     const size_t total = (size_t)B * HW * (C / 8);
-    k_scale_aggregate<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(x.base, x.plane(), feats.base, feats.plane(),
-                                                                                 att, fidx, B, N, HW, C, out.base, out.plane());
-    ESR_LAUNCH_CHECK();
+    ESR_CUDA_CHECK(launch_pdl(k_scale_aggregate, dim3((unsigned)ceil_div64((int64_t)total, 256)), dim3(256), 0, st, x.base, x.plane(), feats.base, feats.plane(),
+                                                                                 att, fidx, B, N, HW, C, out.base, out.plane()));
+    esr::count_launch();
     return ESR_OK;
 }
 
@@ -218,6 +230,8 @@ __global__ void __launch_bounds__(256)
 k_upsample2x(const __nv_bfloat16 *__restrict__ src, size_t s_plane, int n_img, int H, int W, int C,
              __nv_bfloat16 *__restrict__ dst, size_t d_plane)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     const int G = C / 8, H2 = 2 * H, W2 = 2 * W;
     const size_t total = (size_t)n_img * H2 * W2 * G;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -244,9 +258,9 @@ int upsample2x(const SplitTensor &src, int n_img, const SplitTensor &dst, cudaSt
 {
     ESR_REQUIRE(dst.H == 2 * src.H && dst.W == 2 * src.W && dst.C == src.C && src.C % 8 == 0, "upsample2x: bad shapes");
     const size_t total = (size_t)n_img * dst.H * dst.W * (src.C / 8);
-    k_upsample2x<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(src.base, src.plane(), n_img, src.H, src.W, src.C,
-                                                                            dst.base, dst.plane());
-    ESR_LAUNCH_CHECK();
+    ESR_CUDA_CHECK(launch_pdl(k_upsample2x, dim3((unsigned)ceil_div64((int64_t)total, 256)), dim3(256), 0, st, src.base, src.plane(), n_img, src.H, src.W, src.C,
+                                                                            dst.base, dst.plane()));
+    esr::count_launch();
     return ESR_OK;
 }
 
@@ -255,6 +269,8 @@ __global__ void __launch_bounds__(256)
 k_copy_split(const __nv_bfloat16 *__restrict__ src, size_t s_plane, const int *__restrict__ src_img, int n_img, size_t per_img8,
              __nv_bfloat16 *__restrict__ dst, size_t d_plane)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     const size_t total = (size_t)n_img * per_img8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t img = i / per_img8, r = i % per_img8;
@@ -268,8 +284,137 @@ int copy_split(const SplitTensor &src, const int *src_img, int n_img, const Spli
 {
     const size_t per_img8 = (size_t)src.H * src.W * src.C / 8;
     const size_t total = (size_t)n_img * per_img8;
-    k_copy_split<<<(unsigned)ceil_div64((int64_t)total, 256), 256, 0, st>>>(src.base, src.plane(), src_img, n_img, per_img8,
-                                                                            dst.base, dst.plane());
+    ESR_CUDA_CHECK(launch_pdl(k_copy_split, dim3((unsigned)ceil_div64((int64_t)total, 256)), dim3(256), 0, st, src.base, src.plane(), src_img, n_img, per_img8,
+                                                                            dst.base, dst.plane()));
+    esr::count_launch();
+    return ESR_OK;
+}
+
+} // namespace esr
+
+// ------------------------------------------------------------------------------------------------
+// Narrow-output convolutions of a 64-channel split tensor: Cout = 1 or 2, 3x3 (pad 1) or 1x1, sigmoid -- pred_map[1]
+// (models/model.py:59-60), attens[0] (:193) and the spatial-attention kernel (:183).  On the tensor cores these layers pad
+// N to 16 and move a full 128 x 64 A tile per tap for 1-2 useful columns (41 / 22 / 19 us per cfg2 step, 1.2 TB/s); they are
+// reads of an L2-resident tensor with 576 MACs per pixel, so plain fp32 FMAs do: 8 lanes per pixel, 8 channels (16 B hi + 16 B lo)
+// each, 3 shuffles to reduce.  fp32 products of the exact hi + lo values (no operand split needed).
+// ------------------------------------------------------------------------------------------------
+namespace esr {
+
+template <int CIN, int COUT, int TAPS, int ACT, int NCHW>
+__global__ void __launch_bounds__(256)
+k_conv_narrow(const __nv_bfloat16 *__restrict__ x, size_t plane, const int *__restrict__ src_img, const float *__restrict__ w /*[TAPS][CIN][COUT]*/,
+              const float *__restrict__ bias, int n_img, int H, int W, float *__restrict__ out, int crop_top, int crop_left, int out_H,
+              int out_W)
+{
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
+    constexpr int LPP = CIN / 8;                          // lanes per pixel: 8 channels (16 B hi + 16 B lo) each
+    constexpr int PPB = 256 / LPP, TH = PPB / 8;          // pixels per block: 8 wide x TH tall
+    __shared__ float sw[TAPS * CIN * COUT];
+    for (int i = threadIdx.x; i < TAPS * CIN * COUT; i += 256) sw[i] = w[i];
+    __syncthreads();
+    const int lc = threadIdx.x % LPP;                     // channels [8 lc, 8 lc + 8)
+    const int px_in_blk = threadIdx.x / LPP;
+    const int tiles_x = (W + 7) / 8, tiles_y = (H + TH - 1) / TH;
+    const int tile = blockIdx.x % (tiles_x * tiles_y), img = blockIdx.x / (tiles_x * tiles_y);
+    const int y = (tile / tiles_x) * TH + (px_in_blk >> 3), xx = (tile % tiles_x) * 8 + (px_in_blk & 7);
+    const bool valid = y < H && xx < W;
+    const size_t ibase = (size_t)(src_img ? src_img[img] : img) * H * W;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
+    // branch-free taps: out-of-image neighbours read a clamped (valid) address and are zeroed, so all 2 x TAPS loads of a thread are
+    // independent and issue back to back (the first version's per-tap `if` serialised load -> use -> load: 51 us for pred_map[1])
+    uint4 hv[TAPS], lv[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+        const int yy = y + (TAPS == 9 ? t / 3 - 1 : 0), xs = xx + (TAPS == 9 ? t % 3 - 1 : 0);
+        const bool ok = valid && yy >= 0 && yy < H && xs >= 0 && xs < W;
+        const int yc = min(max(yy, 0), H - 1), xc = min(max(xs, 0), W - 1);
+        const __nv_bfloat16 *p = x + ((ibase + (size_t)yc * W + xc) * CIN + lc * 8);
+        hv[t] = *reinterpret_cast<const uint4 *>(p);
+        lv[t] = *reinterpret_cast<const uint4 *>(p + plane);
+        if (!ok) { hv[t] = make_uint4(0u, 0u, 0u, 0u); lv[t] = make_uint4(0u, 0u, 0u, 0u); }
+    }
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+        const uint32_t hw[4] = {hv[t].x, hv[t].y, hv[t].z, hv[t].w}, lw[4] = {lv[t].x, lv[t].y, lv[t].z, lv[t].w};
+        const float *wt = sw + (t * CIN + lc * 8) * COUT;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            const float v1 = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) {
+                acc[c] = fmaf(v0, wt[(2 * e) * COUT + c], acc[c]);
+                acc[c] = fmaf(v1, wt[(2 * e + 1) * COUT + c], acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+#pragma unroll
+        for (int o = 1; o < LPP; o <<= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    if (valid && lc == 0) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+            const float v = acc[c] + bias[c];
+            const float r = ACT == ACT_SIGMOID ? fast_sigmoid(v) : (ACT == ACT_RELU ? fmaxf(v, 0.0f) : v);
+            if (NCHW) {
+                const int oy = y - crop_top, ox = xx - crop_left;
+                if (oy >= 0 && oy < out_H && ox >= 0 && ox < out_W) out[(((size_t)img * COUT + c) * out_H + oy) * out_W + ox] = r;
+            } else {
+                out[(((size_t)img * H + y) * W + xx) * COUT + c] = r;
+            }
+        }
+    }
+}
+
+template <int CIN, int COUT, int TAPS, int ACT, int NCHW>
+static int launch_narrow(const SplitTensor &x, const int *src_img, const float *w, const float *bias, int n_img, float *out, int crop_top,
+                         int crop_left, int out_H, int out_W, cudaStream_t st)
+{
+    constexpr int TH = (256 / (CIN / 8)) / 8;
+    const dim3 grid((unsigned)(n_img * ((x.W + 7) / 8) * ((x.H + TH - 1) / TH)));
+    ESR_CUDA_CHECK(launch_pdl(k_conv_narrow<CIN, COUT, TAPS, ACT, NCHW>, grid, dim3(256), 0, st, x.base, x.plane(), src_img, w, bias, n_img, x.H,
+                              x.W, out, crop_top, crop_left, out_H, out_W));
+    esr::count_launch();
+    return ESR_OK;
+}
+
+int conv_narrow(const SplitTensor &x, const int *src_img, const float *w, const float *bias, int cout, int ntaps, int n_img, float *out,
+                cudaStream_t st)
+{
+    if (x.C == 64 && cout == 1 && ntaps == 9) return launch_narrow<64, 1, 9, ACT_SIGMOID, 0>(x, src_img, w, bias, n_img, out, 0, 0, 0, 0, st);
+    if (x.C == 64 && cout == 2 && ntaps == 1) return launch_narrow<64, 2, 1, ACT_SIGMOID, 0>(x, src_img, w, bias, n_img, out, 0, 0, 0, 0, st);
+    if (x.C == 32 && cout == 1 && ntaps == 9) return launch_narrow<32, 1, 9, ACT_SIGMOID, 0>(x, src_img, w, bias, n_img, out, 0, 0, 0, 0, st);
+    if (x.C == 16 && cout == 1 && ntaps == 9) return launch_narrow<16, 1, 9, ACT_SIGMOID, 0>(x, src_img, w, bias, n_img, out, 0, 0, 0, 0, st);
+    set_error("conv_narrow: C=%d cout=%d taps=%d has no instantiation", x.C, cout, ntaps);
+    return ESR_EINVAL;
+}
+
+// tail (models/model.py:337): 8 -> 2, 3x3, ReLU, fp32 NCHW output cropped back to the un-padded size (CropSize)
+int conv_narrow_tail(const SplitTensor &x, const float *w, const float *bias, int n_img, float *out, int crop_top, int crop_left, int out_H,
+                     int out_W, cudaStream_t st)
+{
+    ESR_REQUIRE(x.C == 8, "conv_narrow_tail: C=%d", x.C);
+    return launch_narrow<8, 2, 9, ACT_RELU, 1>(x, nullptr, w, bias, n_img, out, crop_top, crop_left, out_H, out_W, st);
+}
+
+// fp32 [Cout, 64, k, k] -> [tap][ci][co]
+__global__ void k_pack_narrow_weight(const float *__restrict__ w, int cout, int ntaps, float *__restrict__ dst)
+{
+    const int total = ntaps * 64 * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int co = i % cout, ci = (i / cout) % 64, tap = i / (cout * 64);
+        dst[i] = w[((size_t)co * 64 + ci) * ntaps + tap];
+    }
+}
+int pack_narrow_weight(const float *w, int cout, int ntaps, float *dst, cudaStream_t st)
+{
+    k_pack_narrow_weight<<<(ntaps * 64 * cout + 255) / 256, 256, 0, st>>>(w, cout, ntaps, dst);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

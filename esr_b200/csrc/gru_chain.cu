@@ -31,6 +31,7 @@ struct GruChainArgs {
     float *zbuf;                                // update gate, fp32 [2B, H, W, 64]
     unsigned int *barrier;                      // grid barrier counter (zeroed before the launch)
     int B, N, nsteps, H, W, TW, TH, tiles_x, tiles_y, stages;
+    int cluster;                                // > 1: one thread-block cluster per image (tiles_per_img CTAs), phase barrier through DSMEM mbarriers
 };
 
 __device__ __forceinline__ void gc_grid_barrier(unsigned int *counter, unsigned int target)
@@ -341,7 +342,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
     constexpr uint32_t STAGE = 2u * TC_A_BYTES + 2u * B_MAX;
     const uint32_t bar_base = smem_base + (uint32_t)a.stages * STAGE;
     const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages, bar_accum = bar_base + 16u * a.stages;   // 2 accum barriers
-    const uint32_t tmem_slot = bar_accum + 16u;
+    const uint32_t bar_phase = bar_accum + 16u;                    // cluster mode: one arrival per CTA of the image and phase
+    const uint32_t tmem_slot = bar_phase + 8u;
+    const bool cl = a.cluster > 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B2 = 2 * a.B;
     const int tiles_per_img = a.tiles_x * a.tiles_y;
@@ -360,11 +363,12 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
         mbar_init(bar_accum, 1); mbar_init(bar_accum + 8u, 1);
+        mbar_init(bar_phase, cl ? (uint32_t)a.cluster : 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 256);                    // two 128-column accumulators
     tc_fence_before();
-    __syncthreads();
+    if (cl) pair_sync(); else __syncthreads();                    // cluster mode: every CTA's phase barrier exists before anyone arrives on it
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -384,11 +388,15 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                     if (kb == 9 && p > 0) {
                         // state-side operands are written by every CTA's epilogue of phase p-1: wait for all of them
-                        const unsigned int target = (unsigned int)p * bar_n;
-                        unsigned int v;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
-                        } while (v < target);
+                        if (cl) {
+                            mbar_wait_cluster(bar_phase, (uint32_t)((p - 1) & 1));
+                        } else {
+                            const unsigned int target = (unsigned int)p * bar_n;
+                            unsigned int v;
+                            do {
+                                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
+                            } while (v < target);
+                        }
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
                     mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
@@ -445,12 +453,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
             asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps
             // one release for the CTA: the named barrier orders the other threads' stores before this thread's gpu-scope fence
             // (cumulativity -- the pattern of cooperative-groups grid.sync), so 255 threads skip their own membar.gl
-            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
+            if (warp == 2 && lane == 0) {
+                __threadfence();
+                if (cl) { for (int r = 0; r < a.cluster; ++r) mbar_arrive_remote(bar_phase, (uint32_t)r); }
+                else atomicAdd(bar_ctr, 1u);
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (cl) pair_sync(); else __syncthreads();                    // nobody leaves while a peer may still arrive on its phase barrier
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
@@ -481,7 +493,7 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
     a.B = B; a.N = N; a.nsteps = nsteps; a.H = H; a.W = W; a.TW = TW; a.TH = TH;
     a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH;
     a.stages = 3;
-    p->smem = 1024 + (size_t)a.stages * (2 * TC_A_BYTES + 2 * 128 * 128) + 16 * a.stages + 64;
+    p->smem = 1024 + (size_t)a.stages * (2 * TC_A_BYTES + 2 * 128 * 128) + 16 * a.stages + 96;
     ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     int per_sm = 0;
     ESR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gru_chain, GC_THREADS, p->smem));
@@ -492,6 +504,26 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
     p->grid = n_tiles < max_grid ? n_tiles : max_grid;
     static const bool no_pipe = getenv("ESR_GRU_NO_PIPE") != nullptr;
     p->pipelined = !no_pipe && n_tiles <= max_grid;            // one tile per CTA: overlap the x-side K-blocks with the epilogue
+    // a tile's halo only reaches tiles of its own image: with <= 8 tiles per image each image is ONE thread-block cluster whose
+    // CTAs synchronise phases through mbarriers in each other's shared memory (remote arrive + local try_wait: a few hundred
+    // cycles) instead of a global-memory counter polled with ld.acquire.gpu (~5 k cycles per phase, profiles/r1_notes.md); the
+    // clusters are independent, so no cooperative launch is needed.  ESR_GRU_NO_CLUSTER=1: counter barrier.
+    static const bool no_cluster = getenv("ESR_GRU_NO_CLUSTER") != nullptr;
+    const int tpi = a.tiles_x * a.tiles_y;
+    a.cluster = (p->pipelined && !no_cluster && tpi >= 2 && tpi <= 8) ? tpi : 1;
+    if (a.cluster > 1) {
+        // every image's cluster must be resident at once, or the images run in waves and the serial chain takes twice as long
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(n_tiles); cfg.blockDim = dim3(GC_THREADS); cfg.dynamicSmemBytes = p->smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)a.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, k_gru_chain_pipe, &cfg) != cudaSuccess) { cudaGetLastError(); max_clusters = 0; }
+        if (getenv("ESR_DEBUG")) fprintf(stderr, "[esr] gru_chain: %d clusters of %d CTAs wanted, %d can be resident\n", n_tiles / a.cluster, a.cluster, max_clusters);
+        if (max_clusters * a.cluster < n_tiles) a.cluster = 1;
+    }
     *plan_out = p;
     return ESR_OK;
 }
@@ -500,6 +532,17 @@ int gru_chain_launch(void *plan, cudaStream_t st)
 {
     GruChainPlan *p = (GruChainPlan *)plan;
     ESR_CUDA_CHECK(cudaMemsetAsync(p->args.barrier, 0, 64 * 8 * sizeof(unsigned int), st));   // per-image counters, 32 bytes apart
+    if (p->pipelined && p->args.cluster > 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(p->grid); cfg.blockDim = dim3(GC_THREADS); cfg.dynamicSmemBytes = p->smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)p->args.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        ESR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gru_chain_pipe, p->args));
+        esr::count_launch();
+        return ESR_OK;
+    }
     void *kargs[] = {(void *)&p->args};
     ESR_CUDA_CHECK(cudaLaunchCooperativeKernel(p->pipelined ? (void *)k_gru_chain_pipe : (void *)k_gru_chain, dim3(p->grid),
                                                dim3(GC_THREADS), kargs, p->smem, st));

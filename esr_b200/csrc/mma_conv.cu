@@ -88,6 +88,8 @@ __device__ __forceinline__ void st_split8(uint8_t *hi, uint8_t *lo, const float 
 template <int CIN, int COUT, int STRIDE, bool UPS, int INF, int OUTF, int TW, int TH>
 __global__ void __launch_bounds__(256) k_conv_mma(const DirectArgs a)
 {
+    PDL_LAUNCH_DEPENDENTS();
+    PDL_WAIT();
     using G = MmGeom<CIN, COUT, STRIDE, TW, TH>;
     constexpr int NP = G::NP, NT = G::NT, MT = G::MT, PW = G::PW, PH = G::PH, PITCH = G::PITCH, WP = G::WP, KS = G::KS;
     constexpr int CINP = G::CINP;
@@ -396,7 +398,7 @@ static int launch_mma(const DirectArgs &a, cudaStream_t st)
         attr_set = true;
     }
     dim3 grid((a.Wout + TW - 1) / TW, (a.Hout + TH - 1) / TH, a.n_img);
-    k_conv_mma<CIN, COUT, STRIDE, UPS, INF, OUTF, TW, TH><<<grid, 256, smem, st>>>(a);
+    ESR_CUDA_CHECK(launch_pdl(k_conv_mma<CIN, COUT, STRIDE, UPS, INF, OUTF, TW, TH>, dim3(grid), dim3(256), smem, st, a));
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

@@ -57,6 +57,7 @@ struct ParamLayout {
     size_t dw[D_COUNT], db[D_COUNT];     // direct layers
     size_t dm[D_COUNT];                  // the same weights as the split-bf16 image of the mma.sync kernels
     size_t fc0w, fc0b, fc1w, fc1b;
+    size_t nw_pm1, nw_at0, nw_ker;       // fp32 [tap][ci][co] weights of the narrow-output layers (conv_narrow)
     size_t total;
 };
 static const ParamLayout &param_layout()
@@ -76,6 +77,7 @@ static const ParamLayout &param_layout()
         }
         l.fc0w = take(sizeof(float) * 32 * 64); l.fc0b = take(sizeof(float) * 32);
         l.fc1w = take(sizeof(float) * 128 * 32); l.fc1b = take(sizeof(float) * 128);
+        l.nw_pm1 = take(sizeof(float) * 9 * 64); l.nw_at0 = take(sizeof(float) * 9 * 64); l.nw_ker = take(sizeof(float) * 64 * 2);
         l.total = off;
         return l;
     }();
@@ -420,6 +422,12 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
 #define RUND(name_, kind, dl, args) RUNC(name_, PC_DIRECT, direct_flops(dl, args), direct_bytes(dl, args), conv_direct(kind, args, st))
     const int B = n.B, N = n.N, VB = n.VB, VN = VB * N, nf = (N - 1) * VB, nsteps = n.Wn * N;
     const ParamLayout &L = param_layout();
+    // Cout <= 2 layers on CUDA cores (elementwise.cu conv_narrow).  Measured (profiles/r2_notes.md): only the 1x1 spatial-attention
+    // kernel wins (18.8 -> 14.8 us); the 3x3 ones are latency-bound there (pred_map[1] 41 -> 51, tail 66 -> 93 us) and stay on the
+    // tensor-core / mma.sync kernels.  ESR_NARROW_ALL=1 routes all of them through conv_narrow, ESR_NARROW_TC=1 none.
+    static const bool narrow_all = getenv("ESR_NARROW_ALL") != nullptr;
+    static const bool narrow_ker = narrow_all || getenv("ESR_NARROW_TC") == nullptr;
+    const bool narrow = narrow_all;
     // ---- per-frame work, once per bank frame: head + encoder (models/model.py:329-331) and the three attention maps
     //      of scale_aggre (model.py:259-262), which depend on the encoder features only
     const double px = (double)n.h * n.w;             // feature-resolution pixels per image
@@ -428,12 +436,21 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
          4.0 * a.n_img * ((double)n.H * n.W * 2.0 + (double)a.Hout * a.Wout * 16.0), conv_direct(DK_HEAD_ENC0, a, st));
     RUND("enc1", DK_ENC1, D_ENC1, n.d[D_ENC1]);
     RUND("enc2", DK_ENC2, D_ENC2, n.d[D_ENC2]);
-    RUNT("atten0", n.c_at0);
-    RUND("atten1", DK_ATT32, D_AT1, n.d[D_AT1]);
-    RUND("atten2", DK_ATT16, D_AT2, n.d[D_AT2]);
+    if (narrow) RUNC("atten0", PC_OTHER, 0.0, tc_bytes(n.c_at0), conv_narrow(n.F, nullptr, (const float *)(n.params + L.nw_at0), pb(n, T_AT0), 1, 9, n.FR, n.att0, st));
+    else RUNT("atten0", n.c_at0);
+    if (narrow) {
+        RUNC("atten1", PC_DIRECT, direct_flops(D_AT1, n.d[D_AT1]), direct_bytes(D_AT1, n.d[D_AT1]),
+             conv_narrow(n.t_e1, nullptr, n.d[D_AT1].w, n.d[D_AT1].bias, 1, 9, n.FR, n.att1, st));
+        RUNC("atten2", PC_DIRECT, direct_flops(D_AT2, n.d[D_AT2]), direct_bytes(D_AT2, n.d[D_AT2]),
+             conv_narrow(n.t_e0, nullptr, n.d[D_AT2].w, n.d[D_AT2].bias, 1, 9, n.FR, n.att2, st));
+    } else {
+        RUND("atten1", DK_ATT32, D_AT1, n.d[D_AT1]);
+        RUND("atten2", DK_ATT16, D_AT2, n.d[D_AT2]);
+    }
     // ---- TimePropagation.local_time_corre for every window (model.py:77-89,133-146)
     RUNT("pred_map0", n.c_pm0);
-    RUNT("pred_map1", n.c_pm1);
+    if (narrow) RUNC("pred_map1", PC_OTHER, 0.0, tc_bytes(n.c_pm1), conv_narrow(n.t_pm0, nullptr, (const float *)(n.params + L.nw_pm1), pb(n, T_PM1), 1, 9, VB * (N + 1), n.maps, st));
+    else RUNT("pred_map1", n.c_pm1);
     RUN("ltc_cat", 4.0 * VN * px * (192.0 + 192.0 + 2.0), ltc_cat(n.F, n.maps, n.m_ltc5, VN, n.t_cat, st));
     RUNT("local_fusion.res.conv1", n.c_lf1);
     RUNT("local_fusion.res.conv2", n.c_lf2);
@@ -466,7 +483,8 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     }
     RUNT("convblock0", n.c_cb0);
     RUNT("convblock1", n.c_cb1);
-    RUNT("spatial_kernel", n.c_ker);
+    if (narrow_ker) RUNC("spatial_kernel", PC_OTHER, 0.0, tc_bytes(n.c_ker), conv_narrow(n.feat, nullptr, (const float *)(n.params + L.nw_ker), pb(n, T_KER), 2, 1, nf, n.sk, st));
+    else RUNT("spatial_kernel", n.c_ker);
     RUN("chan_max", 4.0 * nf * px * 64.0, chan_max(n.feat, nf, n.mx, st));
     RUN("attn_mlp", 4.0 * nf * 192.0, attn_mlp(n.mx, nf, (const float *)(n.params + L.fc0w), (const float *)(n.params + L.fc0b),
                  (const float *)(n.params + L.fc1w), (const float *)(n.params + L.fc1b), n.ck, st));
@@ -485,7 +503,8 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     RUN("scale_aggre2", 4.0 * VB * 16.0 * px * (16.0 * (2 + N) + N), scale_aggregate(n.x2, n.t_e0, n.att2, n.m_fr, VB, N, n.pre2, st));
     RUND("recons2", DK_RECON2, D_RC2, n.d[D_RC2]);
     a = n.d[D_TAIL]; a.out_f32 = output;
-    RUNC("tail", PC_DIRECT, direct_flops(D_TAIL, a), 4.0 * a.n_img * ((double)n.Hc * n.Wc * 8.0 + (double)n.H * n.W * 2.0), conv_direct(DK_TAIL, a, st));
+    RUNC("tail", PC_DIRECT, direct_flops(D_TAIL, a), 4.0 * a.n_img * ((double)n.Hc * n.Wc * 8.0 + (double)n.H * n.W * 2.0),
+         narrow ? conv_narrow_tail(n.x3, a.w, a.bias, VB, output, n.pad_top, n.pad_left, n.H, n.W, st) : conv_direct(DK_TAIL, a, st));
 #undef RUN
 #undef RUNT
 #undef RUND
@@ -538,6 +557,9 @@ extern "C" int esr_net_pack_params(const float *const *p, void *blob, esr_stream
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.fc0b, p[P_FC0_B], sizeof(float) * 32, cudaMemcpyDeviceToDevice, st));
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.fc1w, p[P_FC1_W], sizeof(float) * 128 * 32, cudaMemcpyDeviceToDevice, st));
     ESR_CUDA_CHECK(cudaMemcpyAsync(out + L.fc1b, p[P_FC1_B], sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
+    if ((rc = pack_narrow_weight(p[P_PM1_W], 1, 9, (float *)(out + L.nw_pm1), st))) return rc;
+    if ((rc = pack_narrow_weight(p[P_AT0_W], 1, 9, (float *)(out + L.nw_at0), st))) return rc;
+    if ((rc = pack_narrow_weight(p[P_KER_W], 2, 1, (float *)(out + L.nw_ker), st))) return rc;
     return ESR_OK;
 }
 

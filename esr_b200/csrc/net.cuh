@@ -59,6 +59,12 @@ int scale_aggregate(const SplitTensor &x, const SplitTensor &feats, const float 
 // bilinear x2 (align_corners=False) of a split tensor (models/submodules.py:290)
 int upsample2x(const SplitTensor &src, int n_img, const SplitTensor &dst, cudaStream_t st);
 int copy_split(const SplitTensor &src, const int *src_img, int n_img, const SplitTensor &dst, cudaStream_t st);
+// Cout = 1 / 2 convolutions (3x3 or 1x1, sigmoid) of a 64-channel split tensor on CUDA cores: fp32 NHWC out [n_img, H, W, cout]
+int conv_narrow(const SplitTensor &x, const int *src_img, const float *w, const float *bias, int cout, int ntaps, int n_img, float *out,
+                cudaStream_t st);
+int pack_narrow_weight(const float *w, int cout, int ntaps, float *dst, cudaStream_t st);
+int conv_narrow_tail(const SplitTensor &x, const float *w, const float *bias, int n_img, float *out, int crop_top, int crop_left, int out_H,
+                     int out_W, cudaStream_t st);
 
 // ---- deformable sampling (dcn.cu): columns[img][y][x][tap*64 + c] = bilinear(feat[c], y-1+i+off_h, x-1+j+off_w) * mask
 // om: fp32 NHWC [n_img, H, W, 216] = {144 offsets (group-major, (h,w) pairs per tap), 72 masks (already sigmoid)}

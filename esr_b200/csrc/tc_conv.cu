@@ -27,6 +27,7 @@ constexpr int TRACE_N = 512;                 // K-blocks / tiles recorded by the
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const __grid_constant__ ConvTCArgs a)
 {
+    PDL_LAUNCH_DEPENDENTS();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-B alignment
     const uint32_t b_bytes = (uint32_t)a.npad * 128u;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const __grid_constant
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    PDL_WAIT();                      // everything above is CTA-local set-up; global memory only from here on
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const __grid_constant
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_constant__ ConvTCArgs a)
 {
+    PDL_LAUNCH_DEPENDENTS();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)a.npad * 128u;
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    PDL_WAIT();                      // everything above is CTA-local set-up; global memory only from here on
 
     if (warp == 0) {
         if (elect_one_sync()) {
@@ -288,38 +292,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_
 //   * epilogue warps of both CTAs drain their own 128 TMEM lanes and arrive (one lane per warp) on the LEADER's aempty[acc].
 // Same operand order per output element as k_conv_tc / k_conv_tc_persist => bit-identical results.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pair_rank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void pair_sync()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 raddr;\n\t"
-        "mapa.shared::cluster.u32 raddr, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n\t"
-        "}" ::"r"(bar), "r"(cta) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P1;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -751,12 +723,12 @@ int conv_tc_launch(const ConvTCArgs &a, cudaStream_t st)
             ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
             max_set_p = (int)smem_p;
         }
-        k_conv_tc_persist<<<(unsigned)dev_info().sm_count, TC_THREADS, smem_p, st>>>(a);
-        ESR_LAUNCH_CHECK();
+        ESR_CUDA_CHECK(launch_pdl(k_conv_tc_persist, dim3((unsigned)dev_info().sm_count), dim3(TC_THREADS), smem_p, st, a));
+        esr::count_launch();
         return ESR_OK;
     }
-    k_conv_tc<<<grid, TC_THREADS, smem, st>>>(a);
-    ESR_LAUNCH_CHECK();
+    ESR_CUDA_CHECK(launch_pdl(k_conv_tc, dim3(grid), dim3(TC_THREADS), smem, st, a));
+    esr::count_launch();
     return ESR_OK;
 }
 

@@ -38,6 +38,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t smem_addr, uint3
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_constant__ ConvTCArgs a)
 {
+    PDL_LAUNCH_DEPENDENTS();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)a.npad * 128u, b_stage = 2u * b_bytes;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    PDL_WAIT();                      // everything above is CTA-local set-up; global memory only from here on
 
     if (warp == 0) {
         // ===================== TMA producer: per chunk one halo box per plane, then nine weight tiles =====================
@@ -202,8 +204,8 @@ int conv_tc_halo_launch(const ConvTCArgs &a, cudaStream_t st)
     }
     const int n_tiles = a.n_img * a.tiles_x * a.tiles_y;
     const unsigned grid = (unsigned)(n_tiles < dev_info().sm_count ? n_tiles : dev_info().sm_count);
-    k_conv_tc_halo<<<grid, TC_THREADS, smem, st>>>(a);
-    ESR_LAUNCH_CHECK();
+    ESR_CUDA_CHECK(launch_pdl(k_conv_tc_halo, dim3(grid), dim3(TC_THREADS), smem, st, a));
+    esr::count_launch();
     return ESR_OK;
 }
 

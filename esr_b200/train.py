@@ -533,14 +533,30 @@ class GraphedTrainStep:
             for _ in range(warmup):
                 _step_body(model, optimizer, self.frames, self.gt, num_frame, all_reduce)
         torch.cuda.current_stream(device).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = _step_body(model, optimizer, self.frames, self.gt, num_frame, all_reduce)
-        for dst, src in zip((optimizer.flat, optimizer.exp_avg, optimizer.exp_avg_sq), keep):   # undo the warm-up updates
-            dst.copy_(src)
-        if keep_max is not None:
-            optimizer.max_exp_avg_sq.copy_(keep_max)
-        optimizer.step_dev.copy_(keep_step)
+        # capture; with an NCCL all-reduce inside, the FIRST capture on a fresh capture stream can be invalidated by the process
+        # group's first-use bookkeeping (seen at N = 2: first attempt fails, second succeeds) -> one retry; the optimizer state
+        # touched by the warm-up iterations is restored whatever happens
+        def restore():
+            for dst, src in zip((optimizer.flat, optimizer.exp_avg, optimizer.exp_avg_sq), keep):
+                dst.copy_(src)
+            if keep_max is not None:
+                optimizer.max_exp_avg_sq.copy_(keep_max)
+            optimizer.step_dev.copy_(keep_step)
+
+        err = None
+        for attempt in range(2):
+            try:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.loss = _step_body(model, optimizer, self.frames, self.gt, num_frame, all_reduce)
+                err = None
+                break
+            except Exception as e:                                # noqa: BLE001 -- rethrown below
+                err = e
+                torch.cuda.synchronize(device)
+        restore()
+        if err is not None:
+            raise err
 
     def __call__(self, frames, gt):
         self.frames.copy_(frames)
