@@ -38,12 +38,18 @@ k_scatter_cnt(float *__restrict__ xs, float *__restrict__ ys, const float *__res
         const bool oor = (x >= fW) | (x < 0.0f) | (y >= fH) | (y < 0.0f);
         float vpos = __fmul_rn(p, p < 0.0f ? 0.0f : p);
         const float vneg = __fmul_rn(p, p > 0.0f ? 0.0f : p);
-        if (oor) { x = 0.0f; y = 0.0f; vpos = 0.0f; }
+        float vn = vneg;
+        if (oor) {
+            x = 0.0f; y = 0.0f; vpos = 0.0f;
+            // writeback == 2, the order of H5Dataset.__getitem__ (h5dataset.py:337-354): create_stack_encoding has already zeroed x, y AND p
+            // of out-of-range events in place when the frame holds more than 3 events (encodings.py:219-220, 251-256), so they add nothing
+            if (writeback == 2 && end - beg > 3) vn = 0.0f;
+        }
         const long long xi = (long long)x, yi = (long long)y;   // .long(): truncation toward zero
         const size_t pix = (size_t)yi * W + (size_t)xi;
         if (vpos != 0.0f) atomicAdd(img + pix, vpos);
-        if (vneg != 0.0f) atomicAdd(img + (size_t)H * W + pix, vneg);
-        if (writeback && oor) { xs[i] = 0.0f; ys[i] = 0.0f; }
+        if (vn != 0.0f) atomicAdd(img + (size_t)H * W + pix, vn);
+        if (writeback == 1 && oor) { xs[i] = 0.0f; ys[i] = 0.0f; }
     }
 }
 
@@ -545,7 +551,7 @@ extern "C" int esr_scatter_cnt(float *xs, float *ys, const float *ps, const int6
     ESR_REQUIRE(F <= 65535, "esr_scatter_cnt: at most 65535 frames per call");
     dim3 grid((unsigned)bx, (unsigned)F);
     k_scatter_cnt<<<grid, 256, 0, st>>>(xs, ys, ps, frame_off, n_max_frame, H, W, (float)lift_w_lr, (float)lift_w_hr,
-                                         (float)lift_h_lr, (float)lift_h_hr, do_lift, writeback && !do_lift, out);
+                                         (float)lift_h_lr, (float)lift_h_hr, do_lift, writeback == 2 ? 2 : (writeback && !do_lift), out);
     ESR_LAUNCH_CHECK();
     return ESR_OK;
 }

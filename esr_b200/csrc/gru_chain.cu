@@ -31,6 +31,7 @@ struct GruChainArgs {
     float *zbuf;                                // update gate, fp32 [2B, H, W, 64]
     unsigned int *barrier;                      // grid barrier counter (zeroed before the launch)
     int B, N, nsteps, H, W, TW, TH, tiles_x, tiles_y, stages;
+    int wpre;                                   // 1: weight tiles of the first state-side K-blocks are issued before the phase barrier wait (measured slower)
     int cluster;                                // > 1: one thread-block cluster per image (tiles_per_img CTAs), phase barrier through DSMEM mbarriers
 };
 
@@ -383,10 +384,22 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                 const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
                 const CUtensorMap *bmap = which == 0 ? &a.bmap_zr : &a.bmap_go;
                 const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
+                // weight tiles never depend on the recurrent state: for the first `pre` state-side K-blocks they are issued BEFORE the
+                // phase barrier is awaited (as soon as their stages are free), only the h / h*r tiles wait for it
+                const int pre = (p > 0 && a.wpre) ? (a.stages < 9 ? a.stages : 9) : 0;
                 for (int kb = 0; kb < 18; ++kb) {
                     const int src = kb / 9, tap = kb - src * 9;
                     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                     if (kb == 9 && p > 0) {
+                        uint32_t qs = ps, qph = pph;
+                        for (int j = 0; j < pre; ++j) {
+                            mbar_wait(bar_empty + 8u * qs, qph ^ 1u);
+                            mbar_expect_tx(bar_full + 8u * qs, stage_bytes);
+                            const uint32_t stq = smem_base + qs * STAGE;
+                            tma_load_3d(bmap, bar_full + 8u * qs, stq + 2u * TC_A_BYTES, 0, 0, 9 + j);
+                            tma_load_3d(bmap, bar_full + 8u * qs, stq + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + 9 + j);
+                            if (++qs == (uint32_t)a.stages) { qs = 0; qph ^= 1u; }
+                        }
                         // state-side operands are written by every CTA's epilogue of phase p-1: wait for all of them
                         if (cl) {
                             mbar_wait_cluster(bar_phase, (uint32_t)((p - 1) & 1));
@@ -399,15 +412,20 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                         }
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
-                    mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
-                    mbar_expect_tx(bar_full + 8u * ps, stage_bytes);
+                    const bool b_done = kb >= 9 && kb < 9 + pre;          // this stage's weights (and its expect_tx) are already on the way
                     const uint32_t st = smem_base + ps * STAGE;
                     const CUtensorMap *am = src == 0 ? &a.amap_xc : (which == 0 ? &a.amap_hs : &a.amap_rh);
                     const int simg = src == 0 ? xc_img : (which == 0 ? g * B2 + img : img);
+                    if (!b_done) {
+                        mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
+                        mbar_expect_tx(bar_full + 8u * ps, stage_bytes);
+                    }
                     tma_load_5d(am, bar_full + 8u * ps, st, 0, x0 + dx, y0 + dy, simg, 0);
                     tma_load_5d(am, bar_full + 8u * ps, st + TC_A_BYTES, 0, x0 + dx, y0 + dy, simg, 1);
-                    tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, 0, kb);
-                    tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + kb);
+                    if (!b_done) {
+                        tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, 0, kb);
+                        tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + kb);
+                    }
                     if (++ps == (uint32_t)a.stages) { ps = 0; pph ^= 1u; }
                 }
             }
@@ -467,11 +485,243 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Re-scheduled pipelined variant (default when one tile per CTA fits): the update gate z is only needed for the final blend,
+// so the step is split differently from the reference's (update|reset), (candidate) order:
+//   part A   r = sigmoid(conv_r(x, h))                       N = 64: 9 state-side K-blocks on the critical path (was N = 128)
+//            epilogue: h * r (64 columns instead of 128)      -> barrier
+//   part B   z = sigmoid(conv_z(x, h)),  o = tanh(conv_o(x, h * r))      two N = 64 GEMMs into adjacent TMEM columns
+//            z's 18 K-blocks and o's 9 x-side K-blocks depend only on data that was complete before part A's barrier: the producer
+//            / MMA threads run them while the epilogue warps of part A work and the barrier is pending; only o's 9 (h * r)-side
+//            K-blocks wait.  epilogue: h' = h (1 - z) + o z straight from the two accumulators -- z never leaves the SM (the fp32
+//            z buffer round trip is gone).
+// Per output element the sums are those of k_gru_chain_pipe (a GEMM's columns are independent), so the results are
+// bit-identical.  Stages are 48 KB (A 32 KB + two 8 KB weight planes): four fit.  ESR_GRU_RZO=0 selects the older kernel.
+// ------------------------------------------------------------------------------------------------
+struct GruRzoArgs {
+    GruChainArgs g;
+    CUtensorMap bmap_zr64;                      // the update|reset pack with a 64-row box: rows [0, 64) = update (z), [64, 128) = reset (r)
+};
+
+__global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_constant__ GruRzoArgs aa)
+{
+    const GruChainArgs &a = aa.g;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t B_BYTES = 64u * 128u;                              // one plane of a 64-row weight tile
+    constexpr uint32_t STAGE = 2u * TC_A_BYTES + 2u * B_BYTES;            // 48 KB
+    const uint32_t bar_base = smem_base + (uint32_t)a.stages * STAGE;
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages, bar_accum = bar_base + 16u * a.stages;   // [0] = r, [1] = z|o
+    const uint32_t tmem_slot = bar_accum + 16u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B2 = 2 * a.B;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int tile = blockIdx.x;                                  // grid == number of tiles
+    const int img = tile / tiles_per_img;
+    const int trem = tile - img * tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+    const int bb = img < a.B ? img : img - a.B;
+    const bool per_img = B2 <= 64;
+    unsigned int *bar_ctr = a.barrier + (per_img ? img * 8 : 0);
+    const unsigned int bar_n = per_img ? (unsigned int)tiles_per_img : gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        mbar_init(bar_accum, 1); mbar_init(bar_accum + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);                    // r: columns [0, 64); z: [64, 128); o: [128, 192)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // the six K-segments of a step, in issue order: {r: x, h}, {z: x, h}, {o: x, h*r}
+    //   seg     weights            A operand      waits for barrier
+    //   0 r.x   zr64 row 64        xc             -
+    //   1 r.h   zr64 row 64        hs[g]          2g - 1   (state of the previous step; none at g = 0)
+    //   2 z.x   zr64 row 0         xc             -
+    //   3 z.h   zr64 row 0         hs[g]          -        (same data as segment 1)
+    //   4 o.x   go                 xc             -
+    //   5 o.rh  go                 rh             2g       (this step's h * r)
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            uint32_t ps = 0, pph = 0;
+            for (int g = 0; g < a.nsteps; ++g) {
+                const int w_idx = g / a.N, s_idx = g - w_idx * a.N;
+                const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
+                for (int seg = 0; seg < 6; ++seg) {
+                    const CUtensorMap *bmap = seg < 4 ? &aa.bmap_zr64 : &a.bmap_go;
+                    const int brow = seg < 2 ? 64 : 0;
+                    const int kb0 = (seg & 1) ? 9 : 0;
+                    const CUtensorMap *am = (seg & 1) == 0 ? &a.amap_xc : (seg == 5 ? &a.amap_rh : &a.amap_hs);
+                    const int simg = (seg & 1) == 0 ? xc_img : (seg == 5 ? img : g * B2 + img);
+                    const int wait_bar = seg == 1 ? 2 * g - 1 : (seg == 5 ? 2 * g : -1);
+                    int pre = 0;
+                    if (wait_bar >= 0) {
+                        // the weight tiles do not depend on the state: those of the first stages go out before the barrier is awaited
+                        pre = a.wpre ? (a.stages < 9 ? a.stages : 9) : 0;
+                        uint32_t qs = ps, qph = pph;
+                        for (int j = 0; j < pre; ++j) {
+                            mbar_wait(bar_empty + 8u * qs, qph ^ 1u);
+                            mbar_expect_tx(bar_full + 8u * qs, STAGE);
+                            const uint32_t stq = smem_base + qs * STAGE;
+                            tma_load_3d(bmap, bar_full + 8u * qs, stq + 2u * TC_A_BYTES, 0, brow, kb0 + j);
+                            tma_load_3d(bmap, bar_full + 8u * qs, stq + 2u * TC_A_BYTES + B_BYTES, 0, brow, 18 + kb0 + j);
+                            if (++qs == (uint32_t)a.stages) { qs = 0; qph ^= 1u; }
+                        }
+                        const unsigned int target = (unsigned int)(wait_bar + 1) * bar_n;
+                        unsigned int v;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
+                        } while (v < target);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    for (int t = 0; t < 9; ++t) {
+                        const int dy = t / 3 - 1, dx = t % 3 - 1;
+                        const uint32_t st = smem_base + ps * STAGE;
+                        const bool b_done = t < pre;
+                        if (!b_done) {
+                            mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
+                            mbar_expect_tx(bar_full + 8u * ps, STAGE);
+                        }
+                        tma_load_5d(am, bar_full + 8u * ps, st, 0, x0 + dx, y0 + dy, simg, 0);
+                        tma_load_5d(am, bar_full + 8u * ps, st + TC_A_BYTES, 0, x0 + dx, y0 + dy, simg, 1);
+                        if (!b_done) {
+                            tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, brow, kb0 + t);
+                            tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES + B_BYTES, 0, brow, 18 + kb0 + t);
+                        }
+                        if (++ps == (uint32_t)a.stages) { ps = 0; pph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64);
+            uint32_t ms = 0, mph = 0;
+            for (int g = 0; g < a.nsteps; ++g) {
+                for (int seg = 0; seg < 6; ++seg) {
+                    const uint32_t acc = tmem_base + (uint32_t)(seg >> 1) * 64u;          // r | z | o
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(bar_full + 8u * ms, mph);
+                        tc_fence_after();
+                        const uint32_t st = smem_base + ms * STAGE;
+                        const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + B_BYTES;
+                        const uint32_t first = ((seg & 1) == 0 && t == 0) ? 0u : 1u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                            const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                            umma_bf16(acc, dal, dbh, idesc, k == 0 ? first : 1u);
+                            umma_bf16(acc, dah, dbl, idesc, 1u);
+                            umma_bf16(acc, dah, dbh, idesc, 1u);
+                        }
+                        umma_commit(bar_empty + 8u * ms);
+                        if (++ms == (uint32_t)a.stages) { ms = 0; mph ^= 1u; }
+                    }
+                    if (seg == 1) umma_commit(bar_accum);                  // r complete
+                    if (seg == 5) umma_commit(bar_accum + 8u);             // z and o complete
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: 8 warps, two per TMEM lane quadrant, 32 channels each =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int m = quad * 32 + lane;
+        const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+        const bool valid = (y < a.H) && (x < a.W);
+        const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int c0 = half * 32;                                            // this warp's channels
+        for (int g = 0; g < a.nsteps; ++g) {
+            const uint32_t par = (uint32_t)(g & 1);
+            const __nv_bfloat16 *h_prev = a.hs + ((size_t)g * B2 * a.H * a.W + pix) * 64 + c0;
+            // h of this pixel (previous step's state: final before this step's first barrier) -- in flight during the main loops
+            uint4 hh[4], hl[4];
+            if (valid) {
+                const uint4 *ph = reinterpret_cast<const uint4 *>(h_prev), *pl = reinterpret_cast<const uint4 *>(h_prev + a.hs_plane);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { hh[q] = ph[q]; hl[q] = pl[q]; }
+            }
+            float h[32];
+            // ---- part A: r -> h * r
+            mbar_wait_backoff(bar_accum, par);
+            tc_fence_after();
+            {
+                uint32_t raw[32];
+                tmem_ld32(taddr + (uint32_t)c0, raw);
+                if (valid) {
+                    gc_unpack32(hh, hl, h);
+                    float v[32];
+                    const float4 *bp = reinterpret_cast<const float4 *>(a.bias_zr + 64 + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = bp[q];
+                        v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+                        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+                        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+                        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+                    }
+                    act32(v, ACT_SIGMOID);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= h[j];
+                    store_split32(a.rh + pix * 64 + c0, a.rh_plane, v);
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
+            // ---- part B: z, o -> h' = h (1 - z) + o z
+            mbar_wait_backoff(bar_accum + 8u, par);
+            tc_fence_after();
+            {
+                uint32_t rz[32], ro[32];
+                tmem_ld32(taddr + 64u + (uint32_t)c0, rz);
+                tmem_ld32(taddr + 128u + (uint32_t)c0, ro);
+                if (valid) {
+                    float z[32], o[32];
+                    const float4 *bz = reinterpret_cast<const float4 *>(a.bias_zr + c0), *bo = reinterpret_cast<const float4 *>(a.bias_go + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b1 = bz[q], b2 = bo[q];
+                        z[4 * q + 0] = __uint_as_float(rz[4 * q + 0]) + b1.x; o[4 * q + 0] = __uint_as_float(ro[4 * q + 0]) + b2.x;
+                        z[4 * q + 1] = __uint_as_float(rz[4 * q + 1]) + b1.y; o[4 * q + 1] = __uint_as_float(ro[4 * q + 1]) + b2.y;
+                        z[4 * q + 2] = __uint_as_float(rz[4 * q + 2]) + b1.z; o[4 * q + 2] = __uint_as_float(ro[4 * q + 2]) + b2.z;
+                        z[4 * q + 3] = __uint_as_float(rz[4 * q + 3]) + b1.w; o[4 * q + 3] = __uint_as_float(ro[4 * q + 3]) + b2.w;
+                    }
+                    act32(z, ACT_SIGMOID);
+                    act32(o, ACT_TANH);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = h[j] * (1.0f - z[j]) + o[j] * z[j];
+                    __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64 + c0;
+                    store_split32(h_new, a.hs_plane, o);
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct GruChainPlan {
     GruChainArgs args;
     int grid;
     size_t smem;
     bool pipelined;
+    bool rzo = false;               // k_gru_chain_rzo (reset gate first; update gate and candidate together, off the critical path)
+    GruRzoArgs rzo_args;
+    size_t rzo_smem = 0;
 };
 
 int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const void *w_zr,
@@ -493,6 +743,7 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
     a.B = B; a.N = N; a.nsteps = nsteps; a.H = H; a.W = W; a.TW = TW; a.TH = TH;
     a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH;
     a.stages = 3;
+    a.wpre = getenv("ESR_GRU_WPRE") != nullptr;     // 476 -> 492 us with it (profiles/r2_notes.md): off
     p->smem = 1024 + (size_t)a.stages * (2 * TC_A_BYTES + 2 * 128 * 128) + 16 * a.stages + 96;
     ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     int per_sm = 0;
@@ -524,6 +775,15 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
         if (getenv("ESR_DEBUG")) fprintf(stderr, "[esr] gru_chain: %d clusters of %d CTAs wanted, %d can be resident\n", n_tiles / a.cluster, a.cluster, max_clusters);
         if (max_clusters * a.cluster < n_tiles) a.cluster = 1;
     }
+    static const bool rzo_off = getenv("ESR_GRU_RZO") && atoi(getenv("ESR_GRU_RZO")) == 0;
+    if (p->pipelined && a.cluster <= 1 && !rzo_off) {
+        p->rzo = true;
+        p->rzo_args.g = a;
+        p->rzo_args.g.stages = 4;
+        if ((rc = tc_make_bmap(w_zr, 128, 18, 64, &p->rzo_args.bmap_zr64))) { delete p; return rc; }
+        p->rzo_smem = 1024 + (size_t)4 * (2 * TC_A_BYTES + 2 * 64 * 128) + 16 * 4 + 96;
+        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_rzo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->rzo_smem));
+    }
     *plan_out = p;
     return ESR_OK;
 }
@@ -532,6 +792,12 @@ int gru_chain_launch(void *plan, cudaStream_t st)
 {
     GruChainPlan *p = (GruChainPlan *)plan;
     ESR_CUDA_CHECK(cudaMemsetAsync(p->args.barrier, 0, 64 * 8 * sizeof(unsigned int), st));   // per-image counters, 32 bytes apart
+    if (p->rzo) {
+        void *kargs[] = {(void *)&p->rzo_args};
+        ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain_rzo, dim3(p->grid), dim3(GC_THREADS), kargs, p->rzo_smem, st));
+        esr::count_launch();
+        return ESR_OK;
+    }
     if (p->pipelined && p->args.cluster > 1) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(p->grid); cfg.blockDim = dim3(GC_THREADS); cfg.dynamicSmemBytes = p->smem; cfg.stream = st;

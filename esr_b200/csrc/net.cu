@@ -110,6 +110,7 @@ struct Net {
     void *gru_plan = nullptr;          // cooperative whole-chain kernel (gru_chain.cu); nullptr = per-step launches
     unsigned int *gru_barrier = nullptr;
     DirectArgs d[D_COUNT];
+    bool agg_fused = false;            // scale aggregation of decoder levels 1, 2 inside the recons convs' fill
 };
 
 static size_t split_bytes(int n_img, int H, int W, int C) { return (size_t)2 * n_img * H * W * C * sizeof(__nv_bfloat16); }
@@ -371,8 +372,16 @@ static int build(Net &n, cudaStream_t st)
     a = base(D_AT1, ACT_SIGMOID); in_split(a, n.t_e1); a.out_f32 = n.att1; a.Hout = n.t_e1.H; a.Wout = n.t_e1.W; a.n_img = FR; n.d[D_AT1] = a;
     a = base(D_AT2, ACT_SIGMOID); in_split(a, n.t_e0); a.out_f32 = n.att2; a.Hout = n.t_e0.H; a.Wout = n.t_e0.W; a.n_img = FR; n.d[D_AT2] = a;
     a = base(D_RC0, ACT_RELU); in_split(a, n.pre0); out_split(a, n.x1, VB); n.d[D_RC0] = a;
-    a = base(D_RC1, ACT_RELU); in_split(a, n.pre1); out_split(a, n.x2, VB); n.d[D_RC1] = a;
-    a = base(D_RC2, ACT_RELU); in_split(a, n.pre2); out_split(a, n.x3, VB); n.d[D_RC2] = a;
+    // scale aggregation (model.py:259-267) of the two full-resolution decoder levels CAN be folded into the fill of the recons convs
+    // (mma_conv.cu, DirectArgs::agg_*; ESR_AGG_FUSE=1): measured a net loss -- the two k_scale_aggregate launches (64 us) go away but the
+    // latency-bound fills grow by 37 + 38 us (profiles/r2_notes.md) -- so the separate bandwidth-bound pass stays the default.
+    n.agg_fused = getenv("ESR_AGG_FUSE") != nullptr && getenv("ESR_DIRECT_FFMA") == nullptr;
+    a = base(D_RC1, ACT_RELU); in_split(a, n.agg_fused ? n.x1 : n.pre1); out_split(a, n.x2, VB);
+    if (n.agg_fused) { a.agg_feats = n.t_e1.base; a.agg_plane = n.t_e1.plane(); a.agg_att = n.att1; a.agg_idx = n.m_fr; a.agg_N = N; }
+    n.d[D_RC1] = a;
+    a = base(D_RC2, ACT_RELU); in_split(a, n.agg_fused ? n.x2 : n.pre2); out_split(a, n.x3, VB);
+    if (n.agg_fused) { a.agg_feats = n.t_e0.base; a.agg_plane = n.t_e0.plane(); a.agg_att = n.att2; a.agg_idx = n.m_fr; a.agg_N = N; }
+    n.d[D_RC2] = a;
     a = base(D_TAIL, ACT_RELU); in_split(a, n.x3); a.Hout = n.Hc; a.Wout = n.Wc; a.n_img = VB;
     a.crop_top = n.pad_top; a.crop_left = n.pad_left; a.out_H = n.H; a.out_W = n.W; n.d[D_TAIL] = a;
     return ESR_OK;
@@ -498,9 +507,9 @@ static int forward(Net &n, const float *input, const int *in_img, float *output,
     RUN("scale_aggre0", 4.0 * VB * px * (64.0 * (2 + N) + N), scale_aggregate(n.x0, n.F, n.att0, n.m_fr, VB, N, n.pre0, st));
     RUN("upsample2x", 4.0 * VB * px * 64.0 * 5.0, upsample2x(n.pre0, VB, n.up0, st));
     RUNT("recons0", n.c_rc0);
-    RUN("scale_aggre1", 4.0 * VB * 4.0 * px * (32.0 * (2 + N) + N), scale_aggregate(n.x1, n.t_e1, n.att1, n.m_fr, VB, N, n.pre1, st));
+    if (!n.agg_fused) RUN("scale_aggre1", 4.0 * VB * 4.0 * px * (32.0 * (2 + N) + N), scale_aggregate(n.x1, n.t_e1, n.att1, n.m_fr, VB, N, n.pre1, st));
     RUND("recons1", DK_RECON1, D_RC1, n.d[D_RC1]);
-    RUN("scale_aggre2", 4.0 * VB * 16.0 * px * (16.0 * (2 + N) + N), scale_aggregate(n.x2, n.t_e0, n.att2, n.m_fr, VB, N, n.pre2, st));
+    if (!n.agg_fused) RUN("scale_aggre2", 4.0 * VB * 16.0 * px * (16.0 * (2 + N) + N), scale_aggregate(n.x2, n.t_e0, n.att2, n.m_fr, VB, N, n.pre2, st));
     RUND("recons2", DK_RECON2, D_RC2, n.d[D_RC2]);
     a = n.d[D_TAIL]; a.out_f32 = output;
     RUNC("tail", PC_DIRECT, direct_flops(D_TAIL, a), 4.0 * a.n_img * ((double)n.Hc * n.Wc * 8.0 + (double)n.H * n.W * 2.0),

@@ -28,6 +28,9 @@ struct DirectArgs {
     size_t out_plane = 0;
     float *out_f32 = nullptr;
     int crop_top = 0, crop_left = 0, out_H = 0, out_W = 0;          // NCHW output window (tail)
+    // decoder layers (bilinear x2 fused): optional scale aggregation folded into the source-patch fill (models/model.py:259-267):
+    //   source value = in_split[b] + mean_n(agg_feats[agg_idx[b * agg_N + n]] * agg_att[same pixel])
+    const __nv_bfloat16 *agg_feats = nullptr; size_t agg_plane = 0; const float *agg_att = nullptr; const int *agg_idx = nullptr; int agg_N = 0;
 };
 
 int conv_direct(DirectKind kind, const DirectArgs &a, cudaStream_t st);

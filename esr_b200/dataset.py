@@ -152,9 +152,10 @@ def collate_sequence(inp_events, gt_events, inp_resolution, gt_resolution, num_f
     (gx, gy, gp, goff), gmax = flat(gt_events)
     H, W = int(inp_resolution[0]), int(inp_resolution[1])
     kH, kW = int(gt_resolution[0]), int(gt_resolution[1])
-    inp_cnt = encodings.encode_frames(ix, iy, ip, ioff, None, (H, W), imax).view(B, L, 2, H, W)
-    inp_scaled = encodings.encode_frames(ix, iy, ip, ioff, (H, W), (kH, kW), imax).view(B, L, 2, kH, kW)
-    gt_cnt = encodings.encode_frames(gx, gy, gp, goff, None, (kH, kW), gmax).view(B, L, 2, kH, kW)
+    # sanitised: H5Dataset.__getitem__ builds the stack encodings first, which zero out-of-range events in place
+    inp_cnt = encodings.encode_frames(ix, iy, ip, ioff, None, (H, W), imax, sanitised=True).view(B, L, 2, H, W)
+    inp_scaled = encodings.encode_frames(ix, iy, ip, ioff, (H, W), (kH, kW), imax, sanitised=True).view(B, L, 2, kH, kW)
+    gt_cnt = encodings.encode_frames(gx, gy, gp, goff, None, (kH, kW), gmax, sanitised=True).view(B, L, 2, kH, kW)
     bank = {'inp_cnt': inp_cnt, 'inp_scaled_cnt': inp_scaled, 'gt_cnt': gt_cnt}
     return [{'inp_cnt': inp_cnt[:, w:w + num_frame], 'inp_scaled_cnt': inp_scaled[:, w:w + num_frame],
              'gt_cnt': gt_cnt[:, w:w + num_frame], 'bank': bank} for w in range(L - num_frame + 1)]

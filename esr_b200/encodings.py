@@ -145,8 +145,12 @@ def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
     return out if xs.is_cuda else out.cpu()
 
 
-def encode_frames(xs, ys, ps, frame_off, lr_size=None, hr_size=(180, 240), n_max_frame=None, out=None):
+def encode_frames(xs, ys, ps, frame_off, lr_size=None, hr_size=(180, 240), n_max_frame=None, out=None, sanitised=False):
     """F frames of events -> [F,2,H,W] count images in one launch.
+
+    sanitised=True reproduces the call ORDER of H5Dataset.__getitem__ (h5dataset.py:337-354): create_stack_encoding runs first
+    and zeroes x, y, p of out-of-range events in place (frames of more than 3 events), so they add nothing to the count tensors;
+    the default is the standalone events_to_channels, where an out-of-range NEGATIVE event lands on neg[0, 0].
 
     xs, ys, ps: CUDA fp32 [n_total]; frame_off: CUDA int64 [F+1].  With lr_size=(H_lr,W_lr) the coordinates
     are lifted x/W_lr*W_hr (two fp32 roundings, h5dataset.py:515,526) before the scatter = `inp_scaled_cnt`."""
@@ -161,7 +165,7 @@ def encode_frames(xs, ys, ps, frame_off, lr_size=None, hr_size=(180, 240), n_max
     lift = (int(lr_size[1]), W, int(lr_size[0]), H) if lr_size is not None else (0, 0, 0, 0)
     with torch.cuda.device(xs.device):
         _lib.check(_lib.lib().esr_scatter_cnt(_lib.ptr(xs), _lib.ptr(ys), _lib.ptr(ps), _lib.ptr(frame_off), F,
-                                              int(n_max_frame), H, W, *lift, 0, _lib.ptr(out), _lib.stream_ptr()),
+                                              int(n_max_frame), H, W, *lift, 2 if sanitised else 0, _lib.ptr(out), _lib.stream_ptr()),
                    "esr_scatter_cnt")
     return out
 

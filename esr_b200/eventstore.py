@@ -256,12 +256,12 @@ class SequenceReader:
         ix, iy, _, ip, ioff, imax = self._gather(self.inp_cols, self.index.event_indices, frames)
         H, W = self.inp_sensor_resolution
         kH, kW = self.gt_sensor_resolution
-        inp_cnt = encodings.encode_frames(ix, iy, ip, ioff, None, (H, W), imax).view(B, L, 2, H, W)
-        inp_scaled = encodings.encode_frames(ix, iy, ip, ioff, (H, W), (kH, kW), imax).view(B, L, 2, kH, kW)
+        inp_cnt = encodings.encode_frames(ix, iy, ip, ioff, None, (H, W), imax, sanitised=True).view(B, L, 2, H, W)
+        inp_scaled = encodings.encode_frames(ix, iy, ip, ioff, (H, W), (kH, kW), imax, sanitised=True).view(B, L, 2, kH, kW)
         bank = {"inp_cnt": inp_cnt, "inp_scaled_cnt": inp_scaled}
         if self.gt_cols is not None:
             gx, gy, _, gp, goff, gmax = self._gather(self.gt_cols, self.index.gt_event_indices, frames)
-            bank["gt_cnt"] = encodings.encode_frames(gx, gy, gp, goff, None, (kH, kW), gmax).view(B, L, 2, kH, kW)
+            bank["gt_cnt"] = encodings.encode_frames(gx, gy, gp, goff, None, (kH, kW), gmax, sanitised=True).view(B, L, 2, kH, kW)
         N = self.num_frame
         return [dict({k: v[:, w:w + N] for k, v in bank.items()}, bank=bank) for w in range(L - N + 1)]
 

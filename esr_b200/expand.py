@@ -79,48 +79,37 @@ def expand_begin(vals, kind):
     return ctx
 
 
-def expand_finish(ctx, mode):
-    """Phase 2: wait for the statistics (the one inherent host synchronisation: the output length is data dependent), size the
-    output, emit and sort.  Returns CUDA fp32 [B, maxlen, 4]."""
+def _host_plan(ctx):
+    """Wait for a (sub-)batch's statistics -- the one inherent host synchronisation: the output length is data dependent -- and size
+    its output on the host.  Returns None for an all-empty batch (`if event_cnt_round.sum() != 0`, cnt2event.pyx:56)."""
+    ctx.event.synchronize()
+    h = ctx.stats_host.numpy()
+    sums, nev, neg = h[:, 0], h[:, 1], h[:, 2]
+    if int(sums.sum()) == 0:
+        return None
+    active = (sums != 0)
+    if ctx.kind == 0 and bool((active & (neg != 0)).any()):
+        np.random.seed(123)
+        raise ValueError("negative dimensions are not allowed")     # np.zeros([-n, 4]) in the reference
+    ev = np.where(active, nev, 0).astype(np.int64)
+    return {"active": active, "lens": np.where(active, nev, 1).astype(np.int64), "ev": ev, "total": int(ev.sum()),
+            "mx": int(h[:, 3][active].max()) if active.any() else 0}
+
+
+def _emit(ctx, plan, mode, rnd):
     vals, kind = ctx.vals, ctx.kind
     B, P, C, H, W = ctx.dims
-    if ctx.parts is not None:
-        parts = [expand_finish(c, mode) for c in ctx.parts]
-        maxlen = max(p.shape[1] for p in parts)
-        out = vals.new_zeros((B, maxlen, 4))
-        for i, p in enumerate(parts):
-            out[i * 256:i * 256 + p.shape[0], :p.shape[1]] = p
-        return out
     L = _lib.lib()
     dev = vals.device
-    S = P * C * H * W
-    counts = ctx.counts
+    if plan is None:
+        return torch.zeros((B, 1, 4), dtype=torch.float32, device=dev)
+    active, ev, total, mx = plan["active"], plan["ev"], plan["total"], plan["mx"]
+    maxlen = int(plan["lens"].max())
+    start = np.concatenate([[0], np.cumsum(ev)[:-1]]).astype(np.int64)
     with torch.cuda.device(dev):
         st = _lib.stream_ptr()
-        ctx.event.synchronize()                     # the one host sync
-        h = ctx.stats_host.numpy()
-        sums, nev, neg = h[:, 0], h[:, 1], h[:, 2]
-        if int(sums.sum()) == 0:                    # `if event_cnt_round.sum() != 0` (cnt2event.pyx:56)
-            if mode == 1:
-                np.random.seed(123)
-            return torch.zeros((B, 1, 4), dtype=torch.float32, device=dev)
-        active = (sums != 0)
-        if kind == 0 and bool((active & (neg != 0)).any()):
-            np.random.seed(123)
-            raise ValueError("negative dimensions are not allowed")     # np.zeros([-n, 4]) in the reference
-        lens = np.where(active, nev, 1).astype(np.int64)
-        maxlen = int(lens.max())
-        ev = np.where(active, nev, 0).astype(np.int64)
-        total = int(ev.sum())
-        start = np.concatenate([[0], np.cumsum(ev)[:-1]]).astype(np.int64)
         out = torch.zeros((B, maxlen, 4), dtype=torch.float32, device=dev)
-        rnd = None
-        if mode == 1:
-            rnd = torch.from_numpy(_numpy_stream(total)).to(dev)
-        else:
-            np.random.seed(123)                     # visible side effect of every reference call
         rank, rank_m, rank_bits = None, 0, 0
-        mx = int(h[:, 3][active].max()) if active.any() else 0
         if kind == 0 and mode == 0 and 1 <= mx <= 255:
             rank_m = 1 << max(0, (mx - 1).bit_length())            # few distinct table sizes: 1, 2, 4, ... 256
             rank_m = min(rank_m, 255)
@@ -128,10 +117,45 @@ def expand_finish(ctx, mode):
         nbytes = L.esr_expand_workspace_bytes(B, P, C, H, W, total)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         act32 = np.ascontiguousarray(active.astype(np.int32))
-        _lib.check(L.esr_expand_emit(_lib.ptr(vals), _lib.ptr(counts), B, P, C, H, W, kind, int(mode), _lib.ptr(rnd),
+        _lib.check(L.esr_expand_emit(_lib.ptr(vals), _lib.ptr(ctx.counts), B, P, C, H, W, kind, int(mode), _lib.ptr(rnd),
                                      _lib.ptr(rank), rank_m, rank_bits,
                                      act32.ctypes.data_as(ctypes.c_void_p), start.ctypes.data_as(ctypes.c_void_p),
                                      total, maxlen, _lib.ptr(out), _lib.ptr(ws), nbytes, st), "esr_expand_emit")
+    return out
+
+
+def expand_finish(ctx, mode):
+    """Phase 2: wait for the statistics, size the output, emit and sort.  Returns CUDA fp32 [B, maxlen, 4].
+
+    Random mode (mode 1): the reference seeds numpy ONCE per call and draws one continuous stream over all samples in emission
+    order (cnt2event.pyx:25,74; event_redistribute.pyx:24) -- also when the batch is processed in 256-sample parts here (the radix
+    sort carries the sample index in one 8-bit digit): the parts receive consecutive slices of that one stream."""
+    B = ctx.dims[0]
+    dev = ctx.vals.device
+    parts = ctx.parts if ctx.parts is not None else [ctx]
+    plans = [_host_plan(c) for c in parts]
+    rnds = [None] * len(parts)
+    if mode == 1:
+        totals = [0 if pl is None else pl["total"] for pl in plans]
+        if sum(totals) > 0:
+            stream = torch.from_numpy(_numpy_stream(sum(totals))).to(dev)
+            off = 0
+            for i, t in enumerate(totals):
+                rnds[i] = stream[off:off + t] if t > 0 else None
+                off += t
+        else:
+            np.random.seed(123)
+    else:
+        np.random.seed(123)                         # visible side effect of every reference call
+    outs = [_emit(c, pl, mode, r) for c, pl, r in zip(parts, plans, rnds)]
+    if ctx.parts is None:
+        return outs[0]
+    if all(pl is None for pl in plans):             # the whole batch is empty: [B, 1, 4] zeros like one reference call
+        return torch.zeros((B, 1, 4), dtype=torch.float32, device=dev)
+    maxlen = max(o.shape[1] for o in outs)
+    out = ctx.vals.new_zeros((B, maxlen, 4))
+    for i, o in enumerate(outs):
+        out[i * 256:i * 256 + o.shape[0], :o.shape[1]] = o
     return out
 
 

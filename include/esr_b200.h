@@ -43,6 +43,9 @@ int64_t esr_launch_count(void);
  *   writeback  : 1 = reproduce the reference's in-place side effect (out-of-range xs, ys set to 0)
  * Reference quirks kept: out-of-range positive events are dropped, out-of-range NEGATIVE events are
  * counted at neg[0,0]; fractional coordinates truncate toward zero; each event adds ps*ps.
+ * writeback: 0 = leave xs / ys alone, 1 = zero them in place for out-of-range events (standalone events_to_channels), 2 = the
+ * order of H5Dataset.__getitem__ (h5dataset.py:337-354): in frames of more than 3 events out-of-range events of EITHER polarity add
+ * nothing, because create_stack_encoding has sanitised the event tensor before the count encodings see it.
  * --------------------------------------------------------------------------------------------- */
 int esr_scatter_cnt(float *xs, float *ys, const float *ps, const int64_t *frame_off, int F, int64_t n_max_frame,
                     int H, int W, int lift_w_lr, int lift_w_hr, int lift_h_lr, int lift_h_hr, int writeback,

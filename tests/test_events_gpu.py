@@ -272,8 +272,9 @@ def test_dataset_glue_matches_reference_semantics(dev, golden_events):
 
 
 def test_collate_sequence_matches_per_frame_reference_semantics(dev):
-    """The batched GPU collate = per frame create_cnt_encoding / create_normalized_events + create_scaled_encoding('cnt')
-    (oracle restatement of dataloader/h5dataset.py:508-528, 611-619), windowed like custom_collate."""
+    """The batched GPU collate = per frame create_stack_encoding (sanitises out-of-range events in place), create_cnt_encoding,
+    create_normalized_events + create_scaled_encoding('cnt') in the order of H5Dataset.__getitem__ (oracle restatement of
+    dataloader/h5dataset.py:337-354, 508-528, 611-619), windowed like custom_collate."""
     from esr_b200 import dataset as ds
     from oracle import events as oe
     rng = np.random.default_rng(4)
@@ -289,12 +290,35 @@ def test_collate_sequence_matches_per_frame_reference_semantics(dev):
     assert len(wins) == L - 2 and wins[0]['inp_scaled_cnt'].shape == (B, 3, 2, H * k, W * k)
     for b in range(B):
         for l in range(L):
-            x, y, p = (inp[b][l][c].astype(np.float32) for c in (0, 1, 3))
+            # the order of H5Dataset.__getitem__ (h5dataset.py:337-354): the stack encoding runs first and zeroes out-of-range
+            # events in place (frames of more than 3 events), so the count encodings below see the sanitised arrays
+            def formatted(ev):
+                x, y, t, p = (ev[c].astype(np.float32) for c in range(4))
+                if len(t):
+                    t = (t - t[0]) / (t[-1] - t[0] + np.float32(1e-6))
+                return x, y, t.astype(np.float32), p
+            x, y, t, p = formatted(inp[b][l])
+            oe.events_to_stack_no_polarity(x, y, t, p, 1, (H, W))
             want_cnt = oe.events_to_channels(x.copy(), y.copy(), p, (H, W))
             want_scaled = oe.events_to_channels(oe.lift_coords(x, W, W * k), oe.lift_coords(y, H, H * k), p, (H * k, W * k))
-            gx, gy, gp = (gt[b][l][c].astype(np.float32) for c in (0, 1, 3))
+            gx, gy, gtt, gp = formatted(gt[b][l])
+            oe.events_to_stack_no_polarity(gx, gy, gtt, gp, 1, (H * k, W * k))
             want_gt = oe.events_to_channels(gx.copy(), gy.copy(), gp, (H * k, W * k))
             w0 = min(l, L - 3)
             assert np.array_equal(wins[w0]['inp_cnt'][b, l - w0].cpu().numpy(), want_cnt), (b, l)
             assert np.array_equal(wins[w0]['inp_scaled_cnt'][b, l - w0].cpu().numpy(), want_scaled), (b, l)
             assert np.array_equal(wins[w0]['gt_cnt'][b, l - w0].cpu().numpy(), want_gt), (b, l)
+
+
+def test_more_than_256_samples_draw_one_random_stream():
+    """with B > 256 the batch is processed in 256-sample parts; in random-timestamp mode they must share ONE numpy stream
+    (the reference seeds once per call, cnt2event.pyx:25), not restart it per part."""
+    from esr_b200 import cnt2event as c2e
+    from oracle import events as oe
+    rng = np.random.default_rng(5)
+    cnt = rng.poisson(0.4, (300, 2, 6, 7)).astype(np.float32)
+    cnt[260] = 0                                                     # an empty sample in the second part
+    for mode in (0, 1):
+        got = c2e.cnt2event_cuda(torch.from_numpy(cnt).cuda(), mode).cpu().numpy()
+        want = oe.cnt2event(cnt, mode)
+        assert got.shape == want.shape and np.array_equal(got, want), mode

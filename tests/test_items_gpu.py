@@ -80,3 +80,42 @@ def test_interpolate_planes_vs_torch_cpu(shape, size):
     assert not got_cpu_in.is_cuda
     with pytest.raises(ValueError):
         enc.interpolate_planes(x, size, "bilinear")
+
+
+@pytest.mark.gpu
+def test_collate_sequence_follows_getitem_order_for_out_of_range_events():
+    """H5Dataset.__getitem__ builds the stack encoding first, which zeroes out-of-range events in place (frames of
+    more than 3 events), so they add nothing to inp_cnt / inp_scaled_cnt / gt_cnt -- unlike the standalone events_to_channels,
+    where an out-of-range negative event lands on neg[0, 0].  The batched path must equal the per-frame factory (create_item, pinned
+    to the reference's own __getitem__ output) on malformed events, and keep the standalone quirk for frames of <= 3 events."""
+    from esr_b200 import dataset as ds
+    from esr_b200 import encodings as enc
+    rng = np.random.default_rng(7)
+    H, W, k = 24, 32, 2
+
+    def events(n, Hs, Ws, bad):
+        xs = rng.integers(0, Ws, n).astype(np.float64)
+        ys = rng.integers(0, Hs, n).astype(np.float64)
+        ps = rng.choice([-1.0, 1.0], n)
+        idx = rng.choice(n, bad, replace=False)
+        xs[idx[: bad // 2]] = Ws + 3                          # out of range to the right
+        ys[idx[bad // 2:]] = -2                               # out of range above
+        ps[idx] = -1.0                                        # negative: the case the quirk moves to neg[0, 0]
+        return np.stack([xs, ys, np.sort(rng.random(n)) + 5.0, ps])
+    L = 3
+    inp = [[events(400, H, W, 12) for _ in range(L)]]
+    gt = [[events(1600, H * k, W * k, 20) for _ in range(L)]]
+    wins = ds.collate_sequence(inp, gt, (H, W), (H * k, W * k))
+    bank = wins[0]["bank"]
+    for l in range(L):
+        item = ds.create_item(inp[0][l].copy(), gt[0][l].copy(), [H, W], k, 1)
+        for key in ("inp_cnt", "inp_scaled_cnt", "gt_cnt"):
+            assert torch.equal(bank[key][0, l], item[key]), (key, l)
+        assert float(bank["inp_cnt"][0, l, 1, 0, 0]) == float(item["inp_cnt"][1, 0, 0])
+    # frames of <= 3 events: the stack encoding returns early without touching the events -> the standalone quirk applies
+    dev = torch.device("cuda:0")
+    xs = torch.tensor([1.0, W + 5.0, 2.0], device=dev); ys = torch.tensor([1.0, 3.0, 2.0], device=dev); ps = torch.tensor([1.0, -1.0, -1.0], device=dev)
+    off = torch.tensor([0, 3], dtype=torch.int64, device=dev)
+    a = enc.encode_frames(xs.clone(), ys.clone(), ps, off, None, (H, W), 3, sanitised=True)
+    b = enc.encode_frames(xs.clone(), ys.clone(), ps, off, None, (H, W), 3, sanitised=False)
+    assert torch.equal(a, b) and float(a[0, 1, 0, 0]) == 1.0
