@@ -362,7 +362,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_con
                     while (gchunk >= a.chunk_end[src]) { chunk_base = a.chunk_end[src]; ++src; }
                     const int dy = a.ntaps == 9 ? tap / 3 - 1 : 0, dx = a.ntaps == 9 ? tap % 3 - 1 : 0;
                     const int simg = a.src_img[src] ? a.src_img[src][img] : img;
-                    mbar_wait_cluster(bar_empty + 8u * s, ph ^ 1u);
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                     if (tr && tn < TRACE_N) tr[tn * 8 + 0] = clock64();
                     mbar_expect_tx(bar_full + 8u * s, stage_bytes);
                     const uint32_t st = smem_base + s * stage_bytes;
@@ -399,14 +399,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_con
             int tn = 0;
             for (int pr = pair0; pr < n_pairs; pr += pair_step, ++it) {
                 const uint32_t ai = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
-                mbar_wait_cluster(bar_aempty + 8u * ai, aph ^ 1u);  // both CTAs' epilogues of pair it-2 have drained this accumulator
+                mbar_wait(bar_aempty + 8u * ai, aph ^ 1u);  // both CTAs' epilogues of pair it-2 have drained this accumulator
                 tc_fence_after();
                 const uint32_t acc = tmem_base + ai * 256u;
                 for (int kb = 0; kb < a.nkb; ++kb) {
                     if (tr && tn < TRACE_N) tr[tn * 8 + 2] = clock64();
                     mbar_wait(bar_full + 8u * s, ph);
                     if (tr && tn < TRACE_N) tr[tn * 8 + 3] = clock64();
-                    mbar_wait_cluster(bar_pfull + 8u * s, ph);
+                    mbar_wait(bar_pfull + 8u * s, ph);
                     tc_fence_after();
                     if (tr && tn < TRACE_N) tr[tn * 8 + 5] = clock64();
                     const uint32_t st = smem_base + s * stage_bytes;
