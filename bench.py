@@ -647,7 +647,7 @@ def run_workload(args, name, dev, rank, world, dist, steps, warmup, main):
     n_ev = EVENTS_PER_FRAME * B * L
     ev_out = dev_step()[1]
     res["e2e"] = {"value": frames_per_step * steps / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / steps,
-                  "mode": "software-pipelined, three batches in flight: network of batch i+1 | host sizing + emit/sort of batch i | D2H of batch i-1",
+                  "mode": "software-pipelined, three batches in flight: H2D + step graph (encode input -> network -> redistribution) of batch i+1 | host reads batch i's size | D2H of batch i's event list on a side stream",
                   "h2d_bytes_per_step": int(n_ev * 12 + (B * L + 1) * 8), "d2h_bytes_per_step": int(ev_out.numel() * 4)}
     if main:
         res["e2e"]["one_at_a_time"] = {"value": frames_per_step * steps / (ms_e2e_sync / 1e3), "ms_per_step": ms_e2e_sync / steps}
@@ -665,10 +665,25 @@ def run_workload(args, name, dev, rank, world, dist, steps, warmup, main):
         roof, small, ew = rooflines(rows, name, peak_tf, peak_hbm, peak_src)
         res["roofline"] = roof
         res["_small"], res["_ew"], res["_rows"] = small, ew, rows
-        # ---- stage breakdown of one step (device-resident inputs), CUDA events on the launching stream
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        # ---- stage breakdown of one step (device-resident inputs), CUDA events on the launching stream.  With graphs the
+        # redistribution is part of the replay: it is timed as its own small graph (same kernels, memsets and statistics copy) on
+        # the SR counts of this step, and the network is the replay minus that.
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         acc3 = [0.0, 0.0, 0.0]
         reps = 5
+        rd_graph = None
+        if pipe._graph is not None:
+            from esr_b200.expand import FusedCnt2Event
+            f0 = pipe._graphs[0]["fused"]
+            fz = FusedCnt2Event(f0.B, f0.H, f0.W, dev, f0.cap, f0.mcap)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fz.enqueue(pipe._graph_sr)
+            torch.cuda.current_stream().wait_stream(side)
+            rd_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(rd_graph):
+                fz.enqueue(pipe._graph_sr)
         for _ in range(reps):
             flush.zero_()
             torch.cuda.synchronize()
@@ -683,11 +698,25 @@ def run_workload(args, name, dev, rank, world, dist, steps, warmup, main):
                 else:
                     sr_ = pipe._windows()
             ev[2].record()
-            evs = expand(sr_, 0, 0)
-            ev[3].record()
-            torch.cuda.synchronize()
-            for i in range(3):
-                acc3[i] += ev[i].elapsed_time(ev[i + 1]) / reps
+            if rd_graph is not None:
+                torch.cuda.synchronize()
+                flush.zero_()
+                torch.cuda.synchronize()
+                ev[3].record()
+                rd_graph.replay()
+                ev[4].record()
+                torch.cuda.synchronize()
+                evs = fz.result()[0]
+                rd = ev[3].elapsed_time(ev[4])
+                acc3[0] += ev[0].elapsed_time(ev[1]) / reps
+                acc3[1] += (ev[1].elapsed_time(ev[2]) - rd) / reps
+                acc3[2] += rd / reps
+            else:
+                evs = expand(sr_, 0, 0)
+                ev[3].record()
+                torch.cuda.synchronize()
+                for i in range(3):
+                    acc3[i] += ev[i].elapsed_time(ev[i + 1]) / reps
         res["stages_ms_per_step"] = {"encode_ms": acc3[0], "network_ms": acc3[1], "redistribute_ms": acc3[2]}
         # HBM-bound stages against the measured copy bandwidth: SURVEY 8d algorithmic bytes
         nfr, nout = B * L, B * (L - 2)
@@ -699,8 +728,9 @@ def run_workload(args, name, dev, rank, world, dist, steps, warmup, main):
         res["roofline_hbm"] = {
             "scatter": dict(hbm(b_sc, acc3[0]), kernel="k_scatter_cnt (LR->HR lift + count scatter of all B*L frames, one launch)",
                             bytes="12 B per event + 8*H*W per frame (SURVEY 8d)", events=n_ev),
-            "redistribute": dict(hbm(b_rd, acc3[2]), kernel="k_expand_count -> scans -> k_expand_emit -> segmented radix sort (incl. the host sizing sync)",
-                                 bytes="8*H*W per sample + 16 B per event (SURVEY 8d), sort traffic not counted", events=E),
+            "redistribute": dict(hbm(b_rd, acc3[2]), kernel="k_xf_count -> k_xf_scan -> k_xf_emit (csrc/expand_fused.cu: counting sort over the distinct timestamps, sized on the "
+                                        "device, part of the step's CUDA graph); general chain of events.cu when a count exceeds 64",
+                                 bytes="8*H*W per sample + 16 B per event (SURVEY 8d)", events=E),
             "small_convs": small, "elementwise": ew, "peak_source": peak_src + ", copy bandwidth"}
     del pipe, net, flush
     torch.cuda.empty_cache()
@@ -756,10 +786,22 @@ def sweep_events(dev, peak_hbm, cpu=True):
         lam = E / (2.0 * H * H)
         cnt = torch.poisson(torch.full((1, 2, H, H), lam, device=dev), generator=g)
         Et = int(cnt.sum().item())
-        ms = timed(lambda: expand(cnt, 0, 0), reps=3)
+        api_ms = timed(lambda: expand(cnt, 0, 0), reps=3)              # the call a user makes: kernels + host sizing + one sync
+        ms, how = api_ms, "expand() call (general chain of events.cu: a count above 64)"
+        mxc = int(cnt.max().item())
+        if mxc <= 64:                                                   # as inside the pipeline: recorded once, replayed
+            from esr_b200.expand import FusedCnt2Event
+            fz = FusedCnt2Event(1, H, H, dev, int(Et * 1.25) + 4096, 2 * mxc)
+            fz.enqueue(cnt)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fz.enqueue(cnt)
+            ms, how = timed(gr.replay, reps=5), "CUDA-graph replay of esr_cnt2event_fused (as in the pipeline's step graph)"
+            assert fz.result()[0] is not None
         b = 8.0 * H * H + 16.0 * Et
         p = {"op": "cnt2event", "grid": H, "events": Et, "ms": ms, "GBps": b / ms / 1e6, "frac_hbm": b / ms / 1e6 / peak_hbm,
-             "Mev_per_s": Et / ms / 1e3}
+             "Mev_per_s": Et / ms / 1e3, "timed": how, "api_call_ms": api_ms, "max_count": mxc}
         if ref_c2e is not None and E == 10 ** 5:
             c = np.ascontiguousarray(cnt.cpu().numpy(), dtype=np.float32)
             t0 = time.perf_counter()

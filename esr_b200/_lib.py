@@ -32,6 +32,9 @@ SIGNATURES = {
     "esr_expand_emit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_int, c_int,
                                 c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "esr_cnt2event_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "esr_cnt2event_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_void_p,
+                                    c_size_t, c_void_p]),
 }
 
 

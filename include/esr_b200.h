@@ -99,6 +99,23 @@ int esr_expand_emit(const float *vals, uint32_t *counts, int B, int P, int C, in
                     const int64_t *start_host, int64_t total_events, int64_t maxlen, float *out, void *workspace,
                     size_t workspace_bytes, esr_stream_t stream);
 
+/* cnt2event with linear timestamps, whole operator in three launches without a host round trip
+ * (dataloader/cython_cnt2event/cnt2event.pyx:18-116, mode 'linear'; csrc/expand_fused.cu).  vals: device fp32 [B,2,H,W].
+ * The caller supplies `out` with room for cap_rows rows of 4 floats; the kernels compute maxlen = max over samples of the
+ * event count (1 for a sample whose rounded values sum to zero) on the device and write the padded [B, maxlen, 4] result,
+ * zero padding included, at the start of `out`.  stats (device int64 [B,4], same meaning as esr_expand_count) is how the caller
+ * learns maxlen afterwards and whether the result is valid: it is NOT when an active sample holds a negative count (the
+ * reference raises), when the largest count of an active sample exceeds max_count rounded up to a power of two (max_count <= 64:
+ * the caller's guess, it sizes the per-key counters in shared memory), when B * maxlen > cap_rows, or when no sample is
+ * active -- then nothing was written and the caller applies the reference's rules / uses esr_expand_count + esr_expand_emit.
+ * tables: device blob of the 7 key tables for m = 1, 2, 4 .. 64 -- rank uint16 [(m+1)*m] (index of float32(linspace(0,1,n)[j])
+ * among the K distinct values for counts <= m) and uniq float [K]; tables_desc_host: int32 [7][3] = {rank byte offset, uniq
+ * byte offset, K}.  The host builds them with numpy.linspace, the reference's own arithmetic. */
+size_t esr_cnt2event_fused_workspace_bytes(int B, int H, int W);
+int esr_cnt2event_fused(const float *vals, int B, int H, int W, const void *tables, const int32_t *tables_desc_host,
+                        int max_count, int64_t *stats, float *out, int64_t cap_rows, void *workspace, size_t workspace_bytes,
+                        esr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core convolution (tcgen05, TMA-tiled implicit GEMM), layer-level entry point.
  * Replaces: every stride-1 nn.Conv2d at feature resolution in models/model.py / models/submodules.py

@@ -1,5 +1,7 @@
 """GPU parity of the event path: CUDA kernels (through the C ABI) vs the C oracle and the reference-generated
 golden vectors.  Bit-exact (integer / index work; fp32 timestamps are produced by identical float64 arithmetic)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -322,3 +324,63 @@ def test_more_than_256_samples_draw_one_random_stream():
         got = c2e.cnt2event_cuda(torch.from_numpy(cnt).cuda(), mode).cpu().numpy()
         want = oe.cnt2event(cnt, mode)
         assert got.shape == want.shape and np.array_equal(got, want), mode
+
+
+@pytest.mark.parametrize("shape,peak", [((2, 2, 5, 5), 3), ((3, 2, 33, 31), 7), ((2, 2, 64, 64), 64), ((2, 2, 64, 64), 65),
+                                        ((5, 2, 96, 128), 20), ((1, 2, 256, 256), 33)])
+def test_cnt2event_fused_path(dev, shape, peak, monkeypatch):
+    """cnt2event / linear through esr_cnt2event_fused (three launches, rows written before the host knows maxlen) against the
+    oracle and against the general chain: odd sizes (no 16-byte loads), a ragged last tile, counts at the 64 limit and one above
+    (fallback), an inactive sample whose +1 / -1 cancel (cnt2event.pyx:56: rounded sum == 0 emits one zero row), a repeat call
+    (capacity taken from the previous call) and a capacity that is too small (fallback)."""
+    from esr_b200 import cnt2event as c2e, expand as ex
+    from oracle import events as oe
+    rng = np.random.default_rng(peak * 7 + shape[0])
+    cnt = rng.poisson(0.4, shape).astype(np.float32) + ((rng.random(shape) - 0.5) * 0.9).astype(np.float32)
+    cnt = np.maximum(cnt, 0).astype(np.float32)
+    cnt[0, 1, 2, 3] = peak
+    cnt[-1, 0, 0, 0] = max(1, peak - 1)
+    if shape[0] >= 3:
+        cnt[1] = 0
+        cnt[1, 0, 1, 1], cnt[1, 1, 2, 2] = 1, -1                     # sums to zero: the reference treats the sample as empty
+    want = oe.cnt2event(cnt, 0)
+    x = torch.from_numpy(cnt).to(dev)
+    ex._XF_ROWS.clear()
+    got = c2e.cnt2event_cuda(x, 0)
+    assert np.array_equal(got.cpu().numpy(), want)
+    again = c2e.cnt2event_cuda(x, 0)                                  # capacity now comes from the first call
+    assert np.array_equal(again.cpu().numpy(), want)
+    key = (str(x.device), shape[0], shape[2], shape[3])
+    assert ex._XF_ROWS[key][0] == want.shape[0] * want.shape[1]
+    ex._XF_ROWS[key] = (max(1, want.shape[1] // 2), peak)                     # too small a guess: general chain, same answer
+    monkeypatch.setattr(ex, "_XF_SLACK", 0)
+    small = c2e.cnt2event_cuda(x, 0)
+    assert np.array_equal(small.cpu().numpy(), want)
+    monkeypatch.setenv("ESR_EXPAND_FUSED", "0")
+    legacy = c2e.cnt2event_cuda(x, 0)
+    assert np.array_equal(legacy.cpu().numpy(), want)
+
+
+def test_cnt2event_fused_full_size_properties(dev):
+    """BASELINE-sized grid (8 x 2 x 256 x 256, ~2 M events): fused path == general chain bit for bit, rows sorted by time inside
+    each sample, counts recovered by scattering the rows back (size-independent properties; the oracle covers the small cases)."""
+    from esr_b200 import cnt2event as c2e, encodings as enc
+    rng = np.random.default_rng(11)
+    cnt = rng.poisson(1.0, (8, 2, 256, 256)).astype(np.float32)
+    cnt[3] = 0
+    x = torch.from_numpy(cnt).to(dev)
+    got = c2e.cnt2event_cuda(x, 0)
+    os.environ["ESR_EXPAND_FUSED"] = "0"
+    try:
+        ref = c2e.cnt2event_cuda(x, 0)
+    finally:
+        del os.environ["ESR_EXPAND_FUSED"]
+    assert torch.equal(got, ref)
+    for b in range(8):
+        e = got[b]
+        n = int((e[:, 3] != 0).sum())
+        assert n == int(cnt[b].sum())
+        assert n < 2 or bool((e[1:n, 2] >= e[:n - 1, 2]).all())
+        assert not bool(e[n:].any())
+        back = enc.events_to_channels(e[:n, 0].contiguous(), e[:n, 1].contiguous(), e[:n, 3].contiguous(), (256, 256))
+        assert torch.equal(back.cpu(), torch.from_numpy(cnt[b]))
