@@ -20,7 +20,6 @@
 
 namespace esr {
 
-constexpr int TRACE_N = 512;                 // K-blocks / tiles recorded by the ESR_TC_TRACE measurement aid
 
 // ------------------------------------------------------------------------------------------------
 // the kernel: one CTA = one tile of 128 output pixels (TH x TW) of one image, all output channels

@@ -4,6 +4,8 @@
 #include <cuda.h>   // CUtensorMap (types only; the driver entry point is resolved at run time)
 
 namespace esr {
+constexpr int TRACE_N = 512;                 // K-blocks / tiles recorded by the ESR_TC_TRACE measurement aid
+
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3 };
 enum EpiMode : int { EPI_STD = 0, EPI_GRU_ZR = 1, EPI_GRU_OUT = 2 };

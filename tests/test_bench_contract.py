@@ -39,3 +39,32 @@ def test_committed_bench_lines_have_every_key():
         assert d["gpu_launches"] > 0 and d["config"]["workload"], name
     d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_cfg2_n1.json")))
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+
+
+def test_round2_bench_lines_carry_parity_rooflines_and_every_config():
+    """The round-2 lines: the parity check of the measured plan, the family (not best-launch) roofline with the best launch kept
+    beside it, the HBM rooflines of the byte-bound stages, cfg3 / cfg4 with their own parity and CPU baseline, the cfg5 sweep with
+    a CPU column, and -- at N = 2 -- the training iteration captured with its NCCL exchange plus the hardware check of the result."""
+    for name in ("r2_bench_cfg2_n1.json", "r2_bench_cfg2_n2.json"):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        assert (BASE_KEYS - {"cpu_baseline"}) <= set(d) and {"clocks", "gpu_launches", "roofline", "parity", "roofline_hbm", "configs"} <= set(d), name
+        assert d["parity"]["ok"] and d["parity"]["rel_max"] <= 1e-3 and d["parity"]["windows"] == 6, name
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "largest_launch", "best_launch", "per_layer"} <= set(r), name
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["frac"] < r["best_launch"]["frac"], name
+        assert {"scatter", "redistribute", "small_convs", "elementwise"} <= set(d["roofline_hbm"]), name
+        for cfg, windows in (("cfg3", 6), ("cfg4", 14)):
+            c = d["configs"][cfg]
+            assert c["parity"]["ok"] and c["parity"]["windows"] == windows and c["value"] > 0 and c["e2e"]["value"] > 0, (name, cfg)
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"], name
+    d1 = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_cfg2_n1.json")))
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d1["cpu_baseline"])
+    assert all("cpu_baseline" in d1["configs"][c] for c in ("cfg3", "cfg4"))
+    ops = {(p["op"], p["events"] >= 5_000_000) for p in d1["sweep"]}
+    assert ("scatter_cnt", True) in ops and ("cnt2event", True) in ops and any("cpu_Mev_per_s" in p for p in d1["sweep"])
+    d2 = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_cfg2_n2.json")))
+    assert d2["n_gpus"] == 2 and 1.9 < d2["value"] / d1["value"] < 2.1
+    for t in (d2["train"], d2["configs"]["cfg3"]["train"], d2["configs"]["cfg4"]["train"]):
+        assert "NCCL" in t["mode"] and t["gradient_exchange_check"]["ok"] and t["gradient_exchange_check"]["identical_on_all_ranks"]
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_cfg2_reference.json")))
+    assert ref["impl"] == "reference" and ref["metric"] == d1["metric"] and ref["config"]["workload"] == d1["config"]["workload"]
