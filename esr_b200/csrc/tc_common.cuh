@@ -252,6 +252,56 @@ __device__ __forceinline__ void act32(float (&v)[32], int act)
 }
 
 // One thread's 32 accumulator columns [n0, n0+32) of one valid output pixel -> global memory.
+// residual / activation part of the standard epilogue on 32 biased accumulator values (in place)
+__device__ __forceinline__ void epilogue_std_math(const ConvTCArgs &a, float (&v)[32], int n0, int img, int y, int x, bool valid)
+{
+    // activation selector for this chunk: uniform unless act_from falls inside it (conv_offset_mask: 144 = 4.5 chunks)
+    const bool mixed = (a.act_from > n0) && (a.act_from < n0 + 32);
+    const int act = (n0 >= a.act_from) ? a.act : ACT_NONE;
+    float r[32];
+    const bool has_res = valid && a.res_mode != RES_NONE && n0 < a.cout;
+    if (has_res) {
+        const size_t rpix = ((size_t)(a.res_img ? a.res_img[img] : img) * a.H + y) * a.W + x;
+        load_split32(a.res + rpix * a.res_C + n0, a.res_plane, r);
+        if (a.res_mode == RES_PRE_ACT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
+        }
+    }
+    if (!mixed) act32(v, act);
+    else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (n0 + j >= a.act_from) v[j] = apply_act(v[j], a.act);
+    }
+    if (has_res && a.res_mode == RES_POST_ACT) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += r[j];
+    }
+}
+// bias + standard epilogue math of one chunk, values only (the caller stores them): the out_tma path
+__device__ __forceinline__ void epilogue_values(const ConvTCArgs &a, const uint32_t (&raw)[32], int n0, int img, int y, int x, bool valid,
+                                                float (&v)[32])
+{
+    const float4 *bp = reinterpret_cast<const float4 *>(a.bias + n0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 b = bp[q];
+        v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+    }
+    epilogue_std_math(a, v, n0, img, y, x, valid);
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3, int c4)
+{
+    // L2 evict_last: the tensor is the next layer's input and must stay in the 126 MB L2 like the lines of a plain st.global do
+    // (without the hint every consumer kernel got 3-5 us slower: its input came from HBM)
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(0x14F0000000000000ull) : "memory");
+}
+
 __device__ __forceinline__ void epilogue_chunk(const ConvTCArgs &a, const uint32_t (&raw)[32], int n0, size_t pix, int img,
                                                int y, int x)
 {
@@ -309,29 +359,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTCArgs &a, const uint32
         return;
     }
     // ---- standard epilogue: bias (+ residual before or after the activation)
-    // activation selector for this chunk: uniform unless act_from falls inside it (conv_offset_mask: 144 = 4.5 chunks)
-    const bool mixed = (a.act_from > n0) && (a.act_from < n0 + 32);
-    const int act = (n0 >= a.act_from) ? a.act : ACT_NONE;
-    float r[32];
-    const bool has_res = a.res_mode != RES_NONE && n0 < a.cout;
-    if (has_res) {
-        const size_t rpix = ((size_t)(a.res_img ? a.res_img[img] : img) * a.H + y) * a.W + x;
-        load_split32(a.res + rpix * a.res_C + n0, a.res_plane, r);
-        if (a.res_mode == RES_PRE_ACT) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += r[j];
-        }
-    }
-    if (!mixed) act32(v, act);
-    else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (n0 + j >= a.act_from) v[j] = apply_act(v[j], a.act);
-    }
-    if (has_res && a.res_mode == RES_POST_ACT) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += r[j];
-    }
+    epilogue_std_math(a, v, n0, img, y, x, true);
     if (a.out && n0 + 32 <= a.cout) store_split32(a.out + pix * a.out_C + a.out_coff + n0, a.out_plane, v);
     if (a.out_f32 && a.out_f32_nchw) {
         // the autograd layout of the training operators: consecutive lanes = consecutive pixels of a tile row -> each of the

@@ -522,6 +522,22 @@ static int make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap
     return ESR_OK;
 }
 
+// Output side: 32 channels x (BW x BH = 32 pixels) per box, 64-byte rows with the 64-byte swizzle (conflict-free 16-byte
+// shared-memory stores by 32 lanes that own one pixel each).
+int tc_make_omap(const SplitTensor &t, int BW, int BH, CUtensorMap *out)
+{
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ESR_ECUDA; }
+    const cuuint64_t C = t.C, W = t.W, H = t.H, N = t.n_img;
+    cuuint64_t gdim[5] = {C, W, H, N, 2};
+    cuuint64_t gstr[4] = {C * 2, W * C * 2, H * W * C * 2, (cuuint64_t)t.plane() * 2};
+    cuuint32_t box[5] = {32, (cuuint32_t)BW, (cuuint32_t)BH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed: %d (C=%d W=%d H=%d N=%d)", (int)r, t.C, t.W, t.H, t.n_img); return ESR_ECUDA; }
+    return ESR_OK;
+}
 int tc_make_amap(const SplitTensor &t, int BW, int BH, CUtensorMap *out) { return make_amap(t, BW, BH, out); }
 int tc_make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap *out) { return make_bmap(w, npad, nkb, box_rows, out); }
 
@@ -559,8 +575,14 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     // multi-wave 3x3 layers: persistent halo-reuse kernel (tc_conv_halo.cu; ESR_TC_NO_HALO=1 keeps k_conv_tc_persist)
     static const bool no_halo = getenv("ESR_TC_NO_HALO") != nullptr;
     int h_as = 0, h_bs = 0;
-    const bool halo = !v3 && !no_halo && d.ntaps == 9 && getenv("ESR_TC_PAIR") == nullptr &&
-                      d.n_img * ((W + 7) / 8) * ((H + 15) / 16) > dev_info().sm_count && conv_tc_halo_plan(npad_, &h_as, &h_bs);
+    // epilogue through shared memory + TMA stores (ESR_TC_NO_OUT_TMA=1: direct 16-byte stores): plain split outputs only
+    static const bool no_out_tma = getenv("ESR_TC_NO_OUT_TMA") != nullptr;
+    bool out_tma = !no_out_tma && d.out.base && !d.out_f32 && d.epi_mode == EPI_STD && d.cout % 32 == 0 && d.out.C % 8 == 0 && d.out_coff % 8 == 0;
+    bool halo = !v3 && !no_halo && d.ntaps == 9 && getenv("ESR_TC_PAIR") == nullptr &&
+                d.n_img * ((W + 7) / 8) * ((H + 15) / 16) > dev_info().sm_count;
+    if (halo && out_tma && !conv_tc_halo_plan(npad_, true, &h_as, &h_bs)) out_tma = false;
+    if (halo && !out_tma) halo = conv_tc_halo_plan(npad_, false, &h_as, &h_bs);
+    if (!halo) out_tma = false;                                   // (the other kernels keep the direct stores for now)
     if (halo) { TW = 8; TH = 16; BW = 10; BH = 18; }
     for (int s = 0; s < d.n_src; ++s) {
         const SplitTensor &t = d.src[s];
@@ -631,6 +653,10 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
         ESR_REQUIRE(d.out.H == H && d.out.W == W && d.out.n_img >= d.n_img && d.out.C % 8 == 0 && d.out_coff % 8 == 0,
                     "conv_tc: bad split output");
         a.out = d.out.base; a.out_plane = d.out.plane(); a.out_C = d.out.C; a.out_coff = d.out_coff;
+        if (out_tma) {
+            a.out_tma = 1;
+            if ((rc = tc_make_omap(d.out, TW, 32 / TW, &a.omap))) return rc;
+        }
     }
     a.out_f32 = d.out_f32; a.out_f32_C = d.out_f32_C; a.out_f32_nchw = d.out_f32_nchw;
     if (d.epi_mode != EPI_STD) {

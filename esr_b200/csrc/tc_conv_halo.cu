@@ -24,6 +24,8 @@ constexpr int TH_TW = 8, TH_TH = 16;                                   // output
 constexpr int TH_HW = TH_TW + 2, TH_HH = TH_TH + 2;                    // halo box 10 x 18 pixels
 constexpr uint32_t TH_A_PLANE = ((TH_HW * TH_HH * 128 + 1023) / 1024) * 1024;   // 23040 -> 23552: planes stay 1024-B aligned
 constexpr uint32_t TH_A_STAGE = 2 * TH_A_PLANE;
+constexpr uint32_t TH_STG_PLANE = 32 * 64;                             // one warp's 32 pixels x 32 channels of one plane
+constexpr uint32_t TH_STG_BYTES = 4 * 2 * 2 * TH_STG_PLANE;            // 32 KB
 
 __device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes)
 {
@@ -43,7 +45,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)a.npad * 128u, b_stage = 2u * b_bytes;
     const uint32_t a_ring = smem_base, b_ring = smem_base + (uint32_t)a.a_stages * TH_A_STAGE;
-    const uint32_t bar_base = b_ring + (uint32_t)a.stages * b_stage;
+    const uint32_t stg_ring = b_ring + (uint32_t)a.stages * b_stage;            // out_tma: [4 warps][2 buffers][2 planes][32 px x 64 B]
+    const uint32_t bar_base = stg_ring + (a.out_tma ? TH_STG_BYTES : 0u);
     const uint32_t bar_afull = bar_base, bar_aempty = bar_afull + 8u * a.a_stages;
     const uint32_t bar_bfull = bar_aempty + 8u * a.a_stages, bar_bempty = bar_bfull + 8u * a.stages;
     const uint32_t bar_cfull = bar_bempty + 8u * a.stages, bar_cempty = bar_cfull + 16u;        // per accumulator
@@ -65,12 +68,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     PDL_WAIT();                      // everything above is CTA-local set-up; global memory only from here on
+    if (a.trace && (int)blockIdx.x == a.trace_cta && threadIdx.x == 0) a.trace[7] = clock64();
 
     if (warp == 0) {
         // ===================== TMA producer: per chunk one halo box per plane, then nine weight tiles =====================
         if (elect_one_sync()) {
             uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
-            long long *tr = (a.trace && blockIdx.x == 0) ? a.trace : nullptr;      // ESR_TC_TRACE: clock stamps of CTA 0
+            long long *tr = (a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr;      // ESR_TC_TRACE: clock stamps of one CTA
             int pit = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img, trem = tile - img * tiles_per_img;
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
             constexpr uint32_t SBO = (uint32_t)TH_HW * 128u;
             uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
             int it = 0, mit = 0;
-            long long *tr = (a.trace && blockIdx.x == 0) ? a.trace : nullptr;
+            long long *tr = (a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t ai = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
                 if (tr && mit < TRACE_N) tr[mit * 8 + 5] = clock64();
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
         const int quad = warp & 3;
         const int m = quad * 32 + lane;
         int it = 0;
+        uint32_t stg_n = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t ai = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
             const int img = tile / tiles_per_img, trem = tile - img * tiles_per_img;
@@ -177,32 +182,64 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
                 uint32_t raw[32];
                 if (a.stack) tmem_ld_chunk_stacked(taddr, n0, a.npad, raw);
                 else tmem_ld_chunk(taddr, n0, a.npad, raw);
-                if (valid && !(a.diag & 8)) epilogue_chunk(a, raw, n0, pix, img, y, x);
+                if (a.out_tma && !(a.diag & 8)) {
+                    // The direct form (one pixel per lane, 16-byte stores 128+ bytes apart) costs 32 sector writes per store
+                    // instruction and those go through the same L1 / shared-memory pipeline the MMA operands are read from: the
+                    // clock trace shows ~1100 cycles of MMA back-pressure per 32-channel chunk.  Here the warp's 32 pixels x 32
+                    // channels go to shared memory (swizzled: 4 wavefronts per instruction) and leave with one TMA store per plane.
+                    const uint32_t buf = stg_ring + (uint32_t)quad * (4u * TH_STG_PLANE) + (stg_n & 1u) * (2u * TH_STG_PLANE);
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the store that last read this buffer
+                    __syncwarp();
+                    float v[32];
+                    epilogue_values(a, raw, n0, img, y, x, valid, v);
+                    uint32_t hw[16], lw[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) split_pack2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
+                    const uint32_t row = buf + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t o = row + (((uint32_t)q ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(hw[4 * q]), "r"(hw[4 * q + 1]), "r"(hw[4 * q + 2]), "r"(hw[4 * q + 3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + TH_STG_PLANE), "r"(lw[4 * q]), "r"(lw[4 * q + 1]), "r"(lw[4 * q + 2]), "r"(lw[4 * q + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int c0 = a.out_coff + n0, yq = y0 + 4 * quad;
+                        tma_store_5d(&a.omap, buf, c0, x0, yq, img, 0);
+                        tma_store_5d(&a.omap, buf + TH_STG_PLANE, c0, x0, yq, img, 1);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++stg_n;
+                } else if (valid && !(a.diag & 8)) epilogue_chunk(a, raw, n0, pix, img, y, x);
                 else if (a.diag & 8) { if (raw[0] == 0x7fc12345u && raw[31] == 0x7fc54321u) a.out_f32[0] = 1.0f; }   // keep the loads alive
                 __syncwarp();
             }
             tc_fence_before();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_cempty + 8u * ai) : "memory");
         }
+        if (a.out_tma && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffers are read until then
     }
 
     tc_fence_before();
     __syncthreads();
+    if (a.trace && (int)blockIdx.x == a.trace_cta && threadIdx.x == 0) a.trace[15] = clock64();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-static size_t th_smem_bytes(int npad, int a_stages, int b_stages)
+static size_t th_smem_bytes(int npad, int a_stages, int b_stages, bool staging)
 {
-    return 1024 + (size_t)a_stages * TH_A_STAGE + (size_t)b_stages * 2 * npad * 128 + 16 * (size_t)(a_stages + b_stages) + 96;
+    return 1024 + (size_t)a_stages * TH_A_STAGE + (size_t)b_stages * 2 * npad * 128 + (staging ? TH_STG_BYTES : 0) +
+           16 * (size_t)(a_stages + b_stages) + 96;
 }
 
-// pipeline depths for a layer of padded width npad; false if nothing useful fits
-bool conv_tc_halo_plan(int npad, int *a_stages, int *b_stages)
+// pipeline depths for a layer of padded width npad (staging: with the epilogue's TMA-store buffers); false if nothing useful fits
+bool conv_tc_halo_plan(int npad, bool staging, int *a_stages, int *b_stages)
 {
     const size_t cap = (size_t)dev_info().max_smem_optin;
     for (int as = 2; as >= 2; --as) {
         int bs = 9;
-        while (bs >= 2 && th_smem_bytes(npad, as, bs) > cap) --bs;
+        while (bs >= 2 && th_smem_bytes(npad, as, bs, staging) > cap) --bs;
         if (bs >= 2) { *a_stages = as; *b_stages = bs; return true; }
     }
     return false;
@@ -211,7 +248,7 @@ bool conv_tc_halo_plan(int npad, int *a_stages, int *b_stages)
 int conv_tc_halo_launch(const ConvTCArgs &a, cudaStream_t st)
 {
     static int max_set = 0;
-    const size_t smem = th_smem_bytes(a.npad, a.a_stages, a.stages);
+    const size_t smem = th_smem_bytes(a.npad, a.a_stages, a.stages, a.out_tma != 0);
     if ((int)smem > max_set) {
         ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         max_set = (int)smem;
@@ -225,7 +262,7 @@ int conv_tc_halo_launch(const ConvTCArgs &a, cudaStream_t st)
         if (sscanf(trace_path, "%511[^:]:%d:%d", path, &want_n, &want_k) == 3 && want_n == a.npad && want_k == a.nkb) {
             if (!dbuf) cudaMalloc(&dbuf, sizeof(long long) * 8 * TRACE_N);
             cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * TRACE_N, st);
-            ConvTCArgs b = a; b.trace = dbuf;
+            ConvTCArgs b = a; b.trace = dbuf; b.trace_cta = getenv("ESR_TC_TRACE_CTA") ? atoi(getenv("ESR_TC_TRACE_CTA")) : 0;
             k_conv_tc_halo<<<grid, TC_THREADS, smem, st>>>(b);
             cudaStreamSynchronize(st);
             static long long host[8 * TRACE_N];
@@ -234,7 +271,7 @@ int conv_tc_halo_launch(const ConvTCArgs &a, cudaStream_t st)
             if (f) {
                 fprintf(f, "# HALO npad=%d nkb=%d a_stages=%d b_stages=%d tiles=%d stack=%d; per K-block (tap): prod_after_bempty_wait, prod_after_aempty_wait(first tap of a chunk), mma_before_bfull_wait, mma_after_bfull_wait, mma_after_commit, mma_before_cempty_wait(first tap of a tile), mma_before_afull_wait(first tap of a chunk)\n",
                         a.npad, a.nkb, a.a_stages, a.stages, n_tiles, a.stack);
-                for (int i = 0; i < TRACE_N; ++i) { for (int c = 0; c < 7; ++c) fprintf(f, "%lld%c", host[i * 8 + c], c == 6 ? '\n' : ','); }
+                for (int i = 0; i < TRACE_N; ++i) { for (int c = 0; c < 8; ++c) fprintf(f, "%lld%c", host[i * 8 + c], c == 7 ? '\n' : ','); }
                 fclose(f);
             }
             esr::count_launch();
