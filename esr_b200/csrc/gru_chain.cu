@@ -497,10 +497,42 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
 // Per output element the sums are those of k_gru_chain_pipe (a GEMM's columns are independent), so the results are
 // bit-identical.  Stages are 48 KB (A 32 KB + two 8 KB weight planes): four fit.  ESR_GRU_RZO=0 selects the older kernel.
 // ------------------------------------------------------------------------------------------------
+// out_tma epilogue helpers: a warp's 32 pixels x 32 channels -> swizzled shared-memory rows -> one TMA store per plane, and the
+// wait for their COMPLETION (the values are read by other CTAs' TMA loads after the phase barrier)
+__device__ __forceinline__ void gc_stage_split32(uint32_t stg, int lane, const float (&x)[32])
+{
+    uint32_t hw[16], lw[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) split_pack2(x[2 * e], x[2 * e + 1], hw[e], lw[e]);
+    const uint32_t row = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t o = row + (((uint32_t)q ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(hw[4 * q]), "r"(hw[4 * q + 1]), "r"(hw[4 * q + 2]), "r"(hw[4 * q + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + 32u * 64u), "r"(lw[4 * q]), "r"(lw[4 * q + 1]), "r"(lw[4 * q + 2]), "r"(lw[4 * q + 3]) : "memory");
+    }
+}
+__device__ __forceinline__ void gc_tma_store_wait(const CUtensorMap *map, uint32_t stg, int lane, int c0, int x0, int yq, int img)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_5d(map, stg, c0, x0, yq, img, 0);
+        tma_store_5d(map, stg + 32u * 64u, c0, x0, yq, img, 1);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+}
+
 struct GruRzoArgs {
     GruChainArgs g;
     CUtensorMap bmap_zr64;                      // the update|reset pack with a 64-row box: rows [0, 64) = update (z), [64, 128) = reset (r)
+    CUtensorMap omap_rh, omap_hs;               // out_tma: store side of rh / the state slots, box (32 ch, TW, 32 / TW, 1, 1), SWIZZLE_64B
+    int out_tma;                                // 1: h * r and h' leave through shared memory + TMA stores (see tc_conv_halo.cu)
 };
+constexpr uint32_t GC_STG_PLANE = 32 * 64;      // one epilogue warp's 32 pixels x 32 channels of one split plane
+constexpr uint32_t GC_STG_BYTES = 8 * 2 * GC_STG_PLANE;
 
 __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_constant__ GruRzoArgs aa)
 {
@@ -509,7 +541,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t B_BYTES = 64u * 128u;                              // one plane of a 64-row weight tile
     constexpr uint32_t STAGE = 2u * TC_A_BYTES + 2u * B_BYTES;            // 48 KB
-    const uint32_t bar_base = smem_base + (uint32_t)a.stages * STAGE;
+    const uint32_t stg_base = smem_base + (uint32_t)a.stages * STAGE;         // out_tma: [8 epilogue warps][2 planes][32 px x 64 B]
+    const uint32_t bar_base = stg_base + (aa.out_tma ? GC_STG_BYTES : 0u);
     const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages, bar_accum = bar_base + 16u * a.stages;   // [0] = r, [1] = z|o
     const uint32_t tmem_slot = bar_accum + 16u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -634,6 +667,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
         const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int c0 = half * 32;                                            // this warp's channels
+        const uint32_t stg_w = stg_base + (uint32_t)(warp - 2) * (2u * GC_STG_PLANE);
         for (int g = 0; g < a.nsteps; ++g) {
             const uint32_t par = (uint32_t)(g & 1);
             const __nv_bfloat16 *h_prev = a.hs + ((size_t)g * B2 * a.H * a.W + pix) * 64 + c0;
@@ -666,9 +700,11 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
                     act32(v, ACT_SIGMOID);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= h[j];
-                    store_split32(a.rh + pix * 64 + c0, a.rh_plane, v);
+                    if (aa.out_tma) gc_stage_split32(stg_w, lane, v);
+                    else store_split32(a.rh + pix * 64 + c0, a.rh_plane, v);
                 }
                 __syncwarp();
+                if (aa.out_tma) gc_tma_store_wait(&aa.omap_rh, stg_w, lane, c0, x0, y0 + quad * (32 / a.TW), img);
             }
             tc_fence_before();
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -697,9 +733,11 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) o[j] = h[j] * (1.0f - z[j]) + o[j] * z[j];
                     __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64 + c0;
-                    store_split32(h_new, a.hs_plane, o);
+                    if (aa.out_tma) gc_stage_split32(stg_w, lane, o);
+                    else store_split32(h_new, a.hs_plane, o);
                 }
                 __syncwarp();
+                if (aa.out_tma) gc_tma_store_wait(&aa.omap_hs, stg_w, lane, c0, x0, y0 + quad * (32 / a.TW), (g + 1) * B2 + img);
             }
             tc_fence_before();
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -782,6 +820,12 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
         p->rzo_args.g.stages = 4;
         if ((rc = tc_make_bmap(w_zr, 128, 18, 64, &p->rzo_args.bmap_zr64))) { delete p; return rc; }
         p->rzo_smem = 1024 + (size_t)4 * (2 * TC_A_BYTES + 2 * 64 * 128) + 16 * 4 + 96;
+        static const bool no_out_tma = getenv("ESR_TC_NO_OUT_TMA") != nullptr || getenv("ESR_GRU_NO_OUT_TMA") != nullptr;
+        if (!no_out_tma && p->rzo_smem + GC_STG_BYTES <= (size_t)dev_info().max_smem_optin && 32 % TW == 0 &&
+            tc_make_omap(rh, TW, 32 / TW, &p->rzo_args.omap_rh) == ESR_OK && tc_make_omap(hs, TW, 32 / TW, &p->rzo_args.omap_hs) == ESR_OK) {
+            p->rzo_args.out_tma = 1;
+            p->rzo_smem += GC_STG_BYTES;
+        }
         ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_rzo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->rzo_smem));
     }
     *plan_out = p;

@@ -538,6 +538,20 @@ int tc_make_omap(const SplitTensor &t, int BW, int BH, CUtensorMap *out)
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed: %d (C=%d W=%d H=%d N=%d)", (int)r, t.C, t.W, t.H, t.n_img); return ESR_ECUDA; }
     return ESR_OK;
 }
+int tc_make_omap_f32(float *base, int n_img, int H_, int W_, int C_, int BW, int BH, CUtensorMap *out)
+{
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ESR_ECUDA; }
+    const cuuint64_t C = C_, W = W_, H = H_, N = n_img;
+    cuuint64_t gdim[5] = {C, W, H, N, 1};
+    cuuint64_t gstr[4] = {C * 4, W * C * 4, H * W * C * 4, N * H * W * C * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)BW, (cuuint32_t)BH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out f32) failed: %d (C=%d W=%d H=%d N=%d)", (int)r, C_, W_, H_, n_img); return ESR_ECUDA; }
+    return ESR_OK;
+}
 int tc_make_amap(const SplitTensor &t, int BW, int BH, CUtensorMap *out) { return make_amap(t, BW, BH, out); }
 int tc_make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap *out) { return make_bmap(w, npad, nkb, box_rows, out); }
 
@@ -577,12 +591,20 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     int h_as = 0, h_bs = 0;
     // epilogue through shared memory + TMA stores (ESR_TC_NO_OUT_TMA=1: direct 16-byte stores): plain split outputs only
     static const bool no_out_tma = getenv("ESR_TC_NO_OUT_TMA") != nullptr;
-    bool out_tma = !no_out_tma && d.out.base && !d.out_f32 && d.epi_mode == EPI_STD && d.cout % 32 == 0 && d.out.C % 8 == 0 && d.out_coff % 8 == 0;
+    int out_tma = 0, stg_bufs = 0;
+    if (!no_out_tma && d.epi_mode == EPI_STD) {
+        if (d.out.base && !d.out_f32 && d.cout % 32 == 0 && d.out.C % 8 == 0 && d.out_coff % 8 == 0) out_tma = 1;
+        else if (!d.out.base && d.out_f32 && !d.out_f32_nchw && d.out_f32_C % 4 == 0 && ((uintptr_t)d.out_f32 & 15) == 0) out_tma = 2;
+    }
     bool halo = !v3 && !no_halo && d.ntaps == 9 && getenv("ESR_TC_PAIR") == nullptr &&
                 d.n_img * ((W + 7) / 8) * ((H + 15) / 16) > dev_info().sm_count;
-    if (halo && out_tma && !conv_tc_halo_plan(npad_, true, &h_as, &h_bs)) out_tma = false;
-    if (halo && !out_tma) halo = conv_tc_halo_plan(npad_, false, &h_as, &h_bs);
-    if (!halo) out_tma = false;                                   // (the other kernels keep the direct stores for now)
+    if (halo && out_tma) {
+        if (conv_tc_halo_plan(npad_, 2, &h_as, &h_bs)) stg_bufs = 2;
+        else if (conv_tc_halo_plan(npad_, 1, &h_as, &h_bs)) stg_bufs = 1;
+        else out_tma = 0;
+    }
+    if (halo && !out_tma) halo = conv_tc_halo_plan(npad_, 0, &h_as, &h_bs);
+    if (!halo) out_tma = 0;                                       // (the other kernels keep the direct stores for now)
     if (halo) { TW = 8; TH = 16; BW = 10; BH = 18; }
     for (int s = 0; s < d.n_src; ++s) {
         const SplitTensor &t = d.src[s];
@@ -653,10 +675,14 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
         ESR_REQUIRE(d.out.H == H && d.out.W == W && d.out.n_img >= d.n_img && d.out.C % 8 == 0 && d.out_coff % 8 == 0,
                     "conv_tc: bad split output");
         a.out = d.out.base; a.out_plane = d.out.plane(); a.out_C = d.out.C; a.out_coff = d.out_coff;
-        if (out_tma) {
-            a.out_tma = 1;
+        if (out_tma == 1) {
+            a.out_tma = 1; a.stg_bufs = stg_bufs;
             if ((rc = tc_make_omap(d.out, TW, 32 / TW, &a.omap))) return rc;
         }
+    }
+    if (out_tma == 2) {
+        a.out_tma = 2; a.stg_bufs = stg_bufs;
+        if ((rc = tc_make_omap_f32(d.out_f32, d.n_img, H, W, d.out_f32_C, TW, 32 / TW, &a.omap))) return rc;
     }
     a.out_f32 = d.out_f32; a.out_f32_C = d.out_f32_C; a.out_f32_nchw = d.out_f32_nchw;
     if (d.epi_mode != EPI_STD) {

@@ -28,7 +28,9 @@ struct ConvTCArgs {
     CUtensorMap bmap;               // 3-D map over packed weights (64, npad, 2*nkb), box (64, npad, 1)
     CUtensorMap bmap_half;          // same tensor, box (64, npad/2, 1): the half a CTA multicasts in a 2-CTA cluster
     CUtensorMap omap;               // out_tma: 5-D map over the split OUTPUT (C, W, H, img, plane), box (32, TW, 32 / TW, 1, 1), SWIZZLE_64B
-    int out_tma;                    // 1: the epilogue stages each warp's 32 pixels x 32 channels in shared memory and stores them with TMA
+    int out_tma;                    // 1: the epilogue stages each warp's 32 pixels x 32 channels in shared memory and stores them with TMA (split output);
+                                    // 2: same for the fp32 NHWC output (omap: (C, W, H, img, 1) fp32, SWIZZLE_128B)
+    int stg_bufs;                   // staging buffers per epilogue warp (2, or 1 when shared memory is short)
     int kernel_ver;                 // 1: tc_conv.cu (tap-shifted tiles), 3: tc_conv3.cu (halo reuse + weight multicast), 4: tc_conv_halo.cu
     int stack;                      // 1: [B_hi; B_lo] stacked along N -- two MMAs per K-step (A_hi x [B_hi;B_lo], A_lo x B_hi) instead of three
     int pair;                       // 1 (with persist): k_conv_tc_pair, two-CTA clusters issuing tcgen05.mma.cta_group::2
@@ -85,8 +87,9 @@ int conv_tc_launch(const ConvTCArgs &args, cudaStream_t st);
 int tc_make_amap(const SplitTensor &t, int box_w, int box_h, CUtensorMap *out);
 int tc_make_bmap(const void *w, int npad, int nkb, int box_rows, CUtensorMap *out);
 // tc_conv_halo.cu: persistent halo-reuse kernel for multi-wave 3x3 layers (kernel_ver 4)
-bool conv_tc_halo_plan(int npad, bool staging, int *a_stages, int *b_stages);
+bool conv_tc_halo_plan(int npad, int staging_bufs, int *a_stages, int *b_stages);
 int tc_make_omap(const SplitTensor &t, int box_w, int box_h, CUtensorMap *out);
+int tc_make_omap_f32(float *base, int n_img, int H, int W, int C, int box_w, int box_h, CUtensorMap *out);
 int conv_tc_halo_launch(const ConvTCArgs &args, cudaStream_t st);
 // tc_conv3.cu
 bool conv_tc3_plan(int npad, int *a_stages, int *b_stages);

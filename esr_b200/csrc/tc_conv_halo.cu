@@ -24,8 +24,9 @@ constexpr int TH_TW = 8, TH_TH = 16;                                   // output
 constexpr int TH_HW = TH_TW + 2, TH_HH = TH_TH + 2;                    // halo box 10 x 18 pixels
 constexpr uint32_t TH_A_PLANE = ((TH_HW * TH_HH * 128 + 1023) / 1024) * 1024;   // 23040 -> 23552: planes stay 1024-B aligned
 constexpr uint32_t TH_A_STAGE = 2 * TH_A_PLANE;
-constexpr uint32_t TH_STG_PLANE = 32 * 64;                             // one warp's 32 pixels x 32 channels of one plane
-constexpr uint32_t TH_STG_BYTES = 4 * 2 * 2 * TH_STG_PLANE;            // 32 KB
+constexpr uint32_t TH_STG_PLANE = 32 * 64;                             // one warp's 32 pixels x 32 channels of one split plane
+constexpr uint32_t TH_STG_BUF = 2 * TH_STG_PLANE;                      // one staging buffer: two split planes, or 32 pixels x 32 fp32
+static inline uint32_t th_stg_bytes(int bufs) { return 4u * (uint32_t)bufs * TH_STG_BUF; }
 
 __device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes)
 {
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
     const uint32_t b_bytes = (uint32_t)a.npad * 128u, b_stage = 2u * b_bytes;
     const uint32_t a_ring = smem_base, b_ring = smem_base + (uint32_t)a.a_stages * TH_A_STAGE;
     const uint32_t stg_ring = b_ring + (uint32_t)a.stages * b_stage;            // out_tma: [4 warps][2 buffers][2 planes][32 px x 64 B]
-    const uint32_t bar_base = stg_ring + (a.out_tma ? TH_STG_BYTES : 0u);
+    const uint32_t bar_base = stg_ring + (a.out_tma ? 4u * (uint32_t)a.stg_bufs * TH_STG_BUF : 0u);
     const uint32_t bar_afull = bar_base, bar_aempty = bar_afull + 8u * a.a_stages;
     const uint32_t bar_bfull = bar_aempty + 8u * a.a_stages, bar_bempty = bar_bfull + 8u * a.stages;
     const uint32_t bar_cfull = bar_bempty + 8u * a.stages, bar_cempty = bar_cfull + 16u;        // per accumulator
@@ -187,27 +188,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
                     // instruction and those go through the same L1 / shared-memory pipeline the MMA operands are read from: the
                     // clock trace shows ~1100 cycles of MMA back-pressure per 32-channel chunk.  Here the warp's 32 pixels x 32
                     // channels go to shared memory (swizzled: 4 wavefronts per instruction) and leave with one TMA store per plane.
-                    const uint32_t buf = stg_ring + (uint32_t)quad * (4u * TH_STG_PLANE) + (stg_n & 1u) * (2u * TH_STG_PLANE);
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the store that last read this buffer
+                    const bool two = a.stg_bufs == 2;
+                    const uint32_t buf = stg_ring + ((uint32_t)quad * (uint32_t)a.stg_bufs + (two ? (stg_n & 1u) : 0u)) * TH_STG_BUF;
+                    if (lane == 0) {                                    // the store that last read this buffer
+                        if (two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
                     float v[32];
                     epilogue_values(a, raw, n0, img, y, x, valid, v);
-                    uint32_t hw[16], lw[16];
+                    if (a.out_tma == 1) {
+                        uint32_t hw[16], lw[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) split_pack2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
-                    const uint32_t row = buf + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+                        for (int e = 0; e < 16; ++e) split_pack2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
+                        const uint32_t row = buf + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t o = row + (((uint32_t)q ^ sw) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(hw[4 * q]), "r"(hw[4 * q + 1]), "r"(hw[4 * q + 2]), "r"(hw[4 * q + 3]) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + TH_STG_PLANE), "r"(lw[4 * q]), "r"(lw[4 * q + 1]), "r"(lw[4 * q + 2]), "r"(lw[4 * q + 3]) : "memory");
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t o = row + (((uint32_t)q ^ sw) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(hw[4 * q]), "r"(hw[4 * q + 1]), "r"(hw[4 * q + 2]), "r"(hw[4 * q + 3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + TH_STG_PLANE), "r"(lw[4 * q]), "r"(lw[4 * q + 1]), "r"(lw[4 * q + 2]), "r"(lw[4 * q + 3]) : "memory");
+                        }
+                    } else {                                             // fp32 rows of 128 B, SWIZZLE_128B pattern
+                        const uint32_t row = buf + (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t o = row + (((uint32_t)q ^ sw) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(__float_as_uint(v[4 * q])), "r"(__float_as_uint(v[4 * q + 1])),
+                                         "r"(__float_as_uint(v[4 * q + 2])), "r"(__float_as_uint(v[4 * q + 3])) : "memory");
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        const int c0 = a.out_coff + n0, yq = y0 + 4 * quad;
-                        tma_store_5d(&a.omap, buf, c0, x0, yq, img, 0);
-                        tma_store_5d(&a.omap, buf + TH_STG_PLANE, c0, x0, yq, img, 1);
+                        const int yq = y0 + 4 * quad;
+                        if (a.out_tma == 1) {
+                            tma_store_5d(&a.omap, buf, a.out_coff + n0, x0, yq, img, 0);
+                            tma_store_5d(&a.omap, buf + TH_STG_PLANE, a.out_coff + n0, x0, yq, img, 1);
+                        } else {
+                            tma_store_5d(&a.omap, buf, n0, x0, yq, img, 0);      // channels >= out_f32_C are clipped by the tensor map
+                        }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++stg_n;
@@ -227,14 +246,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-static size_t th_smem_bytes(int npad, int a_stages, int b_stages, bool staging)
+static size_t th_smem_bytes(int npad, int a_stages, int b_stages, int staging_bufs)
 {
-    return 1024 + (size_t)a_stages * TH_A_STAGE + (size_t)b_stages * 2 * npad * 128 + (staging ? TH_STG_BYTES : 0) +
+    return 1024 + (size_t)a_stages * TH_A_STAGE + (size_t)b_stages * 2 * npad * 128 + th_stg_bytes(staging_bufs) +
            16 * (size_t)(a_stages + b_stages) + 96;
 }
 
 // pipeline depths for a layer of padded width npad (staging: with the epilogue's TMA-store buffers); false if nothing useful fits
-bool conv_tc_halo_plan(int npad, bool staging, int *a_stages, int *b_stages)
+bool conv_tc_halo_plan(int npad, int staging, int *a_stages, int *b_stages)
 {
     const size_t cap = (size_t)dev_info().max_smem_optin;
     for (int as = 2; as >= 2; --as) {
@@ -248,7 +267,7 @@ bool conv_tc_halo_plan(int npad, bool staging, int *a_stages, int *b_stages)
 int conv_tc_halo_launch(const ConvTCArgs &a, cudaStream_t st)
 {
     static int max_set = 0;
-    const size_t smem = th_smem_bytes(a.npad, a.a_stages, a.stages, a.out_tma != 0);
+    const size_t smem = th_smem_bytes(a.npad, a.a_stages, a.stages, a.out_tma ? a.stg_bufs : 0);
     if ((int)smem > max_set) {
         ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         max_set = (int)smem;
