@@ -26,8 +26,12 @@ constexpr int TC_MAX_SRC = 3;
 struct ConvTCArgs {
     CUtensorMap amap[TC_MAX_SRC];   // 5-D maps over the source split tensors (C, W, H, img, plane), box (64, TW, TH, 1, 1)
     CUtensorMap bmap;               // 3-D map over packed weights (64, npad, 2*nkb), box (64, npad, 1)
-    CUtensorMap bmap_half;          // same tensor, box (64, npad/2, 1): the half a CTA multicasts in a 2-CTA cluster
-    CUtensorMap omap;               // out_tma: 5-D map over the split OUTPUT (C, W, H, img, plane), box (32, TW, 32 / TW, 1, 1), SWIZZLE_64B
+    // The argument block must stay <= 1024 bytes: above that every launch of these kernels measured ~4 us slower (the store-side map
+    // added as its own member made it 1088 bytes and cost 19 launches x 4 us per step).  The two maps below are never used together.
+    union {
+        CUtensorMap bmap_half;      // same tensor, box (64, npad/2, 1): the half a CTA multicasts in a 2-CTA cluster (pair / v3 kernels)
+        CUtensorMap omap;           // out_tma (halo kernel): 5-D map over the OUTPUT (C, W, H, img, plane), box (32, TW, 32 / TW, 1, 1)
+    };
     int out_tma;                    // 1: the epilogue stages each warp's 32 pixels x 32 channels in shared memory and stores them with TMA (split output);
                                     // 2: same for the fp32 NHWC output (omap: (C, W, H, img, 1) fp32, SWIZZLE_128B)
     int stg_bufs;                   // staging buffers per epilogue warp (2, or 1 when shared memory is short)
@@ -55,6 +59,8 @@ struct ConvTCArgs {
     const __nv_bfloat16 *h_prev; size_t h_plane;                  // [*,H,W,64] split
     float *z_buf;                                                 // [n_img,H,W,64] fp32 (ZR writes, OUT reads)
 };
+
+static_assert(sizeof(ConvTCArgs) <= 1024, "ConvTCArgs: keep the kernel argument block within 1 KB");
 
 // Host-side description used to build ConvTCArgs.
 struct ConvTCDesc {
