@@ -640,12 +640,14 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
                         mbar_wait(bar_full + 8u * ms, mph);
                         tc_fence_after();
                         const uint32_t st = smem_base + ms * STAGE;
-                        const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + B_BYTES;
+                        // descriptors as base + immediates (see tc_conv_halo.cu): this thread's instruction stream is on the critical path
+                        constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+                        const uint32_t ah0 = umma_desc_lo(st), al0 = ah0 + (TC_A_BYTES >> 4), bh0 = ah0 + (2u * TC_A_BYTES >> 4), bl0 = bh0 + (B_BYTES >> 4);
                         const uint32_t first = ((seg & 1) == 0 && t == 0) ? 0u : 1u;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                            const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                            const uint64_t dah = umma_desc(ah0 + 2u * k, DESC_HI), dal = umma_desc(al0 + 2u * k, DESC_HI);
+                            const uint64_t dbh = umma_desc(bh0 + 2u * k, DESC_HI), dbl = umma_desc(bl0 + 2u * k, DESC_HI);
                             umma_bf16(acc, dal, dbh, idesc, k == 0 ? first : 1u);
                             umma_bf16(acc, dah, dbl, idesc, 1u);
                             umma_bf16(acc, dah, dbh, idesc, 1u);

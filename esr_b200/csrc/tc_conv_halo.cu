@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
         if (elect_one_sync()) {
             const uint32_t idesc = umma_idesc(TC_BLOCK_M, a.npad), idesc2 = umma_idesc(TC_BLOCK_M, 2 * a.npad);
             constexpr uint32_t SBO = (uint32_t)TH_HW * 128u;
+            constexpr uint32_t A_DESC_HI = (SBO >> 4) | (1u << 14) | (2u << 29), B_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
             uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
             int it = 0, mit = 0;
             long long *const tr = (TRACE && a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr;
@@ -127,28 +128,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_halo(const __grid_con
                     if (tr && mit < TRACE_N) tr[mit * 8 + 6] = clock64();
                     mbar_wait(bar_afull + 8u * sa, pha);
                     const uint32_t a_hi = a_ring + sa * TH_A_STAGE, a_lo = a_hi + TH_A_PLANE;
+                    // This thread's instruction stream between two tcgen05.mma is on the critical path (the tensor pipe's queue is short).
+                    // A descriptor's upper word is a constant and its lower word is the address field plus a constant, so the operands of
+                    // a tap are base + small immediates instead of a shift / mask / or chain per MMA.
+                    const uint32_t ah0 = umma_desc_lo(a_hi), al0 = umma_desc_lo(a_lo);
+#pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         if (tr && mit < TRACE_N) tr[mit * 8 + 2] = clock64();
                         mbar_wait(bar_bfull + 8u * sb, phb);
                         tc_fence_after();
                         if (tr && mit < TRACE_N) tr[mit * 8 + 3] = clock64();
-                        const uint32_t tap_off = (uint32_t)((t / 3) * TH_HW + (t % 3)) * 128u;     // halo pixel (ty, tx)
-                        const uint32_t b_hi = b_ring + sb * b_stage, b_lo = b_hi + b_bytes;
+                        const uint32_t tap16 = (uint32_t)((t / 3) * TH_HW + (t % 3)) * 8u;         // halo pixel (ty, tx), in 16-byte units
+                        const uint32_t b_hi = b_ring + sb * b_stage;
+                        const uint32_t bh0 = umma_desc_lo(b_hi), bl0 = bh0 + (b_bytes >> 4);
                         if (a.stack) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const uint64_t dah = umma_smem_desc_sbo(a_hi + tap_off + 32u * k, SBO);
-                                const uint64_t dal = umma_smem_desc_sbo(a_lo + tap_off + 32u * k, SBO);
-                                const uint64_t dbh = umma_smem_desc(b_hi + 32u * k);
+                                const uint64_t dah = umma_desc(ah0 + tap16 + 2u * k, A_DESC_HI), dal = umma_desc(al0 + tap16 + 2u * k, A_DESC_HI);
+                                const uint64_t dbh = umma_desc(bh0 + 2u * k, B_DESC_HI);
                                 umma_bf16(acc, dah, dbh, idesc2, (c | t | k) != 0 ? 1u : 0u);      // [B_hi; B_lo] as one 2 npad-row operand
                                 umma_bf16(acc, dal, dbh, idesc, 1u);
                             }
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const uint64_t dah = umma_smem_desc_sbo(a_hi + tap_off + 32u * k, SBO);
-                                const uint64_t dal = umma_smem_desc_sbo(a_lo + tap_off + 32u * k, SBO);
-                                const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                                const uint64_t dah = umma_desc(ah0 + tap16 + 2u * k, A_DESC_HI), dal = umma_desc(al0 + tap16 + 2u * k, A_DESC_HI);
+                                const uint64_t dbh = umma_desc(bh0 + 2u * k, B_DESC_HI), dbl = umma_desc(bl0 + 2u * k, B_DESC_HI);
                                 umma_bf16(acc, dal, dbh, idesc, (c | t | k) != 0 ? 1u : 0u);
                                 umma_bf16(acc, dah, dbl, idesc, 1u);
                                 umma_bf16(acc, dah, dbh, idesc, 1u);
