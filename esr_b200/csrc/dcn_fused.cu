@@ -96,9 +96,9 @@ __global__ void __launch_bounds__(DF_THREADS, 2) k_dcn_fused(const __grid_consta
                 const uint32_t b_hi = b_ring + s * DF_B_STAGE;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                    const uint64_t dah = umma_desc(umma_desc_lo(a_hi) + 2u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_lo(a_lo) + 2u * k, UMMA_HI_1024);
                     // stacked weights (tc_conv.cu, ConvTCArgs::stack): [B_hi; B_lo] are adjacent -> one N = 128 operand
-                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k);
+                    const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024);
                     umma_bf16(tmem_base, dah, dbh, idesc2, (t | k) != 0 ? 1u : 0u);
                     umma_bf16(tmem_base, dal, dbh, idesc, 1u);
                 }
@@ -286,9 +286,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) k_dcn_fused_win(const __grid_co
                 const uint32_t b_hi = b_ring + s * DF_B_STAGE;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
+                    const uint64_t dah = umma_desc(umma_desc_lo(a_hi) + 2u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_lo(a_lo) + 2u * k, UMMA_HI_1024);
                     // stacked weights (tc_conv.cu, ConvTCArgs::stack): [B_hi; B_lo] are adjacent -> one N = 128 operand
-                    const uint64_t dbh = umma_smem_desc(b_hi + 32u * k);
+                    const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024);
                     umma_bf16(tmem_base, dah, dbh, idesc2, (t | k) != 0 ? 1u : 0u);
                     umma_bf16(tmem_base, dal, dbh, idesc, 1u);
                 }

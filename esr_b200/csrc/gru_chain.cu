@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain(const __grid_consta
                         const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + b_bytes;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                            const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                            const uint64_t dah = umma_desc(umma_desc_lo(a_hi) + 2u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_lo(a_lo) + 2u * k, UMMA_HI_1024);
+                            const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024), dbl = umma_desc(umma_desc_lo(b_lo) + 2u * k, UMMA_HI_1024);
                             umma_bf16(tmem_base, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
                             umma_bf16(tmem_base, dah, dbl, idesc, 1u);
                             umma_bf16(tmem_base, dah, dbh, idesc, 1u);
@@ -445,8 +445,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                     const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + b_bytes;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                        const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                        const uint64_t dah = umma_desc(umma_desc_lo(a_hi) + 2u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_lo(a_lo) + 2u * k, UMMA_HI_1024);
+                        const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024), dbl = umma_desc(umma_desc_lo(b_lo) + 2u * k, UMMA_HI_1024);
                         umma_bf16(acc, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
                         umma_bf16(acc, dah, dbl, idesc, 1u);
                         umma_bf16(acc, dah, dbh, idesc, 1u);

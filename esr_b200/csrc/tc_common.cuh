@@ -194,6 +194,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr)
 // the operand by n bytes (n a multiple of 16, the result below 256 KB) is lo + n / 16.
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+constexpr uint32_t UMMA_HI_1024 = (1024u >> 4) | (1u << 14) | (2u << 29);      // upper word of umma_smem_desc(): SBO = 1024 B, version 1, SWIZZLE_128B
 // c=F32 [4,6)=1 | a=BF16 [7,10)=1 | b=BF16 [10,13)=1 | K-major A,B | N>>3 [17,23) | M>>4 [24,29)
 __device__ __forceinline__ uint32_t umma_idesc(int M, int N)
 {

@@ -94,16 +94,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const __grid_constant
                     // B_hi and B_lo are adjacent in the stage: ONE descriptor over 2 npad rows = [B_hi; B_lo]
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                        const uint64_t dbh = umma_smem_desc(b_hi + 32u * k);
+                        const uint64_t dah = umma_desc(umma_desc_lo(a_hi) + 2u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_lo(a_lo) + 2u * k, UMMA_HI_1024);
+                        const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024);
                         umma_bf16(tmem_base, dah, dbh, idesc2, (kb | k) != 0 ? 1u : 0u);   // cols [0,npad) += A_hi B_hi, [npad,2npad) += A_hi B_lo
                         umma_bf16(tmem_base, dal, dbh, idesc, 1u);                          // cols [0,npad) += A_lo B_hi
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {                       // 4 x (K = 16 bf16 = 32 bytes) per 128-byte row
-                        const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                        const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                        const uint64_t dah = umma_desc(umma_desc_lo(a_hi) + 2u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_lo(a_lo) + 2u * k, UMMA_HI_1024);
+                        const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024), dbl = umma_desc(umma_desc_lo(b_lo) + 2u * k, UMMA_HI_1024);
                         umma_bf16(tmem_base, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
                         umma_bf16(tmem_base, dah, dbl, idesc, 1u);
                         umma_bf16(tmem_base, dah, dbh, idesc, 1u);
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_
                     const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + b_bytes;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                        const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                        const uint64_t dah = umma_desc(umma_desc_lo(a_hi) + 2u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_lo(a_lo) + 2u * k, UMMA_HI_1024);
+                        const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024), dbl = umma_desc(umma_desc_lo(b_lo) + 2u * k, UMMA_HI_1024);
                         if (a.stack) {
                             umma_bf16(acc, dah, dbh, idesc2, (kb | k) != 0 ? 1u : 0u);   // [B_hi; B_lo] as one 2 npad-row operand
                             umma_bf16(acc, dal, dbh, idesc, 1u);
@@ -412,8 +412,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_con
                     const uint32_t a_hi = st, a_lo = st + TC_A_BYTES, b_hi = st + 2u * TC_A_BYTES, b_lo = b_hi + bh_bytes;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t dah = umma_smem_desc(a_hi + 32u * k), dal = umma_smem_desc(a_lo + 32u * k);
-                        const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                        const uint64_t dah = umma_desc(umma_desc_lo(a_hi) + 2u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_lo(a_lo) + 2u * k, UMMA_HI_1024);
+                        const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024), dbl = umma_desc(umma_desc_lo(b_lo) + 2u * k, UMMA_HI_1024);
                         umma_bf16_pair(acc, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
                         umma_bf16_pair(acc, dah, dbl, idesc, 1u);
                         umma_bf16_pair(acc, dah, dbh, idesc, 1u);

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_conv_tc3(const __grid_constan
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t dah = umma_smem_desc_halo(a_hi + tap_off + 32u * k);
                         const uint64_t dal = umma_smem_desc_halo(a_lo + tap_off + 32u * k);
-                        const uint64_t dbh = umma_smem_desc(b_hi + 32u * k), dbl = umma_smem_desc(b_lo + 32u * k);
+                        const uint64_t dbh = umma_desc(umma_desc_lo(b_hi) + 2u * k, UMMA_HI_1024), dbl = umma_desc(umma_desc_lo(b_lo) + 2u * k, UMMA_HI_1024);
                         umma_bf16(tmem_base, dal, dbh, idesc, (c | t | k) != 0 ? 1u : 0u);
                         umma_bf16(tmem_base, dah, dbl, idesc, 1u);
                         umma_bf16(tmem_base, dah, dbh, idesc, 1u);

@@ -47,6 +47,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lb
     return d;
 }
 
+// lower word of the same descriptor (the upper word is UMMA_HI_1024); advancing the operand by n bytes is lo + n / 16
+__device__ __forceinline__ uint32_t umma_desc_mn_lo(uint32_t smem_addr, uint32_t lbo_bytes)
+{
+    return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constant__ WgradArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -164,8 +170,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {                    // K step k = tile row k: 16 pixels = 16 rows of the halo box
                             const uint32_t sh = (((uint32_t)(k + ky)) * hw + (uint32_t)kx) * 128u;
-                            const uint64_t dah = umma_desc_mn(m_hi + 2048u * k, WG_TILE), dal = umma_desc_mn(m_lo + 2048u * k, WG_TILE);
-                            const uint64_t dbh = umma_desc_mn(xb + sh, WG_TILE), dbl = umma_desc_mn(xb + halo_plane + sh, WG_TILE);
+                            const uint64_t dah = umma_desc(umma_desc_mn_lo(m_hi, WG_TILE) + 128u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_mn_lo(m_lo, WG_TILE) + 128u * k, UMMA_HI_1024);
+                            const uint64_t dbh = umma_desc(umma_desc_mn_lo(xb, WG_TILE) + (sh >> 4), UMMA_HI_1024), dbl = umma_desc(umma_desc_mn_lo(xb + halo_plane, WG_TILE) + (sh >> 4), UMMA_HI_1024);
                             umma_bf16(d, dal, dbh, idesc, (first && k == 0) ? 0u : 1u);
                             umma_bf16(d, dah, dbl, idesc, 1u);
                             umma_bf16(d, dah, dbh, idesc, 1u);
@@ -187,8 +193,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
                     const uint32_t d = tmem_base + (uint32_t)j * 64u;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {                        // 8 x (K = 16 pixels = 16 rows = 2048 bytes)
-                        const uint64_t dah = umma_desc_mn(m_hi + 2048u * k, WG_TILE), dal = umma_desc_mn(m_lo + 2048u * k, WG_TILE);
-                        const uint64_t dbh = umma_desc_mn(n_hi + 2048u * k, WG_TILE), dbl = umma_desc_mn(n_lo + 2048u * k, WG_TILE);
+                        const uint64_t dah = umma_desc(umma_desc_mn_lo(m_hi, WG_TILE) + 128u * k, UMMA_HI_1024), dal = umma_desc(umma_desc_mn_lo(m_lo, WG_TILE) + 128u * k, UMMA_HI_1024);
+                        const uint64_t dbh = umma_desc(umma_desc_mn_lo(n_hi, WG_TILE) + 128u * k, UMMA_HI_1024), dbl = umma_desc(umma_desc_mn_lo(n_lo, WG_TILE) + 128u * k, UMMA_HI_1024);
                         umma_bf16(d, dal, dbh, idesc, (first && k == 0) ? 0u : 1u);
                         umma_bf16(d, dah, dbl, idesc, 1u);
                         umma_bf16(d, dah, dbh, idesc, 1u);
