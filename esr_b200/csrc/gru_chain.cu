@@ -754,6 +754,235 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_gru_chain_x3: the state-independent x-side of all three gates as ONE N = 192 GEMM per step.
+//
+// Every kernel above loads and reads the x tile once per gate (k_gru_chain_rzo: three times, 27 of its 54 K-blocks per step).  The
+// tensor-core convs and this chain are bound by bytes through the shared-memory pipeline (TMA fill + SS-mode operand reads), so:
+//   X(g)   9 K-blocks, A = x,      B = [z; r; o] rows (zr pack + go pack, adjacent in the stage),  N = 192 -> accumulators z | r | o
+//   H(g)   9 K-blocks, A = h,      B = [z; r] (zr pack, state-side K-blocks),                        N = 128 -> += z | r
+//   RH(g)  9 K-blocks, A = h * r,  B = o (go pack, state-side K-blocks),                            N = 64  -> += o
+// 27 K-blocks and 4.3 MB through the pipeline per step and CTA instead of 54 and 6.5 MB; per output element the products are still
+// accumulated x taps 0..8 then state taps 0..8, so the results are bit-identical to the other kernels.
+// X(g + 1) does not depend on the state: it is issued between H(g) and RH(g) -- i.e. while this step's reset epilogue and phase
+// barrier are pending -- into the OTHER of two accumulator sets (2 x 192 TMEM columns).  That set was last read by the part-B
+// epilogue of step g - 1, which precedes phase barrier 2g - 1, which H(g)'s operand loads wait for: no extra synchronisation.
+// Stages are 80 KB (A 32 KB + B 2 x 24 KB): two fit beside the 32 KB store staging.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_x3(const __grid_constant__ GruRzoArgs aa)
+{
+    const GruChainArgs &a = aa.g;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t B_PLANE = 192u * 128u;                             // [z; r; o] rows of one plane: 24 KB
+    constexpr uint32_t STAGE = 2u * TC_A_BYTES + 2u * B_PLANE;            // 80 KB
+    constexpr uint32_t NST = 2;
+    const uint32_t stg_base = smem_base + NST * STAGE;                    // out_tma: [8 epilogue warps][2 planes][32 px x 64 B]
+    const uint32_t bar_base = stg_base + (aa.out_tma ? GC_STG_BYTES : 0u);
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * NST, bar_accum = bar_base + 16u * NST;   // [0] = z|r, [1] = o
+    const uint32_t tmem_slot = bar_accum + 16u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B2 = 2 * a.B;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int tile = blockIdx.x;                                  // grid == number of tiles
+    const int img = tile / tiles_per_img;
+    const int trem = tile - img * tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+    const int bb = img < a.B ? img : img - a.B;
+    const bool per_img = B2 <= 64;
+    unsigned int *bar_ctr = a.barrier + (per_img ? img * 8 : 0);
+    const unsigned int bar_n = per_img ? (unsigned int)tiles_per_img : gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < NST; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        mbar_init(bar_accum, 1); mbar_init(bar_accum + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);                    // two sets of z [0, 64) | r [64, 128) | o [128, 192)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // issue order (producer and MMA thread alike): X(0), then per step g: H(g), X(g + 1), RH(g)
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            uint32_t ps = 0, pph = 0;
+            auto xc_of = [&](int g) {
+                const int w_idx = g / a.N, s_idx = g - w_idx * a.N;
+                return (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
+            };
+            auto wait_phase = [&](int idx) {
+                const unsigned int target = (unsigned int)(idx + 1) * bar_n;
+                unsigned int v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
+                } while (v < target);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            };
+            // kind 0: X, 1: H, 2: RH
+            auto segment = [&](int kind, const CUtensorMap *am, int simg) {
+                const uint32_t bytes = 2u * TC_A_BYTES + (kind == 0 ? 2u * B_PLANE : kind == 1 ? 2u * 128u * 128u : 2u * 64u * 128u);
+                for (int t = 0; t < 9; ++t) {
+                    const int dy = t / 3 - 1, dx = t % 3 - 1;
+                    const uint32_t st = smem_base + ps * STAGE, bf = bar_full + 8u * ps;
+                    mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
+                    mbar_expect_tx(bf, bytes);
+                    tma_load_5d(am, bf, st, 0, x0 + dx, y0 + dy, simg, 0);
+                    tma_load_5d(am, bf, st + TC_A_BYTES, 0, x0 + dx, y0 + dy, simg, 1);
+                    const uint32_t bh = st + 2u * TC_A_BYTES, bl = bh + B_PLANE;
+                    if (kind == 0) {                  // [z; r] from the zr pack, o from the go pack, x-side K-block t
+                        tma_load_3d(&a.bmap_zr, bf, bh, 0, 0, t);
+                        tma_load_3d(&a.bmap_zr, bf, bl, 0, 0, 18 + t);
+                        tma_load_3d(&a.bmap_go, bf, bh + 128u * 128u, 0, 0, t);
+                        tma_load_3d(&a.bmap_go, bf, bl + 128u * 128u, 0, 0, 18 + t);
+                    } else if (kind == 1) {           // [z; r], state-side K-block 9 + t
+                        tma_load_3d(&a.bmap_zr, bf, bh, 0, 0, 9 + t);
+                        tma_load_3d(&a.bmap_zr, bf, bl, 0, 0, 18 + 9 + t);
+                    } else {                          // o, state-side K-block 9 + t
+                        tma_load_3d(&a.bmap_go, bf, bh, 0, 0, 9 + t);
+                        tma_load_3d(&a.bmap_go, bf, bl, 0, 0, 18 + 9 + t);
+                    }
+                    if (++ps == NST) { ps = 0; pph ^= 1u; }
+                }
+            };
+            segment(0, &a.amap_xc, xc_of(0));
+            for (int g = 0; g < a.nsteps; ++g) {
+                if (g > 0) wait_phase(2 * g - 1);                             // h of the previous step
+                segment(1, &a.amap_hs, g * B2 + img);
+                if (g + 1 < a.nsteps) segment(0, &a.amap_xc, xc_of(g + 1));
+                wait_phase(2 * g);                                            // this step's h * r
+                segment(2, &a.amap_rh, img);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            const uint32_t id192 = umma_idesc(TC_BLOCK_M, 192), id128 = umma_idesc(TC_BLOCK_M, 128), id64 = umma_idesc(TC_BLOCK_M, 64);
+            uint32_t ms = 0, mph = 0;
+            auto segment = [&](uint32_t acc, uint32_t idesc, bool fresh) {
+#pragma unroll 1
+                for (int t = 0; t < 9; ++t) {
+                    mbar_wait(bar_full + 8u * ms, mph);
+                    tc_fence_after();
+                    const uint32_t ah0 = umma_desc_lo(smem_base + ms * STAGE), al0 = ah0 + (TC_A_BYTES >> 4);
+                    const uint32_t bh0 = ah0 + (2u * TC_A_BYTES >> 4), bl0 = bh0 + (B_PLANE >> 4);
+                    const uint32_t first = (fresh && t == 0) ? 0u : 1u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t dah = umma_desc(ah0 + 2u * k, UMMA_HI_1024), dal = umma_desc(al0 + 2u * k, UMMA_HI_1024);
+                        const uint64_t dbh = umma_desc(bh0 + 2u * k, UMMA_HI_1024), dbl = umma_desc(bl0 + 2u * k, UMMA_HI_1024);
+                        umma_bf16(acc, dal, dbh, idesc, k == 0 ? first : 1u);
+                        umma_bf16(acc, dah, dbl, idesc, 1u);
+                        umma_bf16(acc, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(bar_empty + 8u * ms);
+                    if (++ms == NST) { ms = 0; mph ^= 1u; }
+                }
+            };
+            segment(tmem_base, id192, true);
+            for (int g = 0; g < a.nsteps; ++g) {
+                const uint32_t set = tmem_base + (uint32_t)(g & 1) * 192u, other = tmem_base + (uint32_t)((g + 1) & 1) * 192u;
+                segment(set, id128, false);
+                umma_commit(bar_accum);                                       // z and r of step g complete
+                if (g + 1 < a.nsteps) segment(other, id192, true);
+                segment(set + 128u, id64, false);
+                umma_commit(bar_accum + 8u);                                  // o complete
+            }
+        }
+    } else {
+        // ===================== epilogue: 8 warps, two per TMEM lane quadrant, 32 channels each =====================
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int m = quad * 32 + lane;
+        const int y = y0 + m / a.TW, x = x0 + m % a.TW;
+        const bool valid = (y < a.H) && (x < a.W);
+        const size_t pix = ((size_t)img * a.H + (valid ? y : 0)) * a.W + (valid ? x : 0);
+        const int c0 = half * 32;                                            // this warp's channels
+        const uint32_t stg_w = stg_base + (uint32_t)(warp - 2) * (2u * GC_STG_PLANE);
+        for (int g = 0; g < a.nsteps; ++g) {
+            const uint32_t par = (uint32_t)(g & 1);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + par * 192u;
+            const __nv_bfloat16 *h_prev = a.hs + ((size_t)g * B2 * a.H * a.W + pix) * 64 + c0;
+            // h of this pixel (previous step's state: final before this step's first barrier) -- in flight during the main loops
+            uint4 hh[4], hl[4];
+            if (valid) {
+                const uint4 *ph = reinterpret_cast<const uint4 *>(h_prev), *pl = reinterpret_cast<const uint4 *>(h_prev + a.hs_plane);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { hh[q] = ph[q]; hl[q] = pl[q]; }
+            }
+            float h[32];
+            // ---- part A: r -> h * r
+            mbar_wait_backoff(bar_accum, par);
+            tc_fence_after();
+            {
+                uint32_t raw[32];
+                tmem_ld32(taddr + 64u + (uint32_t)c0, raw);
+                if (valid) {
+                    gc_unpack32(hh, hl, h);
+                    float v[32];
+                    const float4 *bp = reinterpret_cast<const float4 *>(a.bias_zr + 64 + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = bp[q];
+                        v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+                        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+                        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+                        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+                    }
+                    act32(v, ACT_SIGMOID);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= h[j];
+                    if (aa.out_tma) gc_stage_split32(stg_w, lane, v);
+                    else store_split32(a.rh + pix * 64 + c0, a.rh_plane, v);
+                }
+                __syncwarp();
+                if (aa.out_tma) gc_tma_store_wait(&aa.omap_rh, stg_w, lane, c0, x0, y0 + quad * (32 / a.TW), img);
+            }
+            tc_fence_before();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
+            // ---- part B: z, o -> h' = h (1 - z) + o z
+            mbar_wait_backoff(bar_accum + 8u, par);
+            tc_fence_after();
+            {
+                uint32_t rz[32], ro[32];
+                tmem_ld32(taddr + (uint32_t)c0, rz);
+                tmem_ld32(taddr + 128u + (uint32_t)c0, ro);
+                if (valid) {
+                    float z[32], o[32];
+                    const float4 *bz = reinterpret_cast<const float4 *>(a.bias_zr + c0), *bo = reinterpret_cast<const float4 *>(a.bias_go + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b1 = bz[q], b2 = bo[q];
+                        z[4 * q + 0] = __uint_as_float(rz[4 * q + 0]) + b1.x; o[4 * q + 0] = __uint_as_float(ro[4 * q + 0]) + b2.x;
+                        z[4 * q + 1] = __uint_as_float(rz[4 * q + 1]) + b1.y; o[4 * q + 1] = __uint_as_float(ro[4 * q + 1]) + b2.y;
+                        z[4 * q + 2] = __uint_as_float(rz[4 * q + 2]) + b1.z; o[4 * q + 2] = __uint_as_float(ro[4 * q + 2]) + b2.z;
+                        z[4 * q + 3] = __uint_as_float(rz[4 * q + 3]) + b1.w; o[4 * q + 3] = __uint_as_float(ro[4 * q + 3]) + b2.w;
+                    }
+                    act32(z, ACT_SIGMOID);
+                    act32(o, ACT_TANH);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = h[j] * (1.0f - z[j]) + o[j] * z[j];
+                    __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64 + c0;
+                    if (aa.out_tma) gc_stage_split32(stg_w, lane, o);
+                    else store_split32(h_new, a.hs_plane, o);
+                }
+                __syncwarp();
+                if (aa.out_tma) gc_tma_store_wait(&aa.omap_hs, stg_w, lane, c0, x0, y0 + quad * (32 / a.TW), (g + 1) * B2 + img);
+            }
+            tc_fence_before();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct GruChainPlan {
     GruChainArgs args;
     int grid;
@@ -762,6 +991,8 @@ struct GruChainPlan {
     bool rzo = false;               // k_gru_chain_rzo (reset gate first; update gate and candidate together, off the critical path)
     GruRzoArgs rzo_args;
     size_t rzo_smem = 0;
+    bool x3 = false;                // k_gru_chain_x3 (x-side of the three gates as one N = 192 GEMM); ESR_GRU_X3=1
+    size_t x3_smem = 0;
 };
 
 int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitTensor &rh, float *zbuf, const void *w_zr,
@@ -828,6 +1059,12 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
             p->rzo_args.out_tma = 1;
             p->rzo_smem += GC_STG_BYTES;
         }
+        static const bool x3_on = getenv("ESR_GRU_X3") && atoi(getenv("ESR_GRU_X3")) != 0;
+        p->x3_smem = 1024 + (size_t)2 * (2 * TC_A_BYTES + 2 * 192 * 128) + (p->rzo_args.out_tma ? GC_STG_BYTES : 0) + 16 * 2 + 96;
+        if (x3_on && p->x3_smem <= (size_t)dev_info().max_smem_optin) {
+            p->x3 = true;
+            ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->x3_smem));
+        }
         ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_rzo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->rzo_smem));
     }
     *plan_out = p;
@@ -838,6 +1075,12 @@ int gru_chain_launch(void *plan, cudaStream_t st)
 {
     GruChainPlan *p = (GruChainPlan *)plan;
     ESR_CUDA_CHECK(cudaMemsetAsync(p->args.barrier, 0, 64 * 8 * sizeof(unsigned int), st));   // per-image counters, 32 bytes apart
+    if (p->rzo && p->x3) {
+        void *kargs[] = {(void *)&p->rzo_args};
+        ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain_x3, dim3(p->grid), dim3(GC_THREADS), kargs, p->x3_smem, st));
+        esr::count_launch();
+        return ESR_OK;
+    }
     if (p->rzo) {
         void *kargs[] = {(void *)&p->rzo_args};
         ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain_rzo, dim3(p->grid), dim3(GC_THREADS), kargs, p->rzo_smem, st));
