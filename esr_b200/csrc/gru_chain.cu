@@ -31,6 +31,7 @@ struct GruChainArgs {
     float *zbuf;                                // update gate, fp32 [2B, H, W, 64]
     unsigned int *barrier;                      // grid barrier counter (zeroed before the launch)
     int B, N, nsteps, H, W, TW, TH, tiles_x, tiles_y, stages;
+    int diag;                                   // measurement aid (ESR_GRU_DIAG): 1 = the epilogue skips its global stores, 2 = also its global loads (wrong results)
     int wpre;                                   // 1: weight tiles of the first state-side K-blocks are issued before the phase barrier wait (measured slower)
     int cluster;                                // > 1: one thread-block cluster per image (tiles_per_img CTAs), phase barrier through DSMEM mbarriers
 };
@@ -84,22 +85,26 @@ __device__ __forceinline__ void gc_epilogue(const GruChainArgs &a, int which, in
                 act32(v, ACT_SIGMOID);
                 if (n0 < 64) {                                      // update gate z (fp32)
                     float4 *zp = reinterpret_cast<float4 *>(a.zbuf + pix * 64 + n0);
+                    if (!(a.diag & 1)) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) zp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
                 } else {                                            // reset gate r -> h * r
                     float h[32];
-                    load_split32(h_prev + (n0 - 64), a.hs_plane, h);
+                    if (!(a.diag & 2)) load_split32(h_prev + (n0 - 64), a.hs_plane, h);
+                    else { for (int j = 0; j < 32; ++j) h[j] = 1.0f; }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= h[j];
-                    store_split32(a.rh + pix * 64 + (n0 - 64), a.rh_plane, v);
+                    if (!(a.diag & 1)) store_split32(a.rh + pix * 64 + (n0 - 64), a.rh_plane, v);
                 }
             } else {                                                // h' = h (1 - z) + tanh(.) z
                 float h[32];
-                load_split32(h_prev + n0, a.hs_plane, h);
+                if (!(a.diag & 2)) load_split32(h_prev + n0, a.hs_plane, h);
+                else { for (int j = 0; j < 32; ++j) h[j] = 1.0f; }
                 const float4 *zp = reinterpret_cast<const float4 *>(a.zbuf + pix * 64 + n0);
                 float4 zq[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) zq[q] = zp[q];
+                for (int q = 0; q < 8; ++q) zq[q] = (a.diag & 2) ? make_float4(0.5f, 0.5f, 0.5f, 0.5f) : zp[q];
                 act32(v, ACT_TANH);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -111,7 +116,7 @@ __device__ __forceinline__ void gc_epilogue(const GruChainArgs &a, int which, in
                     }
                 }
                 __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64;
-                store_split32(h_new + n0, a.hs_plane, v);
+                if (!(a.diag & 1)) store_split32(h_new + n0, a.hs_plane, v);
             }
         }
         __syncwarp();
@@ -218,7 +223,7 @@ __device__ __forceinline__ void gc_epilogue_pre(const GruChainArgs &a, int which
                     }
                 }
                 __nv_bfloat16 *h_new = a.hs + ((size_t)(g + 1) * B2 * a.H * a.W + pix) * 64;
-                store_split32(h_new + n0, a.hs_plane, v);
+                if (!(a.diag & 1)) store_split32(h_new + n0, a.hs_plane, v);
             }
         }
         __syncwarp();
@@ -530,6 +535,7 @@ struct GruRzoArgs {
     CUtensorMap bmap_zr64;                      // the update|reset pack with a 64-row box: rows [0, 64) = update (z), [64, 128) = reset (r)
     CUtensorMap omap_rh, omap_hs;               // out_tma: store side of rh / the state slots, box (32 ch, TW, 32 / TW, 1, 1), SWIZZLE_64B
     int out_tma;                                // 1: h * r and h' leave through shared memory + TMA stores (see tc_conv_halo.cu)
+    int tiles_per_cta;                          // k_gru_chain_mt: consecutive tiles owned by one CTA (<= 4)
 };
 constexpr uint32_t GC_STG_PLANE = 32 * 64;      // one epilogue warp's 32 pixels x 32 channels of one split plane
 constexpr uint32_t GC_STG_BYTES = 8 * 2 * GC_STG_PLANE;
@@ -983,6 +989,204 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_x3(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_gru_chain_mt: the chain when there are more tiles than SMs (4x SR configurations: 256 / 512 tiles).
+//
+// k_gru_chain above serialises main loop and epilogue per tile (one 128-column accumulator, a block barrier per tile), stores z in
+// fp32 and reads z and h back with one-pixel-per-lane accesses: at cfg4 the epilogue's strided loads and stores alone are 23 % of its
+// 4.97 ms (ESR_GRU_DIAG).  Here a CTA owns up to FOUR tiles and gives each its own 128 TMEM columns for the whole step:
+//     columns [128 t, 128 t + 64)      z of tile t  -- written in phase 1, read in phase 2, never leaves the SM
+//     columns [128 t + 64, 128 t + 128) r in phase 1, then the candidate o in phase 2 (r is dead once h * r is stored)
+// so the MMA thread runs ahead into the next tile while the eight epilogue warps drain the previous one, and no barrier separates the
+// tiles of a phase.  h arrives through TMA into a per-warp 4 KB buffer (issued before the accumulator is awaited), h * r and h' leave
+// from the same buffer by TMA stores (tc_conv_halo.cu explains why strided per-lane accesses are to be avoided in these kernels).
+// Same K-block order and per-element accumulation order as every other chain kernel: bit-identical results.
+// ------------------------------------------------------------------------------------------------
+constexpr int GC_MT_MAX = 4;
+
+__global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_mt(const __grid_constant__ GruRzoArgs aa)
+{
+    const GruChainArgs &a = aa.g;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t B_MAX = 128u * 128u;                               // one plane of the N = 128 weight tile
+    constexpr uint32_t STAGE = 2u * TC_A_BYTES + 2u * B_MAX;              // 64 KB
+    const uint32_t stg_base = smem_base + (uint32_t)a.stages * STAGE;     // [8 epilogue warps][2 planes][32 px x 64 B]
+    const uint32_t bar_base = stg_base + GC_STG_BYTES;
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages, bar_accum = bar_base + 16u * a.stages;   // [GC_MT_MAX]
+    const uint32_t bar_hload = bar_accum + 8u * GC_MT_MAX;                // [8]: one per epilogue warp
+    const uint32_t tmem_slot = bar_hload + 64u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B2 = 2 * a.B;
+    const int tiles_per_img = a.tiles_x * a.tiles_y, n_tiles = B2 * tiles_per_img;
+    const int per_cta = aa.tiles_per_cta;
+    const int tile0 = blockIdx.x * per_cta;
+    const int my_tiles = min(per_cta, n_tiles - tile0);                   // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        for (int t = 0; t < GC_MT_MAX; ++t) mbar_init(bar_accum + 8u * t, 1);
+        for (int w = 0; w < 8; ++w) mbar_init(bar_hload + 8u * w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    uint32_t ps = 0, pph = 0, ms = 0, mph = 0;
+    uint32_t hl_ph = 0;                                                    // parity of this warp's h-load barrier
+    for (int p = 0; p < 2 * a.nsteps; ++p) {
+        const int g = p >> 1, which = p & 1;              // which: 0 = update|reset gates, 1 = candidate + blend
+        const int w_idx = g / a.N, s_idx = g - w_idx * a.N;
+        const int npad = which == 0 ? 128 : 64;
+        const uint32_t b_bytes = (uint32_t)npad * 128u;
+        const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+        const CUtensorMap *bmap = which == 0 ? &a.bmap_zr : &a.bmap_go;
+        if (warp == 0) {
+            if (elect_one_sync()) {
+                for (int t = 0; t < my_tiles; ++t) {
+                    const int tile = tile0 + t;
+                    const int img = tile / tiles_per_img, trem = tile - img * tiles_per_img;
+                    const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+                    const int bb = img < a.B ? img : img - a.B;
+                    const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
+                    for (int kb = 0; kb < 18; ++kb) {
+                        const int src = kb / 9, tap = kb - src * 9;
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        mbar_wait(bar_empty + 8u * ps, pph ^ 1u);
+                        mbar_expect_tx(bar_full + 8u * ps, stage_bytes);
+                        const uint32_t st = smem_base + ps * STAGE;
+                        const CUtensorMap *am = src == 0 ? &a.amap_xc : (which == 0 ? &a.amap_hs : &a.amap_rh);
+                        const int simg = src == 0 ? xc_img : (which == 0 ? g * B2 + img : img);
+                        tma_load_5d(am, bar_full + 8u * ps, st, 0, x0 + dx, y0 + dy, simg, 0);
+                        tma_load_5d(am, bar_full + 8u * ps, st + TC_A_BYTES, 0, x0 + dx, y0 + dy, simg, 1);
+                        tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES, 0, 0, kb);
+                        tma_load_3d(bmap, bar_full + 8u * ps, st + 2u * TC_A_BYTES + b_bytes, 0, 0, 18 + kb);
+                        if (++ps == (uint32_t)a.stages) { ps = 0; pph ^= 1u; }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one_sync()) {
+                const uint32_t idesc = umma_idesc(TC_BLOCK_M, npad);
+                for (int t = 0; t < my_tiles; ++t) {
+                    const uint32_t acc = tmem_base + (uint32_t)t * 128u + (which ? 64u : 0u);
+#pragma unroll 1
+                    for (int kb = 0; kb < 18; ++kb) {
+                        mbar_wait(bar_full + 8u * ms, mph);
+                        tc_fence_after();
+                        const uint32_t ah0 = umma_desc_lo(smem_base + ms * STAGE), al0 = ah0 + (TC_A_BYTES >> 4);
+                        const uint32_t bh0 = ah0 + (2u * TC_A_BYTES >> 4), bl0 = bh0 + (b_bytes >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t dah = umma_desc(ah0 + 2u * k, UMMA_HI_1024), dal = umma_desc(al0 + 2u * k, UMMA_HI_1024);
+                            const uint64_t dbh = umma_desc(bh0 + 2u * k, UMMA_HI_1024), dbl = umma_desc(bl0 + 2u * k, UMMA_HI_1024);
+                            umma_bf16(acc, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_bf16(acc, dah, dbl, idesc, 1u);
+                            umma_bf16(acc, dah, dbh, idesc, 1u);
+                        }
+                        umma_commit(bar_empty + 8u * ms);
+                        if (++ms == (uint32_t)a.stages) { ms = 0; mph ^= 1u; }
+                    }
+                    umma_commit(bar_accum + 8u * t);
+                }
+            }
+        } else {
+            // ===================== epilogue: 8 warps, two per TMEM lane quadrant, 32 channels each =====================
+            const int quad = warp & 3, half = (warp - 2) >> 2;
+            const int c0 = half * 32;
+            const uint32_t stg_w = stg_base + (uint32_t)(warp - 2) * (2u * GC_STG_PLANE);
+            const uint32_t hbar = bar_hload + 8u * (uint32_t)(warp - 2);
+            const uint32_t row = stg_w + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int tile = tile0 + t;
+                const int img = tile / tiles_per_img, trem = tile - img * tiles_per_img;
+                const int y0 = (trem / a.tiles_x) * a.TH, x0 = (trem % a.tiles_x) * a.TW;
+                const int yq = y0 + quad * (32 / a.TW);
+                // h of this warp's 32 pixels x 32 channels (the previous step's state) -> staging buffer, while the tile's MMAs run
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the store that last read the buffer
+                    mbar_expect_tx(hbar, 2u * GC_STG_PLANE);
+                    tma_load_5d(&aa.omap_hs, hbar, stg_w, c0, x0, yq, g * B2 + img, 0);
+                    tma_load_5d(&aa.omap_hs, hbar, stg_w + GC_STG_PLANE, c0, x0, yq, g * B2 + img, 1);
+                }
+                mbar_wait_backoff(bar_accum + 8u * t, (uint32_t)(p & 1));
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)t * 128u;
+                uint32_t raw[32];
+                tmem_ld32(taddr + 64u + (uint32_t)c0, raw);              // r (phase 1) or o (phase 2)
+                mbar_wait(hbar, hl_ph);
+                hl_ph ^= 1u;
+                float h[32];
+                {
+                    uint4 hh[4], hl[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t o = row + (((uint32_t)q ^ sw) << 4);
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh[q].x), "=r"(hh[q].y), "=r"(hh[q].z), "=r"(hh[q].w) : "r"(o));
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hl[q].x), "=r"(hl[q].y), "=r"(hl[q].z), "=r"(hl[q].w) : "r"(o + GC_STG_PLANE));
+                    }
+                    gc_unpack32(hh, hl, h);
+                }
+                float v[32];
+                if (which == 0) {
+                    const float4 *bp = reinterpret_cast<const float4 *>(a.bias_zr + 64 + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = bp[q];
+                        v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b.x;
+                        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+                        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+                        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+                    }
+                    act32(v, ACT_SIGMOID);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= h[j];
+                } else {
+                    uint32_t rz[32];
+                    tmem_ld32(taddr + (uint32_t)c0, rz);                 // z, still where phase 1 left it
+                    float z[32];
+                    const float4 *bz = reinterpret_cast<const float4 *>(a.bias_zr + c0), *bo = reinterpret_cast<const float4 *>(a.bias_go + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b1 = bz[q], b2 = bo[q];
+                        z[4 * q + 0] = __uint_as_float(rz[4 * q + 0]) + b1.x; v[4 * q + 0] = __uint_as_float(raw[4 * q + 0]) + b2.x;
+                        z[4 * q + 1] = __uint_as_float(rz[4 * q + 1]) + b1.y; v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b2.y;
+                        z[4 * q + 2] = __uint_as_float(rz[4 * q + 2]) + b1.z; v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b2.z;
+                        z[4 * q + 3] = __uint_as_float(rz[4 * q + 3]) + b1.w; v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b2.w;
+                    }
+                    act32(z, ACT_SIGMOID);
+                    act32(v, ACT_TANH);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = h[j] * (1.0f - z[j]) + v[j] * z[j];
+                }
+                __syncwarp();                                             // every lane has read its h row
+                gc_stage_split32(stg_w, lane, v);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    const CUtensorMap *om = which == 0 ? &aa.omap_rh : &aa.omap_hs;
+                    const int oimg = which == 0 ? img : (g + 1) * B2 + img;
+                    tma_store_5d(om, stg_w, c0, x0, yq, oimg, 0);
+                    tma_store_5d(om, stg_w + GC_STG_PLANE, c0, x0, yq, oimg, 1);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                tc_fence_before();
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // complete before the phase barrier releases
+        }
+        gc_grid_barrier(a.barrier, (unsigned int)(p + 1) * gridDim.x);
+        tc_fence_after();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct GruChainPlan {
     GruChainArgs args;
     int grid;
@@ -991,6 +1195,9 @@ struct GruChainPlan {
     bool rzo = false;               // k_gru_chain_rzo (reset gate first; update gate and candidate together, off the critical path)
     GruRzoArgs rzo_args;
     size_t rzo_smem = 0;
+    bool mt = false;                // k_gru_chain_mt (more tiles than SMs); ESR_GRU_MT=0: k_gru_chain
+    int mt_grid = 0;
+    size_t mt_smem = 0;
     bool x3 = false;                // k_gru_chain_x3 (x-side of the three gates as one N = 192 GEMM); ESR_GRU_X3=1
     size_t x3_smem = 0;
 };
@@ -1014,6 +1221,7 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
     a.B = B; a.N = N; a.nsteps = nsteps; a.H = H; a.W = W; a.TW = TW; a.TH = TH;
     a.tiles_x = (W + TW - 1) / TW; a.tiles_y = (H + TH - 1) / TH;
     a.stages = 3;
+    a.diag = getenv("ESR_GRU_DIAG") ? atoi(getenv("ESR_GRU_DIAG")) : 0;
     a.wpre = getenv("ESR_GRU_WPRE") != nullptr;     // 476 -> 492 us with it (profiles/r2_notes.md): off
     p->smem = 1024 + (size_t)a.stages * (2 * TC_A_BYTES + 2 * 128 * 128) + 16 * a.stages + 96;
     ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
@@ -1046,6 +1254,21 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
         if (getenv("ESR_DEBUG")) fprintf(stderr, "[esr] gru_chain: %d clusters of %d CTAs wanted, %d can be resident\n", n_tiles / a.cluster, a.cluster, max_clusters);
         if (max_clusters * a.cluster < n_tiles) a.cluster = 1;
     }
+    static const bool mt_off = getenv("ESR_GRU_MT") && atoi(getenv("ESR_GRU_MT")) == 0;
+    if (!p->pipelined && !mt_off && 32 % TW == 0) {
+        const int per_cta = (n_tiles + dev_info().sm_count - 1) / dev_info().sm_count;
+        const size_t smem_mt = 1024 + (size_t)3 * (2 * TC_A_BYTES + 2 * 128 * 128) + GC_STG_BYTES + 16 * 3 + 8 * GC_MT_MAX + 64 + 96;
+        if (per_cta <= GC_MT_MAX && smem_mt <= (size_t)dev_info().max_smem_optin &&
+            tc_make_omap(rh, TW, 32 / TW, &p->rzo_args.omap_rh) == ESR_OK && tc_make_omap(hs, TW, 32 / TW, &p->rzo_args.omap_hs) == ESR_OK) {
+            p->mt = true;
+            p->rzo_args.g = a;
+            p->rzo_args.g.stages = 3;
+            p->rzo_args.tiles_per_cta = per_cta;
+            p->mt_grid = (n_tiles + per_cta - 1) / per_cta;
+            p->mt_smem = smem_mt;
+            ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_mt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mt));
+        }
+    }
     static const bool rzo_off = getenv("ESR_GRU_RZO") && atoi(getenv("ESR_GRU_RZO")) == 0;
     if (p->pipelined && a.cluster <= 1 && !rzo_off) {
         p->rzo = true;
@@ -1075,6 +1298,12 @@ int gru_chain_launch(void *plan, cudaStream_t st)
 {
     GruChainPlan *p = (GruChainPlan *)plan;
     ESR_CUDA_CHECK(cudaMemsetAsync(p->args.barrier, 0, 64 * 8 * sizeof(unsigned int), st));   // per-image counters, 32 bytes apart
+    if (p->mt) {
+        void *kargs[] = {(void *)&p->rzo_args};
+        ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain_mt, dim3(p->mt_grid), dim3(GC_THREADS), kargs, p->mt_smem, st));
+        esr::count_launch();
+        return ESR_OK;
+    }
     if (p->rzo && p->x3) {
         void *kargs[] = {(void *)&p->rzo_args};
         ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain_x3, dim3(p->grid), dim3(GC_THREADS), kargs, p->x3_smem, st));
