@@ -82,6 +82,8 @@ class EventSRPipeline:
     def _grow(self, rows, mx):
         """A step fell outside the recorded capacity: record the graphs again, larger (takes effect from the next step)."""
         f = self._graphs[0]["fused"]
+        if rows <= f.cap and f.mcap >= 64:
+            return                                   # a count above 64: outside the fused path whatever the graphs were recorded with
         self.capture(len(self._graphs), max(int(rows * 1.5) + 65536, f.cap), max(2 * mx, f.mcap))
 
     def _replay(self, slot, mode):
