@@ -63,7 +63,7 @@ def test_round2_bench_lines_carry_parity_rooflines_and_every_config():
     ops = {(p["op"], p["events"] >= 5_000_000) for p in d1["sweep"]}
     assert ("scatter_cnt", True) in ops and ("cnt2event", True) in ops and any("cpu_Mev_per_s" in p for p in d1["sweep"])
     d2 = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_cfg2_n2.json")))
-    assert d2["n_gpus"] == 2 and 1.6 < d2["value"] / d1["value"] < 2.4          # (the two lines may come from different builds of the round)
+    assert d2["n_gpus"] == 2 and 1.9 < d2["value"] / d1["value"] < 2.1
     for t in (d2["train"], d2["configs"]["cfg3"]["train"], d2["configs"]["cfg4"]["train"]):
         assert "NCCL" in t["mode"] and t["gradient_exchange_check"]["ok"] and t["gradient_exchange_check"]["identical_on_all_ranks"]
     ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_cfg2_reference.json")))
