@@ -232,34 +232,38 @@ k_upsample2x(const __nv_bfloat16 *__restrict__ src, size_t s_plane, int n_img, i
 {
     PDL_LAUNCH_DEPENDENTS();
     PDL_WAIT();
-    const int G = C / 8, H2 = 2 * H, W2 = 2 * W;
-    const size_t total = (size_t)n_img * H2 * W2 * G;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % G);
-        const size_t p = i / G;
-        const int x = (int)(p % W2), y = (int)((p / W2) % H2), img = (int)(p / ((size_t)W2 * H2));
-        const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f), fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-        const float ly = fy - (float)y0, lx = fx - (float)x0;
-        const size_t b0 = ((size_t)img * H + y0) * W, b1 = ((size_t)img * H + y1) * W;
+    // grid = (chunks of an output row, output rows, images): no 64-bit index arithmetic per element (the flat-index form spent more
+    // instructions on its divisions than on the interpolation: 29 us for 63 MB at cfg2)
+    const int G = C / 8, W2 = 2 * W;
+    const int y = blockIdx.y, img = blockIdx.z;
+    const float fy = fmaxf(0.0f, ((float)y + 0.5f) * 0.5f - 0.5f);
+    const int y0 = (int)fy, y1 = min(y0 + 1, H - 1);
+    const float ly = fy - (float)y0;
+    const __nv_bfloat16 *r0 = src + ((size_t)img * H + y0) * W * C, *r1 = src + ((size_t)img * H + y1) * W * C;
+    __nv_bfloat16 *drow = dst + ((size_t)img * 2 * H + y) * W2 * C;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W2 * G; i += gridDim.x * blockDim.x) {
+        const int x = i / G, g = i - x * G;
+        const float fx = fmaxf(0.0f, ((float)x + 0.5f) * 0.5f - 0.5f);
+        const int x0 = (int)fx, x1 = min(x0 + 1, W - 1);
+        const float lx = fx - (float)x0;
         float v00[8], v01[8], v10[8], v11[8], o[8];
-        load8(src + (b0 + x0) * C + g * 8, s_plane, v00);
-        load8(src + (b0 + x1) * C + g * 8, s_plane, v01);
-        load8(src + (b1 + x0) * C + g * 8, s_plane, v10);
-        load8(src + (b1 + x1) * C + g * 8, s_plane, v11);
+        load8(r0 + x0 * C + g * 8, s_plane, v00);
+        load8(r0 + x1 * C + g * 8, s_plane, v01);
+        load8(r1 + x0 * C + g * 8, s_plane, v10);
+        load8(r1 + x1 * C + g * 8, s_plane, v11);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
             o[e] = (1.0f - ly) * ((1.0f - lx) * v00[e] + lx * v01[e]) + ly * ((1.0f - lx) * v10[e] + lx * v11[e]);
-        store8(dst + p * C + g * 8, d_plane, o);
+        store8(drow + (size_t)i * 8, d_plane, o);
     }
 }
 int upsample2x(const SplitTensor &src, int n_img, const SplitTensor &dst, cudaStream_t st)
 {
     ESR_REQUIRE(dst.H == 2 * src.H && dst.W == 2 * src.W && dst.C == src.C && src.C % 8 == 0, "upsample2x: bad shapes");
-    const size_t total = (size_t)n_img * dst.H * dst.W * (src.C / 8);
-    ESR_CUDA_CHECK(launch_pdl(k_upsample2x, dim3((unsigned)ceil_div64((int64_t)total, 256)), dim3(256), 0, st, src.base, src.plane(), n_img, src.H, src.W, src.C,
-                                                                            dst.base, dst.plane()));
+    ESR_REQUIRE(dst.H <= 65535 && n_img <= 65535, "upsample2x: grid too large");
+    const int row_items = dst.W * (src.C / 8);
+    ESR_CUDA_CHECK(launch_pdl(k_upsample2x, dim3((unsigned)((row_items + 255) / 256), (unsigned)dst.H, (unsigned)n_img), dim3(256), 0, st, src.base, src.plane(),
+                              n_img, src.H, src.W, src.C, dst.base, dst.plane()));
     esr::count_launch();
     return ESR_OK;
 }
