@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_pipe(const __grid_c
                             unsigned int v;
                             do {
                                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
-                            } while (v < target);
+                                                        } while (v < target);
                         }
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
@@ -536,13 +536,20 @@ struct GruRzoArgs {
     CUtensorMap omap_rh, omap_hs;               // out_tma: store side of rh / the state slots, box (32 ch, TW, 32 / TW, 1, 1), SWIZZLE_64B
     int out_tma;                                // 1: h * r and h' leave through shared memory + TMA stores (see tc_conv_halo.cu)
     int tiles_per_cta;                          // k_gru_chain_mt: consecutive tiles owned by one CTA (<= 4)
+    int sched;                                  // k_gru_chain_rzo: 1 = candidate's x-side issued with the NEXT step's reset x-side (see the kernel)
+    long long *trace;                           // ESR_GRU_TRACE: [nsteps][8] clock stamps of CTA 0 (k_gru_chain_rzo<true>)
 };
 constexpr uint32_t GC_STG_PLANE = 32 * 64;      // one epilogue warp's 32 pixels x 32 channels of one split plane
 constexpr uint32_t GC_STG_BYTES = 8 * 2 * GC_STG_PLANE;
 
+// TRACE: clock stamps of CTA 0 per step (ESR_GRU_TRACE=<file>), a separate instantiation (see tc_conv_halo.cu).  Columns per step:
+// 0 MMA thread: reset-side GEMM issued, 1 before / 2 after its wait for the first candidate-side (h * r) K-block, 3 candidate-side issued,
+// 4 epilogue (warp 2): reset accumulator ready, 5 h * r stored and complete, 6 barrier arrival done, 7 producer: barrier 2g seen
+template <bool TRACE>
 __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_constant__ GruRzoArgs aa)
 {
     const GruChainArgs &a = aa.g;
+    long long *const tr = (TRACE && blockIdx.x == 0) ? aa.trace : nullptr;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t B_BYTES = 64u * 128u;                              // one plane of a 64-row weight tile
@@ -586,10 +593,10 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
     if (warp == 0) {
         if (elect_one_sync()) {
             uint32_t ps = 0, pph = 0;
-            for (int g = 0; g < a.nsteps; ++g) {
-                const int w_idx = g / a.N, s_idx = g - w_idx * a.N;
-                const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
-                for (int seg = 0; seg < 6; ++seg) {
+            auto do_seg = [&](int seg, int g) {
+                {
+                    const int w_idx = g / a.N, s_idx = g - w_idx * a.N;
+                    const int xc_img = (w_idx * a.B + bb) * a.N + (img < a.B ? s_idx : a.N - 1 - s_idx);
                     const CUtensorMap *bmap = seg < 4 ? &aa.bmap_zr64 : &a.bmap_go;
                     const int brow = seg < 2 ? 64 : 0;
                     const int kb0 = (seg & 1) ? 9 : 0;
@@ -613,8 +620,9 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
                         unsigned int v;
                         do {
                             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
-                        } while (v < target);
+                                                } while (v < target);
                         asm volatile("fence.proxy.async;" ::: "memory");
+                        if (tr && seg == 5) tr[g * 8 + 7] = clock64();
                     }
                     for (int t = 0; t < 9; ++t) {
                         const int dy = t / 3 - 1, dx = t % 3 - 1;
@@ -633,18 +641,33 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
                         if (++ps == (uint32_t)a.stages) { ps = 0; pph ^= 1u; }
                     }
                 }
+            };
+            // sched 1: between the reset-side GEMM r.h and the candidate-side GEMM o.rh only z.x and z.h are issued (what fits into the
+            // epilogue + barrier turnaround between them, profiles/r2_trace_gru.csv); the candidate's x-side moves next to the NEXT
+            // step's reset x-side, into the turnaround after o.rh, and writes the other of two candidate accumulators.
+            if (aa.sched) {
+                do_seg(0, 0); do_seg(4, 0);
+                for (int g = 0; g < a.nsteps; ++g) {
+                    do_seg(1, g); do_seg(2, g); do_seg(3, g); do_seg(5, g);
+                    if (g + 1 < a.nsteps) { do_seg(0, g + 1); do_seg(4, g + 1); }
+                }
+            } else {
+                for (int g = 0; g < a.nsteps; ++g)
+                    for (int seg = 0; seg < 6; ++seg) do_seg(seg, g);
             }
         }
     } else if (warp == 1) {
         if (elect_one_sync()) {
             const uint32_t idesc = umma_idesc(TC_BLOCK_M, 64);
             uint32_t ms = 0, mph = 0;
-            for (int g = 0; g < a.nsteps; ++g) {
-                for (int seg = 0; seg < 6; ++seg) {
-                    const uint32_t acc = tmem_base + (uint32_t)(seg >> 1) * 64u;          // r | z | o
+            auto do_seg = [&](int seg, int g) {
+                {
+                    const uint32_t acc = tmem_base + (uint32_t)(seg >> 1) * 64u + ((aa.sched && seg >= 4) ? (uint32_t)(g & 1) * 64u : 0u);   // r | z | o (| o')
                     for (int t = 0; t < 9; ++t) {
+                        if (tr && seg == 5 && t == 0) tr[g * 8 + 1] = clock64();
                         mbar_wait(bar_full + 8u * ms, mph);
                         tc_fence_after();
+                        if (tr && seg == 5 && t == 0) tr[g * 8 + 2] = clock64();
                         const uint32_t st = smem_base + ms * STAGE;
                         // descriptors as base + immediates (see tc_conv_halo.cu): this thread's instruction stream is on the critical path
                         constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -661,9 +684,19 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
                         umma_commit(bar_empty + 8u * ms);
                         if (++ms == (uint32_t)a.stages) { ms = 0; mph ^= 1u; }
                     }
-                    if (seg == 1) umma_commit(bar_accum);                  // r complete
-                    if (seg == 5) umma_commit(bar_accum + 8u);             // z and o complete
+                    if (seg == 1) { umma_commit(bar_accum); if (tr) tr[g * 8 + 0] = clock64(); }                 // r complete
+                    if (seg == 5) { umma_commit(bar_accum + 8u); if (tr) tr[g * 8 + 3] = clock64(); }            // z and o complete
                 }
+            };
+            if (aa.sched) {
+                do_seg(0, 0); do_seg(4, 0);
+                for (int g = 0; g < a.nsteps; ++g) {
+                    do_seg(1, g); do_seg(2, g); do_seg(3, g); do_seg(5, g);
+                    if (g + 1 < a.nsteps) { do_seg(0, g + 1); do_seg(4, g + 1); }
+                }
+            } else {
+                for (int g = 0; g < a.nsteps; ++g)
+                    for (int seg = 0; seg < 6; ++seg) do_seg(seg, g);
             }
         }
     } else {
@@ -690,6 +723,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
             // ---- part A: r -> h * r
             mbar_wait_backoff(bar_accum, par);
             tc_fence_after();
+            if (tr && warp == 2 && lane == 0) tr[g * 8 + 4] = clock64();
             {
                 uint32_t raw[32];
                 tmem_ld32(taddr + (uint32_t)c0, raw);
@@ -714,17 +748,18 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
                 __syncwarp();
                 if (aa.out_tma) gc_tma_store_wait(&aa.omap_rh, stg_w, lane, c0, x0, y0 + quad * (32 / a.TW), img);
             }
+            if (tr && warp == 2 && lane == 0) tr[g * 8 + 5] = clock64();
             tc_fence_before();
             asm volatile("fence.proxy.async;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
+            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); if (tr) tr[g * 8 + 6] = clock64(); }
             // ---- part B: z, o -> h' = h (1 - z) + o z
             mbar_wait_backoff(bar_accum + 8u, par);
             tc_fence_after();
             {
                 uint32_t rz[32], ro[32];
                 tmem_ld32(taddr + 64u + (uint32_t)c0, rz);
-                tmem_ld32(taddr + 128u + (uint32_t)c0, ro);
+                tmem_ld32(taddr + 128u + (aa.sched ? (uint32_t)(g & 1) * 64u : 0u) + (uint32_t)c0, ro);
                 if (valid) {
                     float z[32], o[32];
                     const float4 *bz = reinterpret_cast<const float4 *>(a.bias_zr + c0), *bo = reinterpret_cast<const float4 *>(a.bias_go + c0);
@@ -823,7 +858,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_x3(const __grid_con
                 unsigned int v;
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar_ctr) : "memory");
-                } while (v < target);
+                                } while (v < target);
                 asm volatile("fence.proxy.async;" ::: "memory");
             };
             // kind 0: X, 1: H, 2: RH
@@ -1273,6 +1308,7 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
     if (p->pipelined && a.cluster <= 1 && !rzo_off) {
         p->rzo = true;
         p->rzo_args.g = a;
+        { static const bool sched_off = getenv("ESR_GRU_SCHED") && atoi(getenv("ESR_GRU_SCHED")) == 0; p->rzo_args.sched = sched_off ? 0 : 1; }
         p->rzo_args.g.stages = 4;
         if ((rc = tc_make_bmap(w_zr, 128, 18, 64, &p->rzo_args.bmap_zr64))) { delete p; return rc; }
         p->rzo_smem = 1024 + (size_t)4 * (2 * TC_A_BYTES + 2 * 64 * 128) + 16 * 4 + 96;
@@ -1288,7 +1324,8 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
             p->x3 = true;
             ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->x3_smem));
         }
-        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_rzo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->rzo_smem));
+        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_rzo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->rzo_smem));
+        ESR_CUDA_CHECK(cudaFuncSetAttribute(k_gru_chain_rzo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->rzo_smem));
     }
     *plan_out = p;
     return ESR_OK;
@@ -1311,8 +1348,29 @@ int gru_chain_launch(void *plan, cudaStream_t st)
         return ESR_OK;
     }
     if (p->rzo) {
+        static const char *trace_path = getenv("ESR_GRU_TRACE");          // measurement aid: clock stamps of CTA 0, one row per step
+        if (trace_path) {
+            static long long *dbuf = nullptr;
+            const int ns = p->rzo_args.g.nsteps;
+            if (!dbuf) cudaMalloc(&dbuf, sizeof(long long) * 8 * 256);
+            cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * 256, st);
+            GruRzoArgs b = p->rzo_args; b.trace = dbuf;
+            void *targs[] = {(void *)&b};
+            ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain_rzo<true>, dim3(p->grid), dim3(GC_THREADS), targs, p->rzo_smem, st));
+            cudaStreamSynchronize(st);
+            static long long host[8 * 256];
+            cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
+            FILE *f = fopen(trace_path, "w");
+            if (f) {
+                fprintf(f, "# per step: mma_reset_side_issued, mma_before_wait_rh, mma_after_wait_rh, mma_candidate_issued, epi_reset_acc_ready, epi_rh_stored, epi_barrier_arrived, prod_barrier_seen\n");
+                for (int i = 0; i < ns && i < 256; ++i) { for (int c = 0; c < 8; ++c) fprintf(f, "%lld%c", host[i * 8 + c], c == 7 ? '\n' : ','); }
+                fclose(f);
+            }
+            esr::count_launch();
+            return ESR_OK;
+        }
         void *kargs[] = {(void *)&p->rzo_args};
-        ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain_rzo, dim3(p->grid), dim3(GC_THREADS), kargs, p->rzo_smem, st));
+        ESR_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_gru_chain_rzo<false>, dim3(p->grid), dim3(GC_THREADS), kargs, p->rzo_smem, st));
         esr::count_launch();
         return ESR_OK;
     }
