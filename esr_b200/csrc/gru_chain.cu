@@ -536,6 +536,7 @@ struct GruRzoArgs {
     CUtensorMap omap_rh, omap_hs;               // out_tma: store side of rh / the state slots, box (32 ch, TW, 32 / TW, 1, 1), SWIZZLE_64B
     int out_tma;                                // 1: h * r and h' leave through shared memory + TMA stores (see tc_conv_halo.cu)
     int tiles_per_cta;                          // k_gru_chain_mt: consecutive tiles owned by one CTA (<= 4)
+    int warp_arrive;                            // k_gru_chain_rzo with out_tma: per-warp barrier arrivals (ESR_GRU_WARP_ARRIVE=0: one per CTA behind a CTA barrier + membar)
     int sched;                                  // k_gru_chain_rzo: 1 = candidate's x-side issued with the NEXT step's reset x-side (see the kernel)
     long long *trace;                           // ESR_GRU_TRACE: [nsteps][8] clock stamps of CTA 0 (k_gru_chain_rzo<true>)
 };
@@ -568,7 +569,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
     const int bb = img < a.B ? img : img - a.B;
     const bool per_img = B2 <= 64;
     unsigned int *bar_ctr = a.barrier + (per_img ? img * 8 : 0);
-    const unsigned int bar_n = per_img ? (unsigned int)tiles_per_img : gridDim.x;
+    const bool warp_arrive = aa.out_tma && aa.warp_arrive;               // each epilogue warp releases the phase barrier itself (8 arrivals per CTA)
+    const unsigned int bar_n = (per_img ? (unsigned int)tiles_per_img : gridDim.x) * (warp_arrive ? 8u : 1u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
@@ -712,12 +714,14 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
         for (int g = 0; g < a.nsteps; ++g) {
             const uint32_t par = (uint32_t)(g & 1);
             const __nv_bfloat16 *h_prev = a.hs + ((size_t)g * B2 * a.H * a.W + pix) * 64 + c0;
-            // h of this pixel (previous step's state: final before this step's first barrier) -- in flight during the main loops
+            // h of this pixel (previous step's state: final before this step's first barrier) -- in flight during the main loops.
+            // L2 loads (ld.cg): with per-warp arrivals no CTA barrier separates this read from the OTHER half-warp's store of the same
+            // 128-byte line, and an L1 copy taken now could serve that warp's own read a stale half later
             uint4 hh[4], hl[4];
             if (valid) {
                 const uint4 *ph = reinterpret_cast<const uint4 *>(h_prev), *pl = reinterpret_cast<const uint4 *>(h_prev + a.hs_plane);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { hh[q] = ph[q]; hl[q] = pl[q]; }
+                for (int q = 0; q < 4; ++q) { hh[q] = __ldcg(ph + q); hl[q] = __ldcg(pl + q); }
             }
             float h[32];
             // ---- part A: r -> h * r
@@ -750,9 +754,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
             }
             if (tr && warp == 2 && lane == 0) tr[g * 8 + 5] = clock64();
             tc_fence_before();
-            asm volatile("fence.proxy.async;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); if (tr) tr[g * 8 + 6] = clock64(); }
+            if (warp_arrive) {
+                // this warp's h * r went out as bulk stores that gc_tma_store_wait() has seen COMPLETE, and its TMEM reads are done:
+                // nothing of the other warps is needed for its arrival (no CTA barrier, no membar in the turnaround)
+                if (lane == 0) { atomicAdd(bar_ctr, 1u); if (tr && warp == 2) tr[g * 8 + 6] = clock64(); }
+                __syncwarp();
+            } else {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); if (tr) tr[g * 8 + 6] = clock64(); }
+            }
             // ---- part B: z, o -> h' = h (1 - z) + o z
             mbar_wait_backoff(bar_accum + 8u, par);
             tc_fence_after();
@@ -783,9 +794,14 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gru_chain_rzo(const __grid_co
                 if (aa.out_tma) gc_tma_store_wait(&aa.omap_hs, stg_w, lane, c0, x0, y0 + quad * (32 / a.TW), (g + 1) * B2 + img);
             }
             tc_fence_before();
-            asm volatile("fence.proxy.async;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
+            if (warp_arrive) {
+                if (lane == 0) atomicAdd(bar_ctr, 1u);
+                __syncwarp();
+            } else {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 2 && lane == 0) { __threadfence(); atomicAdd(bar_ctr, 1u); }
+            }
         }
     }
 
@@ -1309,6 +1325,7 @@ int gru_chain_prepare(const SplitTensor &xc, const SplitTensor &hs, const SplitT
         p->rzo = true;
         p->rzo_args.g = a;
         { static const bool sched_off = getenv("ESR_GRU_SCHED") && atoi(getenv("ESR_GRU_SCHED")) == 0; p->rzo_args.sched = sched_off ? 0 : 1; }
+        { static const bool wa_off = getenv("ESR_GRU_WARP_ARRIVE") && atoi(getenv("ESR_GRU_WARP_ARRIVE")) == 0; p->rzo_args.warp_arrive = wa_off ? 0 : 1; }
         p->rzo_args.g.stages = 4;
         if ((rc = tc_make_bmap(w_zr, 128, 18, 64, &p->rzo_args.bmap_zr64))) { delete p; return rc; }
         p->rzo_smem = 1024 + (size_t)4 * (2 * TC_A_BYTES + 2 * 64 * 128) + 16 * 4 + 96;
