@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const __grid_constant
 // the MMA thread starts tile i+1 in the other accumulator while the epilogue warps drain tile i; the TMA producer simply
 // streams K-blocks across tile boundaries.  Same operand order, same epilogue code: results are bit-identical to k_conv_tc.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t TCP_STG_PLANE = 32 * 64, TCP_STG_BUF = 2 * TCP_STG_PLANE;   // per-warp staging of the TMA-store epilogue (split outputs)
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_constant__ ConvTCArgs a)
 {
     PDL_LAUNCH_DEPENDENTS();
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)a.npad * 128u;
     const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
-    const uint32_t bar_base = smem_base + (uint32_t)a.stages * stage_bytes;
+    const uint32_t stg_ring = smem_base + (uint32_t)a.stages * stage_bytes;      // out_tma: [4 warps][2 buffers][2 planes][32 px x 64 B] (tc_conv_halo.cu)
+    const uint32_t bar_base = stg_ring + (a.out_tma ? 4u * 2u * TCP_STG_BUF : 0u);
     const uint32_t bar_full = bar_base, bar_empty = bar_base + 8u * a.stages;
     const uint32_t bar_afull = bar_base + 16u * a.stages, bar_aempty = bar_afull + 16u;      // per accumulator
     const uint32_t tmem_slot = bar_aempty + 16u;
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_
         const int quad = warp & 3;
         const int m = quad * 32 + lane;
         int it = 0;
+        uint32_t stg_n = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t ai = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
             const int img = tile / tiles_per_img, trem = tile - img * tiles_per_img;
@@ -261,6 +264,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_
                 if (a.diag & 16) continue;                          // measurement aid: no TMEM reads, no stores
                 if (a.stack) tmem_ld_chunk_stacked(taddr, n0, a.npad, raw);
                 else tmem_ld_chunk(taddr, n0, a.npad, raw);
+                if (a.out_tma == 1 && !(a.diag & 8)) {
+                    // staged epilogue as in k_conv_tc_halo: this warp's 32 pixels x 32 channels -> swizzled shared memory -> TMA store
+                    const uint32_t buf = stg_ring + ((uint32_t)quad * 2u + (stg_n & 1u)) * TCP_STG_BUF;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    float v[32];
+                    epilogue_values(a, raw, n0, img, y, x, valid, v);
+                    uint32_t hw[16], lw[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) split_pack2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
+                    const uint32_t row = buf + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t o = row + (((uint32_t)q ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(hw[4 * q]), "r"(hw[4 * q + 1]), "r"(hw[4 * q + 2]), "r"(hw[4 * q + 3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + TCP_STG_PLANE), "r"(lw[4 * q]), "r"(lw[4 * q + 1]), "r"(lw[4 * q + 2]), "r"(lw[4 * q + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int rows = 32 / a.TW, yq = y0 + quad * rows;
+                        tma_store_5d(&a.omap, buf, a.out_coff + n0, x0, yq, img, 0);
+                        tma_store_5d(&a.omap, buf + TCP_STG_PLANE, a.out_coff + n0, x0, yq, img, 1);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++stg_n;
+                } else
                 if (valid && !(a.diag & 8)) epilogue_chunk(a, raw, n0, pix, img, y, x);
                 else if (a.diag & 8) { if (raw[0] == 0x7fc12345u && raw[31] == 0x7fc54321u) a.out_f32[0] = 1.0f; }   // keep the loads alive
                 __syncwarp();
@@ -269,6 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc_persist(const __grid_
             if (a.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < TRACE_N) a.trace[it * 8 + 6] = clock64();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_aempty + 8u * ai) : "memory");
         }
+        if (a.out_tma == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -604,7 +635,8 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
         else out_tma = 0;
     }
     if (halo && !out_tma) halo = conv_tc_halo_plan(npad_, 0, &h_as, &h_bs);
-    if (!halo) out_tma = 0;                                       // (the other kernels keep the direct stores for now)
+    const int out_tma_req = out_tma;                              // eligibility of the output, whichever kernel takes the layer
+    if (!halo) out_tma = 0;                                       // (decided below for the persistent kernel; the one-tile kernel keeps direct stores)
     if (halo) { TW = 8; TH = 16; BW = 10; BH = 18; }
     for (int s = 0; s < d.n_src; ++s) {
         const SplitTensor &t = d.src[s];
@@ -638,6 +670,11 @@ int conv_tc_prepare(const ConvTCDesc &d, ConvTCArgs *args)
     // multi-wave grids of layers with N >= 64: persistent CTAs (one per SM, all the stages that fit) with two TMEM accumulators
     static const int persist_min_n = getenv("ESR_TC_NO_PERSIST") ? 1 << 30 : (getenv("ESR_TC_PERSIST_MIN_N") ? atoi(getenv("ESR_TC_PERSIST_MIN_N")) : 64);   // measured: 129 -> 3.196 ms, 64 -> 3.159 ms, 16 -> 3.165 ms per cfg2 step
     a.persist = (!v3 && !halo && a.npad >= persist_min_n && n_tiles > dev_info().sm_count) ? 1 : 0;
+    if (a.persist && out_tma_req == 1 && 32 % TW == 0 && getenv("ESR_TC_PAIR") == nullptr) {
+        int st2 = stages;                                         // staged TMA-store epilogue also here: 32 KB of staging beside the ring
+        while (st2 > 2 && tc_smem_bytes(a.npad, st2) + 64 + 4 * 2 * 4096 > smem_cap) --st2;
+        if (tc_smem_bytes(a.npad, st2) + 64 + 4 * 2 * 4096 <= smem_cap) { stages = st2; out_tma = 1; stg_bufs = 2; }
+    }
     if (n_tiles > dev_info().sm_count && !a.persist) {
         int s2 = stages;
         while (s2 > 2 && 2 * (tc_smem_bytes(a.npad, s2) + 1024) > smem_cap) --s2;
@@ -752,7 +789,7 @@ int conv_tc_launch(const ConvTCArgs &a, cudaStream_t st)
                 cudaMemsetAsync(dbuf, 0, sizeof(long long) * 8 * TRACE_N, st);
                 ConvTCArgs b = a; b.trace = dbuf;
                 static int max_set_t = 0;
-                const size_t smem_t = smem + 64;
+                const size_t smem_t = smem + 64 + (a.out_tma ? 4 * 2 * 4096 : 0);
                 if ((int)smem_t > max_set_t) { cudaFuncSetAttribute(k_conv_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t); max_set_t = (int)smem_t; }
                 k_conv_tc_persist<<<(unsigned)dev_info().sm_count, TC_THREADS, smem_t, st>>>(b);
                 cudaStreamSynchronize(st);
@@ -769,7 +806,7 @@ int conv_tc_launch(const ConvTCArgs &a, cudaStream_t st)
             }
         }
         static int max_set_p = 0;
-        const size_t smem_p = smem + 64;
+        const size_t smem_p = smem + 64 + (a.out_tma ? 4 * 2 * 4096 : 0);
         if ((int)smem_p > max_set_p) {
             ESR_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
             max_set_p = (int)smem_p;
