@@ -44,26 +44,34 @@ _XF_SLACK = 4096
 _XF_ROWS = {}                 # (device, B, H, W) -> (rows, largest count) of the last call: sizes the next call's guesses
 
 
-def _xf_tables(dev):
+def _xf_tables_host():
     """Key tables of the fused cnt2event path for m = 1, 2, 4 .. 64, built with numpy.linspace (the reference's arithmetic,
-    cnt2event.pyx:74): rank uint16 [(m+1), m] and the K(m) distinct fp32 timestamps.  One device blob per device."""
+    cnt2event.pyx:74): per m a rank table uint16 [(m+1), m] -- rank[n, j] = index of float32(linspace(0, 1, n)[j]) among the K(m)
+    distinct timestamps counts <= m can produce -- and those timestamps, ascending.  Returns (blob bytes, desc int32 [7, 3] =
+    rank byte offset, timestamps byte offset, K)."""
+    blob = bytearray()
+    desc = np.zeros((7, 3), dtype=np.int32)
+    for i in range(7):
+        m = 1 << i
+        vals = [np.linspace(0, 1, n).astype(np.float32) for n in range(1, m + 1)]
+        uniq = np.unique(np.concatenate(vals))
+        table = np.zeros((m + 1, m), dtype=np.uint16)
+        for n in range(1, m + 1):
+            table[n, :n] = np.searchsorted(uniq, vals[n - 1])
+        for j, arr in enumerate((table, uniq.astype(np.float32))):
+            blob.extend(b"\0" * (-len(blob) % 16))
+            desc[i, j] = len(blob)
+            blob.extend(arr.tobytes())
+        desc[i, 2] = len(uniq)
+    return bytes(blob), np.ascontiguousarray(desc)
+
+
+def _xf_tables(dev):
+    """One device copy of _xf_tables_host() per device."""
     key = str(dev)
     if key not in _XF_TABLES:
-        blob = bytearray()
-        desc = np.zeros((7, 3), dtype=np.int32)
-        for i in range(7):
-            m = 1 << i
-            vals = [np.linspace(0, 1, n).astype(np.float32) for n in range(1, m + 1)]
-            uniq = np.unique(np.concatenate(vals))
-            table = np.zeros((m + 1, m), dtype=np.uint16)
-            for n in range(1, m + 1):
-                table[n, :n] = np.searchsorted(uniq, vals[n - 1])
-            for j, arr in enumerate((table, uniq.astype(np.float32))):
-                blob.extend(b"\0" * (-len(blob) % 16))
-                desc[i, j] = len(blob)
-                blob.extend(arr.tobytes())
-            desc[i, 2] = len(uniq)
-        _XF_TABLES[key] = (torch.from_numpy(np.frombuffer(bytes(blob), dtype=np.uint8).copy()).to(dev), np.ascontiguousarray(desc))
+        blob, desc = _xf_tables_host()
+        _XF_TABLES[key] = (torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).to(dev), desc)
     return _XF_TABLES[key]
 
 

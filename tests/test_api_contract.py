@@ -30,3 +30,27 @@ def test_fused_cnt2event_sizing_rules_without_a_gpu():
     stats([[5, 5, 0, 9], [1, 1, 0, 1], [2, 2, 0, 1]])          # a count above the recorded limit
     assert f.result() == (None, 15, 9)
     assert np.random.get_state()[1][0] == np.random.RandomState(123).get_state()[1][0]     # the reference's reseeding side effect
+
+
+def test_fused_cnt2event_key_tables():
+    """The tables the fused redistribution sorts by (esr_b200.expand._xf_tables_host): for every count n <= m and event j < n the key
+    indexes exactly the timestamp the reference assigns, float32(np.linspace(0, 1, n)[j]) (cnt2event.pyx:74); keys are strictly
+    increasing in j (so a pixel emits a key at most once -- what lets the kernels derive key histograms from count histograms) and
+    ascend with the timestamp (so the counting sort over keys is the reference's stable sort by time)."""
+    import numpy as np
+    from esr_b200.expand import _xf_tables_host
+    blob, desc = _xf_tables_host()
+    ks = []
+    for i in range(7):
+        m = 1 << i
+        ro, uo, K = (int(v) for v in desc[i])
+        assert ro % 16 == 0 and uo % 16 == 0
+        rank = np.frombuffer(blob, dtype=np.uint16, count=(m + 1) * m, offset=ro).reshape(m + 1, m)
+        uniq = np.frombuffer(blob, dtype=np.float32, count=K, offset=uo)
+        assert np.all(np.diff(uniq) > 0) and uniq[0] == 0.0 and (m == 1 or uniq[-1] == 1.0)
+        for n in range(1, m + 1):
+            want = np.linspace(0, 1, n).astype(np.float32)
+            assert np.array_equal(uniq[rank[n, :n]], want), (m, n)
+            assert np.all(np.diff(rank[n, :n].astype(np.int64)) > 0), (m, n)
+        ks.append(K)
+    assert ks == [1, 2, 5, 19, 73, 309, 1229]          # the kernels size their per-key counters by these (XF_MAXK = 1232)
